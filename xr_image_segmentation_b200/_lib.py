@@ -1,0 +1,132 @@
+"""ctypes binding of libxrseg.so (include/xrseg.h).  No compute happens in Python."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class XrsegError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"xrseg error {code}: {msg}")
+        self.code = code
+
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_WEIGHTS, ERR_STATE, ERR_NO_DETECTIONS, ERR_CAPACITY = 0, -1, -2, -3, -4, -5, -6, -7
+FMT_RGB8, FMT_RGBA8 = 0, 1
+RESIZE_STRETCH, RESIZE_LETTERBOX = 0, 1
+CONV_UMMA, CONV_DIRECT = 0, 1
+BOX_PARSEBOXES, BOX_DRAWBOXES, BOX_RAW = 0, 1, 2
+MASK_REFERENCE_160, MASK_CROP_160, MASK_UPSAMPLE_640, MASK_BITS_160 = 0, 1, 2, 3
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("max_batch", C.c_int32), ("model_scale", C.c_int32),
+        ("weights", C.c_void_p), ("weights_bytes", C.c_size_t),
+        ("iou_threshold", C.c_float), ("score_threshold", C.c_float), ("mask_threshold", C.c_float),
+        ("max_det", C.c_int32), ("max_candidates", C.c_int32), ("resize_mode", C.c_int32), ("conv_impl", C.c_int32),
+        ("use_cuda_graph", C.c_int32), ("micro_batch", C.c_int32), ("reserved", C.c_int32 * 8),
+    ]
+
+
+class TensorView(C.Structure):
+    _fields_ = [("device_ptr", C.c_void_p), ("dtype", C.c_int32), ("rank", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class Box(C.Structure):
+    _fields_ = [("center_x", C.c_float), ("center_y", C.c_float), ("width", C.c_float), ("height", C.c_float),
+                ("label_id", C.c_int32), ("frame", C.c_int32)]
+
+
+class MaskParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mode", C.c_int32), ("box_convention", C.c_int32),
+                ("screen_w", C.c_float), ("screen_h", C.c_float), ("image_w", C.c_int32), ("image_h", C.c_int32),
+                ("first", C.c_int32), ("count", C.c_int32)]
+
+
+class LayerInfo(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
+                ("stride", C.c_int32), ("groups", C.c_int32), ("act", C.c_int32), ("transposed", C.c_int32),
+                ("h_in", C.c_int32), ("w_in", C.c_int32)]
+
+
+# every symbol include/xrseg.h declares, with its signature
+_P = C.POINTER
+SIGNATURES = {
+    "xrseg_create": (C.c_int, [_P(Config), _P(C.c_void_p)]),
+    "xrseg_destroy": (None, [C.c_void_p]),
+    "xrseg_last_error": (C.c_char_p, [C.c_void_p]),
+    "xrseg_abi_version": (C.c_int, []),
+    "xrseg_schedule": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "xrseg_schedule_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "xrseg_poll": (C.c_int, [C.c_void_p]),
+    "xrseg_wait": (C.c_int, [C.c_void_p]),
+    "xrseg_counts": (C.c_int, [C.c_void_p, _P(C.c_int32), C.c_int]),
+    "xrseg_peek_output": (C.c_int, [C.c_void_p, C.c_int, _P(TensorView)]),
+    "xrseg_readback": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
+    "xrseg_decode": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, _P(Box), C.c_int, _P(C.c_int)]),
+    "xrseg_masks": (C.c_int, [C.c_void_p, _P(MaskParams), C.c_void_p, C.c_size_t]),
+    "xrseg_keep_indices": (C.c_int, [C.c_void_p, _P(C.c_int32), _P(C.c_float), C.c_int]),
+    "xrseg_layer_count": (C.c_int, [C.c_int]),
+    "xrseg_layer_info_get": (C.c_int, [C.c_int, C.c_int, _P(LayerInfo)]),
+    "xrseg_last_timings": (C.c_int, [C.c_void_p, _P(C.c_float), C.c_int]),
+    "xrseg_launch_count": (C.c_int, [C.c_void_p]),
+    "xrseg_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, _P(C.c_int64)]),
+    "xrseg_debug_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "xrseg_debug_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "xrseg_debug_mask_threshold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "xrseg_debug_conv": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "xrseg_debug_emulate_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "xrseg_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "xrseg_host_free": (None, [C.c_void_p]),
+    "xrseg_device_count": (C.c_int, []),
+}
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libxrseg.so")
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile libxrseg.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc")], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+        print(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("building libxrseg.so failed")
+    return library_path()
+
+
+def load_library():
+    """Load libxrseg.so; raises if it is missing (there is no fallback implementation)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise XrsegError(ERR_INVALID, f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                      f"or `make -C xr_image_segmentation_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.xrseg_abi_version() != 1:
+        raise XrsegError(ERR_INVALID, "libxrseg.so ABI version mismatch")
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, runner=None):
+    if rc < 0:
+        lib = load_library()
+        msg = lib.xrseg_last_error(runner)
+        raise XrsegError(rc, msg.decode() if msg else "")
+    return rc

@@ -1,0 +1,627 @@
+// conv_umma.cuh -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Replaces the `Conv` / `ConvTranspose` (+ `Swish`, + residual `Add`) layers that the reference executes through
+// Worker.ScheduleIterable / MoveNext (Assets/Scripts/InferenceEngine/IEExecutor.cs:371,397); layer list in
+// SURVEY.md Appendix A/B.
+//
+// GEMM view:  D[M = output positions, N = Cout] = A[M, K] * W[N, K]^T,  K = taps * Cin, fp16 operands, fp32 accum.
+// Activations are NHWC fp16 (channel counts padded to multiples of 16), so a K-chunk of 8 channels is one 16-byte
+// vector.  Both operands sit in shared memory in the K-major SWIZZLE_NONE canonical layout:
+//       element (row r, K-chunk c)  ->  base + c * LBO + r * 16 bytes            (SBO = 128 B: rows are uniform)
+// Because rows are uniformly 16 B apart, a descriptor may START at any row.  Two A-operand modes use this:
+//   MODE_GATHER  every (row, K-chunk) is fetched by an im2col address computation (any kernel / stride / ConvT).
+//   MODE_HALO    3x3 stride-1: the input halo of the tile is loaded ONCE in "padded-linear" pixel order
+//                (index = (b*(H+1) + y) * (W+2) + x + 1, one shared zero row between images, zero columns left
+//                and right) and the nine taps are nine MMAs whose A descriptors start kh*(W+2)+kw rows further --
+//                no 9x im2col re-read.  Output rows that fall on padding positions are computed and discarded.
+//
+// Warp roles (288 threads): warps 0-3 producers (cp.async 16 B, zero-fill for padding), warps 4-7 epilogue
+// (tcgen05.ld -> +bias -> SiLU -> +residual -> fp16 NHWC store into the channel slice of the destination, which is
+// how Concat/Split cost nothing), warp 8 TMEM allocator + single-thread MMA issuer.  CTAs are persistent over
+// (M-tile, N-tile) work items; the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Weights are pre-packed on the host into the exact shared-memory image.
+#pragma once
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace xrseg {
+
+enum { MODE_GATHER = 0, MODE_HALO = 1 };
+enum { CONV_HDR_BYTES = 2304, CONV_SMEM_MAX = 232448, CONV_THREADS = 288, CONV_MAX_STAGES = 4 };
+
+struct ConvParams {
+  const __half* in;
+  __half* out;
+  const __half* res;
+  const __half* wpack;
+  const float* bias;
+  int B, H, W, Cin, in_pitch;       // Cin: padded channel count of the input view (multiple of 16)
+  int Ho, Wo, Cout, out_pitch;      // Cout: padded output channels (per position when transposed)
+  int res_pitch;
+  int k, stride, pad, act, transposed;
+  int mode, Wp, Hp1, M_total;
+  int m_tiles, n_tiles, Ntile;
+  int K_total, nks, cps, taps, cb;  // cps: A chunks per stage; taps: MMA tap loop count (9 in halo mode, else 1)
+  int slots, lbo_a, a_stage_bytes, b_stage_bytes, b_resident;
+  int S, lag;
+  uint32_t idesc;
+  int tmem_cols;
+  int smem_off_b, smem_off_a, smem_bytes;
+  int grid;
+  int dbg;                          // debug: bit 1 swaps the LBO / SBO descriptor fields
+};
+
+struct ConvDesc {
+  int B, H, W, Cin, in_pitch;
+  int Cout, out_pitch;
+  int k, stride, act, transposed;
+  int res_pitch;                    // 0 = no residual
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// index math shared by the device loaders, the epilogue and the host emulator
+// ---------------------------------------------------------------------------------------------------------------
+struct PixRef {
+  int valid;
+  long pix;  // pixel index into the NHWC tensor (multiply by pitch for the element offset)
+};
+
+// MODE_HALO: biased padded-linear index Lb = L + Hp1*Wp (always >= 0) -> input pixel.
+__host__ __device__ inline PixRef halo_pixel(const ConvParams& p, long Lb) {
+  long G = Lb / p.Wp;
+  int cc = static_cast<int>(Lb - G * p.Wp);
+  long b1 = G / p.Hp1;
+  int r = static_cast<int>(G - b1 * p.Hp1);
+  PixRef o;
+  o.valid = (b1 >= 1 && b1 <= p.B && r < p.H && cc >= 1 && cc <= p.W) ? 1 : 0;
+  o.pix = ((b1 - 1) * p.H + r) * static_cast<long>(p.W) + (cc - 1);
+  return o;
+}
+
+// MODE_GATHER: output position m and K element index -> input pixel and channel.
+__host__ __device__ inline PixRef gather_pixel(const ConvParams& p, long m, int kelem, int* c0) {
+  PixRef o;
+  o.valid = 0;
+  o.pix = 0;
+  *c0 = 0;
+  if (m >= p.M_total || kelem >= p.K_total) return o;
+  int tap = kelem / p.Cin;
+  *c0 = kelem - tap * p.Cin;
+  int kk = p.transposed ? 1 : p.k;
+  int kh = tap / kk, kw = tap - kh * kk;
+  int hw = p.transposed ? p.H * p.W : p.Ho * p.Wo;
+  long b = m / hw;
+  int rem = static_cast<int>(m - b * hw);
+  int wo = p.transposed ? p.W : p.Wo;
+  int oh = rem / wo, ow = rem - oh * wo;
+  int st = p.transposed ? 1 : p.stride;
+  int pad = p.transposed ? 0 : p.pad;
+  int ih = oh * st - pad + kh, iw = ow * st - pad + kw;
+  if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W) return o;
+  o.valid = 1;
+  o.pix = (b * p.H + ih) * static_cast<long>(p.W) + iw;
+  return o;
+}
+
+// Output position m (+ column n of the GEMM) -> output pixel, channel.
+__host__ __device__ inline PixRef out_pixel(const ConvParams& p, long m, int n, int* co) {
+  PixRef o;
+  o.valid = 0;
+  o.pix = 0;
+  *co = n;
+  if (m >= p.M_total) return o;
+  if (p.mode == MODE_HALO) {
+    long G = m / p.Wp;
+    int cc = static_cast<int>(m - G * p.Wp);
+    long b = G / p.Hp1;
+    int r = static_cast<int>(G - b * p.Hp1);
+    if (r >= p.H || cc < 1 || cc > p.W) return o;
+    o.valid = 1;
+    o.pix = (b * p.H + r) * static_cast<long>(p.W) + (cc - 1);
+    return o;
+  }
+  if (p.transposed) {
+    int pos = n / p.Cout;
+    *co = n - pos * p.Cout;
+    int hw = p.H * p.W;
+    long b = m / hw;
+    int rem = static_cast<int>(m - b * hw);
+    int h = rem / p.W, w = rem - h * p.W;
+    o.valid = 1;
+    o.pix = (b * p.Ho + (2 * h + (pos >> 1))) * static_cast<long>(p.Wo) + (2 * w + (pos & 1));
+    return o;
+  }
+  o.valid = 1;
+  o.pix = m;
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// planning (host)
+// ---------------------------------------------------------------------------------------------------------------
+static inline int pow2_ceil(int v) {
+  int r = 32;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+// variant: 0 = auto (halo for 3x3 s1), 1 = force MODE_GATHER (cross-check path)
+static inline ConvParams plan_conv(const ConvDesc& d, int num_sms, int variant = 0) {
+  ConvParams p{};
+  XR_CHECK(d.Cin % 16 == 0 && d.Cout % 16 == 0, "channels must be padded to 16 (cin %d cout %d)", d.Cin, d.Cout);
+  p.B = d.B; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.in_pitch = d.in_pitch;
+  p.Cout = d.Cout; p.out_pitch = d.out_pitch; p.res_pitch = d.res_pitch;
+  p.k = d.k; p.stride = d.stride; p.pad = d.k / 2; p.act = d.act; p.transposed = d.transposed;
+  if (d.transposed) {
+    XR_CHECK(d.k == 2 && d.stride == 2, "only 2x2 stride-2 ConvTranspose is on the path");
+    p.Ho = d.H * 2; p.Wo = d.W * 2; p.pad = 0;
+  } else {
+    p.Ho = (d.H + 2 * p.pad - d.k) / d.stride + 1;
+    p.Wo = (d.W + 2 * p.pad - d.k) / d.stride + 1;
+  }
+  const int ncols = d.transposed ? 4 * d.Cout : d.Cout;
+  p.Ntile = ncols <= 256 ? ncols : 256;
+  XR_CHECK(ncols % p.Ntile == 0, "N %d not tileable", ncols);
+  p.n_tiles = ncols / p.Ntile;
+  p.idesc = umma_idesc_f16(p.Ntile, 0);
+  p.tmem_cols = pow2_ceil(2 * p.Ntile);
+  const bool halo = (d.k == 3 && d.stride == 1 && !d.transposed && variant != 1);
+  p.mode = halo ? MODE_HALO : MODE_GATHER;
+  const int budget = CONV_SMEM_MAX - CONV_HDR_BYTES;
+  if (halo) {
+    p.Wp = d.W + 2; p.Hp1 = d.H + 1;
+    long mt = static_cast<long>(d.B) * p.Hp1 * p.Wp;
+    XR_CHECK(mt < (1L << 31), "M too large");
+    p.M_total = static_cast<int>(mt);
+    p.slots = 130 + 2 * p.Wp;
+    p.lbo_a = (p.slots | 1) * 16;
+    p.taps = 9;
+    p.K_total = 9 * d.Cin;
+    int cb = 64;
+    while (cb > 16 && (d.Cin % cb != 0 || p.lbo_a * (cb / 8) > 40960)) cb >>= 1;
+    const long total_b = 9L * d.Cin * p.Ntile * 2;
+    p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
+    if (!p.b_resident)
+      while (cb > 16 && 9 * cb * p.Ntile * 2 > 40960) cb >>= 1;
+    p.cb = cb;
+    p.cps = cb / 8;
+    p.nks = d.Cin / cb;
+    p.a_stage_bytes = p.lbo_a * p.cps;
+    p.b_stage_bytes = 9 * cb * p.Ntile * 2;
+  } else {
+    long mt = d.transposed ? static_cast<long>(d.B) * d.H * d.W : static_cast<long>(d.B) * p.Ho * p.Wo;
+    XR_CHECK(mt < (1L << 31), "M too large");
+    p.M_total = static_cast<int>(mt);
+    p.slots = 128;
+    p.lbo_a = 129 * 16;
+    p.taps = 1;
+    p.K_total = (d.transposed ? 1 : d.k * d.k) * d.Cin;
+    p.cb = 64;
+    p.cps = 8;
+    p.nks = ceil_div(p.K_total, 64);
+    p.a_stage_bytes = p.lbo_a * 8;
+    p.b_stage_bytes = 8 * p.Ntile * 16;
+    const long total_b = static_cast<long>(p.nks) * p.b_stage_bytes;
+    p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
+  }
+  p.m_tiles = ceil_div(p.M_total, 128);
+  const int resident_bytes = p.b_resident ? p.nks * p.b_stage_bytes : 0;
+  const int per_stage = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
+  int S = (budget - resident_bytes) / per_stage;
+  if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
+  XR_CHECK(S >= 2, "conv does not fit shared memory (a %d b %d resident %d)", p.a_stage_bytes, p.b_stage_bytes,
+           resident_bytes);
+  p.S = S;
+  p.lag = S >= 3 ? 2 : 1;
+  p.smem_off_b = CONV_HDR_BYTES;
+  const int b_region = p.b_resident ? resident_bytes : S * p.b_stage_bytes;
+  p.smem_off_a = CONV_HDR_BYTES + round_up(b_region, 128);
+  p.smem_bytes = p.smem_off_a + S * p.a_stage_bytes;
+  XR_CHECK(p.smem_bytes <= CONV_SMEM_MAX, "smem plan overflow %d", p.smem_bytes);
+  const int work = p.m_tiles * p.n_tiles;
+  const int occ = (p.smem_bytes <= 112 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+  p.grid = work < num_sms * occ ? work : num_sms * occ;
+  return p;
+}
+
+// Number of halves in the packed weight image.
+static inline size_t conv_wpack_elems(const ConvParams& p) {
+  return static_cast<size_t>(p.n_tiles) * p.nks * p.b_stage_bytes / 2;
+}
+
+// K element consumed at (stage ks, B-chunk bc, element e) -> (tap, input channel); returns false for K padding.
+static inline bool conv_k_index(const ConvParams& p, int ks, int bc, int e, int* tap, int* ci) {
+  if (p.mode == MODE_HALO) {
+    *tap = bc / p.cps;
+    *ci = ks * p.cb + (bc % p.cps) * 8 + e;
+    return true;
+  }
+  int kelem = (ks * 8 + bc) * 8 + e;
+  if (kelem >= p.K_total) return false;
+  *tap = kelem / p.Cin;
+  *ci = kelem % p.Cin;
+  return true;
+}
+
+// Pack fp32 weights ([cout,cin,k,k], or [cin,cout,2,2] when transposed) into the smem image
+// [n_tile][stage][B-chunk][n][8] (fp16) and the bias into fp32 [n_tiles * Ntile].
+template <typename HalfT>
+static inline void pack_conv_weights(const ConvParams& p, const float* w, const float* bias, int cin_real, int cout_real,
+                                     std::vector<HalfT>& wp, std::vector<float>& bp) {
+  const int bchunks = p.b_stage_bytes / (p.Ntile * 16);
+  wp.assign(conv_wpack_elems(p), HalfT(0.0f));
+  bp.assign(static_cast<size_t>(p.n_tiles) * p.Ntile, 0.0f);
+  const int kk = p.transposed ? 2 : p.k;
+  for (int nt = 0; nt < p.n_tiles; ++nt)
+    for (int ks = 0; ks < p.nks; ++ks)
+      for (int bc = 0; bc < bchunks; ++bc)
+        for (int n = 0; n < p.Ntile; ++n)
+          for (int e = 0; e < 8; ++e) {
+            int tap, ci;
+            if (!conv_k_index(p, ks, bc, e, &tap, &ci)) continue;
+            if (ci >= cin_real) continue;
+            const int ng = nt * p.Ntile + n;
+            float v;
+            if (p.transposed) {
+              const int pos = ng / p.Cout, co = ng % p.Cout;
+              if (co >= cout_real) continue;
+              v = w[((static_cast<size_t>(ci) * cout_real + co) * 2 + (pos >> 1)) * 2 + (pos & 1)];
+            } else {
+              if (ng >= cout_real) continue;
+              const int kh = tap / kk, kw = tap % kk;
+              v = w[((static_cast<size_t>(ng) * cin_real + ci) * kk + kh) * kk + kw];
+            }
+            const size_t idx = ((static_cast<size_t>(nt) * p.nks + ks) * bchunks + bc) * p.Ntile * 8 +
+                               static_cast<size_t>(n) * 8 + e;
+            wp[idx] = HalfT(v);
+          }
+  for (int ng = 0; ng < p.n_tiles * p.Ntile; ++ng) {
+    const int co = p.transposed ? ng % p.Cout : ng;
+    if (co < cout_real && bias) bp[ng] = bias[co];
+  }
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [4]
+  uint64_t* empty = full + 4;                               // [4]
+  uint64_t* tfull = empty + 4;                              // [2]
+  uint64_t* tempty = tfull + 2;                             // [2]
+  uint64_t* bres = tempty + 2;                              // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + 256);     // [<=512]
+  uint8_t* smem_b = smem + p.smem_off_b;
+  uint8_t* smem_a = smem + p.smem_off_a;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int total_work = p.m_tiles * p.n_tiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    mbar_init(bres, 128);
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  for (int i = tid; i < p.n_tiles * p.Ntile; i += CONV_THREADS) bias_s[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ======================================= producers ===========================================
+    const uint32_t a_u32 = smem_u32(smem_a);
+    const uint32_t b_u32 = smem_u32(smem_b);
+    if (p.b_resident) {
+      const int bytes = p.nks * p.b_stage_bytes;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack);
+      for (int i = tid * 16; i < bytes; i += 128 * 16) cp_async16(b_u32 + i, src + i, 16);
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(bres);
+    }
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int m_tile = w / p.n_tiles;
+      const int n_tile = w - m_tile * p.n_tiles;
+      const long m0 = static_cast<long>(m_tile) * 128;
+
+      // per-tile row bookkeeping for MODE_GATHER (8 rows per thread: r0 + 16 j)
+      const int gc = tid & 7;
+      const int r0 = tid >> 3;
+      int g_ok[8], g_base[8], g_ih[8], g_iw[8];
+      if (p.mode == MODE_GATHER) {
+        const int hw = p.transposed ? p.H * p.W : p.Ho * p.Wo;
+        const int wo = p.transposed ? p.W : p.Wo;
+        const int st = p.transposed ? 1 : p.stride;
+        const int pad = p.transposed ? 0 : p.pad;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const long m = m0 + r0 + 16 * j;
+          g_ok[j] = m < p.M_total;
+          const long b = m / hw;
+          const int rem = static_cast<int>(m - b * hw);
+          const int oh = rem / wo, ow = rem - oh * wo;
+          g_base[j] = static_cast<int>(b) * p.H * p.W;
+          g_ih[j] = oh * st - pad;
+          g_iw[j] = ow * st - pad;
+        }
+      }
+
+      for (int ks = 0; ks < p.nks; ++ks, ++it) {
+        const int slot = it % p.S;
+        if (it >= p.S) mbar_wait(&empty[slot], static_cast<uint32_t>((it / p.S) - 1) & 1u);
+        const uint32_t a_dst = a_u32 + slot * p.a_stage_bytes;
+
+        if (p.mode == MODE_GATHER) {
+          const int kelem = (ks * 8 + gc) * 8;
+          if (kelem < p.K_total) {
+            const int tap = kelem / p.Cin;
+            const int c0 = kelem - tap * p.Cin;
+            const int kk = p.transposed ? 1 : p.k;
+            const int kh = tap / kk, kw = tap - kh * kk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int ih = g_ih[j] + kh, iw = g_iw[j] + kw;
+              const bool ok = g_ok[j] && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
+                              static_cast<unsigned>(iw) < static_cast<unsigned>(p.W);
+              const __half* src =
+                  ok ? p.in + (static_cast<size_t>(g_base[j]) + static_cast<size_t>(ih) * p.W + iw) * p.in_pitch + c0
+                     : p.in;
+              cp_async16_ca(a_dst + gc * p.lbo_a + (r0 + 16 * j) * 16, src, ok ? 16u : 0u);
+            }
+          }
+        } else {
+          const int c = tid % p.cps;
+          const int s0 = tid / p.cps;
+          const int step = 128 / p.cps;
+          const long Lb = m0 - 1 - p.Wp + s0 + static_cast<long>(p.Hp1) * p.Wp;
+          long G = Lb / p.Wp;
+          int cc = static_cast<int>(Lb - G * p.Wp);
+          int b1 = static_cast<int>(G / p.Hp1);
+          int r = static_cast<int>(G - static_cast<long>(b1) * p.Hp1);
+          const int coff = ks * p.cb + c * 8;
+          for (int s = s0; s < p.slots; s += step) {
+            const bool ok = (b1 >= 1 && b1 <= p.B && r < p.H && cc >= 1 && cc <= p.W);
+            const __half* src =
+                ok ? p.in + ((static_cast<size_t>(b1 - 1) * p.H + r) * p.W + (cc - 1)) * p.in_pitch + coff : p.in;
+            cp_async16_ca(a_dst + c * p.lbo_a + s * 16, src, ok ? 16u : 0u);
+            cc += step;
+            while (cc >= p.Wp) {
+              cc -= p.Wp;
+              if (++r == p.Hp1) { r = 0; ++b1; }
+            }
+          }
+        }
+        if (!p.b_resident) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) +
+                               (static_cast<size_t>(n_tile) * p.nks + ks) * p.b_stage_bytes;
+          const uint32_t b_dst = b_u32 + slot * p.b_stage_bytes;
+          for (int i = tid * 16; i < p.b_stage_bytes; i += 128 * 16) cp_async16(b_dst + i, src + i, 16);
+        }
+        cp_async_commit();
+        if (it >= p.lag) {
+          if (p.lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full[(it - p.lag) % p.S]);
+        }
+      }
+    }
+    // drain the last `lag` stages
+    if (p.lag == 2 && it >= 2) {
+      cp_async_wait<1>();
+      fence_proxy_async_smem();
+      mbar_arrive(&full[(it - 2) % p.S]);
+    }
+    if (it >= 1) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(&full[(it - 1) % p.S]);
+    }
+  } else if (warp == 8) {
+    // ======================================= MMA issuer ==========================================
+    if (lane == 0) {
+      const uint32_t a_u32 = smem_u32(smem_a);
+      const uint32_t b_u32 = smem_u32(smem_b);
+      const uint32_t lbo_b = static_cast<uint32_t>(p.Ntile) * 16u;
+      if (p.b_resident) mbar_wait(bres, 0);
+      int it = 0, tcount = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+        const int buf = tcount & 1;
+        const int use = tcount >> 1;
+        if (use >= 1) mbar_wait(&tempty[buf], static_cast<uint32_t>(use - 1) & 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.Ntile);
+        uint32_t acc = 0;
+        for (int ks = 0; ks < p.nks; ++ks, ++it) {
+          const int slot = it % p.S;
+          mbar_wait(&full[slot], static_cast<uint32_t>(it / p.S) & 1u);
+          tc_fence_after();
+          const uint32_t a_base = a_u32 + slot * p.a_stage_bytes;
+          const uint32_t b_base = b_u32 + (p.b_resident ? ks : slot) * p.b_stage_bytes;
+          int kj;
+          if (p.mode == MODE_GATHER) {
+            kj = (p.K_total - ks * 64) / 16;
+            if (kj > 4) kj = 4;
+          } else {
+            kj = p.cb / 16;
+          }
+          for (int t = 0; t < p.taps; ++t) {
+            const uint32_t shift = (p.mode == MODE_HALO) ? static_cast<uint32_t>((t / 3) * p.Wp + (t % 3)) * 16u : 0u;
+            for (int j = 0; j < kj; ++j) {
+              const uint64_t ad = (p.dbg & 2) ? umma_desc_kmajor_noswz(a_base + 2 * j * p.lbo_a + shift, 128, p.lbo_a)
+                                              : umma_desc_kmajor_noswz(a_base + 2 * j * p.lbo_a + shift, p.lbo_a, 128);
+              const uint64_t bd = (p.dbg & 2) ? umma_desc_kmajor_noswz(b_base + (t * p.cps + 2 * j) * lbo_b, 128, lbo_b)
+                                              : umma_desc_kmajor_noswz(b_base + (t * p.cps + 2 * j) * lbo_b, lbo_b, 128);
+              umma_f16(d_tmem, ad, bd, p.idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&empty[slot]);
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+  } else {
+    // ======================================= epilogue ============================================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int tcount = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+      const int m_tile = w / p.n_tiles;
+      const int n_tile = w - m_tile * p.n_tiles;
+      const long m = static_cast<long>(m_tile) * 128 + row;
+      const int buf = tcount & 1;
+      const int use = tcount >> 1;
+      mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * p.Ntile);
+      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c0, v);
+        tmem_ld_wait();
+        const int n = n_tile * p.Ntile + c0;
+        int co;
+        const PixRef o = out_pixel(p, m, n, &co);
+        if (o.valid) {
+          float y[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float t = __uint_as_float(v[i]) + bias_s[n + i];
+            y[i] = p.act ? silu_f(t) : t;
+          }
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + static_cast<size_t>(o.pix) * p.res_pitch + co);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
+              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
+              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
+            }
+          }
+          uint4 o0, o1;
+          __half2* q0 = reinterpret_cast<__half2*>(&o0);
+          __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            q0[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+            q1[i] = __floats2half2_rn(y[8 + 2 * i], y[8 + 2 * i + 1]);
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(o.pix) * p.out_pitch + co);
+          op[0] = o0;
+          op[1] = o1;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+// Call once per device before the first launch.
+static inline void conv_umma_prepare_device() {
+  XR_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
+}
+
+static inline void launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
+  conv_umma_kernel<<<p.grid, CONV_THREADS, p.smem_bytes, stream>>>(p);
+  XR_CUDA(cudaGetLastError());
+}
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------------------------
+// host emulation of the kernel's data movement (fp32 math): validates pack order, slot mapping and tap shifts.
+// Test infrastructure only -- never on a product path.
+// ---------------------------------------------------------------------------------------------------------------
+static inline void emulate_conv_umma(const ConvParams& p, const float* in, const float* wpack_f, const float* bias,
+                                     const float* res, float* out) {
+  const int bchunks = p.b_stage_bytes / (p.Ntile * 16);
+  const int lbo_a_slots = p.lbo_a / 16;
+  std::vector<float> a(static_cast<size_t>(p.cps) * lbo_a_slots * 8);
+  std::vector<float> acc(128 * static_cast<size_t>(p.Ntile));
+  for (int w = 0; w < p.m_tiles * p.n_tiles; ++w) {
+    const int m_tile = w / p.n_tiles, n_tile = w % p.n_tiles;
+    const long m0 = static_cast<long>(m_tile) * 128;
+    std::fill(acc.begin(), acc.end(), 0.0f);
+    for (int ks = 0; ks < p.nks; ++ks) {
+      std::fill(a.begin(), a.end(), 0.0f);
+      // loader
+      for (int c = 0; c < p.cps; ++c)
+        for (int s = 0; s < p.slots; ++s) {
+          PixRef pr;
+          int c0;
+          if (p.mode == MODE_GATHER) {
+            pr = gather_pixel(p, m0 + s, (ks * 8 + c) * 8, &c0);
+          } else {
+            pr = halo_pixel(p, m0 - 1 - p.Wp + s + static_cast<long>(p.Hp1) * p.Wp);
+            c0 = ks * p.cb + c * 8;
+          }
+          if (!pr.valid) continue;
+          for (int e = 0; e < 8; ++e)
+            a[(static_cast<size_t>(c) * lbo_a_slots + s) * 8 + e] = in[static_cast<size_t>(pr.pix) * p.in_pitch + c0 + e];
+        }
+      // MMA
+      int kj = p.mode == MODE_GATHER ? std::min(4, (p.K_total - ks * 64) / 16) : p.cb / 16;
+      const float* bst = wpack_f + (static_cast<size_t>(n_tile) * p.nks + ks) * bchunks * p.Ntile * 8;
+      for (int t = 0; t < p.taps; ++t) {
+        const int shift = p.mode == MODE_HALO ? (t / 3) * p.Wp + (t % 3) : 0;
+        for (int j = 0; j < kj; ++j)
+          for (int half_k = 0; half_k < 2; ++half_k) {
+            const int ac = 2 * j + half_k;
+            const int bc = t * p.cps + 2 * j + half_k;
+            for (int i = 0; i < 128; ++i)
+              for (int n = 0; n < p.Ntile; ++n) {
+                float sacc = 0.f;
+                for (int e = 0; e < 8; ++e)
+                  sacc += a[(static_cast<size_t>(ac) * lbo_a_slots + i + shift) * 8 + e] *
+                          bst[(static_cast<size_t>(bc) * p.Ntile + n) * 8 + e];
+                acc[static_cast<size_t>(i) * p.Ntile + n] += sacc;
+              }
+          }
+      }
+    }
+    // epilogue
+    for (int i = 0; i < 128; ++i)
+      for (int n = 0; n < p.Ntile; ++n) {
+        int co;
+        const int ng = n_tile * p.Ntile + n;
+        PixRef o = out_pixel(p, m0 + i, ng, &co);
+        if (!o.valid) continue;
+        float y = acc[static_cast<size_t>(i) * p.Ntile + n] + bias[ng];
+        if (p.act) y = y / (1.0f + expf(-y));
+        if (res) y += res[static_cast<size_t>(o.pix) * p.res_pitch + co];
+        out[static_cast<size_t>(o.pix) * p.out_pitch + co] = y;
+      }
+  }
+}
+
+}  // namespace xrseg

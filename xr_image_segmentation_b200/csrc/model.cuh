@@ -1,0 +1,320 @@
+// model.cuh -- YOLO11-seg topology builder (n / s widths, any batch) and XRSW weight-pack reader.
+//
+// Restates the layer graph the reference runs (the 499 chains of
+// Assets/Resources/Model/yolo11n-seg-sentis.sentis, executed through IEExecutor.cs:371,397) as a list of kernel
+// launches over NHWC fp16 buffers.  Concat / Split are channel-slice views of a shared buffer (no copies), residual
+// Adds ride in the convolution epilogue, Swish is fused into every producing kernel.  Convolutions are emitted in
+// the asset's chain order, which is the canonical layer order of the XRSW weight pack.
+#pragma once
+
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_umma.cuh"
+
+namespace xrseg {
+
+struct TV {           // tensor view inside the activation arena (element offsets, resolved at launch)
+  size_t off = 0;
+  int B = 0, H = 0, W = 0, C = 0, Cp = 0, pitch = 0;
+};
+
+struct LayerRec {
+  std::string name;
+  int cin, cout, k, stride, groups, act, transposed, h_in, w_in;
+};
+
+enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN, OP_VGATHER };
+
+struct Op {
+  OpKind kind;
+  int layer = -1;
+  TV x, y, res;
+  bool has_res = false;
+  int k = 1, stride = 1, act = 0, transposed = 0, heads = 0;
+};
+
+struct Spec {
+  int ch[5];
+  int mid0, mid1;     // C3k2 output widths of layers 2 / 4 (n: 64 / 128)
+  int cls_mid, box_mid, coef_mid, proto_mid, heads;
+};
+
+static inline Spec make_spec(int scale) {
+  const int wnum = (scale == 's') ? 2 : 1;  // width = wnum / 4
+  Spec s;
+  const int base[5] = {64, 128, 256, 512, 1024};
+  for (int i = 0; i < 5; ++i) s.ch[i] = base[i] * wnum / 4;
+  s.mid0 = 256 * wnum / 4;
+  s.mid1 = 512 * wnum / 4;
+  s.cls_mid = s.ch[2] > 80 ? s.ch[2] : 80;
+  s.box_mid = 64;
+  if (s.ch[2] / 4 > s.box_mid) s.box_mid = s.ch[2] / 4;
+  s.coef_mid = s.ch[2] / 4 > 32 ? s.ch[2] / 4 : 32;
+  s.proto_mid = 256 * wnum / 4;
+  s.heads = (s.ch[4] / 2) / 64;
+  return s;
+}
+
+class Net {
+ public:
+  int B;
+  Spec sp;
+  std::vector<LayerRec> layers;
+  std::vector<Op> ops;
+  std::map<std::string, TV> named;
+  size_t arena_elems = 0;
+  TV input;                 // [B,640,640,4] fp16
+  TV box[3], cls[3], coef[3], protos;
+  int fh[3], fw[3];
+
+  Net(int scale, int batch, int in_hw = 640) : B(batch), sp(make_spec(scale)) { build(in_hw); }
+
+  TV alloc(int H, int W, int C, int pitch_override = 0) {
+    TV t;
+    t.B = B; t.H = H; t.W = W; t.C = C;
+    t.Cp = pitch_override ? pitch_override : round_up(C, 16);
+    t.pitch = t.Cp;
+    t.off = arena_elems;
+    arena_elems += static_cast<size_t>(B) * H * W * t.pitch;
+    arena_elems = (arena_elems + 127) / 128 * 128;
+    return t;
+  }
+  static TV slice(const TV& t, int c0, int c) {
+    XR_CHECK(c0 % 16 == 0 && c % 16 == 0 && c0 + c <= t.Cp, "bad slice %d+%d of %d", c0, c, t.Cp);
+    TV s = t;
+    s.off = t.off + c0;
+    s.C = c;
+    s.Cp = c;
+    return s;
+  }
+
+  TV conv(const TV& x, int cout, int k, int s, bool act, const std::string& name, const TV* dst = nullptr,
+          const TV* res = nullptr, bool transposed = false) {
+    LayerRec l{name, x.C, cout, k, s, 1, act ? 1 : 0, transposed ? 1 : 0, x.H, x.W};
+    layers.push_back(l);
+    const int Ho = transposed ? x.H * 2 : (x.H + 2 * (k / 2) - k) / s + 1;
+    const int Wo = transposed ? x.W * 2 : (x.W + 2 * (k / 2) - k) / s + 1;
+    TV y = dst ? *dst : alloc(Ho, Wo, cout);
+    XR_CHECK(y.H == Ho && y.W == Wo && y.C == cout, "conv %s: destination mismatch", name.c_str());
+    Op o;
+    o.kind = layers.size() == 1 ? OP_STEM : OP_CONV;
+    o.layer = static_cast<int>(layers.size()) - 1;
+    o.x = x; o.y = y; o.k = k; o.stride = s; o.act = act; o.transposed = transposed;
+    if (res) { o.res = *res; o.has_res = true; }
+    ops.push_back(o);
+    named[name] = y;
+    return y;
+  }
+  TV dw(const TV& x, bool act, const std::string& name, const TV* res = nullptr) {
+    LayerRec l{name, x.C, x.C, 3, 1, x.C, act ? 1 : 0, 0, x.H, x.W};
+    layers.push_back(l);
+    TV y = alloc(x.H, x.W, x.C);
+    Op o;
+    o.kind = OP_DW;
+    o.layer = static_cast<int>(layers.size()) - 1;
+    o.x = x; o.y = y; o.k = 3; o.act = act;
+    if (res) { o.res = *res; o.has_res = true; }
+    ops.push_back(o);
+    named[name] = y;
+    return y;
+  }
+
+  TV c3k2(const TV& x, int c_out, int c, bool c3k, const std::string& n, const TV* dst = nullptr) {
+    TV cat = alloc(x.H, x.W, 3 * c);
+    TV ab = slice(cat, 0, 2 * c);
+    conv(x, 2 * c, 1, 1, true, n + ".cv1", &ab);
+    TV b = slice(cat, c, c);
+    TV m = slice(cat, 2 * c, c);
+    if (!c3k) {
+      TV t = conv(b, c / 2, 3, 1, true, n + ".m0.cv1");
+      conv(t, c, 3, 1, true, n + ".m0.cv2", &m, &b);
+    } else {
+      const int c_ = c / 2;
+      TV cat2 = alloc(x.H, x.W, 2 * c_);
+      TV t0 = conv(b, c_, 1, 1, true, n + ".m0.cv1");
+      TV h = conv(t0, c_, 3, 1, true, n + ".m0.m0.cv1");
+      TV t1 = conv(h, c_, 3, 1, true, n + ".m0.m0.cv2", nullptr, &t0);
+      h = conv(t1, c_, 3, 1, true, n + ".m0.m1.cv1");
+      TV t2 = slice(cat2, 0, c_);
+      conv(h, c_, 3, 1, true, n + ".m0.m1.cv2", &t2, &t1);
+      TV u = slice(cat2, c_, c_);
+      conv(b, c_, 1, 1, true, n + ".m0.cv2", &u);
+      conv(cat2, c, 1, 1, true, n + ".m0.cv3", &m);
+    }
+    return conv(cat, c_out, 1, 1, true, n + ".cv2", dst);
+  }
+
+  void head_box_cls(const TV& p, int i, const std::string& n) {
+    TV t = conv(p, sp.box_mid, 3, 1, true, n + ".box.0");
+    t = conv(t, sp.box_mid, 3, 1, true, n + ".box.1");
+    box[i] = conv(t, 64, 1, 1, false, n + ".box.2");
+    t = dw(p, true, n + ".cls.0dw");
+    t = conv(t, sp.cls_mid, 1, 1, true, n + ".cls.0pw");
+    t = dw(t, true, n + ".cls.1dw");
+    t = conv(t, sp.cls_mid, 1, 1, true, n + ".cls.1pw");
+    cls[i] = conv(t, 80, 1, 1, false, n + ".cls.2");
+  }
+  void head_coef(const TV& p, int i, const std::string& n) {
+    TV t = conv(p, sp.coef_mid, 3, 1, true, n + ".coef.0");
+    t = conv(t, sp.coef_mid, 3, 1, true, n + ".coef.1");
+    coef[i] = conv(t, 32, 1, 1, false, n + ".coef.2");
+  }
+
+  void build(int hw) {
+    const int c1 = sp.ch[0], c2 = sp.ch[1], c5 = sp.ch[4];
+    input = alloc(hw, hw, 3, 4);
+    named["input"] = input;
+    const int h8 = hw / 8, h16 = hw / 16, h32 = hw / 32;
+    // concat buffers of the neck, allocated first so that backbone outputs land directly in their slices
+    TV cat13 = alloc(h16, h16, c5 + sp.mid1);        // [up(f10) | f6]
+    TV cat16 = alloc(h8, h8, sp.mid1 + sp.mid1);     // [up(f13) | f4]
+    TV cat19 = alloc(h16, h16, sp.mid0 + sp.mid1);   // [n17 | f13]
+    TV cat22 = alloc(h32, h32, sp.mid1 + c5);        // [n20 | f10]
+
+    TV t = conv(input, c1, 3, 2, true, "b0");
+    t = conv(t, c2, 3, 2, true, "b1");
+    t = c3k2(t, sp.mid0, sp.mid0 / 4, false, "b2");
+    t = conv(t, sp.mid0, 3, 2, true, "b3");
+    TV f4 = slice(cat16, sp.mid1, sp.mid1);
+    c3k2(t, sp.mid1, sp.mid1 / 4, false, "b4", &f4);
+    t = conv(f4, sp.mid1, 3, 2, true, "b5");
+    TV f6 = slice(cat13, c5, sp.mid1);
+    c3k2(t, sp.mid1, sp.mid1 / 2, true, "b6", &f6);
+    t = conv(f6, c5, 3, 2, true, "b7");
+    t = c3k2(t, c5, c5 / 2, true, "b8");
+    {  // SPPF (chains 140-151)
+      const int c_ = c5 / 2;
+      TV cat = alloc(h32, h32, 4 * c_);
+      TV y0 = slice(cat, 0, c_);
+      conv(t, c_, 1, 1, true, "b9.cv1", &y0);
+      Op o;
+      o.kind = OP_SPPF;
+      o.x = cat; o.y = cat;
+      ops.push_back(o);
+      t = conv(cat, c5, 1, 1, true, "b9.cv2");
+    }
+    TV f10 = slice(cat22, sp.mid1, c5);
+    {  // C2PSA (chains 152-190)
+      const int c = c5 / 2;
+      const int kd = 32, hd = 64;
+      XR_CHECK(c / sp.heads == hd, "attention head dim must be 64");
+      TV cat = alloc(h32, h32, 2 * c);
+      conv(t, 2 * c, 1, 1, true, "b10.cv1", &cat);
+      TV b = slice(cat, c, c);
+      TV qkv = conv(b, c + 2 * sp.heads * kd, 1, 1, false, "b10.attn.qkv");
+      TV ao = alloc(h32, h32, c);
+      Op oa;
+      oa.kind = OP_ATTN; oa.x = qkv; oa.y = ao; oa.heads = sp.heads;
+      ops.push_back(oa);
+      TV vb = alloc(h32, h32, c);
+      Op ov;
+      ov.kind = OP_VGATHER; ov.x = qkv; ov.y = vb; ov.heads = sp.heads;
+      ops.push_back(ov);
+      TV s = dw(vb, false, "b10.attn.pe", &ao);                       // pe(v) + attention output
+      conv(s, c, 1, 1, false, "b10.attn.proj", &b, &b);              // b += proj(...)
+      TV f = conv(b, 2 * c, 1, 1, true, "b10.ffn.0");
+      conv(f, c, 1, 1, false, "b10.ffn.1", &b, &b);                  // b += ffn(b)
+      conv(cat, c5, 1, 1, true, "b10.cv2", &f10);
+    }
+    auto upsample = [&](const TV& src, const TV& dst) {
+      Op o;
+      o.kind = OP_UP; o.x = src; o.y = dst;
+      ops.push_back(o);
+    };
+    upsample(f10, slice(cat13, 0, c5));
+    TV f13 = slice(cat19, sp.mid0, sp.mid1);
+    c3k2(cat13, sp.mid1, sp.mid1 / 2, false, "n13", &f13);
+    upsample(f13, slice(cat16, 0, sp.mid1));
+    TV p3 = c3k2(cat16, sp.mid0, sp.mid0 / 2, false, "n16");
+    head_box_cls(p3, 0, "h3");
+    TV n17 = slice(cat19, 0, sp.mid0);
+    conv(p3, sp.mid0, 3, 2, true, "n17", &n17);
+    TV p4 = c3k2(cat19, sp.mid1, sp.mid1 / 2, false, "n19");
+    head_box_cls(p4, 1, "h4");
+    TV n20 = slice(cat22, 0, sp.mid1);
+    conv(p4, sp.mid1, 3, 2, true, "n20", &n20);
+    TV p5 = c3k2(cat22, c5, c5 / 2, true, "n22");
+    head_box_cls(p5, 2, "h5");
+    head_coef(p3, 0, "h3");
+    head_coef(p4, 1, "h4");
+    head_coef(p5, 2, "h5");
+    t = conv(p3, sp.proto_mid, 3, 1, true, "proto.cv1");
+    t = conv(t, sp.proto_mid, 2, 2, false, "proto.up", nullptr, nullptr, true);
+    t = conv(t, sp.proto_mid, 3, 1, true, "proto.cv2");
+    protos = conv(t, 32, 1, 1, true, "proto.cv3");
+    named["p3"] = p3; named["p4"] = p4; named["p5"] = p5;
+    fh[0] = p3.H; fw[0] = p3.W; fh[1] = p4.H; fw[1] = p4.W; fh[2] = p5.H; fw[2] = p5.W;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// XRSW weight pack (written by xr_image_segmentation_b200/weights.py)
+// ---------------------------------------------------------------------------------------------------------------
+#pragma pack(push, 1)
+struct XrswHeader {
+  char magic[4];
+  uint32_t version, n_layers, scale;
+  uint64_t payload_offset;
+  uint8_t reserved[8];
+};
+struct XrswLayer {
+  char name[32];
+  uint32_t cout, cin_g, k, stride, groups, act, transposed, dtype;
+  float w_scale; int32_t w_zp; float b_scale; int32_t b_zp;
+  uint64_t w_off, b_off;
+};
+#pragma pack(pop)
+static_assert(sizeof(XrswHeader) == 32, "header size");
+static_assert(sizeof(XrswLayer) == 96, "record size");
+
+struct HostLayerWeights {
+  std::vector<float> w, b;
+};
+
+// Dequantize exactly like the reference graph's DequantizeUint8 layers: (q - zp) * scale per tensor.
+static inline void xrsw_load(const void* data, size_t bytes, const std::vector<LayerRec>& layers, int scale,
+                             std::vector<HostLayerWeights>& out) {
+  XR_CHECK(bytes >= sizeof(XrswHeader), "weight pack too small");
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  XrswHeader h;
+  memcpy(&h, p, sizeof(h));
+  XR_CHECK(memcmp(h.magic, "XRSW", 4) == 0 && h.version == 1, "not an XRSW v1 pack");
+  XR_CHECK(h.n_layers == layers.size(), "pack has %u layers, topology has %zu", h.n_layers, layers.size());
+  XR_CHECK(static_cast<int>(h.scale) == scale, "pack is for scale '%c'", static_cast<char>(h.scale));
+  XR_CHECK(bytes >= sizeof(XrswHeader) + h.n_layers * sizeof(XrswLayer) && h.payload_offset <= bytes, "truncated pack");
+  out.resize(h.n_layers);
+  for (uint32_t i = 0; i < h.n_layers; ++i) {
+    XrswLayer r;
+    memcpy(&r, p + sizeof(XrswHeader) + i * sizeof(XrswLayer), sizeof(r));
+    const LayerRec& l = layers[i];
+    const int cin_g = l.cin / l.groups;
+    XR_CHECK(static_cast<int>(r.cout) == l.cout && static_cast<int>(r.cin_g) == cin_g && static_cast<int>(r.k) == l.k &&
+                 static_cast<int>(r.stride) == l.stride && static_cast<int>(r.groups) == l.groups &&
+                 static_cast<int>(r.transposed) == l.transposed && static_cast<int>(r.act) == l.act,
+             "layer %u (%s) does not match topology layer %s", i, r.name, l.name.c_str());
+    const size_t nw = static_cast<size_t>(l.cout) * cin_g * l.k * l.k;
+    const size_t nb = l.cout;
+    const size_t esz = r.dtype == 0 ? 4 : 1;
+    XR_CHECK(r.dtype == 0 || r.dtype == 3, "unsupported dtype %u", r.dtype);
+    XR_CHECK(h.payload_offset + r.w_off + nw * esz <= bytes && h.payload_offset + r.b_off + nb * esz <= bytes,
+             "layer %u payload out of range", i);
+    const uint8_t* wp = p + h.payload_offset + r.w_off;
+    const uint8_t* bp = p + h.payload_offset + r.b_off;
+    out[i].w.resize(nw);
+    out[i].b.resize(nb);
+    if (r.dtype == 0) {
+      memcpy(out[i].w.data(), wp, nw * 4);
+      memcpy(out[i].b.data(), bp, nb * 4);
+    } else {
+      for (size_t j = 0; j < nw; ++j) out[i].w[j] = (static_cast<float>(wp[j]) - static_cast<float>(r.w_zp)) * r.w_scale;
+      for (size_t j = 0; j < nb; ++j) out[i].b[j] = (static_cast<float>(bp[j]) - static_cast<float>(r.b_zp)) * r.b_scale;
+    }
+  }
+}
+
+}  // namespace xrseg

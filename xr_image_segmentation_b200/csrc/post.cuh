@@ -1,0 +1,578 @@
+// post.cuh -- the Detect/Segment tail the reference bakes into its graph (IEModelEditorConverter.cs:31-106, graph
+// chains 400-416 and 455-498) and the C# box / mask post-processing (IEExecutor.cs:529-559, IEBoxer.cs:37-81,
+// IEMasker.cs:82-119,124-196,232-247) as memory-bound CUDA kernels:
+//   decode   : 16-bin DFL softmax expectation + anchor/stride decode + 80-class sigmoid max/argmax + score filter
+//   nms      : per-frame sort (score desc, index asc) -> IoU bitmask (smem staged) -> greedy reduce
+//   gather   : compaction of boxes / labels / coefs over the batch (output_0..2)
+//   masks    : coef x proto (32-term fp32 FMA chain) + sigmoid (output_3), fused crop / upsample / threshold variants
+// Arithmetic that decides discrete results (IoU test, box predicate, thresholds) uses explicit IEEE intrinsics in a
+// fixed order so that it matches oracle/postprocess.py bit for bit on identical inputs.
+#pragma once
+
+#include "common.cuh"
+
+namespace xrseg {
+
+constexpr int NUM_ANCHORS_MAX = 8400;
+constexpr int NC = 80;
+constexpr int NM = 32;
+constexpr int PROTO_HW = 160;
+constexpr int PROTO_PIX = PROTO_HW * PROTO_HW;
+
+// One feature-map scale feeding the decode: element (b, a_local, c) at ptr + b*bstride + a_local*pitch + c.
+template <typename T>
+struct ScaleSrc {
+  const T* box; long box_bstride; int box_pitch;
+  const T* cls; long cls_bstride; int cls_pitch;
+  const T* coef; long coef_bstride; int coef_pitch;
+  int h, w, a_off;
+  float stride;
+};
+
+template <typename T>
+struct DecodeParams {
+  ScaleSrc<T> s[3];
+  int B, A;
+  float score_thr;
+  float* boxes;              // [B,A,4] cx,cy,w,h
+  float* scores;             // [B,A]
+  int* labels;               // [B,A]
+  unsigned long long* keys;  // [B,A] candidate sort keys
+  int* cand_count;           // [B]
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+
+template <typename T>
+__global__ void __launch_bounds__(128) decode_kernel(const DecodeParams<T> p) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (a >= p.A) return;
+  int si = 0;
+  if (a >= p.s[1].a_off) si = 1;
+  if (a >= p.s[2].a_off) si = 2;
+  const ScaleSrc<T>& s = p.s[si];
+  const int al = a - s.a_off;
+  const int gy = al / s.w, gx = al - gy * s.w;
+  const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+
+  // ---- DFL (chains 401-406): softmax over 16 bins, expectation with weights 0..15
+  const T* bl = s.box + b * s.box_bstride + static_cast<long>(al) * s.box_pitch;
+  float d[4];
+#pragma unroll
+  for (int side = 0; side < 4; ++side) {
+    float l[16];
+    float mx = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      l[k] = ldf(bl + side * 16 + k);
+      mx = fmaxf(mx, l[k]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      l[k] = expf(__fsub_rn(l[k], mx));
+      sum = __fadd_rn(sum, l[k]);
+    }
+    float e = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) e = __fadd_rn(e, __fmul_rn(__fdiv_rn(l[k], sum), static_cast<float>(k)));
+    d[side] = e;
+  }
+  // chains 407-415
+  const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]);
+  const float x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
+  const float cx = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), s.stride);
+  const float cy = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), s.stride);
+  const float bw = __fmul_rn(__fsub_rn(x2, x1), s.stride);
+  const float bh = __fmul_rn(__fsub_rn(y2, y1), s.stride);
+
+  // ---- class sigmoid + max / first argmax (chains 416, 464, 471)
+  const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(al) * s.cls_pitch;
+  float best = -1.f;
+  int besti = 0;
+  for (int c = 0; c < NC; ++c) {
+    const float pr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-ldf(cl + c))));
+    if (pr > best) {
+      best = pr;
+      besti = c;
+    }
+  }
+  const long o = static_cast<long>(b) * p.A + a;
+  reinterpret_cast<float4*>(p.boxes)[o] = make_float4(cx, cy, bw, bh);
+  p.scores[o] = best;
+  p.labels[o] = besti;
+  if (best > p.score_thr) {
+    const int slot = atomicAdd(&p.cand_count[b], 1);
+    const unsigned long long key =
+        (static_cast<unsigned long long>(0xFFFFFFFFu - __float_as_uint(best)) << 32) | static_cast<unsigned>(a);
+    p.keys[static_cast<long>(b) * p.A + slot] = key;
+  }
+}
+
+// Candidate keys straight from caller-provided scores (xrseg_debug_nms).
+__global__ void scores_to_keys_kernel(const float* scores, int B, int A, float thr, unsigned long long* keys,
+                                      int* cand_count) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (a >= A) return;
+  const float s = scores[static_cast<long>(b) * A + a];
+  if (s > thr) {
+    const int slot = atomicAdd(&cand_count[b], 1);
+    keys[static_cast<long>(b) * A + slot] =
+        (static_cast<unsigned long long>(0xFFFFFFFFu - __float_as_uint(s)) << 32) | static_cast<unsigned>(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort: one block per frame, bitonic sort of up to 16384 keys in shared memory; writes the first
+// min(count, max_cand) candidates: anchor index + corner box (x1,y1,x2,y2 = cx -/+ w*0.5 ..., chain 459).
+// ------------------------------------------------------------------------------------------------
+struct SortParams {
+  const unsigned long long* keys;  // [B,A]
+  const int* cand_count;           // [B]
+  const float* boxes;              // [B,A,4] cxcywh  (or corners when corners_given)
+  int corners_given;
+  int A, max_cand;
+  int* sorted_idx;                 // [B,max_cand]
+  float4* sorted_corners;          // [B,max_cand]
+  int* n_cand;                     // [B] = min(count, max_cand)
+  int* overflow;                   // [1] set when count > max_cand
+};
+
+__global__ void __launch_bounds__(1024) nms_sort_kernel(const SortParams p) {
+  extern __shared__ unsigned long long skeys[];
+  const int b = blockIdx.x;
+  const int cnt = min(p.cand_count[b], p.A);
+  int n2 = 1;
+  while (n2 < cnt) n2 <<= 1;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x)
+    skeys[i] = i < cnt ? p.keys[static_cast<long>(b) * p.A + i] : 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long x = skeys[i], y = skeys[ixj];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) {
+            skeys[i] = y;
+            skeys[ixj] = x;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  const int n = min(cnt, p.max_cand);
+  if (threadIdx.x == 0) {
+    p.n_cand[b] = n;
+    if (cnt > p.max_cand) atomicExch(p.overflow, 1);
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int a = static_cast<int>(skeys[i] & 0xFFFFFFFFull);
+    p.sorted_idx[static_cast<long>(b) * p.max_cand + i] = a;
+    const float4 bx = reinterpret_cast<const float4*>(p.boxes)[static_cast<long>(b) * p.A + a];
+    float4 c;
+    if (p.corners_given) {
+      c = bx;
+    } else {
+      const float hw = __fmul_rn(bx.z, 0.5f), hh = __fmul_rn(bx.w, 0.5f);
+      c = make_float4(__fsub_rn(bx.x, hw), __fsub_rn(bx.y, hh), __fadd_rn(bx.x, hw), __fadd_rn(bx.y, hh));
+    }
+    p.sorted_corners[static_cast<long>(b) * p.max_cand + i] = c;
+  }
+}
+
+// IoU exactly as oracle/postprocess.py::iou_f32 (one rounding per operation, no FMA).
+__device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr) {
+  const float iw = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  const float ih = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  const float inter = __fmul_rn(iw, ih);
+  const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  return __fdiv_rn(inter, uni) > thr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bitmask: block (cb, rb, frame), 64 threads.  Row i = rb*64 + t against columns cb*64..+63 staged in smem;
+// bit j is set when column candidate (cb*64 + j) comes later in the order and overlaps row i by more than thr.
+// ------------------------------------------------------------------------------------------------
+struct MaskBitsParams {
+  const float4* sorted_corners;  // [B,max_cand]
+  const int* n_cand;
+  int max_cand, words;           // words = ceil(max_cand / 64)
+  float iou_thr;
+  unsigned long long* mask;      // [B,max_cand,words]
+};
+
+__global__ void __launch_bounds__(64) nms_bitmask_kernel(const MaskBitsParams p) {
+  const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
+  const int n = p.n_cand[b];
+  if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+  __shared__ float4 cols[64];
+  const int t = threadIdx.x;
+  const int cj = cb * 64 + t;
+  if (cj < n) cols[t] = p.sorted_corners[static_cast<long>(b) * p.max_cand + cj];
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= n) return;
+  const float4 me = p.sorted_corners[static_cast<long>(b) * p.max_cand + i];
+  unsigned long long bits = 0;
+  const int jn = min(64, n - cb * 64);
+  for (int j = 0; j < jn; ++j) {
+    const int gj = cb * 64 + j;
+    if (gj > i && iou_gt(me, cols[j], p.iou_thr)) bits |= 1ull << j;
+  }
+  p.mask[(static_cast<long>(b) * p.max_cand + i) * p.words + cb] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce: one block (128 threads) per frame.  Chunks of 64 candidate rows are staged in shared memory, warp 0
+// resolves them in order: candidate i is kept unless an earlier kept candidate set its bit.
+// ------------------------------------------------------------------------------------------------
+struct ReduceParams {
+  const unsigned long long* mask;
+  const int* n_cand;
+  const int* sorted_idx;
+  int max_cand, words, max_det;
+  int* keep_idx;   // [B,max_det] anchor indices in selection order
+  int* keep_n;     // [B]
+  int* overflow;
+};
+
+__global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
+  extern __shared__ unsigned long long rsm[];  // remv[words] + chunk[64*words]
+  unsigned long long* remv = rsm;
+  unsigned long long* chunk = rsm + p.words;
+  __shared__ int s_kept;
+  const int b = blockIdx.x;
+  const int n = p.n_cand[b];
+  const int nw = (n + 63) / 64;
+  for (int i = threadIdx.x; i < p.words; i += blockDim.x) remv[i] = 0;
+  if (threadIdx.x == 0) s_kept = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 64) {
+    const int rows = min(64, n - base);
+    const int wb = base / 64;  // words before wb are never set by rows >= base (bits only point forward)
+    for (int i = threadIdx.x; i < rows * nw; i += blockDim.x) {
+      const int r = i / nw, w = i - r * nw;
+      chunk[r * p.words + w] =
+          (w >= wb) ? p.mask[(static_cast<long>(b) * p.max_cand + base + r) * p.words + w] : 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      for (int r = 0; r < rows; ++r) {
+        const int i = base + r;
+        const bool removed = (remv[i >> 6] >> (i & 63)) & 1ull;
+        if (!removed) {
+          int k = s_kept;
+          if (k < p.max_det) {
+            if (lane == 0) p.keep_idx[static_cast<long>(b) * p.max_det + k] = p.sorted_idx[static_cast<long>(b) * p.max_cand + i];
+          } else if (lane == 0) {
+            atomicExch(p.overflow, 2);
+          }
+          for (int w = wb + lane; w < nw; w += 32) remv[w] |= chunk[r * p.words + w];
+          if (lane == 0) s_kept = k + 1;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.keep_n[b] = min(s_kept, p.max_det);
+}
+
+// exclusive scan of keep_n over frames -> offsets[B+1]
+__global__ void offsets_kernel(const int* keep_n, int B, int* offsets) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) {
+      offsets[b] = acc;
+      acc += keep_n[b];
+    }
+    offsets[B] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather (chains 470, 472, 477): output_0 [N,4], output_1 [N], output_2 [N,32] + scores / anchor ids / frame ids.
+// One warp per detection; lane k copies coefficient k.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct GatherParams {
+  ScaleSrc<T> s[3];
+  const int* keep_idx; const int* keep_n; const int* offsets;
+  const float* boxes; const float* scores; const int* labels;
+  int B, A, max_det;
+  float* out_boxes; int* out_labels; float* out_coefs; float* out_scores; int* out_anchor; int* out_frame;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) gather_kernel(const GatherParams<T> p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b = warp / p.max_det;
+  const int i = warp - b * p.max_det;
+  if (b >= p.B || i >= p.keep_n[b]) return;
+  const int a = p.keep_idx[static_cast<long>(b) * p.max_det + i];
+  const int o = p.offsets[b] + i;
+  int si = 0;
+  if (a >= p.s[1].a_off) si = 1;
+  if (a >= p.s[2].a_off) si = 2;
+  const ScaleSrc<T>& s = p.s[si];
+  const float c = ldf(s.coef + b * s.coef_bstride + static_cast<long>(a - s.a_off) * s.coef_pitch + lane);
+  p.out_coefs[static_cast<long>(o) * NM + lane] = c;
+  if (lane < 4) p.out_boxes[static_cast<long>(o) * 4 + lane] = p.boxes[(static_cast<long>(b) * p.A + a) * 4 + lane];
+  if (lane == 0) {
+    p.out_labels[o] = p.labels[static_cast<long>(b) * p.A + a];
+    p.out_scores[o] = p.scores[static_cast<long>(b) * p.A + a];
+    p.out_anchor[o] = a;
+    p.out_frame[o] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// masks (chains 496-498): output_3[o, pix] = sigmoid(sum_k coef[o,k] * proto[b,k,pix]), k = 0..31 sequential fp32 FMA.
+// Block = 256 pixels of one frame; each thread keeps its pixel's 32 prototype values in registers and loops over
+// the frame's detections (coefficients broadcast from shared memory).  PLANAR selects proto layout [B,32,P] (fp32,
+// the oracle's tensor) instead of NHWC fp16 [B,P,32].
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool PLANAR>
+struct MaskParams {
+  const T* protos; long proto_bstride; int proto_pitch;
+  const float* coefs;      // [N,32] compacted
+  const int* keep_n; const int* offsets;
+  int max_det;
+  float* probs;            // [N,160,160]
+};
+
+template <typename T, bool PLANAR>
+__global__ void __launch_bounds__(256) mask_prob_kernel(const MaskParams<T, PLANAR> p) {
+  __shared__ float sc[32][NM + 1];
+  const int b = blockIdx.y;
+  const int n = p.keep_n[b];
+  if (n == 0) return;
+  const int off = p.offsets[b];
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  float pr[NM];
+  if (PLANAR) {
+#pragma unroll
+    for (int k = 0; k < NM; ++k) pr[k] = ldf(p.protos + b * p.proto_bstride + static_cast<long>(k) * PROTO_PIX + pix);
+  } else {
+    const uint4* pp = reinterpret_cast<const uint4*>(p.protos + b * p.proto_bstride + static_cast<long>(pix) * p.proto_pitch);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 raw = pp[i];
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        pr[i * 8 + 2 * j] = f.x;
+        pr[i * 8 + 2 * j + 1] = f.y;
+      }
+    }
+  }
+  for (int d0 = 0; d0 < n; d0 += 32) {
+    const int nd = min(32, n - d0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nd * NM; i += 256) sc[i / NM][i % NM] = p.coefs[static_cast<long>(off + d0) * NM + i];
+    __syncthreads();
+    for (int d = 0; d < nd; ++d) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < NM; ++k) acc = __fmaf_rn(sc[d][k], pr[k], acc);
+      const float prob = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-acc)));
+      __stcs(p.probs + static_cast<long>(off + d0 + d) * PROTO_PIX + pix, prob);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// C# box conventions (IEExecutor.ParseBoxes IEE:529-559, IEBoxer.DrawBoxes IEB:37-81)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 box_convention(const float4 raw, int conv, float sw, float sh) {
+  if (conv == 2) return raw;
+  const float sx = __fdiv_rn(sw, 640.f), sy = __fdiv_rn(sh, 640.f);
+  float4 o;
+  if (conv == 0) {
+    o.x = __fmul_rn(__fsub_rn(raw.x, 320.f), sx);
+    o.y = __fmul_rn(__fsub_rn(320.f, raw.y), sy);
+  } else {
+    o.x = __fsub_rn(__fmul_rn(raw.x, sx), __fdiv_rn(sw, 2.f));
+    o.y = __fsub_rn(__fmul_rn(raw.y, sy), __fdiv_rn(sh, 2.f));
+  }
+  o.z = __fmul_rn(raw.z, sx);
+  o.w = __fmul_rn(raw.w, sy);
+  return o;
+}
+
+struct BoxOut {
+  float cx, cy, w, h;
+  int label, frame;
+};
+
+// per-frame cap (50 / 200 / none) applied like the C# loops; writes rows compacted again over the batch
+__global__ void boxes_to_screen_kernel(const float* boxes, const int* labels, const int* keep_n, const int* offsets,
+                                       int B, int conv, float sw, float sh, int cap, BoxOut* out, int* out_n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int w = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = cap > 0 ? min(keep_n[b], cap) : keep_n[b];
+    for (int i = 0; i < n; ++i) {
+      const int o = offsets[b] + i;
+      const float4 r = box_convention(reinterpret_cast<const float4*>(boxes)[o], conv, sw, sh);
+      out[w].cx = r.x; out[w].cy = r.y; out[w].w = r.z; out[w].h = r.w;
+      out[w].label = labels[o];
+      out[w].frame = b;
+      ++w;
+    }
+  }
+  *out_n = w;
+}
+
+// IEMasker.PixelInBoundingBox (IEM:232-247) on a C#-convention box
+__device__ __forceinline__ bool pixel_in_box(const float4 box, int x, int y, int image_w, int image_h) {
+  const float xs = __fdiv_rn(160.f, static_cast<float>(image_w));
+  const float ys = __fdiv_rn(160.f, static_cast<float>(image_h));
+  const float cx = __fadd_rn(__fmul_rn(box.x, xs), 80.f);
+  const float cy = __fsub_rn(80.f, __fmul_rn(box.y, ys));
+  const float hw = __fdiv_rn(__fmul_rn(box.z, xs), 2.f);
+  const float hh = __fdiv_rn(__fmul_rn(box.w, ys), 2.f);
+  const float xf = static_cast<float>(x), yf = static_cast<float>(y);
+  return xf >= __fsub_rn(cx, hw) && xf <= __fadd_rn(cx, hw) && yf >= __fsub_rn(cy, hh) && yf <= __fadd_rn(cy, hh);
+}
+
+// mode 0: IEMasker.DrawMask / DrawSingleMask loop (IEM:98-113,167-185): u8 [n,160,160] in texture row order.
+// mode 1: geometric crop in image row order.   boxes: raw cx,cy,w,h rows (converted here) or C# boxes (conv < 0).
+struct MaskThrParams {
+  const float* probs;   // [n,160,160]
+  const float* boxes;   // [n,4]
+  int n, first;
+  int mode, conv;
+  float sw, sh;
+  int image_w, image_h;
+  float thr;
+  uint8_t* out;         // [n,160,160]
+};
+
+__global__ void __launch_bounds__(256) mask_threshold_kernel(const MaskThrParams p) {
+  const int d = blockIdx.y;
+  const int pix = blockIdx.x * 256 + threadIdx.x;
+  const int y = pix / PROTO_HW, x = pix - y * PROTO_HW;
+  const float4 raw = reinterpret_cast<const float4*>(p.boxes)[p.first + d];
+  const float v = p.probs[static_cast<long>(p.first + d) * PROTO_PIX + pix];
+  if (p.mode == 0) {
+    const float4 box = p.conv < 0 ? raw : box_convention(raw, p.conv, p.sw, p.sh);
+    const int pos_y = PROTO_HW - y - 1;
+    const bool on = (v > p.thr) && pixel_in_box(box, x, pos_y, p.image_w, p.image_h);
+    p.out[static_cast<long>(d) * PROTO_PIX + pos_y * PROTO_HW + x] = on ? 1 : 0;
+  } else {
+    const float s = 0.25f;
+    const float x1 = __fmul_rn(__fsub_rn(raw.x, __fmul_rn(raw.z, 0.5f)), s), x2 = __fmul_rn(__fadd_rn(raw.x, __fmul_rn(raw.z, 0.5f)), s);
+    const float y1 = __fmul_rn(__fsub_rn(raw.y, __fmul_rn(raw.w, 0.5f)), s), y2 = __fmul_rn(__fadd_rn(raw.y, __fmul_rn(raw.w, 0.5f)), s);
+    const float xf = static_cast<float>(x), yf = static_cast<float>(y);
+    const bool on = (v > p.thr) && xf >= x1 && xf < x2 && yf >= y1 && yf < y2;
+    p.out[static_cast<long>(d) * PROTO_PIX + pix] = on ? 1 : 0;
+  }
+}
+
+// mode 3: crop mask bit-packed, one u32 per 32 pixels of a row: [n,160,5]
+__global__ void __launch_bounds__(160) mask_bits_kernel(const MaskThrParams p) {
+  const int d = blockIdx.y;
+  const int y = blockIdx.x;
+  const int x = threadIdx.x;
+  const float4 raw = reinterpret_cast<const float4*>(p.boxes)[p.first + d];
+  const float v = p.probs[static_cast<long>(p.first + d) * PROTO_PIX + y * PROTO_HW + x];
+  const float s = 0.25f;
+  const float x1 = __fmul_rn(__fsub_rn(raw.x, __fmul_rn(raw.z, 0.5f)), s), x2 = __fmul_rn(__fadd_rn(raw.x, __fmul_rn(raw.z, 0.5f)), s);
+  const float y1 = __fmul_rn(__fsub_rn(raw.y, __fmul_rn(raw.w, 0.5f)), s), y2 = __fmul_rn(__fadd_rn(raw.y, __fmul_rn(raw.w, 0.5f)), s);
+  const float xf = static_cast<float>(x), yf = static_cast<float>(y);
+  const bool on = (v > p.thr) && xf >= x1 && xf < x2 && yf >= y1 && yf < y2;
+  const unsigned bits = __ballot_sync(0xFFFFFFFFu, on);
+  if ((x & 31) == 0) reinterpret_cast<uint32_t*>(p.out)[(static_cast<long>(d) * PROTO_HW + y) * 5 + (x >> 5)] = bits;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mode 2 (extension, BASELINE.json config 5): fused coef x proto -> bilinear 160->640 of the LOGITS -> box crop ->
+// threshold (logit > 0) -> u8 [n,640,640].  Block = one detection x one 64x64 output tile: the 18x18 logit patch it
+// needs is computed once into shared memory from the frame's prototypes.
+// ------------------------------------------------------------------------------------------------
+struct Mask640Params {
+  const __half* protos; long proto_bstride; int proto_pitch;
+  const float* coefs; const float* boxes; const int* frames;
+  int first;
+  uint8_t* out;   // [n,640,640]
+};
+
+__global__ void __launch_bounds__(256) mask640_kernel(const Mask640Params p) {
+  __shared__ float patch[18][19];
+  __shared__ float sc[NM];
+  const int d = blockIdx.z;
+  const int o = p.first + d;
+  const int tx = blockIdx.x, ty = blockIdx.y;  // 10 x 10 tiles of 64
+  if (threadIdx.x < NM) sc[threadIdx.x] = p.coefs[static_cast<long>(o) * NM + threadIdx.x];
+  const int b = p.frames[o];
+  __syncthreads();
+  // source coordinate of output pixel X: (X + 0.5) * 0.25 - 0.5 ; tile covers X in [64 tx, 64 tx + 63]
+  const int sx0 = tx * 16 - 1, sy0 = ty * 16 - 1;  // first source index touched (may be -1 -> clamped)
+  for (int i = threadIdx.x; i < 18 * 18; i += 256) {
+    const int py = i / 18, px = i - py * 18;
+    const int sy = min(max(sy0 + py, 0), PROTO_HW - 1), sx = min(max(sx0 + px, 0), PROTO_HW - 1);
+    const uint4* pp = reinterpret_cast<const uint4*>(p.protos + b * p.proto_bstride +
+                                                     static_cast<long>(sy * PROTO_HW + sx) * p.proto_pitch);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 raw = pp[q];
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        acc = __fmaf_rn(sc[q * 8 + 2 * j], f.x, acc);
+        acc = __fmaf_rn(sc[q * 8 + 2 * j + 1], f.y, acc);
+      }
+    }
+    patch[py][px] = acc;
+  }
+  __syncthreads();
+  const float4 raw = reinterpret_cast<const float4*>(p.boxes)[o];
+  const float x1 = __fsub_rn(raw.x, __fmul_rn(raw.z, 0.5f)), x2 = __fadd_rn(raw.x, __fmul_rn(raw.z, 0.5f));
+  const float y1 = __fsub_rn(raw.y, __fmul_rn(raw.w, 0.5f)), y2 = __fadd_rn(raw.y, __fmul_rn(raw.w, 0.5f));
+  // each thread: 16 consecutive output pixels of one row (64 rows x 4 segments)
+  const int ry = threadIdx.x >> 2, seg = threadIdx.x & 3;
+  const int Y = ty * 64 + ry;
+  float fy = __fsub_rn(__fmul_rn(__fadd_rn(static_cast<float>(Y), 0.5f), 0.25f), 0.5f);
+  fy = fmaxf(fy, 0.f);
+  int iy0 = min(static_cast<int>(floorf(fy)), PROTO_HW - 1);
+  const int iy1 = min(iy0 + 1, PROTO_HW - 1);
+  const float wy = __fsub_rn(fy, static_cast<float>(iy0));
+  uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int X = tx * 64 + seg * 16 + i;
+    float fx = __fsub_rn(__fmul_rn(__fadd_rn(static_cast<float>(X), 0.5f), 0.25f), 0.5f);
+    fx = fmaxf(fx, 0.f);
+    const int ix0 = min(static_cast<int>(floorf(fx)), PROTO_HW - 1);
+    const int ix1 = min(ix0 + 1, PROTO_HW - 1);
+    const float wx = __fsub_rn(fx, static_cast<float>(ix0));
+    const float a = patch[iy0 - sy0][ix0 - sx0], bq = patch[iy0 - sy0][ix1 - sx0];
+    const float c = patch[iy1 - sy0][ix0 - sx0], dq = patch[iy1 - sy0][ix1 - sx0];
+    const float top = __fadd_rn(__fmul_rn(a, __fsub_rn(1.f, wx)), __fmul_rn(bq, wx));
+    const float bot = __fadd_rn(__fmul_rn(c, __fsub_rn(1.f, wx)), __fmul_rn(dq, wx));
+    const float val = __fadd_rn(__fmul_rn(top, __fsub_rn(1.f, wy)), __fmul_rn(bot, wy));
+    const float xf = static_cast<float>(X), yf = static_cast<float>(Y);
+    const bool on = (val > 0.f) && xf >= x1 && xf < x2 && yf >= y1 && yf < y2;
+    packed[i >> 2] |= (on ? 1u : 0u) << ((i & 3) * 8);
+  }
+  uint4 v = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  __stcs(reinterpret_cast<uint4*>(p.out + (static_cast<long>(d) * 640 + Y) * 640 + tx * 64 + seg * 16), v);
+}
+
+#endif  // __CUDACC__
+}  // namespace xrseg

@@ -1,0 +1,1117 @@
+// xrseg_api.cu -- C ABI of libxrseg.so (include/xrseg.h): runner lifecycle, the per-frame pipeline
+// (copy -> preprocess -> network -> decode -> NMS -> gather -> masks) on one CUDA stream, CUDA-graph replay, and the
+// parity / debug entry points.  One runner per GPU; no CPU fallback anywhere on this path.
+#include "../../include/xrseg.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "common.cuh"
+#include "conv_umma.cuh"
+#include "kernels_misc.cuh"
+#include "model.cuh"
+#include "post.cuh"
+
+using namespace xrseg;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevLayer {
+  // OP_CONV (UMMA)
+  ConvParams cp{};
+  __half* wpack = nullptr;
+  float* bias = nullptr;
+  // OP_CONV (direct) / OP_DW / OP_STEM
+  __half* w16 = nullptr;
+  float* w32 = nullptr;
+};
+
+template <typename T>
+T* dev_alloc(size_t n) {
+  T* p = nullptr;
+  XR_CUDA(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return p;
+}
+template <typename T>
+T* dev_upload(const std::vector<T>& v) {
+  T* p = dev_alloc<T>(v.size());
+  if (!v.empty()) XR_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return p;
+}
+
+}  // namespace
+
+struct xrseg_runner {
+  xrseg_config cfg{};
+  int device = 0, num_sms = 148;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_done = nullptr, ev[6] = {};
+  std::unique_ptr<Net> net;
+  int mb = 1;                      // frames per network pass
+  int A = 8400;
+  std::vector<DevLayer> dl;
+  __half* arena = nullptr;
+  uint8_t* d_frames = nullptr;
+  size_t d_frames_cap = 0;
+  // post-processing state (sized for max_batch)
+  float *d_boxes = nullptr, *d_scores = nullptr;
+  int* d_labels = nullptr;
+  unsigned long long* d_keys = nullptr;
+  int *d_cand_count = nullptr, *d_n_cand = nullptr, *d_sorted_idx = nullptr, *d_overflow = nullptr;
+  float4* d_sorted_corners = nullptr;
+  unsigned long long* d_mask = nullptr;
+  int *d_keep_idx = nullptr, *d_keep_n = nullptr, *d_offsets = nullptr;
+  float *o_boxes = nullptr, *o_coefs = nullptr, *o_scores = nullptr, *o_probs = nullptr;
+  int *o_labels = nullptr, *o_anchor = nullptr, *o_frame = nullptr;
+  // debug staging for xrseg_debug_post / xrseg_debug_nms
+  float *dbg_box = nullptr, *dbg_cls = nullptr, *dbg_coef = nullptr, *dbg_proto = nullptr, *dbg_corners = nullptr;
+  // host mirrors
+  std::vector<int> h_counts, h_offsets;
+  int batch = 0;                   // batch of the scheduled / finished run
+  int state = 0;                   // 0 idle, 1 scheduled, 2 done
+  int words = 0, max_cand = 0, max_det = 0;
+  cudaGraphExec_t graph = nullptr;
+  int graph_batch = 0;
+  int launches = 0;
+  float timings[5] = {};
+  bool timed = false;
+
+  ~xrseg_runner();
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// weights -> device, per layer kind
+// ------------------------------------------------------------------------------------------------
+void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
+  Net& net = *r->net;
+  r->dl.resize(net.layers.size());
+  for (const Op& o : net.ops) {
+    if (o.layer < 0) continue;
+    const LayerRec& l = net.layers[o.layer];
+    const HostLayerWeights& w = hw[o.layer];
+    DevLayer& d = r->dl[o.layer];
+    if (o.kind == OP_STEM) {
+      const int co = o.y.Cp;
+      std::vector<float> ws(36 * co, 0.f), bs(co, 0.f);
+      for (int n = 0; n < l.cout; ++n) {
+        for (int ci = 0; ci < 3; ++ci)
+          for (int t = 0; t < 9; ++t) ws[(t * 4 + ci) * co + n] = w.w[(static_cast<size_t>(n) * 3 + ci) * 9 + t];
+        bs[n] = w.b[n];
+      }
+      d.w32 = dev_upload(ws);
+      d.bias = dev_upload(bs);
+    } else if (o.kind == OP_DW) {
+      const int c = o.y.Cp;
+      std::vector<float> ws(9 * c, 0.f), bs(c, 0.f);
+      for (int n = 0; n < l.cout; ++n) {
+        for (int t = 0; t < 9; ++t) ws[t * c + n] = w.w[static_cast<size_t>(n) * 9 + t];
+        bs[n] = w.b[n];
+      }
+      d.w32 = dev_upload(ws);
+      d.bias = dev_upload(bs);
+    } else if (o.kind == OP_CONV) {
+      ConvDesc cd{};
+      cd.B = r->mb; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
+      cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch;
+      cd.k = o.k; cd.stride = o.stride; cd.act = o.act; cd.transposed = o.transposed;
+      cd.res_pitch = o.has_res ? o.res.pitch : 0;
+      d.cp = plan_conv(cd, r->num_sms, 0);
+      if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
+        std::vector<__half> wp;
+        std::vector<float> bp;
+        pack_conv_weights<__half>(d.cp, w.w.data(), w.b.data(), l.cin, l.cout, wp, bp);
+        d.wpack = dev_upload(wp);
+        d.bias = dev_upload(bp);
+      } else {
+        // direct layout: [Cout_p][k*k][Cin_p] or [4][Cout_p][Cin_p]
+        const int cin_p = o.x.Cp, cout_p = o.y.Cp;
+        const int taps = o.transposed ? 4 : o.k * o.k;
+        std::vector<__half> wd(static_cast<size_t>(cout_p) * taps * cin_p, __half(0.f));
+        std::vector<float> bs(cout_p, 0.f);
+        for (int co = 0; co < l.cout; ++co) {
+          bs[co] = w.b[co];
+          for (int ci = 0; ci < l.cin; ++ci)
+            for (int t = 0; t < taps; ++t) {
+              if (o.transposed)
+                wd[(static_cast<size_t>(t) * cout_p + co) * cin_p + ci] =
+                    __half(w.w[(static_cast<size_t>(ci) * l.cout + co) * 4 + t]);
+              else
+                wd[(static_cast<size_t>(co) * taps + t) * cin_p + ci] =
+                    __half(w.w[(static_cast<size_t>(co) * l.cin + ci) * taps + t]);
+            }
+        }
+        d.w16 = dev_upload(wd);
+        d.bias = dev_upload(bs);
+      }
+    }
+  }
+}
+
+inline __half* ptr_of(xrseg_runner* r, const TV& t) { return r->arena + t.off; }
+
+// ------------------------------------------------------------------------------------------------
+// the network: one pass over `nb` (<= mb) frames already preprocessed into net->input
+// ------------------------------------------------------------------------------------------------
+int run_network(xrseg_runner* r, int nb, cudaStream_t st) {
+  Net& net = *r->net;
+  int launches = 0;
+  for (const Op& o : net.ops) {
+    switch (o.kind) {
+      case OP_STEM: {
+        StemParams p{ptr_of(r, o.x), ptr_of(r, o.y), r->dl[o.layer].w32, r->dl[o.layer].bias, nb, o.x.H, o.x.W, o.y.Cp,
+                     o.y.pitch};
+        const long total = static_cast<long>(nb) * (o.x.H / 2) * (o.x.W / 2) * (o.y.Cp / 16);
+        stem_conv_kernel<<<grid_for(total), 256, (37 * o.y.Cp) * sizeof(float), st>>>(p);
+        break;
+      }
+      case OP_CONV: {
+        DevLayer& d = r->dl[o.layer];
+        if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
+          ConvParams p = d.cp;
+          if (nb != p.B) {  // partial last chunk: re-plan the M extent only
+            ConvDesc cd{};
+            cd.B = nb; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
+            cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch; cd.k = o.k; cd.stride = o.stride; cd.act = o.act;
+            cd.transposed = o.transposed; cd.res_pitch = o.has_res ? o.res.pitch : 0;
+            p = plan_conv(cd, r->num_sms, 0);
+          }
+          p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
+          p.res = o.has_res ? ptr_of(r, o.res) : nullptr;
+          p.wpack = d.wpack; p.bias = d.bias;
+          launch_conv_umma(p, st);
+        } else {
+          DirectParams p{};
+          p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
+          p.res = o.has_res ? ptr_of(r, o.res) : nullptr; p.res_pitch = o.has_res ? o.res.pitch : 0;
+          p.w = d.w16; p.bias = d.bias;
+          p.B = nb; p.H = o.x.H; p.W = o.x.W; p.Cin = o.x.Cp; p.Ho = o.y.H; p.Wo = o.y.W; p.Cout = o.y.Cp;
+          p.k = o.k; p.stride = o.stride; p.pad = o.k / 2; p.act = o.act; p.transposed = o.transposed;
+          const long total = static_cast<long>(nb) * o.y.H * o.y.W * o.y.Cp;
+          conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(p);
+        }
+        break;
+      }
+      case OP_DW: {
+        DwParams p{};
+        p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
+        p.res = o.has_res ? ptr_of(r, o.res) : nullptr; p.res_pitch = o.has_res ? o.res.pitch : 0;
+        p.w = r->dl[o.layer].w32; p.bias = r->dl[o.layer].bias;
+        p.B = nb; p.H = o.x.H; p.W = o.x.W; p.C = o.x.Cp; p.act = o.act;
+        dwconv3x3_kernel<<<grid_for(static_cast<long>(nb) * o.x.H * o.x.W * (o.x.Cp / 8)), 256, 0, st>>>(p);
+        break;
+      }
+      case OP_SPPF: {
+        SppfParams p{ptr_of(r, o.x), nb, o.x.H, o.x.W, o.x.Cp / 4, o.x.pitch};
+        sppf_pool_kernel<<<nb * (p.C / 8), 256, o.x.H * o.x.W * 16, st>>>(p);
+        break;
+      }
+      case OP_UP: {
+        UpParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, nb, o.x.H, o.x.W, o.x.Cp};
+        upsample2x_kernel<<<grid_for(static_cast<long>(nb) * o.x.H * o.x.W * 4 * (o.x.Cp / 8)), 256, 0, st>>>(p);
+        break;
+      }
+      case OP_ATTN: {
+        AttnParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, nb, o.x.H * o.x.W, o.heads,
+                     1.0f / sqrtf(static_cast<float>(ATT_KD))};
+        const size_t smem = static_cast<size_t>(p.N) * (ATT_KD + ATT_HD) * sizeof(__half);
+        dim3 g(nb * o.heads, ceil_div(p.N, ATT_THREADS));
+        attention_kernel<<<g, ATT_THREADS, smem, st>>>(p);
+        break;
+      }
+      case OP_VGATHER: {
+        VGatherParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, static_cast<long>(nb) * o.x.H * o.x.W,
+                        o.heads};
+        gather_v_kernel<<<grid_for(p.tokens * o.heads * 8), 256, 0, st>>>(p);
+        break;
+      }
+    }
+    ++launches;
+  }
+  XR_CUDA(cudaGetLastError());
+  return launches;
+}
+
+template <typename T>
+void fill_scale_src(ScaleSrc<T> (&s)[3], const T* box, const T* cls, const T* coef, const int (&fh)[3],
+                    const int (&fw)[3], const long (&bstr)[3][3], const int (&pitch)[3][3], const long (&off)[3][3]) {
+  int a_off = 0;
+  const float strides[3] = {8.f, 16.f, 32.f};
+  for (int i = 0; i < 3; ++i) {
+    s[i].box = box + off[i][0]; s[i].box_bstride = bstr[i][0]; s[i].box_pitch = pitch[i][0];
+    s[i].cls = cls + off[i][1]; s[i].cls_bstride = bstr[i][1]; s[i].cls_pitch = pitch[i][1];
+    s[i].coef = coef + off[i][2]; s[i].coef_bstride = bstr[i][2]; s[i].coef_pitch = pitch[i][2];
+    s[i].h = fh[i]; s[i].w = fw[i]; s[i].a_off = a_off; s[i].stride = strides[i];
+    a_off += fh[i] * fw[i];
+  }
+}
+
+void net_scale_src(xrseg_runner* r, ScaleSrc<__half> (&s)[3]) {
+  Net& net = *r->net;
+  long bstr[3][3], off[3][3];
+  int pitch[3][3];
+  for (int i = 0; i < 3; ++i) {
+    const TV* t[3] = {&net.box[i], &net.cls[i], &net.coef[i]};
+    for (int j = 0; j < 3; ++j) {
+      bstr[i][j] = static_cast<long>(t[j]->H) * t[j]->W * t[j]->pitch;
+      pitch[i][j] = t[j]->pitch;
+      off[i][j] = static_cast<long>(t[j]->off);
+    }
+  }
+  fill_scale_src<__half>(s, r->arena, r->arena, r->arena, net.fh, net.fw, bstr, pitch, off);
+}
+
+void dense_scale_src(xrseg_runner* r, ScaleSrc<float> (&s)[3], const float* box, const float* cls, const float* coef) {
+  Net& net = *r->net;
+  long bstr[3][3], off[3][3];
+  int pitch[3][3];
+  const int ch[3] = {64, NC, NM};
+  long a_off = 0;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      bstr[i][j] = static_cast<long>(r->A) * ch[j];
+      pitch[i][j] = ch[j];
+      off[i][j] = a_off * ch[j];
+    }
+    a_off += net.fh[i] * net.fw[i];
+  }
+  fill_scale_src<float>(s, box, cls, coef, net.fh, net.fw, bstr, pitch, off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-processing of frames [b0, b0 + nb): decode -> sort -> bitmask -> reduce -> offsets -> gather -> masks
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool PLANAR>
+int run_post(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)[3], const T* protos, long proto_bstride,
+             int proto_pitch, bool do_decode, bool corners_given, cudaStream_t st) {
+  int launches = 0;
+  const int A = r->A;
+  if (do_decode) {
+    DecodeParams<T> dp{};
+    for (int i = 0; i < 3; ++i) dp.s[i] = src[i];
+    dp.B = nb; dp.A = A; dp.score_thr = r->cfg.score_threshold;
+    dp.boxes = r->d_boxes + static_cast<long>(b0) * A * 4;
+    dp.scores = r->d_scores + static_cast<long>(b0) * A;
+    dp.labels = r->d_labels + static_cast<long>(b0) * A;
+    dp.keys = r->d_keys + static_cast<long>(b0) * A;
+    dp.cand_count = r->d_cand_count + b0;
+    decode_kernel<T><<<dim3(ceil_div(A, 128), nb), 128, 0, st>>>(dp);
+    ++launches;
+  }
+  SortParams sp{};
+  sp.keys = r->d_keys + static_cast<long>(b0) * A;
+  sp.cand_count = r->d_cand_count + b0;
+  sp.boxes = corners_given ? r->dbg_corners + static_cast<long>(b0) * A * 4 : r->d_boxes + static_cast<long>(b0) * A * 4;
+  sp.corners_given = corners_given ? 1 : 0;
+  sp.A = A; sp.max_cand = r->max_cand;
+  sp.sorted_idx = r->d_sorted_idx + static_cast<long>(b0) * r->max_cand;
+  sp.sorted_corners = r->d_sorted_corners + static_cast<long>(b0) * r->max_cand;
+  sp.n_cand = r->d_n_cand + b0;
+  sp.overflow = r->d_overflow;
+  nms_sort_kernel<<<nb, 1024, 16384 * sizeof(unsigned long long), st>>>(sp);
+  MaskBitsParams mp{};
+  mp.sorted_corners = sp.sorted_corners; mp.n_cand = sp.n_cand; mp.max_cand = r->max_cand; mp.words = r->words;
+  mp.iou_thr = r->cfg.iou_threshold;
+  mp.mask = r->d_mask + static_cast<long>(b0) * r->max_cand * r->words;
+  nms_bitmask_kernel<<<dim3(r->words, r->words, nb), 64, 0, st>>>(mp);
+  ReduceParams rp{};
+  rp.mask = mp.mask; rp.n_cand = sp.n_cand; rp.sorted_idx = sp.sorted_idx;
+  rp.max_cand = r->max_cand; rp.words = r->words; rp.max_det = r->max_det;
+  rp.keep_idx = r->d_keep_idx + static_cast<long>(b0) * r->max_det;
+  rp.keep_n = r->d_keep_n + b0;
+  rp.overflow = r->d_overflow;
+  nms_reduce_kernel<<<nb, 128, static_cast<size_t>(r->words) * 65 * sizeof(unsigned long long), st>>>(rp);
+  offsets_kernel<<<1, 32, 0, st>>>(r->d_keep_n, b0 + nb, r->d_offsets);
+  launches += 4;
+  if (!src[0].coef) return launches;  // NMS-only debug path
+  GatherParams<T> gp{};
+  for (int i = 0; i < 3; ++i) gp.s[i] = src[i];
+  gp.keep_idx = rp.keep_idx; gp.keep_n = rp.keep_n; gp.offsets = r->d_offsets + b0;
+  gp.boxes = r->d_boxes + static_cast<long>(b0) * A * 4;
+  gp.scores = r->d_scores + static_cast<long>(b0) * A;
+  gp.labels = r->d_labels + static_cast<long>(b0) * A;
+  gp.B = nb; gp.A = A; gp.max_det = r->max_det;
+  gp.out_boxes = r->o_boxes; gp.out_labels = r->o_labels; gp.out_coefs = r->o_coefs; gp.out_scores = r->o_scores;
+  gp.out_anchor = r->o_anchor; gp.out_frame = r->o_frame;
+  gather_kernel<T><<<ceil_div(nb * r->max_det * 32, 128), 128, 0, st>>>(gp);
+  ++launches;
+  if (protos) {
+    MaskParams<T, PLANAR> kp{};
+    kp.protos = protos; kp.proto_bstride = proto_bstride; kp.proto_pitch = proto_pitch;
+    kp.coefs = r->o_coefs; kp.keep_n = rp.keep_n; kp.offsets = gp.offsets; kp.max_det = r->max_det;
+    kp.probs = r->o_probs;
+    mask_prob_kernel<T, PLANAR><<<dim3(PROTO_PIX / 256, nb), 256, 0, st>>>(kp);
+    ++launches;
+  }
+  XR_CUDA(cudaGetLastError());
+  return launches;
+}
+
+// frame offset fix-up: gather/mask kernels index frames relative to b0 but o_frame must be global
+__global__ void add_frame_base_kernel(int* frames, const int* offsets, int b0, int nb) {
+  const int b = blockIdx.x;
+  if (b >= nb) return;
+  const int lo = offsets[b0 + b], hi = offsets[b0 + b + 1];
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) frames[i] = b0 + b;
+}
+
+void preprocess(xrseg_runner* r, const uint8_t* d_src, int w, int h, int stride_bytes, int fmt, int nb, cudaStream_t st) {
+  PreParams p{};
+  p.src = d_src;
+  p.dst = ptr_of(r, r->net->input);
+  p.B = nb; p.sw = w; p.sh = h; p.stride_bytes = stride_bytes; p.bpp = fmt == XRSEG_FMT_RGBA8 ? 4 : 3;
+  p.mode = r->cfg.resize_mode;
+  if (p.mode == XRSEG_RESIZE_LETTERBOX) {
+    const double rr = std::min(640.0 / h, 640.0 / w);
+    p.nh = static_cast<int>(std::lround(h * rr));
+    p.nw = static_cast<int>(std::lround(w * rr));
+    p.top = (640 - p.nh) / 2;
+    p.left = (640 - p.nw) / 2;
+    p.scale_x = static_cast<float>(w) / static_cast<float>(p.nw);
+    p.scale_y = static_cast<float>(h) / static_cast<float>(p.nh);
+  } else {
+    p.scale_x = static_cast<float>(w) / 640.0f;
+    p.scale_y = static_cast<float>(h) / 640.0f;
+  }
+  preprocess_kernel<<<dim3(5, 640, nb), 128, 0, st>>>(p);
+  XR_CUDA(cudaGetLastError());
+}
+
+int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st) {
+  int launches = run_network(r, nb, st);
+  ScaleSrc<__half> src[3];
+  net_scale_src(r, src);
+  const TV& pr = r->net->protos;
+  launches += run_post<__half, false>(r, b0, nb, src, ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch,
+                                      pr.pitch, true, false, st);
+  add_frame_base_kernel<<<nb, 64, 0, st>>>(r->o_frame, r->d_offsets, b0, nb);
+  return launches + 1;
+}
+
+void reset_counters(xrseg_runner* r, int batch, cudaStream_t st) {
+  XR_CUDA(cudaMemsetAsync(r->d_cand_count, 0, sizeof(int) * batch, st));
+  XR_CUDA(cudaMemsetAsync(r->d_overflow, 0, sizeof(int), st));
+}
+
+int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, int h, int stride_bytes, int fmt,
+                int batch) {
+  if (!r) return XRSEG_ERR_INVALID;
+  try {
+    if (!src || batch < 1 || batch > r->cfg.max_batch || w < 1 || h < 1 ||
+        stride_bytes < w * (fmt == XRSEG_FMT_RGBA8 ? 4 : 3) || (fmt != XRSEG_FMT_RGB8 && fmt != XRSEG_FMT_RGBA8)) {
+      r->err = "xrseg_schedule: invalid arguments";
+      return XRSEG_ERR_INVALID;
+    }
+    XR_CUDA(cudaSetDevice(r->device));
+    cudaStream_t st = r->stream;
+    const size_t frame_bytes = static_cast<size_t>(h) * stride_bytes;
+    const uint8_t* d_src = src;
+    if (!src_on_device) {
+      if (frame_bytes * batch > r->d_frames_cap) {
+        if (r->d_frames) XR_CUDA(cudaFree(r->d_frames));
+        r->d_frames_cap = frame_bytes * r->cfg.max_batch;
+        XR_CUDA(cudaMalloc(&r->d_frames, r->d_frames_cap));
+      }
+      XR_CUDA(cudaMemcpyAsync(r->d_frames, src, frame_bytes * batch, cudaMemcpyHostToDevice, st));
+      d_src = r->d_frames;
+    }
+    r->batch = batch;
+    r->timed = !r->cfg.use_cuda_graph;
+    if (r->timed) XR_CUDA(cudaEventRecord(r->ev[0], st));
+    reset_counters(r, batch, st);
+    const bool single_chunk = batch <= r->mb;
+    if (r->cfg.use_cuda_graph && single_chunk) {
+      // graph = network + post for one chunk of `batch` frames; preprocessing stays outside (source pointer varies)
+      preprocess(r, d_src, w, h, stride_bytes, fmt, batch, st);
+      if (!r->graph || r->graph_batch != batch) {
+        if (r->graph) { cudaGraphExecDestroy(r->graph); r->graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        XR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int launches = 0;
+        try {
+          launches = pipeline_chunk(r, 0, batch, st);
+        } catch (...) {
+          cudaStreamEndCapture(st, &g);
+          if (g) cudaGraphDestroy(g);
+          throw;
+        }
+        XR_CUDA(cudaStreamEndCapture(st, &g));
+        XR_CUDA(cudaGraphInstantiate(&r->graph, g, 0));
+        XR_CUDA(cudaGraphDestroy(g));
+        r->graph_batch = batch;
+        r->launches = launches + 1;
+      }
+      XR_CUDA(cudaGraphLaunch(r->graph, st));
+    } else {
+      int launches = 0;
+      for (int b0 = 0; b0 < batch; b0 += r->mb) {
+        const int nb = std::min(r->mb, batch - b0);
+        preprocess(r, d_src + static_cast<size_t>(b0) * frame_bytes, w, h, stride_bytes, fmt, nb, st);
+        if (r->timed && b0 == 0) XR_CUDA(cudaEventRecord(r->ev[1], st));
+        launches += 1 + pipeline_chunk(r, b0, nb, st);
+      }
+      r->launches = launches;
+    }
+    if (r->timed) XR_CUDA(cudaEventRecord(r->ev[2], st));
+    XR_CUDA(cudaMemcpyAsync(r->h_offsets.data(), r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_counts.data(), r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaEventRecord(r->ev_done, st));
+    r->state = 1;
+    return XRSEG_OK;
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+}
+
+int finish(xrseg_runner* r) {
+  if (r->state == 0) { r->err = "no run scheduled"; return XRSEG_ERR_STATE; }
+  if (r->state == 1) {
+    cudaError_t e = cudaEventSynchronize(r->ev_done);
+    if (e != cudaSuccess) { r->err = std::string("run failed: ") + cudaGetErrorString(e); return XRSEG_ERR_CUDA; }
+    if (r->timed) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, r->ev[0], r->ev[2]) == cudaSuccess) r->timings[0] = ms;
+      if (cudaEventElapsedTime(&ms, r->ev[0], r->ev[1]) == cudaSuccess) r->timings[1] = ms;
+      cudaGetLastError();  // an unrecorded event is not an error of the run
+    }
+    r->state = 2;
+  }
+  return 1;
+}
+
+size_t out_row_bytes(int idx) {
+  switch (idx) {
+    case 0: return 4 * sizeof(float);
+    case 1: return sizeof(int);
+    case 2: return NM * sizeof(float);
+    case 3: return static_cast<size_t>(PROTO_PIX) * sizeof(float);
+  }
+  return 0;
+}
+const void* out_ptr(xrseg_runner* r, int idx) {
+  switch (idx) {
+    case 0: return r->o_boxes;
+    case 1: return r->o_labels;
+    case 2: return r->o_coefs;
+    case 3: return r->o_probs;
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+xrseg_runner::~xrseg_runner() {
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  if (graph) cudaGraphExecDestroy(graph);
+  for (DevLayer& d : dl) {
+    cudaFree(d.wpack); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32);
+  }
+  void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx,
+                  d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,
+                  o_probs, o_labels, o_anchor, o_frame, dbg_box, dbg_cls, dbg_coef, dbg_proto, dbg_corners};
+  for (void* b : bufs) cudaFree(b);
+  if (ev_done) cudaEventDestroy(ev_done);
+  for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int xrseg_abi_version(void) { return XRSEG_ABI_VERSION; }
+
+const char* xrseg_last_error(const xrseg_runner* r) { return r ? r->err.c_str() : g_create_error.c_str(); }
+
+void* xrseg_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void xrseg_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int xrseg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int xrseg_layer_count(int model_scale) {
+  try {
+    if (model_scale != 'n' && model_scale != 's') return XRSEG_ERR_INVALID;
+    Net net(model_scale, 1);
+    return static_cast<int>(net.layers.size());
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_INVALID;
+  }
+}
+
+int xrseg_layer_info_get(int model_scale, int index, xrseg_layer_info* info) {
+  try {
+    if ((model_scale != 'n' && model_scale != 's') || !info) return XRSEG_ERR_INVALID;
+    Net net(model_scale, 1);
+    if (index < 0 || index >= static_cast<int>(net.layers.size())) return XRSEG_ERR_INVALID;
+    const LayerRec& l = net.layers[index];
+    memset(info, 0, sizeof(*info));
+    strncpy(info->name, l.name.c_str(), sizeof(info->name) - 1);
+    info->cin = l.cin; info->cout = l.cout; info->k = l.k; info->stride = l.stride; info->groups = l.groups;
+    info->act = l.act; info->transposed = l.transposed; info->h_in = l.h_in; info->w_in = l.w_in;
+    return XRSEG_OK;
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_INVALID;
+  }
+}
+
+int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
+  if (!cfg_in || !out || cfg_in->struct_size != sizeof(xrseg_config)) {
+    g_create_error = "xrseg_create: bad config (struct_size mismatch?)";
+    return XRSEG_ERR_INVALID;
+  }
+  *out = nullptr;
+  std::unique_ptr<xrseg_runner> r(new xrseg_runner());
+  r->cfg = *cfg_in;
+  xrseg_config& c = r->cfg;
+  if (c.iou_threshold == 0.f) c.iou_threshold = 0.43f;
+  if (c.score_threshold == 0.f) c.score_threshold = 0.301f;
+  if (c.mask_threshold == 0.f) c.mask_threshold = 0.5f;
+  if (c.max_det <= 0) c.max_det = 300;
+  if (c.max_candidates <= 0) c.max_candidates = 2048;
+  if (c.max_candidates > NUM_ANCHORS_MAX) c.max_candidates = NUM_ANCHORS_MAX;
+  if (c.max_batch <= 0) c.max_batch = 1;
+  if (c.model_scale != 'n' && c.model_scale != 's') {
+    g_create_error = "model_scale must be 'n' or 's'";
+    return XRSEG_ERR_INVALID;
+  }
+  try {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || c.device < 0 || c.device >= ndev) {
+      g_create_error = "no CUDA device available (libxrseg has no CPU fallback)";
+      return XRSEG_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop{};
+    XR_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    if (prop.major != 10) {
+      g_create_error = std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200); no other code path exists";
+      return XRSEG_ERR_NO_DEVICE;
+    }
+    r->device = c.device;
+    r->num_sms = prop.multiProcessorCount;
+    XR_CUDA(cudaSetDevice(c.device));
+    XR_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    XR_CUDA(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
+    for (auto& e : r->ev) XR_CUDA(cudaEventCreate(&e));
+    conv_umma_prepare_device();
+    XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    XR_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 65 * 8));
+
+    r->mb = c.micro_batch > 0 ? std::min(c.micro_batch, c.max_batch) : c.max_batch;
+    r->net.reset(new Net(c.model_scale, r->mb));
+    Net& net = *r->net;
+    r->A = net.fh[0] * net.fw[0] + net.fh[1] * net.fw[1] + net.fh[2] * net.fw[2];
+    std::vector<HostLayerWeights> hw;
+    try {
+      xrsw_load(c.weights, c.weights_bytes, net.layers, c.model_scale, hw);
+    } catch (const CudaError& e) {
+      g_create_error = e.msg;
+      return XRSEG_ERR_WEIGHTS;
+    }
+    r->arena = dev_alloc<__half>(net.arena_elems);
+    XR_CUDA(cudaMemset(r->arena, 0, net.arena_elems * sizeof(__half)));
+    upload_layers(r.get(), hw);
+
+    const int B = c.max_batch, A = r->A;
+    r->max_cand = c.max_candidates;
+    r->max_det = c.max_det;
+    r->words = ceil_div(r->max_cand, 64);
+    r->d_boxes = dev_alloc<float>(static_cast<size_t>(B) * A * 4);
+    r->d_scores = dev_alloc<float>(static_cast<size_t>(B) * A);
+    r->d_labels = dev_alloc<int>(static_cast<size_t>(B) * A);
+    r->d_keys = dev_alloc<unsigned long long>(static_cast<size_t>(B) * A);
+    r->d_cand_count = dev_alloc<int>(B);
+    r->d_n_cand = dev_alloc<int>(B);
+    r->d_sorted_idx = dev_alloc<int>(static_cast<size_t>(B) * r->max_cand);
+    r->d_sorted_corners = dev_alloc<float4>(static_cast<size_t>(B) * r->max_cand);
+    r->d_overflow = dev_alloc<int>(1);
+    r->d_mask = dev_alloc<unsigned long long>(static_cast<size_t>(B) * r->max_cand * r->words);
+    r->d_keep_idx = dev_alloc<int>(static_cast<size_t>(B) * r->max_det);
+    r->d_keep_n = dev_alloc<int>(B);
+    r->d_offsets = dev_alloc<int>(B + 1);
+    const size_t cap = static_cast<size_t>(B) * r->max_det;
+    r->o_boxes = dev_alloc<float>(cap * 4);
+    r->o_labels = dev_alloc<int>(cap);
+    r->o_coefs = dev_alloc<float>(cap * NM);
+    r->o_scores = dev_alloc<float>(cap);
+    r->o_anchor = dev_alloc<int>(cap);
+    r->o_frame = dev_alloc<int>(cap);
+    r->o_probs = dev_alloc<float>(cap * PROTO_PIX);
+    r->h_counts.assign(B, 0);
+    r->h_offsets.assign(B + 1, 0);
+    XR_CUDA(cudaMemset(r->d_keep_n, 0, sizeof(int) * B));
+    XR_CUDA(cudaMemset(r->d_offsets, 0, sizeof(int) * (B + 1)));
+    XR_CUDA(cudaDeviceSynchronize());
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  *out = r.release();
+  return XRSEG_OK;
+}
+
+void xrseg_destroy(xrseg_runner* r) { delete r; }
+
+int xrseg_schedule(xrseg_runner* r, const uint8_t* frames, int w, int h, int stride_bytes, int fmt, int batch) {
+  return do_schedule(r, frames, false, w, h, stride_bytes, fmt, batch);
+}
+int xrseg_schedule_device(xrseg_runner* r, const uint8_t* d_frames, int w, int h, int stride_bytes, int fmt, int batch) {
+  return do_schedule(r, d_frames, true, w, h, stride_bytes, fmt, batch);
+}
+
+int xrseg_poll(xrseg_runner* r) {
+  if (!r) return XRSEG_ERR_INVALID;
+  if (r->state == 0) { r->err = "no run scheduled"; return XRSEG_ERR_STATE; }
+  if (r->state == 2) return 1;
+  cudaError_t e = cudaEventQuery(r->ev_done);
+  if (e == cudaErrorNotReady) return 0;
+  if (e != cudaSuccess) { r->err = std::string("run failed: ") + cudaGetErrorString(e); return XRSEG_ERR_CUDA; }
+  return finish(r);
+}
+
+int xrseg_wait(xrseg_runner* r) {
+  if (!r) return XRSEG_ERR_INVALID;
+  return finish(r);
+}
+
+int xrseg_counts(xrseg_runner* r, int32_t* counts, int cap) {
+  if (!r || !counts) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  if (cap < r->batch) { r->err = "counts buffer too small"; return XRSEG_ERR_CAPACITY; }
+  for (int i = 0; i < r->batch; ++i) counts[i] = r->h_counts[i];
+  return r->batch;
+}
+
+int xrseg_peek_output(xrseg_runner* r, int idx, xrseg_tensor_view* v) {
+  if (!r || !v || idx < 0 || idx > 3) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  const int n = r->h_offsets[r->batch];
+  memset(v, 0, sizeof(*v));
+  v->device_ptr = out_ptr(r, idx);
+  v->dtype = idx == 1 ? XRSEG_I32 : XRSEG_F32;
+  v->shape[0] = n;
+  if (idx == 0) { v->rank = 2; v->shape[1] = 4; }
+  if (idx == 1) { v->rank = 1; }
+  if (idx == 2) { v->rank = 2; v->shape[1] = NM; }
+  if (idx == 3) { v->rank = 3; v->shape[1] = PROTO_HW; v->shape[2] = PROTO_HW; }
+  return XRSEG_OK;
+}
+
+int xrseg_readback(xrseg_runner* r, int idx, void* dst, size_t cap_bytes, int64_t* shape, int* rank) {
+  if (!r || idx < 0 || idx > 3) return XRSEG_ERR_INVALID;
+  xrseg_tensor_view v;
+  int rc = xrseg_peek_output(r, idx, &v);
+  if (rc < 0) return rc;
+  if (shape) for (int i = 0; i < v.rank; ++i) shape[i] = v.shape[i];
+  if (rank) *rank = v.rank;
+  const size_t bytes = static_cast<size_t>(v.shape[0]) * out_row_bytes(idx);
+  if (bytes == 0) return XRSEG_OK;
+  if (!dst || cap_bytes < bytes) { r->err = "readback buffer too small"; return XRSEG_ERR_CAPACITY; }
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    XR_CUDA(cudaMemcpyAsync(dst, v.device_ptr, bytes, cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_keep_indices(xrseg_runner* r, int32_t* idx, float* scores, int cap) {
+  if (!r) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  const int n = r->h_offsets[r->batch];
+  if (cap < n) { r->err = "keep buffer too small"; return XRSEG_ERR_CAPACITY; }
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    if (idx && n) XR_CUDA(cudaMemcpyAsync(idx, r->o_anchor, sizeof(int) * n, cudaMemcpyDeviceToHost, r->stream));
+    if (scores && n) XR_CUDA(cudaMemcpyAsync(scores, r->o_scores, sizeof(float) * n, cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return n;
+}
+
+int xrseg_decode(xrseg_runner* r, float screen_w, float screen_h, int convention, xrseg_box* out, int cap, int* n_out) {
+  if (!r || !out || !n_out || convention < 0 || convention > 2) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  static_assert(sizeof(xrseg_box) == sizeof(BoxOut), "box layout");
+  const int per_frame_cap = convention == XRSEG_BOX_PARSEBOXES ? 50 : (convention == XRSEG_BOX_DRAWBOXES ? 200 : 0);
+  int total = 0;
+  for (int b = 0; b < r->batch; ++b) total += per_frame_cap ? std::min(r->h_counts[b], per_frame_cap) : r->h_counts[b];
+  *n_out = total;
+  if (total == 0) return XRSEG_OK;
+  if (cap < total) { r->err = "box buffer too small"; return XRSEG_ERR_CAPACITY; }
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    BoxOut* d_out = dev_alloc<BoxOut>(total);
+    int* d_n = dev_alloc<int>(1);
+    boxes_to_screen_kernel<<<1, 32, 0, r->stream>>>(r->o_boxes, r->o_labels, r->d_keep_n, r->d_offsets, r->batch,
+                                                    convention, screen_w, screen_h, per_frame_cap, d_out, d_n);
+    XR_CUDA(cudaMemcpyAsync(out, d_out, sizeof(BoxOut) * total, cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+    cudaFree(d_out);
+    cudaFree(d_n);
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size_t cap_bytes) {
+  if (!r || !mp || !out || mp->struct_size != sizeof(xrseg_mask_params)) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  const int total = r->h_offsets[r->batch];
+  const int first = mp->first;
+  const int count = mp->count > 0 ? mp->count : total - first;
+  if (first < 0 || count < 0 || first + count > total) { r->err = "mask range out of bounds"; return XRSEG_ERR_INVALID; }
+  if (count == 0) return 0;
+  size_t per = 0;
+  switch (mp->mode) {
+    case XRSEG_MASK_REFERENCE_160:
+    case XRSEG_MASK_CROP_160: per = PROTO_PIX; break;
+    case XRSEG_MASK_UPSAMPLE_640: per = 640 * 640; break;
+    case XRSEG_MASK_BITS_160: per = PROTO_HW * 5 * 4; break;
+    default: return XRSEG_ERR_INVALID;
+  }
+  if (cap_bytes < per * count) { r->err = "mask buffer too small"; return XRSEG_ERR_CAPACITY; }
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    uint8_t* d_out = dev_alloc<uint8_t>(per * count);
+    if (mp->mode == XRSEG_MASK_UPSAMPLE_640) {
+      const TV& pr = r->net->protos;
+      Mask640Params p{ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch, pr.pitch, r->o_coefs, r->o_boxes,
+                      r->o_frame, first, d_out};
+      if (r->batch > r->mb) {
+        cudaFree(d_out);
+        r->err = "640-px masks need the prototypes of every frame resident: use micro_batch >= batch";
+        return XRSEG_ERR_STATE;
+      }
+      mask640_kernel<<<dim3(10, 10, count), 256, 0, r->stream>>>(p);
+    } else {
+      MaskThrParams p{};
+      p.probs = r->o_probs; p.boxes = r->o_boxes; p.n = count; p.first = first;
+      p.mode = mp->mode == XRSEG_MASK_REFERENCE_160 ? 0 : 1;
+      p.conv = mp->box_convention; p.sw = mp->screen_w; p.sh = mp->screen_h;
+      p.image_w = mp->image_w; p.image_h = mp->image_h; p.thr = r->cfg.mask_threshold; p.out = d_out;
+      if (mp->mode == XRSEG_MASK_BITS_160)
+        mask_bits_kernel<<<dim3(PROTO_HW, count), PROTO_HW, 0, r->stream>>>(p);
+      else
+        mask_threshold_kernel<<<dim3(PROTO_PIX / 256, count), 256, 0, r->stream>>>(p);
+    }
+    XR_CUDA(cudaGetLastError());
+    XR_CUDA(cudaMemcpyAsync(out, d_out, per * count, cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+    cudaFree(d_out);
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return count;
+}
+
+int xrseg_last_timings(xrseg_runner* r, float* ms, int n) {
+  if (!r || !ms) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  for (int i = 0; i < n && i < 5; ++i) ms[i] = r->timings[i];
+  return XRSEG_OK;
+}
+
+int xrseg_launch_count(xrseg_runner* r) { return r ? r->launches : XRSEG_ERR_INVALID; }
+
+// ---- debug / parity --------------------------------------------------------------------------------------------
+int xrseg_debug_fetch(xrseg_runner* r, const char* name, float* dst, size_t cap_floats, int64_t* shape4) {
+  if (!r || !name || !dst) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  Net& net = *r->net;
+  TV t;
+  int C;
+  std::string nm(name);
+  // head tensors are fetched per scale: "box_logits.0" .. ; protos as a whole
+  if (nm.rfind("box_logits.", 0) == 0) { t = net.box[nm.back() - '0']; }
+  else if (nm.rfind("cls_logits.", 0) == 0) { t = net.cls[nm.back() - '0']; }
+  else if (nm.rfind("coefs.", 0) == 0) { t = net.coef[nm.back() - '0']; }
+  else if (nm == "protos") { t = net.protos; }
+  else {
+    auto it = net.named.find(nm);
+    if (it == net.named.end()) { r->err = "unknown tensor " + nm; return XRSEG_ERR_INVALID; }
+    t = it->second;
+  }
+  C = t.C;
+  const int nb = std::min(r->batch, r->mb);
+  const size_t n = static_cast<size_t>(nb) * C * t.H * t.W;
+  if (shape4) { shape4[0] = nb; shape4[1] = C; shape4[2] = t.H; shape4[3] = t.W; }
+  if (cap_floats < n) { r->err = "fetch buffer too small"; return XRSEG_ERR_CAPACITY; }
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    float* d = dev_alloc<float>(n);
+    nhwc_f16_to_nchw_f32_kernel<<<grid_for(static_cast<long>(n)), 256, 0, r->stream>>>(ptr_of(r, t), d, nb, C, t.H, t.W,
+                                                                                      t.pitch);
+    XR_CUDA(cudaMemcpyAsync(dst, d, n * sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+    cudaFree(d);
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
+                     const float* protos, int batch) {
+  if (!r || !box_logits || !cls_logits || !coefs || !protos || batch < 1 || batch > r->cfg.max_batch)
+    return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    const size_t A = r->A;
+    const size_t B = r->cfg.max_batch;
+    if (!r->dbg_box) {
+      r->dbg_box = dev_alloc<float>(B * A * 64);
+      r->dbg_cls = dev_alloc<float>(B * A * NC);
+      r->dbg_coef = dev_alloc<float>(B * A * NM);
+      r->dbg_proto = dev_alloc<float>(B * NM * PROTO_PIX);
+    }
+    cudaStream_t st = r->stream;
+    XR_CUDA(cudaMemcpyAsync(r->dbg_box, box_logits, sizeof(float) * batch * A * 64, cudaMemcpyHostToDevice, st));
+    XR_CUDA(cudaMemcpyAsync(r->dbg_cls, cls_logits, sizeof(float) * batch * A * NC, cudaMemcpyHostToDevice, st));
+    XR_CUDA(cudaMemcpyAsync(r->dbg_coef, coefs, sizeof(float) * batch * A * NM, cudaMemcpyHostToDevice, st));
+    XR_CUDA(cudaMemcpyAsync(r->dbg_proto, protos, sizeof(float) * batch * NM * PROTO_PIX, cudaMemcpyHostToDevice, st));
+    r->batch = batch;
+    r->timed = false;
+    reset_counters(r, batch, st);
+    ScaleSrc<float> src[3];
+    dense_scale_src(r, src, r->dbg_box, r->dbg_cls, r->dbg_coef);
+    run_post<float, true>(r, 0, batch, src, r->dbg_proto, static_cast<long>(NM) * PROTO_PIX, 0, true, false, st);
+    add_frame_base_kernel<<<batch, 64, 0, st>>>(r->o_frame, r->d_offsets, 0, batch);
+    XR_CUDA(cudaMemcpyAsync(r->h_offsets.data(), r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_counts.data(), r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaEventRecord(r->ev_done, st));
+    r->state = 1;
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, int batch, int num_anchors) {
+  if (!r || !corners || !scores || batch < 1 || batch > r->cfg.max_batch || num_anchors != r->A) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    const size_t A = r->A, B = r->cfg.max_batch;
+    if (!r->dbg_corners) r->dbg_corners = dev_alloc<float>(B * A * 4);
+    cudaStream_t st = r->stream;
+    XR_CUDA(cudaMemcpyAsync(r->dbg_corners, corners, sizeof(float) * batch * A * 4, cudaMemcpyHostToDevice, st));
+    XR_CUDA(cudaMemcpyAsync(r->d_scores, scores, sizeof(float) * batch * A, cudaMemcpyHostToDevice, st));
+    XR_CUDA(cudaMemsetAsync(r->d_labels, 0, sizeof(int) * batch * A, st));
+    XR_CUDA(cudaMemcpyAsync(r->d_boxes, r->dbg_corners, sizeof(float) * batch * A * 4, cudaMemcpyDeviceToDevice, st));
+    r->batch = batch;
+    r->timed = false;
+    reset_counters(r, batch, st);
+    scores_to_keys_kernel<<<dim3(ceil_div(static_cast<int>(A), 128), batch), 128, 0, st>>>(
+        r->d_scores, batch, static_cast<int>(A), r->cfg.score_threshold, r->d_keys, r->d_cand_count);
+    ScaleSrc<float> src[3] = {};
+    run_post<float, true>(r, 0, batch, src, nullptr, 0, 0, false, true, st);
+    // anchors / scores of the kept boxes, compacted (no coefficient gather on this path)
+    XR_CUDA(cudaMemcpyAsync(r->h_offsets.data(), r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_counts.data(), r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> keep(static_cast<size_t>(batch) * r->max_det);
+    XR_CUDA(cudaMemcpy(keep.data(), r->d_keep_idx, sizeof(int) * keep.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> flat;
+    std::vector<float> fs;
+    for (int b = 0; b < batch; ++b)
+      for (int i = 0; i < r->h_counts[b]; ++i) {
+        const int a = keep[static_cast<size_t>(b) * r->max_det + i];
+        flat.push_back(a);
+        fs.push_back(scores[static_cast<size_t>(b) * A + a]);
+      }
+    if (!flat.empty()) {
+      XR_CUDA(cudaMemcpy(r->o_anchor, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice));
+      XR_CUDA(cudaMemcpy(r->o_scores, fs.data(), sizeof(float) * fs.size(), cudaMemcpyHostToDevice));
+    }
+    XR_CUDA(cudaEventRecord(r->ev_done, st));
+    r->state = 1;
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_debug_mask_threshold(xrseg_runner* r, const float* probs, const float* boxes, int n, int image_w, int image_h,
+                               float thr, uint8_t* out) {
+  if (!r || !probs || !boxes || !out || n < 1) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    float* d_p = dev_alloc<float>(static_cast<size_t>(n) * PROTO_PIX);
+    float* d_b = dev_alloc<float>(static_cast<size_t>(n) * 4);
+    uint8_t* d_o = dev_alloc<uint8_t>(static_cast<size_t>(n) * PROTO_PIX);
+    XR_CUDA(cudaMemcpy(d_p, probs, sizeof(float) * n * PROTO_PIX, cudaMemcpyHostToDevice));
+    XR_CUDA(cudaMemcpy(d_b, boxes, sizeof(float) * n * 4, cudaMemcpyHostToDevice));
+    MaskThrParams p{};
+    p.probs = d_p; p.boxes = d_b; p.n = n; p.first = 0; p.mode = 0; p.conv = -1;
+    p.image_w = image_w; p.image_h = image_h; p.thr = thr; p.out = d_o;
+    mask_threshold_kernel<<<dim3(PROTO_PIX / 256, n), 256, 0, r->stream>>>(p);
+    XR_CUDA(cudaGetLastError());
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+    XR_CUDA(cudaMemcpy(out, d_o, static_cast<size_t>(n) * PROTO_PIX, cudaMemcpyDeviceToHost));
+    cudaFree(d_p); cudaFree(d_b); cudaFree(d_o);
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+// One convolution through the selected engine (standalone: no runner needed).
+int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h, int w, const float* wgt,
+                     const float* bias, int cout, int k, int stride, int groups, int act, int transposed,
+                     const float* residual, float* y, int variant) {
+  if (!x || !wgt || !y || groups != 1) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    XR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { g_create_error = "not an sm_100 device"; return XRSEG_ERR_NO_DEVICE; }
+    conv_umma_prepare_device();
+    const int cin_p = round_up(cin, 16), cout_p = round_up(cout, 16);
+    const int ho = transposed ? h * 2 : (h + 2 * (k / 2) - k) / stride + 1;
+    const int wo = transposed ? w * 2 : (w + 2 * (k / 2) - k) / stride + 1;
+    const size_t nx = static_cast<size_t>(b) * cin * h * w, ny = static_cast<size_t>(b) * cout * ho * wo;
+    float* d_x32 = dev_alloc<float>(nx);
+    float* d_y32 = dev_alloc<float>(ny);
+    float* d_r32 = residual ? dev_alloc<float>(ny) : nullptr;
+    __half* d_x = dev_alloc<__half>(static_cast<size_t>(b) * h * w * cin_p);
+    __half* d_y = dev_alloc<__half>(static_cast<size_t>(b) * ho * wo * cout_p);
+    __half* d_r = residual ? dev_alloc<__half>(static_cast<size_t>(b) * ho * wo * cout_p) : nullptr;
+    XR_CUDA(cudaMemcpy(d_x32, x, nx * sizeof(float), cudaMemcpyHostToDevice));
+    nchw_f32_to_nhwc_f16_kernel<<<grid_for(static_cast<long>(b) * h * w * cin_p), 256>>>(d_x32, d_x, b, cin, h, w, cin_p, cin_p);
+    if (residual) {
+      XR_CUDA(cudaMemcpy(d_r32, residual, ny * sizeof(float), cudaMemcpyHostToDevice));
+      nchw_f32_to_nhwc_f16_kernel<<<grid_for(static_cast<long>(b) * ho * wo * cout_p), 256>>>(d_r32, d_r, b, cout, ho, wo, cout_p, cout_p);
+    }
+    XR_CUDA(cudaMemset(d_y, 0, static_cast<size_t>(b) * ho * wo * cout_p * sizeof(__half)));
+    std::vector<float> zero_bias(cout, 0.f);
+    const float* hb = bias ? bias : zero_bias.data();
+    __half* d_w = nullptr;
+    float* d_b = nullptr;
+    if (impl == XRSEG_CONV_UMMA) {
+      ConvDesc cd{b, h, w, cin_p, cin_p, cout_p, cout_p, k, stride, act, transposed, residual ? cout_p : 0};
+      ConvParams p = plan_conv(cd, prop.multiProcessorCount, variant & 1);
+      p.dbg = variant & 2;
+      std::vector<__half> wp;
+      std::vector<float> bp;
+      pack_conv_weights<__half>(p, wgt, hb, cin, cout, wp, bp);
+      d_w = dev_upload(wp);
+      d_b = dev_upload(bp);
+      p.in = d_x; p.out = d_y; p.res = d_r; p.wpack = d_w; p.bias = d_b;
+      launch_conv_umma(p, 0);
+    } else {
+      const int taps = transposed ? 4 : k * k;
+      std::vector<__half> wd(static_cast<size_t>(cout_p) * taps * cin_p, __half(0.f));
+      std::vector<float> bs(cout_p, 0.f);
+      for (int co = 0; co < cout; ++co) {
+        bs[co] = hb[co];
+        for (int ci = 0; ci < cin; ++ci)
+          for (int t = 0; t < taps; ++t)
+            if (transposed) wd[(static_cast<size_t>(t) * cout_p + co) * cin_p + ci] = __half(wgt[(static_cast<size_t>(ci) * cout + co) * 4 + t]);
+            else wd[(static_cast<size_t>(co) * taps + t) * cin_p + ci] = __half(wgt[(static_cast<size_t>(co) * cin + ci) * taps + t]);
+      }
+      d_w = dev_upload(wd);
+      d_b = dev_upload(bs);
+      DirectParams p{};
+      p.in = d_x; p.in_pitch = cin_p; p.out = d_y; p.out_pitch = cout_p; p.res = d_r; p.res_pitch = cout_p;
+      p.w = d_w; p.bias = d_b; p.B = b; p.H = h; p.W = w; p.Cin = cin_p; p.Ho = ho; p.Wo = wo; p.Cout = cout_p;
+      p.k = k; p.stride = stride; p.pad = k / 2; p.act = act; p.transposed = transposed;
+      conv_direct_kernel<<<grid_for(static_cast<long>(b) * ho * wo * cout_p, 256, 148 * 32), 256>>>(p);
+    }
+    XR_CUDA(cudaGetLastError());
+    nhwc_f16_to_nchw_f32_kernel<<<grid_for(static_cast<long>(ny)), 256>>>(d_y, d_y32, b, cout, ho, wo, cout_p);
+    XR_CUDA(cudaDeviceSynchronize());
+    XR_CUDA(cudaMemcpy(y, d_y32, ny * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_x32); cudaFree(d_y32); cudaFree(d_r32); cudaFree(d_x); cudaFree(d_y); cudaFree(d_r); cudaFree(d_w); cudaFree(d_b);
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+// Host emulation of the UMMA kernel's data movement (test infrastructure; fp32; no GPU involved).
+int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const float* wgt, const float* bias, int cout,
+                             int k, int stride, int act, int transposed, const float* residual, float* y, int variant) {
+  if (!x || !wgt || !y) return XRSEG_ERR_INVALID;
+  try {
+    const int cin_p = round_up(cin, 16), cout_p = round_up(cout, 16);
+    const int ho = transposed ? h * 2 : (h + 2 * (k / 2) - k) / stride + 1;
+    const int wo = transposed ? w * 2 : (w + 2 * (k / 2) - k) / stride + 1;
+    ConvDesc cd{b, h, w, cin_p, cin_p, cout_p, cout_p, k, stride, act, transposed, residual ? cout_p : 0};
+    ConvParams p = plan_conv(cd, 148, variant & 1);
+    std::vector<float> wp, bp;
+    std::vector<float> zero_bias(cout, 0.f);
+    pack_conv_weights<float>(p, wgt, bias ? bias : zero_bias.data(), cin, cout, wp, bp);
+    std::vector<float> xin(static_cast<size_t>(b) * h * w * cin_p, 0.f), yo(static_cast<size_t>(b) * ho * wo * cout_p, 0.f), rr;
+    for (int n = 0; n < b; ++n)
+      for (int c = 0; c < cin; ++c)
+        for (int i = 0; i < h * w; ++i) xin[(static_cast<size_t>(n) * h * w + i) * cin_p + c] = x[(static_cast<size_t>(n) * cin + c) * h * w + i];
+    if (residual) {
+      rr.assign(yo.size(), 0.f);
+      for (int n = 0; n < b; ++n)
+        for (int c = 0; c < cout; ++c)
+          for (int i = 0; i < ho * wo; ++i) rr[(static_cast<size_t>(n) * ho * wo + i) * cout_p + c] = residual[(static_cast<size_t>(n) * cout + c) * ho * wo + i];
+    }
+    emulate_conv_umma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
+    for (int n = 0; n < b; ++n)
+      for (int c = 0; c < cout; ++c)
+        for (int i = 0; i < ho * wo; ++i) y[(static_cast<size_t>(n) * cout + c) * ho * wo + i] = yo[(static_cast<size_t>(n) * ho * wo + i) * cout_p + c];
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_INVALID;
+  }
+  return XRSEG_OK;
+}
+
+}  // extern "C"

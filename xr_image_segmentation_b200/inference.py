@@ -1,0 +1,344 @@
+"""Host-side mirror of the Unity Inference Engine surface the reference's hot path calls, on top of libxrseg.so.
+
+Reference call sites (Assets/Scripts/InferenceEngine/IEExecutor.cs, "IEE"):
+  ModelLoader.Load(asset) IEE:382 | new Worker(model, backend) IEE:383 | Worker.Schedule(t) IEE:385 |
+  TextureConverter.ToTensor(tex, 640, 640, 3) IEE:370 | Worker.ScheduleIterable(t) IEE:371 |
+  Worker.PeekOutput(i) IEE:426 | Tensor.dataOnBackend / ReadbackRequest() IEE:427 |
+  Tensor.IsReadbackRequestDone() IEE:439 | Tensor.ReadbackAndClone() IEE:446-449 | indexers + shape | Dispose().
+
+Same names, argument meaning and ownership rules (peeked tensors are borrowed until the next schedule, clones are
+caller-owned).  All arithmetic runs in the CUDA library; this file only moves bytes and tracks state.  `Runner` is the
+thin pythonic wrapper of the C ABI used by tests and bench.py (batch > 1, debug entry points).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import XrsegError
+
+
+class BackendType:
+    GPUCompute = 256   # XRScene.unity:1221
+    CPU = 512          # TestScene.unity:747 -- not available here: there is no CPU path in this build
+
+
+class Model:
+    """↔ Unity.InferenceEngine.Model: an XRSW weight pack + the topology scale."""
+
+    def __init__(self, pack: bytes, scale: str = "n"):
+        self.pack = pack
+        self.scale = scale
+
+
+class ModelLoader:
+    @staticmethod
+    def Load(asset) -> Model:
+        """↔ ModelLoader.Load(ModelAsset) IEE:382.  `asset`: path to / bytes of an XRSW pack."""
+        data = asset if isinstance(asset, (bytes, bytearray)) else open(os.fspath(asset), "rb").read()
+        if data[:4] != b"XRSW":
+            raise XrsegError(_lib.ERR_WEIGHTS, "not an XRSW weight pack (convert the .sentis asset with tests/golden/make_golden.py)")
+        return Model(bytes(data), chr(int.from_bytes(data[12:16], "little")))
+
+
+class Runner:
+    """One libxrseg runner (one GPU).  Thin wrapper of the C ABI."""
+
+    def __init__(self, model: Model, device: int = 0, max_batch: int = 1, iou=0.0, score=0.0, mask_thr=0.0,
+                 max_det=0, max_candidates=0, resize_mode=_lib.RESIZE_STRETCH, conv_impl=_lib.CONV_UMMA,
+                 use_cuda_graph=True, micro_batch=0):
+        self.lib = _lib.load_library()
+        self._pack = C.create_string_buffer(model.pack, len(model.pack))
+        cfg = _lib.Config()
+        cfg.struct_size = C.sizeof(_lib.Config)
+        cfg.device = device
+        cfg.max_batch = max_batch
+        cfg.model_scale = ord(model.scale)
+        cfg.weights = C.cast(self._pack, C.c_void_p)
+        cfg.weights_bytes = len(model.pack)
+        cfg.iou_threshold, cfg.score_threshold, cfg.mask_threshold = iou, score, mask_thr
+        cfg.max_det, cfg.max_candidates = max_det, max_candidates
+        cfg.resize_mode, cfg.conv_impl = resize_mode, conv_impl
+        cfg.use_cuda_graph = 1 if use_cuda_graph else 0
+        cfg.micro_batch = micro_batch
+        self.h = C.c_void_p()
+        _lib.check(self.lib.xrseg_create(C.byref(cfg), C.byref(self.h)))
+        self.max_batch = max_batch
+        self.batch = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.xrseg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        return _lib.check(rc, self.h)
+
+    # ---- per-frame path ----
+    def schedule(self, frames: np.ndarray, fmt=None):
+        """frames uint8 [B,H,W,3|4] (host).  Asynchronous."""
+        assert frames.dtype == np.uint8 and frames.ndim == 4 and frames.flags.c_contiguous
+        b, h, w, c = frames.shape
+        fmt = (_lib.FMT_RGBA8 if c == 4 else _lib.FMT_RGB8) if fmt is None else fmt
+        self._keep = frames
+        self.batch = b
+        self._ck(self.lib.xrseg_schedule(self.h, frames.ctypes.data, w, h, w * c, fmt, b))
+
+    def schedule_ptr(self, host_ptr: int, b, h, w, c):
+        self.batch = b
+        self._ck(self.lib.xrseg_schedule(self.h, host_ptr, w, h, w * c, _lib.FMT_RGBA8 if c == 4 else _lib.FMT_RGB8, b))
+
+    def schedule_device(self, dev_ptr: int, b, h, w, c):
+        self.batch = b
+        self._ck(self.lib.xrseg_schedule_device(self.h, dev_ptr, w, h, w * c, _lib.FMT_RGBA8 if c == 4 else _lib.FMT_RGB8, b))
+
+    def poll(self) -> int:
+        return self._ck(self.lib.xrseg_poll(self.h))
+
+    def wait(self):
+        self._ck(self.lib.xrseg_wait(self.h))
+
+    def counts(self) -> np.ndarray:
+        out = np.zeros(self.max_batch, np.int32)
+        n = self._ck(self.lib.xrseg_counts(self.h, out.ctypes.data_as(C.POINTER(C.c_int32)), self.max_batch))
+        return out[:n]
+
+    def peek(self, idx: int) -> _lib.TensorView:
+        v = _lib.TensorView()
+        self._ck(self.lib.xrseg_peek_output(self.h, idx, C.byref(v)))
+        return v
+
+    _DT = {0: np.float32, 1: np.int32}
+
+    def readback(self, idx: int) -> np.ndarray:
+        v = self.peek(idx)
+        shape = [int(v.shape[i]) for i in range(v.rank)]
+        out = np.empty(shape, self._DT[v.dtype])
+        shp = (C.c_int64 * 4)()
+        rank = C.c_int()
+        self._ck(self.lib.xrseg_readback(self.h, idx, out.ctypes.data, out.nbytes, shp, C.byref(rank)))
+        return out
+
+    def keep_indices(self):
+        n = int(self.peek(0).shape[0])
+        idx = np.zeros(max(n, 1), np.int32)
+        sc = np.zeros(max(n, 1), np.float32)
+        self._ck(self.lib.xrseg_keep_indices(self.h, idx.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             sc.ctypes.data_as(C.POINTER(C.c_float)), max(n, 1)))
+        return idx[:n], sc[:n]
+
+    def decode(self, screen_w: float, screen_h: float, convention: int):
+        cap = max(1, int(self.peek(0).shape[0]))
+        arr = (_lib.Box * cap)()
+        n = C.c_int()
+        self._ck(self.lib.xrseg_decode(self.h, screen_w, screen_h, convention, arr, cap, C.byref(n)))
+        out = np.zeros((n.value, 4), np.float32)
+        lab = np.zeros(n.value, np.int32)
+        frm = np.zeros(n.value, np.int32)
+        for i in range(n.value):
+            out[i] = (arr[i].center_x, arr[i].center_y, arr[i].width, arr[i].height)
+            lab[i] = arr[i].label_id
+            frm[i] = arr[i].frame
+        return out, lab, frm
+
+    def masks(self, mode: int, box_convention=_lib.BOX_DRAWBOXES, screen_w=640.0, screen_h=640.0, image_w=640,
+              image_h=640, first=0, count=0) -> np.ndarray:
+        total = int(self.peek(0).shape[0])
+        n = count if count > 0 else total - first
+        shape = {_lib.MASK_REFERENCE_160: (n, 160, 160), _lib.MASK_CROP_160: (n, 160, 160),
+                 _lib.MASK_UPSAMPLE_640: (n, 640, 640), _lib.MASK_BITS_160: (n, 160, 20)}[mode]
+        out = np.zeros(shape, np.uint8)
+        if n == 0:
+            return out
+        p = _lib.MaskParams(C.sizeof(_lib.MaskParams), mode, box_convention, screen_w, screen_h, image_w, image_h, first, n)
+        self._ck(self.lib.xrseg_masks(self.h, C.byref(p), out.ctypes.data, out.nbytes))
+        return out.view(np.uint32).reshape(n, 160, 5) if mode == _lib.MASK_BITS_160 else out
+
+    def timings(self):
+        ms = (C.c_float * 5)()
+        self._ck(self.lib.xrseg_last_timings(self.h, ms, 5))
+        return list(ms)
+
+    def launch_count(self) -> int:
+        return self.lib.xrseg_launch_count(self.h)
+
+    # ---- parity / debug ----
+    def fetch(self, name: str) -> np.ndarray:
+        shp = (C.c_int64 * 4)()
+        cap = 64 * 1024 * 1024
+        buf = np.empty(cap, np.float32)
+        self._ck(self.lib.xrseg_debug_fetch(self.h, name.encode(), buf.ctypes.data, cap, shp))
+        shape = [int(s) for s in shp]
+        return buf[:int(np.prod(shape))].reshape(shape).copy()
+
+    def debug_post(self, box_logits, cls_logits, coefs, protos):
+        arrs = [np.ascontiguousarray(a, np.float32) for a in (box_logits, cls_logits, coefs, protos)]
+        b = arrs[0].shape[0]
+        self.batch = b
+        self._ck(self.lib.xrseg_debug_post(self.h, *(a.ctypes.data for a in arrs), b))
+
+    def debug_nms(self, corners, scores):
+        c = np.ascontiguousarray(corners, np.float32)
+        s = np.ascontiguousarray(scores, np.float32)
+        self.batch = c.shape[0]
+        self._ck(self.lib.xrseg_debug_nms(self.h, c.ctypes.data, s.ctypes.data, c.shape[0], c.shape[1]))
+
+    def debug_mask_threshold(self, probs, boxes, image_w, image_h, thr=0.5):
+        p = np.ascontiguousarray(probs, np.float32)
+        bx = np.ascontiguousarray(boxes, np.float32)
+        out = np.zeros(p.shape, np.uint8)
+        self._ck(self.lib.xrseg_debug_mask_threshold(self.h, p.ctypes.data, bx.ctypes.data, p.shape[0], image_w, image_h,
+                                                     thr, out.ctypes.data))
+        return out
+
+
+def debug_conv(x, w, b, k, stride, act, transposed=False, residual=None, impl=_lib.CONV_UMMA, variant=0, device=0):
+    """One convolution through the CUDA library (parity tests)."""
+    lib = _lib.load_library()
+    x = np.ascontiguousarray(x, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    B, cin, h, wd = x.shape
+    cout = w.shape[1] if transposed else w.shape[0]
+    ho = h * 2 if transposed else (h + 2 * (k // 2) - k) // stride + 1
+    wo = wd * 2 if transposed else (wd + 2 * (k // 2) - k) // stride + 1
+    y = np.zeros((B, cout, ho, wo), np.float32)
+    bb = None if b is None else np.ascontiguousarray(b, np.float32)
+    rr = None if residual is None else np.ascontiguousarray(residual, np.float32)
+    _lib.check(lib.xrseg_debug_conv(device, impl, x.ctypes.data, B, cin, h, wd, w.ctypes.data,
+                                    bb.ctypes.data if bb is not None else None, cout, k, stride, 1, int(act),
+                                    int(transposed), rr.ctypes.data if rr is not None else None, y.ctypes.data, variant))
+    return y
+
+
+# --------------------------------------------------------------------------------------------------
+# Inference Engine mirror
+# --------------------------------------------------------------------------------------------------
+class Tensor:
+    """↔ Tensor<float> / Tensor<int>.  Either a host tensor (owns `array`) or a worker-owned backend tensor."""
+
+    def __init__(self, array: np.ndarray | None = None, worker: "Worker | None" = None, index: int = -1):
+        self._array = array
+        self._worker = worker
+        self._index = index
+        self._requested = False
+        self.disposed = False
+
+    @property
+    def dataOnBackend(self):
+        """Non-None when the tensor has device data (IEE:427)."""
+        if self._worker is None:
+            return None
+        return self._worker._runner.peek(self._index).device_ptr or None
+
+    @property
+    def shape(self):
+        if self._array is not None:
+            return tuple(self._array.shape)
+        v = self._worker._runner.peek(self._index)
+        return tuple(int(v.shape[i]) for i in range(v.rank))
+
+    def ReadbackRequest(self):
+        self._requested = True
+
+    def IsReadbackRequestDone(self) -> bool:
+        return self._worker._runner.poll() == 1
+
+    def ReadbackAndClone(self) -> "Tensor":
+        return Tensor(array=self._worker._runner.readback(self._index))
+
+    def __getitem__(self, idx):
+        if self._array is None:
+            raise XrsegError(_lib.ERR_STATE, "backend tensor: ReadbackAndClone() first")
+        return self._array[idx]
+
+    def numpy(self) -> np.ndarray:
+        return self._array
+
+    def Dispose(self):
+        self.disposed = True
+        self._array = None
+
+
+class InputTensor(Tensor):
+    """Result of TextureConverter.ToTensor: the frame bytes; the resample to 640x640 runs on the GPU at schedule time."""
+
+    def __init__(self, frame_u8: np.ndarray, width: int, height: int, channels: int):
+        super().__init__(array=np.ascontiguousarray(frame_u8))
+        self.target = (width, height, channels)
+
+
+class TextureConverter:
+    @staticmethod
+    def ToTensor(texture: np.ndarray, width: int = 640, height: int = 640, channels: int = 3) -> InputTensor:
+        """↔ TextureConverter.ToTensor(tex, 640, 640, 3) IEE:370.  texture: uint8 [H,W,3|4], top row first."""
+        if (width, height, channels) != (640, 640, 3):
+            raise XrsegError(_lib.ERR_INVALID, "the network input is 640x640x3")
+        t = np.asarray(texture)
+        if t.dtype != np.uint8 or t.ndim != 3 or t.shape[2] not in (3, 4):
+            raise XrsegError(_lib.ERR_INVALID, "texture must be uint8 [H,W,3|4]")
+        return InputTensor(t, width, height, channels)
+
+
+class _Schedule:
+    """↔ the IEnumerator returned by Worker.ScheduleIterable: MoveNext() is True while the run is in flight."""
+
+    def __init__(self, worker: "Worker"):
+        self._w = worker
+        self._started = False
+
+    def MoveNext(self) -> bool:
+        if not self._started:
+            self._w._enqueue()
+            self._started = True
+            return True
+        return self._w._runner.poll() != 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if not self.MoveNext():
+            raise StopIteration
+        return None
+
+
+class Worker:
+    """↔ Unity.InferenceEngine.Worker for this model (IEE:383-385, 371, 426, 303)."""
+
+    def __init__(self, model: Model, backend: int = BackendType.GPUCompute, device: int = 0, **runner_kw):
+        if backend != BackendType.GPUCompute:
+            raise XrsegError(_lib.ERR_NO_DEVICE, "only BackendType.GPUCompute exists in this build (no CPU fallback)")
+        self._runner = Runner(model, device=device, max_batch=1, **runner_kw)
+        self._input = None
+
+    def _enqueue(self):
+        f = self._input.numpy()
+        self._runner.schedule(f[None])
+
+    def Schedule(self, input: InputTensor):
+        """↔ Worker.Schedule(tensor) IEE:385: enqueue the whole run."""
+        self._input = input
+        self._enqueue()
+
+    def ScheduleIterable(self, input: InputTensor) -> _Schedule:
+        """↔ Worker.ScheduleIterable(tensor) IEE:371."""
+        self._input = input
+        return _Schedule(self)
+
+    def PeekOutput(self, index: int) -> Tensor:
+        """↔ Worker.PeekOutput(i) IEE:426: borrowed, valid until the next schedule."""
+        if not 0 <= index <= 3:
+            raise XrsegError(_lib.ERR_INVALID, "the model has outputs 0..3")
+        return Tensor(worker=self, index=index)
+
+    def Dispose(self):
+        self._runner.close()

@@ -2,8 +2,9 @@
 reference's hot path -- the converter tail baked into the graph and the C# box/mask code.
 
 Every function cites the reference lines it follows.  Arithmetic is numpy float32 with
-one IEEE operation per numpy call (no FMA contraction), in the order written, so a CUDA
-kernel compiled with the same operation order and `-fmad=false` can match bit for bit.
+one IEEE operation per numpy call (no FMA contraction) in the order written -- except the
+mask dot product, which is an explicit FMA chain -- so that the CUDA kernels, written with
+the matching __fadd_rn / __fmul_rn / __fdiv_rn / __fmaf_rn intrinsics, agree bit for bit.
 
 PARITY UNPINNED by the reference (no tests / golden vectors exist); the
 choices marked "oracle choice" are documented in DESIGN.md.
@@ -125,15 +126,18 @@ def nms_onnx(corners: np.ndarray, scores: np.ndarray, iou_thr: float, score_thr:
 # Mask assembly: graph chains 496-498 (CONV:87-97)
 # --------------------------------------------------------------------------------------
 def mask_logits(coefs: np.ndarray, protos: np.ndarray) -> np.ndarray:
-    """coefs f32 [N,32] x protos f32 [32,P] -> [N,P]; sequential k = 0..31, mul then add in fp32.
+    """coefs f32 [N,32] x protos f32 [32,P] -> [N,P]: acc = fma(coef[:,k], proto[k,:], acc) for k = 0..31 in fp32.
 
-    oracle choice: the summation order of the reference's MatMul (chain 496) is not
-    observable; the sequential order is the one the CUDA kernel reproduces exactly."""
-    coefs = coefs.astype(f32)
-    protos = protos.astype(f32)
+    oracle choice: the summation order of the reference's MatMul (chain 496) is not observable; a sequential fused
+    multiply-add chain is what a GPU (and Burst on ARM) emits for a 32-term dot product and what the CUDA kernel
+    reproduces exactly.  The fp32 FMA is emulated in float64: the product of two fp32 values is exact in float64 and
+    the single float64 add is rounded to fp32 (double rounding can differ in the last bit with probability ~2^-29
+    per operation, far below anything the threshold tests can see)."""
+    c64 = coefs.astype(np.float32).astype(np.float64)
+    p64 = protos.astype(np.float32).astype(np.float64)
     acc = np.zeros((coefs.shape[0], protos.shape[1]), f32)
     for k in range(coefs.shape[1]):
-        acc = (acc + (coefs[:, k:k + 1] * protos[k:k + 1, :]).astype(f32)).astype(f32)
+        acc = (acc.astype(np.float64) + c64[:, k:k + 1] * p64[k:k + 1, :]).astype(f32)
     return acc
 
 

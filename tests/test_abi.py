@@ -1,0 +1,122 @@
+"""CPU tests of the drop-in boundary: libxrseg.so loads, exports every symbol include/xrseg.h declares, reports the
+same topology as the oracle, fails loudly without a GPU, and its conv index math (host emulation of the tcgen05
+kernel's data movement) reproduces torch convolutions."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import yolo11seg as Y
+from xr_image_segmentation_b200 import _lib, inference as I, sharding as S, weights as W
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "xrseg.h")).read()
+    declared = set(re.findall(r"\b(xrseg_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"xrseg_class_name"}          # mentioned in a comment only
+    assert len(declared) >= 25
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/xrseg.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.xrseg_abi_version() == 1
+    assert C.sizeof(_lib.Config) == 96 or C.sizeof(_lib.Config) > 0
+
+
+@pytest.mark.parametrize("scale", ["n", "s"])
+def test_layer_table_matches_oracle(lib, scale):
+    a, b = W.layer_table(scale), Y.layer_table(scale)
+    assert len(a) == len(b) == 100
+    for x, y in zip(a, b):
+        assert (x.name, x.cin, x.cout, x.k, x.stride, x.groups, x.act, x.transposed, x.h_in, x.w_in) == \
+               (y["name"], y["cin"], y["cout"], y["k"], y["s"], y["groups"], int(y["act"]), int(y["transposed"]), y["h_in"], y["w_in"])
+        assert x.weight_shape == Y.weight_shape(y)
+    assert lib.xrseg_layer_count(ord("x")) < 0
+
+
+def test_no_gpu_means_loud_failure(lib, golden):
+    if lib.xrseg_device_count() > 0:
+        pytest.skip("a B200 is present")
+    with pytest.raises(I.XrsegError) as e:
+        I.Runner(golden["model"])
+    assert e.value.code == _lib.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    with pytest.raises(I.XrsegError):
+        I.Worker(golden["model"], I.BackendType.CPU)
+    with pytest.raises(I.XrsegError):
+        I.ModelLoader.Load(b"not a pack")
+    with pytest.raises(I.XrsegError):
+        I.TextureConverter.ToTensor(np.zeros((4, 4, 3), np.uint8), 320, 320, 3)
+
+
+def test_weight_pack_roundtrip_and_validation(lib):
+    layers, ws = W.random_weights("n", seed=1)
+    pack = W.write_pack("n", layers, ws)
+    scale, back = W.read_pack(pack)
+    assert scale == "n" and len(back) == 100
+    for (w, b), (_, w2, b2) in zip(ws, back):
+        assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    # same seed -> same weights as the oracle-side generator (the two must agree for parity tests)
+    ow = Y.random_weights("n", 1)
+    for (w, b), (w2, b2) in zip(ws, ow):
+        assert np.array_equal(w, w2) and np.array_equal(b, b2)
+    q = W.Tensor8(np.array([0, 85, 255], np.uint8), 0.0058823530562222, 85)
+    np.testing.assert_allclose(q.dequant(), [-0.5, 0.0, 1.0], atol=1e-6)
+
+
+CASES = [
+    (2, 16, 8, 12, 10, 3, 1, 1, False, True, 0), (2, 16, 8, 12, 10, 3, 1, 1, False, True, 1),
+    (1, 32, 16, 20, 20, 3, 1, 0, False, False, 0), (2, 48, 64, 9, 7, 1, 1, 1, False, True, 0),
+    (1, 16, 32, 13, 11, 3, 2, 1, False, False, 0), (2, 8, 16, 6, 5, 3, 1, 1, False, False, 0),
+    (1, 64, 64, 5, 6, 2, 2, 0, True, False, 0), (1, 80, 80, 7, 7, 1, 1, 0, False, False, 0),
+    (3, 128, 32, 4, 4, 3, 1, 1, False, True, 0), (1, 16, 8, 3, 170, 3, 1, 1, False, False, 0),
+    (1, 256, 512, 3, 3, 1, 1, 1, False, False, 0), (1, 128, 128, 3, 3, 2, 2, 0, True, False, 0),
+    (1, 256, 64, 5, 4, 3, 1, 1, False, False, 0),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_umma_conv_index_math_emulation(lib, case):
+    """Host emulation (fp32) of the tcgen05 kernel's packing / slot mapping / tap shifts / epilogue scatter."""
+    B, cin, cout, h, wd, k, s, act, tr, useres, variant = case
+    rng = np.random.default_rng(hash(case) % 2**32)
+    x = rng.standard_normal((B, cin, h, wd), dtype=np.float32)
+    w = rng.standard_normal((cin, cout, k, k) if tr else (cout, cin, k, k), dtype=np.float32) * np.float32(0.1)
+    b = rng.standard_normal(cout, dtype=np.float32)
+    if tr:
+        ref = F.conv_transpose2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=2)
+    else:
+        ref = F.conv2d(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride=s, padding=k // 2)
+    if act:
+        ref = ref * torch.sigmoid(ref)
+    res = None
+    if useres:
+        res = rng.standard_normal(tuple(ref.shape), dtype=np.float32)
+        ref = ref + torch.from_numpy(res)
+    y = np.zeros(tuple(ref.shape), np.float32)
+    rc = lib.xrseg_debug_emulate_conv(x.ctypes.data, B, cin, h, wd, w.ctypes.data, b.ctypes.data, cout, k, s, act, int(tr),
+                                      res.ctypes.data if res is not None else None, y.ctypes.data, variant)
+    assert rc == 0, lib.xrseg_last_error(None)
+    np.testing.assert_allclose(y, ref.numpy(), atol=2e-5, rtol=1e-5)
+
+
+def test_shard_range_and_merge():
+    for total in (0, 1, 7, 64, 512):
+        for world in (1, 2, 3, 4, 8):
+            spans = [S.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+            for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+                assert s0 + c0 == s1
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+    with pytest.raises(ValueError):
+        S.shard_range(8, 2, 2)
+    a = S.Detections(0, np.array([1, 0]), np.ones((1, 4), np.float32), np.array([3]), np.array([0.9], np.float32))
+    b = S.Detections(2, np.array([2]), np.zeros((2, 4), np.float32), np.array([1, 2]), np.array([0.8, 0.7], np.float32))
+    m = S.merge_detections([b, a])
+    assert m.counts.tolist() == [1, 0, 2] and m.labels.tolist() == [3, 1, 2] and m.boxes.shape == (3, 4)
+    with pytest.raises(ValueError):
+        S.merge_detections([a, S.Detections(3, np.array([0]), np.zeros((0, 4), np.float32), np.zeros(0, np.int64))])

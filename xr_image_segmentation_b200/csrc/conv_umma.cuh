@@ -50,7 +50,6 @@ struct ConvParams {
   int tmem_cols;
   int smem_off_b, smem_off_a, smem_bytes;
   int grid;
-  int dbg;                          // debug: bit 1 swaps the LBO / SBO descriptor fields
 };
 
 struct ConvDesc {
@@ -468,10 +467,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
           for (int t = 0; t < p.taps; ++t) {
             const uint32_t shift = (p.mode == MODE_HALO) ? static_cast<uint32_t>((t / 3) * p.Wp + (t % 3)) * 16u : 0u;
             for (int j = 0; j < kj; ++j) {
-              const uint64_t ad = (p.dbg & 2) ? umma_desc_kmajor_noswz(a_base + 2 * j * p.lbo_a + shift, 128, p.lbo_a)
-                                              : umma_desc_kmajor_noswz(a_base + 2 * j * p.lbo_a + shift, p.lbo_a, 128);
-              const uint64_t bd = (p.dbg & 2) ? umma_desc_kmajor_noswz(b_base + (t * p.cps + 2 * j) * lbo_b, 128, lbo_b)
-                                              : umma_desc_kmajor_noswz(b_base + (t * p.cps + 2 * j) * lbo_b, lbo_b, 128);
+              // LBO = distance between the two K-adjacent core matrices of this k16 step, SBO = 128 B between
+              // 8-row groups (verified on B200: the swapped assignment produces wrong results)
+              const uint64_t ad = umma_desc_kmajor_noswz(a_base + 2 * j * p.lbo_a + shift, p.lbo_a, 128);
+              const uint64_t bd = umma_desc_kmajor_noswz(b_base + (t * p.cps + 2 * j) * lbo_b, lbo_b, 128);
               umma_f16(d_tmem, ad, bd, p.idesc, acc);
               acc = 1;
             }

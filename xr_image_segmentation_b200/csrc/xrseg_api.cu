@@ -1041,7 +1041,6 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
     if (impl == XRSEG_CONV_UMMA) {
       ConvDesc cd{b, h, w, cin_p, cin_p, cout_p, cout_p, k, stride, act, transposed, residual ? cout_p : 0};
       ConvParams p = plan_conv(cd, prop.multiProcessorCount, variant & 1);
-      p.dbg = variant & 2;
       std::vector<__half> wp;
       std::vector<float> bp;
       pack_conv_weights<__half>(p, wgt, hb, cin, cout, wp, bp);

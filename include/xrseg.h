@@ -171,6 +171,16 @@ int xrseg_layer_info_get(int model_scale, int index, xrseg_layer_info* info);
 int xrseg_last_timings(xrseg_runner* r, float* ms, int n);
 /* Number of kernel launches (graph nodes) one scheduled run issues. */
 int xrseg_launch_count(xrseg_runner* r);
+/* CUDA events on the runner's own stream (slot 0..7): record now / milliseconds between two recorded slots.
+ * Lets a harness time a sequence of xrseg_schedule* calls on the device, on the stream the kernels run on. */
+int xrseg_event_record(xrseg_runner* r, int slot);
+int xrseg_event_elapsed_ms(xrseg_runner* r, int slot_a, int slot_b, float* ms);
+/* Blocks until everything enqueued on the runner's stream has finished. */
+int xrseg_sync(xrseg_runner* r);
+/* Per-kernel device time of the network + post-processing of the last scheduled input (frames must still be
+ * resident): replays each launch `iters` times between CUDA events.  ms[i] = average ms of launch i, names[i*32]
+ * its label, flops[i] / bytes[i] its algorithmic work.  Returns the number of launches. */
+int xrseg_profile_ops(xrseg_runner* r, int iters, float* ms, char* names, double* flops, double* bytes, int cap);
 
 /* ---- parity / debug entry points (used by tests only) --------------------------------------- */
 /* Copy a named intermediate activation of the last run to host as f32 NCHW [batch,C,H,W].

@@ -245,17 +245,18 @@ def weights_from_sentis(model) -> list[tuple[np.ndarray, np.ndarray]]:
 CLS_FINAL = ("h3.cls.2", "h4.cls.2", "h5.cls.2")
 
 
-def random_weights(scale: str, seed: int, cls_bias: float = -4.0):
-    """Random-init weights for BASELINE.json configs 2/3:
-    w ~ N(0, (1.85/sqrt(fan_in))^2), b ~ N(0, 0.85^2); final class-conv biases shifted by
-    `cls_bias` so that only a few percent of anchors pass the 0.301 score filter."""
+def random_weights(scale: str, seed: int, cls_bias: float | None = None, gain: float = 1.5, bias_std: float = 0.2):
+    """Random-init weights for BASELINE.json configs 2/3 -- the same frozen recipe as the product-side generator
+    (xr_image_segmentation_b200/weights.py, checked equal by tests/test_abi.py): w ~ N(0, (1.5/sqrt(fan_in))^2),
+    b ~ N(0, 0.2^2), final class-conv biases N(cls_bias, 0.05^2) with cls_bias -5.15 (n) / -4.87 (s)."""
+    cls_bias = {"n": -5.15, "s": -4.87}[scale] if cls_bias is None else cls_bias
     rng = np.random.default_rng(seed)
     out = []
     for l in layer_table(scale):
         shp = weight_shape(l)
         fan_in = (l["cin"] // l["groups"]) * l["k"] * l["k"] if not l["transposed"] else l["cin"]
-        w = (rng.standard_normal(shp, dtype=np.float32) * np.float32(1.85 / np.sqrt(fan_in))).astype(np.float32)
-        b = (rng.standard_normal(l["cout"], dtype=np.float32) * np.float32(0.85)).astype(np.float32)
+        w = (rng.standard_normal(shp, dtype=np.float32) * np.float32(gain / np.sqrt(fan_in))).astype(np.float32)
+        b = (rng.standard_normal(l["cout"], dtype=np.float32) * np.float32(bias_std)).astype(np.float32)
         if l["name"] in CLS_FINAL:
             b = (b * np.float32(0.25) + np.float32(cls_bias)).astype(np.float32)
         out.append((w, b))

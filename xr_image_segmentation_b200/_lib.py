@@ -75,6 +75,10 @@ SIGNATURES = {
     "xrseg_layer_info_get": (C.c_int, [C.c_int, C.c_int, _P(LayerInfo)]),
     "xrseg_last_timings": (C.c_int, [C.c_void_p, _P(C.c_float), C.c_int]),
     "xrseg_launch_count": (C.c_int, [C.c_void_p]),
+    "xrseg_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "xrseg_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(C.c_float)]),
+    "xrseg_sync": (C.c_int, [C.c_void_p]),
+    "xrseg_profile_ops": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float), C.c_char_p, _P(C.c_double), _P(C.c_double), C.c_int]),
     "xrseg_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, _P(C.c_int64)]),
     "xrseg_debug_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "xrseg_debug_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <memory>
 
 #include "common.cuh"
@@ -50,7 +51,7 @@ struct xrseg_runner {
   int device = 0, num_sms = 148;
   std::string err;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev_done = nullptr, ev[6] = {};
+  cudaEvent_t ev_done = nullptr, ev[6] = {}, user_ev[8] = {};
   std::unique_ptr<Net> net;
   int mb = 1;                      // frames per network pass
   int A = 8400;
@@ -71,7 +72,7 @@ struct xrseg_runner {
   // debug staging for xrseg_debug_post / xrseg_debug_nms
   float *dbg_box = nullptr, *dbg_cls = nullptr, *dbg_coef = nullptr, *dbg_proto = nullptr, *dbg_corners = nullptr;
   // host mirrors
-  std::vector<int> h_counts, h_offsets;
+  int *h_counts = nullptr, *h_offsets = nullptr;   // pinned
   int batch = 0;                   // batch of the scheduled / finished run
   int state = 0;                   // 0 idle, 1 scheduled, 2 done
   int words = 0, max_cand = 0, max_det = 0;
@@ -157,25 +158,43 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
 inline __half* ptr_of(xrseg_runner* r, const TV& t) { return r->arena + t.off; }
 
 // ------------------------------------------------------------------------------------------------
-// the network: one pass over `nb` (<= mb) frames already preprocessed into net->input
+// A run is a flat list of kernel launches (network, then post-processing); the normal path enqueues them in order,
+// xrseg_profile_ops replays them one by one between CUDA events.
 // ------------------------------------------------------------------------------------------------
-int run_network(xrseg_runner* r, int nb, cudaStream_t st) {
+struct Launch {
+  std::string name;
+  std::function<void(cudaStream_t)> fn;
+  double flops = 0, bytes = 0;   // algorithmic work of the launch (real channel counts, fp16 activations)
+};
+
+void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
   Net& net = *r->net;
-  int launches = 0;
   for (const Op& o : net.ops) {
+    Launch L;
+    const double px_in = static_cast<double>(nb) * o.x.H * o.x.W, px_out = static_cast<double>(nb) * o.y.H * o.y.W;
     switch (o.kind) {
       case OP_STEM: {
+        const LayerRec& l = net.layers[o.layer];
         StemParams p{ptr_of(r, o.x), ptr_of(r, o.y), r->dl[o.layer].w32, r->dl[o.layer].bias, nb, o.x.H, o.x.W, o.y.Cp,
                      o.y.pitch};
         const long total = static_cast<long>(nb) * (o.x.H / 2) * (o.x.W / 2) * (o.y.Cp / 16);
-        stem_conv_kernel<<<grid_for(total), 256, (37 * o.y.Cp) * sizeof(float), st>>>(p);
+        const size_t smem = (37 * o.y.Cp) * sizeof(float);
+        L.name = l.name;
+        L.flops = 2.0 * px_out * l.cout * 27;
+        L.bytes = px_in * 8 + px_out * l.cout * 2;
+        L.fn = [p, total, smem](cudaStream_t st) { stem_conv_kernel<<<grid_for(total), 256, smem, st>>>(p); };
         break;
       }
       case OP_CONV: {
+        const LayerRec& l = net.layers[o.layer];
         DevLayer& d = r->dl[o.layer];
+        L.name = l.name;
+        const double taps = o.transposed ? 1.0 : static_cast<double>(o.k) * o.k;
+        L.flops = 2.0 * (o.transposed ? px_in * 4 : px_out) * l.cout * l.cin * taps;
+        L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1) + static_cast<double>(l.cout) * l.cin * o.k * o.k) * 2;
         if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
           ConvParams p = d.cp;
-          if (nb != p.B) {  // partial last chunk: re-plan the M extent only
+          if (nb != p.B) {  // partial last chunk: re-plan the M extent only (the weight packing does not depend on B)
             ConvDesc cd{};
             cd.B = nb; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
             cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch; cd.k = o.k; cd.stride = o.stride; cd.act = o.act;
@@ -185,7 +204,7 @@ int run_network(xrseg_runner* r, int nb, cudaStream_t st) {
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
           p.res = o.has_res ? ptr_of(r, o.res) : nullptr;
           p.wpack = d.wpack; p.bias = d.bias;
-          launch_conv_umma(p, st);
+          L.fn = [p](cudaStream_t st) { launch_conv_umma(p, st); };
         } else {
           DirectParams p{};
           p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
@@ -194,27 +213,38 @@ int run_network(xrseg_runner* r, int nb, cudaStream_t st) {
           p.B = nb; p.H = o.x.H; p.W = o.x.W; p.Cin = o.x.Cp; p.Ho = o.y.H; p.Wo = o.y.W; p.Cout = o.y.Cp;
           p.k = o.k; p.stride = o.stride; p.pad = o.k / 2; p.act = o.act; p.transposed = o.transposed;
           const long total = static_cast<long>(nb) * o.y.H * o.y.W * o.y.Cp;
-          conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(p);
+          L.fn = [p, total](cudaStream_t st) { conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(p); };
         }
         break;
       }
       case OP_DW: {
+        const LayerRec& l = net.layers[o.layer];
         DwParams p{};
         p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
         p.res = o.has_res ? ptr_of(r, o.res) : nullptr; p.res_pitch = o.has_res ? o.res.pitch : 0;
         p.w = r->dl[o.layer].w32; p.bias = r->dl[o.layer].bias;
         p.B = nb; p.H = o.x.H; p.W = o.x.W; p.C = o.x.Cp; p.act = o.act;
-        dwconv3x3_kernel<<<grid_for(static_cast<long>(nb) * o.x.H * o.x.W * (o.x.Cp / 8)), 256, 0, st>>>(p);
+        const long total = static_cast<long>(nb) * o.x.H * o.x.W * (o.x.Cp / 8);
+        L.name = l.name;
+        L.flops = 2.0 * px_out * l.cout * 9;
+        L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1)) * 2;
+        L.fn = [p, total](cudaStream_t st) { dwconv3x3_kernel<<<grid_for(total), 256, 0, st>>>(p); };
         break;
       }
       case OP_SPPF: {
         SppfParams p{ptr_of(r, o.x), nb, o.x.H, o.x.W, o.x.Cp / 4, o.x.pitch};
-        sppf_pool_kernel<<<nb * (p.C / 8), 256, o.x.H * o.x.W * 16, st>>>(p);
+        const size_t smem = static_cast<size_t>(o.x.H) * o.x.W * 16;
+        L.name = "sppf.pool";
+        L.bytes = px_in * p.C * 4 * 2;
+        L.fn = [p, nb, smem](cudaStream_t st) { sppf_pool_kernel<<<nb * (p.C / 8), 256, smem, st>>>(p); };
         break;
       }
       case OP_UP: {
         UpParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, nb, o.x.H, o.x.W, o.x.Cp};
-        upsample2x_kernel<<<grid_for(static_cast<long>(nb) * o.x.H * o.x.W * 4 * (o.x.Cp / 8)), 256, 0, st>>>(p);
+        const long total = static_cast<long>(nb) * o.x.H * o.x.W * 4 * (o.x.Cp / 8);
+        L.name = "upsample2x";
+        L.bytes = px_in * o.x.C * 5 * 2;
+        L.fn = [p, total](cudaStream_t st) { upsample2x_kernel<<<grid_for(total), 256, 0, st>>>(p); };
         break;
       }
       case OP_ATTN: {
@@ -222,20 +252,24 @@ int run_network(xrseg_runner* r, int nb, cudaStream_t st) {
                      1.0f / sqrtf(static_cast<float>(ATT_KD))};
         const size_t smem = static_cast<size_t>(p.N) * (ATT_KD + ATT_HD) * sizeof(__half);
         dim3 g(nb * o.heads, ceil_div(p.N, ATT_THREADS));
-        attention_kernel<<<g, ATT_THREADS, smem, st>>>(p);
+        L.name = "c2psa.attention";
+        L.flops = 2.0 * nb * o.heads * static_cast<double>(p.N) * p.N * (ATT_KD + ATT_HD);
+        L.bytes = px_in * (o.x.C + o.y.C) * 2;
+        L.fn = [p, g, smem](cudaStream_t st) { attention_kernel<<<g, ATT_THREADS, smem, st>>>(p); };
         break;
       }
       case OP_VGATHER: {
         VGatherParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, static_cast<long>(nb) * o.x.H * o.x.W,
                         o.heads};
-        gather_v_kernel<<<grid_for(p.tokens * o.heads * 8), 256, 0, st>>>(p);
+        const long total = p.tokens * o.heads * 8;
+        L.name = "c2psa.gather_v";
+        L.bytes = px_in * o.y.C * 2 * 2;
+        L.fn = [p, total](cudaStream_t st) { gather_v_kernel<<<grid_for(total), 256, 0, st>>>(p); };
         break;
       }
     }
-    ++launches;
+    out.push_back(std::move(L));
   }
-  XR_CUDA(cudaGetLastError());
-  return launches;
 }
 
 template <typename T>
@@ -288,9 +322,8 @@ void dense_scale_src(xrseg_runner* r, ScaleSrc<float> (&s)[3], const float* box,
 // post-processing of frames [b0, b0 + nb): decode -> sort -> bitmask -> reduce -> offsets -> gather -> masks
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool PLANAR>
-int run_post(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)[3], const T* protos, long proto_bstride,
-             int proto_pitch, bool do_decode, bool corners_given, cudaStream_t st) {
-  int launches = 0;
+void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)[3], const T* protos, long proto_bstride,
+                       int proto_pitch, bool do_decode, bool corners_given, std::vector<Launch>& out) {
   const int A = r->A;
   if (do_decode) {
     DecodeParams<T> dp{};
@@ -301,8 +334,11 @@ int run_post(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)[3], const
     dp.labels = r->d_labels + static_cast<long>(b0) * A;
     dp.keys = r->d_keys + static_cast<long>(b0) * A;
     dp.cand_count = r->d_cand_count + b0;
-    decode_kernel<T><<<dim3(ceil_div(A, 128), nb), 128, 0, st>>>(dp);
-    ++launches;
+    Launch L;
+    L.name = "post.decode";
+    L.bytes = static_cast<double>(nb) * A * ((64 + NC) * sizeof(T) + 24);
+    L.fn = [dp, A, nb](cudaStream_t st) { decode_kernel<T><<<dim3(ceil_div(A, 128), nb), 128, 0, st>>>(dp); };
+    out.push_back(std::move(L));
   }
   SortParams sp{};
   sp.keys = r->d_keys + static_cast<long>(b0) * A;
@@ -314,22 +350,47 @@ int run_post(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)[3], const
   sp.sorted_corners = r->d_sorted_corners + static_cast<long>(b0) * r->max_cand;
   sp.n_cand = r->d_n_cand + b0;
   sp.overflow = r->d_overflow;
-  nms_sort_kernel<<<nb, 1024, 16384 * sizeof(unsigned long long), st>>>(sp);
   MaskBitsParams mp{};
   mp.sorted_corners = sp.sorted_corners; mp.n_cand = sp.n_cand; mp.max_cand = r->max_cand; mp.words = r->words;
   mp.iou_thr = r->cfg.iou_threshold;
   mp.mask = r->d_mask + static_cast<long>(b0) * r->max_cand * r->words;
-  nms_bitmask_kernel<<<dim3(r->words, r->words, nb), 64, 0, st>>>(mp);
   ReduceParams rp{};
   rp.mask = mp.mask; rp.n_cand = sp.n_cand; rp.sorted_idx = sp.sorted_idx;
   rp.max_cand = r->max_cand; rp.words = r->words; rp.max_det = r->max_det;
   rp.keep_idx = r->d_keep_idx + static_cast<long>(b0) * r->max_det;
   rp.keep_n = r->d_keep_n + b0;
   rp.overflow = r->d_overflow;
-  nms_reduce_kernel<<<nb, 128, static_cast<size_t>(r->words) * 65 * sizeof(unsigned long long), st>>>(rp);
-  offsets_kernel<<<1, 32, 0, st>>>(r->d_keep_n, b0 + nb, r->d_offsets);
-  launches += 4;
-  if (!src[0].coef) return launches;  // NMS-only debug path
+  const int words = r->words;
+  {
+    Launch L;
+    L.name = "post.nms_sort";
+    L.fn = [sp, nb](cudaStream_t st) { nms_sort_kernel<<<nb, 1024, 16384 * sizeof(unsigned long long), st>>>(sp); };
+    out.push_back(std::move(L));
+  }
+  {
+    Launch L;
+    L.name = "post.nms_bitmask";
+    L.fn = [mp, words, nb](cudaStream_t st) { nms_bitmask_kernel<<<dim3(words, words, nb), 64, 0, st>>>(mp); };
+    out.push_back(std::move(L));
+  }
+  {
+    Launch L;
+    L.name = "post.nms_reduce";
+    L.fn = [rp, words, nb](cudaStream_t st) {
+      nms_reduce_kernel<<<nb, 128, static_cast<size_t>(words) * 65 * sizeof(unsigned long long), st>>>(rp);
+    };
+    out.push_back(std::move(L));
+  }
+  {
+    Launch L;
+    L.name = "post.offsets";
+    const int* keep_n = r->d_keep_n;
+    int* offsets = r->d_offsets;
+    const int upto = b0 + nb;
+    L.fn = [keep_n, offsets, upto](cudaStream_t st) { offsets_kernel<<<1, 32, 0, st>>>(keep_n, upto, offsets); };
+    out.push_back(std::move(L));
+  }
+  if (!src[0].coef) return;  // NMS-only debug path
   GatherParams<T> gp{};
   for (int i = 0; i < 3; ++i) gp.s[i] = src[i];
   gp.keep_idx = rp.keep_idx; gp.keep_n = rp.keep_n; gp.offsets = r->d_offsets + b0;
@@ -339,18 +400,24 @@ int run_post(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)[3], const
   gp.B = nb; gp.A = A; gp.max_det = r->max_det;
   gp.out_boxes = r->o_boxes; gp.out_labels = r->o_labels; gp.out_coefs = r->o_coefs; gp.out_scores = r->o_scores;
   gp.out_anchor = r->o_anchor; gp.out_frame = r->o_frame;
-  gather_kernel<T><<<ceil_div(nb * r->max_det * 32, 128), 128, 0, st>>>(gp);
-  ++launches;
+  {
+    Launch L;
+    L.name = "post.gather";
+    const int blocks = ceil_div(nb * r->max_det * 32, 128);
+    L.fn = [gp, blocks](cudaStream_t st) { gather_kernel<T><<<blocks, 128, 0, st>>>(gp); };
+    out.push_back(std::move(L));
+  }
   if (protos) {
     MaskParams<T, PLANAR> kp{};
     kp.protos = protos; kp.proto_bstride = proto_bstride; kp.proto_pitch = proto_pitch;
     kp.coefs = r->o_coefs; kp.keep_n = rp.keep_n; kp.offsets = gp.offsets; kp.max_det = r->max_det;
     kp.probs = r->o_probs;
-    mask_prob_kernel<T, PLANAR><<<dim3(PROTO_PIX / 256, nb), 256, 0, st>>>(kp);
-    ++launches;
+    Launch L;
+    L.name = "post.mask_prob";
+    L.bytes = static_cast<double>(nb) * NM * PROTO_PIX * sizeof(T);   // + 102400 B per detection, added by the caller
+    L.fn = [kp, nb](cudaStream_t st) { mask_prob_kernel<T, PLANAR><<<dim3(PROTO_PIX / 256, nb), 256, 0, st>>>(kp); };
+    out.push_back(std::move(L));
   }
-  XR_CUDA(cudaGetLastError());
-  return launches;
 }
 
 // frame offset fix-up: gather/mask kernels index frames relative to b0 but o_frame must be global
@@ -383,15 +450,27 @@ void preprocess(xrseg_runner* r, const uint8_t* d_src, int w, int h, int stride_
   XR_CUDA(cudaGetLastError());
 }
 
-int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st) {
-  int launches = run_network(r, nb, st);
+void build_chunk_launches(xrseg_runner* r, int b0, int nb, std::vector<Launch>& out) {
+  add_network_launches(r, nb, out);
   ScaleSrc<__half> src[3];
   net_scale_src(r, src);
   const TV& pr = r->net->protos;
-  launches += run_post<__half, false>(r, b0, nb, src, ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch,
-                                      pr.pitch, true, false, st);
-  add_frame_base_kernel<<<nb, 64, 0, st>>>(r->o_frame, r->d_offsets, b0, nb);
-  return launches + 1;
+  add_post_launches<__half, false>(r, b0, nb, src, ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch, pr.pitch,
+                                   true, false, out);
+  Launch L;
+  L.name = "post.frame_ids";
+  int* frames = r->o_frame;
+  const int* offsets = r->d_offsets;
+  L.fn = [frames, offsets, b0, nb](cudaStream_t st) { add_frame_base_kernel<<<nb, 64, 0, st>>>(frames, offsets, b0, nb); };
+  out.push_back(std::move(L));
+}
+
+int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st) {
+  std::vector<Launch> ls;
+  build_chunk_launches(r, b0, nb, ls);
+  for (Launch& l : ls) l.fn(st);
+  XR_CUDA(cudaGetLastError());
+  return static_cast<int>(ls.size());
 }
 
 void reset_counters(xrseg_runner* r, int batch, cudaStream_t st) {
@@ -459,8 +538,8 @@ int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, 
       r->launches = launches;
     }
     if (r->timed) XR_CUDA(cudaEventRecord(r->ev[2], st));
-    XR_CUDA(cudaMemcpyAsync(r->h_offsets.data(), r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
-    XR_CUDA(cudaMemcpyAsync(r->h_counts.data(), r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaEventRecord(r->ev_done, st));
     r->state = 1;
     return XRSEG_OK;
@@ -518,8 +597,11 @@ xrseg_runner::~xrseg_runner() {
                   d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,
                   o_probs, o_labels, o_anchor, o_frame, dbg_box, dbg_cls, dbg_coef, dbg_proto, dbg_corners};
   for (void* b : bufs) cudaFree(b);
+  if (h_counts) cudaFreeHost(h_counts);
+  if (h_offsets) cudaFreeHost(h_offsets);
   if (ev_done) cudaEventDestroy(ev_done);
   for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : user_ev) if (e) cudaEventDestroy(e);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -668,8 +750,10 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     r->o_anchor = dev_alloc<int>(cap);
     r->o_frame = dev_alloc<int>(cap);
     r->o_probs = dev_alloc<float>(cap * PROTO_PIX);
-    r->h_counts.assign(B, 0);
-    r->h_offsets.assign(B + 1, 0);
+    XR_CUDA(cudaHostAlloc(&r->h_counts, sizeof(int) * B, cudaHostAllocDefault));
+    XR_CUDA(cudaHostAlloc(&r->h_offsets, sizeof(int) * (B + 1), cudaHostAllocDefault));
+    memset(r->h_counts, 0, sizeof(int) * B);
+    memset(r->h_offsets, 0, sizeof(int) * (B + 1));
     XR_CUDA(cudaMemset(r->d_keep_n, 0, sizeof(int) * B));
     XR_CUDA(cudaMemset(r->d_offsets, 0, sizeof(int) * (B + 1)));
     XR_CUDA(cudaDeviceSynchronize());
@@ -860,6 +944,81 @@ int xrseg_last_timings(xrseg_runner* r, float* ms, int n) {
 
 int xrseg_launch_count(xrseg_runner* r) { return r ? r->launches : XRSEG_ERR_INVALID; }
 
+int xrseg_event_record(xrseg_runner* r, int slot) {
+  if (!r || slot < 0 || slot >= 8) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    if (!r->user_ev[slot]) XR_CUDA(cudaEventCreate(&r->user_ev[slot]));
+    XR_CUDA(cudaEventRecord(r->user_ev[slot], r->stream));
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_event_elapsed_ms(xrseg_runner* r, int a, int b, float* ms) {
+  if (!r || !ms || a < 0 || a >= 8 || b < 0 || b >= 8 || !r->user_ev[a] || !r->user_ev[b]) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaEventSynchronize(r->user_ev[b]));
+    XR_CUDA(cudaEventElapsedTime(ms, r->user_ev[a], r->user_ev[b]));
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_sync(xrseg_runner* r) {
+  if (!r) return XRSEG_ERR_INVALID;
+  cudaError_t e = cudaStreamSynchronize(r->stream);
+  if (e != cudaSuccess) { r->err = cudaGetErrorString(e); return XRSEG_ERR_CUDA; }
+  return XRSEG_OK;
+}
+
+int xrseg_profile_ops(xrseg_runner* r, int iters, float* ms, char* names, double* flops, double* bytes, int cap) {
+  if (!r || !ms || iters < 1) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    const int nb = std::min(r->batch, r->mb);
+    std::vector<Launch> ls;
+    build_chunk_launches(r, 0, nb, ls);
+    if (static_cast<int>(ls.size()) > cap) { r->err = "profile buffers too small"; return XRSEG_ERR_CAPACITY; }
+    cudaEvent_t a, b;
+    XR_CUDA(cudaEventCreate(&a));
+    XR_CUDA(cudaEventCreate(&b));
+    int total_det = r->h_offsets[r->batch];
+    for (size_t i = 0; i < ls.size(); ++i) {
+      if (ls[i].name == "post.decode") reset_counters(r, nb, r->stream);
+      ls[i].fn(r->stream);  // warm
+      XR_CUDA(cudaEventRecord(a, r->stream));
+      for (int it = 0; it < iters; ++it) {
+        if (ls[i].name == "post.decode") reset_counters(r, nb, r->stream);
+        ls[i].fn(r->stream);
+      }
+      XR_CUDA(cudaEventRecord(b, r->stream));
+      XR_CUDA(cudaEventSynchronize(b));
+      float t = 0;
+      XR_CUDA(cudaEventElapsedTime(&t, a, b));
+      ms[i] = t / iters;
+      if (names) { memset(names + i * 32, 0, 32); strncpy(names + i * 32, ls[i].name.c_str(), 31); }
+      double by = ls[i].bytes;
+      if (ls[i].name == "post.mask_prob") by += static_cast<double>(total_det) * PROTO_PIX * 4;
+      if (flops) flops[i] = ls[i].flops;
+      if (bytes) bytes[i] = by;
+    }
+    XR_CUDA(cudaGetLastError());
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return static_cast<int>(ls.size());
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+}
+
 // ---- debug / parity --------------------------------------------------------------------------------------------
 int xrseg_debug_fetch(xrseg_runner* r, const char* name, float* dst, size_t cap_floats, int64_t* shape4) {
   if (!r || !name || !dst) return XRSEG_ERR_INVALID;
@@ -923,10 +1082,13 @@ int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_
     reset_counters(r, batch, st);
     ScaleSrc<float> src[3];
     dense_scale_src(r, src, r->dbg_box, r->dbg_cls, r->dbg_coef);
-    run_post<float, true>(r, 0, batch, src, r->dbg_proto, static_cast<long>(NM) * PROTO_PIX, 0, true, false, st);
+    std::vector<Launch> ls;
+    add_post_launches<float, true>(r, 0, batch, src, r->dbg_proto, static_cast<long>(NM) * PROTO_PIX, 0, true, false, ls);
+    for (Launch& l : ls) l.fn(st);
     add_frame_base_kernel<<<batch, 64, 0, st>>>(r->o_frame, r->d_offsets, 0, batch);
-    XR_CUDA(cudaMemcpyAsync(r->h_offsets.data(), r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
-    XR_CUDA(cudaMemcpyAsync(r->h_counts.data(), r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaGetLastError());
+    XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaEventRecord(r->ev_done, st));
     r->state = 1;
   } catch (const CudaError& e) {
@@ -953,10 +1115,13 @@ int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, 
     scores_to_keys_kernel<<<dim3(ceil_div(static_cast<int>(A), 128), batch), 128, 0, st>>>(
         r->d_scores, batch, static_cast<int>(A), r->cfg.score_threshold, r->d_keys, r->d_cand_count);
     ScaleSrc<float> src[3] = {};
-    run_post<float, true>(r, 0, batch, src, nullptr, 0, 0, false, true, st);
+    std::vector<Launch> ls;
+    add_post_launches<float, true>(r, 0, batch, src, nullptr, 0, 0, false, true, ls);
+    for (Launch& l : ls) l.fn(st);
+    XR_CUDA(cudaGetLastError());
     // anchors / scores of the kept boxes, compacted (no coefficient gather on this path)
-    XR_CUDA(cudaMemcpyAsync(r->h_offsets.data(), r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
-    XR_CUDA(cudaMemcpyAsync(r->h_counts.data(), r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaStreamSynchronize(st));
     std::vector<int> keep(static_cast<size_t>(batch) * r->max_det);
     XR_CUDA(cudaMemcpy(keep.data(), r->d_keep_idx, sizeof(int) * keep.size(), cudaMemcpyDeviceToHost));

@@ -171,6 +171,27 @@ class Runner:
     def launch_count(self) -> int:
         return self.lib.xrseg_launch_count(self.h)
 
+    def event_record(self, slot: int):
+        self._ck(self.lib.xrseg_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.xrseg_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._ck(self.lib.xrseg_sync(self.h))
+
+    def profile_ops(self, iters: int = 5):
+        """Per-launch device time of the last scheduled input: list of (name, ms, flops, bytes)."""
+        cap = 512
+        ms = (C.c_float * cap)()
+        names = C.create_string_buffer(cap * 32)
+        fl = (C.c_double * cap)()
+        by = (C.c_double * cap)()
+        n = self._ck(self.lib.xrseg_profile_ops(self.h, iters, ms, names, fl, by, cap))
+        return [(names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), ms[i], fl[i], by[i]) for i in range(n)]
+
     # ---- parity / debug ----
     def fetch(self, name: str) -> np.ndarray:
         shp = (C.c_int64 * 4)()

@@ -120,17 +120,27 @@ def read_pack(data: bytes):
     return chr(scale), out
 
 
-def random_weights(scale: str, seed: int, cls_bias: float = -4.0):
-    """Random-init network of BASELINE.json configs 2/3: w ~ N(0, (1.85/sqrt(fan_in))^2),
-    b ~ N(0, 0.85^2); the three final class convolutions get bias N(cls_bias, 0.2125^2) so that only a few percent of
-    the anchors pass the 0.301 score filter.  Returns (layers, [(w, b)])."""
+# Frozen random-init recipe.  The survey proposed gain 1.85 / bias std 0.85 (medians of the
+# trained asset); measured here, that init diverges through the ~30 sequential SiLU layers (head logits ~1e6, fp16
+# overflow), so the generator uses a variance-preserving gain instead.  The three final class convolutions get their
+# bias shifted so that ~1.5 % of the 8400 anchors pass the 0.301 score filter on uniform-noise frames (a trained net
+# on a real image: 43 / 8400); the shift was tuned once per scale on frames of seed 0 and is frozen.
+INIT_GAIN = 1.5
+INIT_BIAS_STD = 0.2
+INIT_CLS_BIAS = {"n": -5.15, "s": -4.87}
+
+
+def random_weights(scale: str, seed: int, cls_bias: float | None = None):
+    """Random-init network of BASELINE.json configs 2/3: w ~ N(0, (1.5/sqrt(fan_in))^2), b ~ N(0, 0.2^2), final class
+    conv biases N(cls_bias, 0.05^2).  Returns (layers, [(w, b)])."""
+    cls_bias = INIT_CLS_BIAS[scale] if cls_bias is None else cls_bias
     rng = np.random.default_rng(seed)
     layers = layer_table(scale)
     out = []
     for l in layers:
         fan_in = l.cin if l.transposed else (l.cin // l.groups) * l.k * l.k
-        w = (rng.standard_normal(l.weight_shape, dtype=np.float32) * np.float32(1.85 / np.sqrt(fan_in))).astype(np.float32)
-        b = (rng.standard_normal(l.cout, dtype=np.float32) * np.float32(0.85)).astype(np.float32)
+        w = (rng.standard_normal(l.weight_shape, dtype=np.float32) * np.float32(INIT_GAIN / np.sqrt(fan_in))).astype(np.float32)
+        b = (rng.standard_normal(l.cout, dtype=np.float32) * np.float32(INIT_BIAS_STD)).astype(np.float32)
         if l.name in CLS_FINAL:
             b = (b * np.float32(0.25) + np.float32(cls_bias)).astype(np.float32)
         out.append((w, b))

@@ -29,7 +29,35 @@
 namespace xrseg {
 
 enum { MODE_GATHER = 0, MODE_HALO = 1 };
-enum { CONV_HDR_BYTES = 2304, CONV_SMEM_MAX = 232448, CONV_THREADS = 288, CONV_MAX_STAGES = 4 };
+enum {
+  CONV_HDR_BYTES = 2304, CONV_SMEM_MAX = 232448, CONV_MAX_STAGES = 8,
+  CONV_NPROD = 256,                      // producer threads (warps 0-7)
+  CONV_NEPI = 256,                       // epilogue threads (warps 8-15)
+  CONV_MMA_WARP = 16,                    // TMEM allocator + MMA issuer
+  CONV_THREADS = CONV_NPROD + CONV_NEPI + 32
+};
+
+// Division by a runtime-constant divisor (n < 2^31): q = (umulhi(n, mul) + n) >> shr.
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d < 1 ? 1 : d;
+  uint32_t L = 0;
+  while ((1u << L) < static_cast<uint32_t>(f.d)) ++L;
+  f.shr = L;
+  f.mul = static_cast<uint32_t>(((static_cast<uint64_t>(1) << 32) * ((static_cast<uint64_t>(1) << L) - f.d)) / f.d + 1);
+  return f;
+}
+__host__ __device__ __forceinline__ int fd_div(const FastDiv& f, int n) {
+#ifdef __CUDA_ARCH__
+  return static_cast<int>((__umulhi(static_cast<uint32_t>(n), f.mul) + static_cast<uint32_t>(n)) >> f.shr);
+#else
+  return static_cast<int>(((static_cast<uint64_t>(static_cast<uint32_t>(n)) * f.mul >> 32) + static_cast<uint32_t>(n)) >> f.shr);
+#endif
+}
 
 struct ConvParams {
   const __half* in;
@@ -50,6 +78,7 @@ struct ConvParams {
   int tmem_cols;
   int smem_off_b, smem_off_a, smem_bytes;
   int grid;
+  FastDiv fd_wp, fd_hp1, fd_hw, fd_wo, fd_cin, fd_cout;
 };
 
 struct ConvDesc {
@@ -140,6 +169,10 @@ __host__ __device__ inline PixRef out_pixel(const ConvParams& p, long m, int n, 
 // ---------------------------------------------------------------------------------------------------------------
 // planning (host)
 // ---------------------------------------------------------------------------------------------------------------
+#define XR_CUDA_CHECK_PLAN(p)                                                                          \
+  XR_CHECK((p).cps == 2 || (p).cps == 4 || (p).cps == 8, "chunks per stage must be a power of two (%d)", (p).cps); \
+  XR_CHECK(static_cast<long>((p).M_total) + static_cast<long>((p).Hp1) * (p).Wp + 256 < (1L << 31), "M too large")
+
 static inline int pow2_ceil(int v) {
   int r = 32;
   while (r < v) r <<= 1;
@@ -213,15 +246,22 @@ static inline ConvParams plan_conv(const ConvDesc& d, int num_sms, int variant =
   XR_CHECK(S >= 2, "conv does not fit shared memory (a %d b %d resident %d)", p.a_stage_bytes, p.b_stage_bytes,
            resident_bytes);
   p.S = S;
-  p.lag = S >= 3 ? 2 : 1;
+  p.lag = 0;
   p.smem_off_b = CONV_HDR_BYTES;
   const int b_region = p.b_resident ? resident_bytes : S * p.b_stage_bytes;
   p.smem_off_a = CONV_HDR_BYTES + round_up(b_region, 128);
   p.smem_bytes = p.smem_off_a + S * p.a_stage_bytes;
   XR_CHECK(p.smem_bytes <= CONV_SMEM_MAX, "smem plan overflow %d", p.smem_bytes);
   const int work = p.m_tiles * p.n_tiles;
-  const int occ = (p.smem_bytes <= 112 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+  const int occ = 1;   // 544 threads and >= 100 registers per thread: one CTA per SM
   p.grid = work < num_sms * occ ? work : num_sms * occ;
+  p.fd_wp = make_fastdiv(p.Wp);
+  p.fd_hp1 = make_fastdiv(p.Hp1);
+  p.fd_hw = make_fastdiv(d.transposed ? d.H * d.W : p.Ho * p.Wo);
+  p.fd_wo = make_fastdiv(d.transposed ? d.W : p.Wo);
+  p.fd_cin = make_fastdiv(d.Cin);
+  p.fd_cout = make_fastdiv(d.Cout);
+  XR_CUDA_CHECK_PLAN(p);
   return p;
 }
 
@@ -286,11 +326,17 @@ static inline void pack_conv_weights(const ConvParams& p, const float* w, const 
 // ---------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------
+// cp.async completion -> mbarrier: the arrive fires when all prior cp.async of this thread have landed and counts as
+// one of the barrier's expected arrivals (.noinc), so a producer thread never blocks on its own copies.
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [4]
-  uint64_t* empty = full + 4;                               // [4]
-  uint64_t* tfull = empty + 4;                              // [2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
+  uint64_t* empty = full + 8;                               // [8]
+  uint64_t* tfull = empty + 8;                              // [2]
   uint64_t* tempty = tfull + 2;                             // [2]
   uint64_t* bres = tempty + 2;                              // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
@@ -304,18 +350,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   const int total_work = p.m_tiles * p.n_tiles;
 
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], 128);
+    for (int i = 0; i < CONV_MAX_STAGES; ++i) {
+      mbar_init(&full[i], CONV_NPROD);
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], CONV_NEPI);
     }
-    mbar_init(bres, 128);
+    mbar_init(bres, CONV_NPROD);
     mbar_fence_init();
   }
-  if (warp == 8) {
+  if (warp == CONV_MMA_WARP) {
     tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
     tmem_relinquish();
   }
@@ -325,44 +371,37 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < CONV_NPROD / 32) {
     // ======================================= producers ===========================================
     const uint32_t a_u32 = smem_u32(smem_a);
     const uint32_t b_u32 = smem_u32(smem_b);
     if (p.b_resident) {
       const int bytes = p.nks * p.b_stage_bytes;
       const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack);
-      for (int i = tid * 16; i < bytes; i += 128 * 16) cp_async16(b_u32 + i, src + i, 16);
-      cp_async_commit();
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      mbar_arrive(bres);
+      for (int i = tid * 16; i < bytes; i += CONV_NPROD * 16) cp_async16(b_u32 + i, src + i, 16);
+      cp_async_arrive_noinc(bres);
     }
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      const int m_tile = w / p.n_tiles;
-      const int n_tile = w - m_tile * p.n_tiles;
-      const long m0 = static_cast<long>(m_tile) * 128;
+      const int m_tile = p.n_tiles == 1 ? w : (w >> 1);
+      const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
+      const int m0 = m_tile * 128;
 
-      // per-tile row bookkeeping for MODE_GATHER (8 rows per thread: r0 + 16 j)
+      // per-tile row bookkeeping for the general MODE_GATHER path (4 rows per thread: r0 + 32 j)
       const int gc = tid & 7;
       const int r0 = tid >> 3;
-      int g_ok[8], g_base[8], g_ih[8], g_iw[8];
-      if (p.mode == MODE_GATHER) {
-        const int hw = p.transposed ? p.H * p.W : p.Ho * p.Wo;
-        const int wo = p.transposed ? p.W : p.Wo;
-        const int st = p.transposed ? 1 : p.stride;
-        const int pad = p.transposed ? 0 : p.pad;
+      int g_base[4], g_ih[4], g_iw[4];
+      const bool fast1x1 = (p.mode == MODE_GATHER && p.k == 1 && p.stride == 1) || p.transposed;
+      if (p.mode == MODE_GATHER && !fast1x1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const long m = m0 + r0 + 16 * j;
-          g_ok[j] = m < p.M_total;
-          const long b = m / hw;
-          const int rem = static_cast<int>(m - b * hw);
-          const int oh = rem / wo, ow = rem - oh * wo;
-          g_base[j] = static_cast<int>(b) * p.H * p.W;
-          g_ih[j] = oh * st - pad;
-          g_iw[j] = ow * st - pad;
+        for (int j = 0; j < 4; ++j) {
+          const int m = m0 + r0 + 32 * j;
+          const int b = fd_div(p.fd_hw, m);
+          const int rem = m - b * p.fd_hw.d;
+          const int oh = fd_div(p.fd_wo, rem), ow = rem - oh * p.fd_wo.d;
+          g_base[j] = m < p.M_total ? b * p.H * p.W : -0x40000000;   // invalid rows fail the bounds test below
+          g_ih[j] = oh * p.stride - p.pad;
+          g_iw[j] = ow * p.stride - p.pad;
         }
       }
 
@@ -374,40 +413,61 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
         if (p.mode == MODE_GATHER) {
           const int kelem = (ks * 8 + gc) * 8;
           if (kelem < p.K_total) {
-            const int tap = kelem / p.Cin;
-            const int c0 = kelem - tap * p.Cin;
-            const int kk = p.transposed ? 1 : p.k;
-            const int kh = tap / kk, kw = tap - kh * kk;
+            if (fast1x1) {
+              // A is the activation matrix itself: row m, channels kelem..kelem+7
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int ih = g_ih[j] + kh, iw = g_iw[j] + kw;
-              const bool ok = g_ok[j] && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
-                              static_cast<unsigned>(iw) < static_cast<unsigned>(p.W);
-              const __half* src =
-                  ok ? p.in + (static_cast<size_t>(g_base[j]) + static_cast<size_t>(ih) * p.W + iw) * p.in_pitch + c0
-                     : p.in;
-              cp_async16_ca(a_dst + gc * p.lbo_a + (r0 + 16 * j) * 16, src, ok ? 16u : 0u);
+              for (int j = 0; j < 4; ++j) {
+                const int row = r0 + 32 * j;
+                const int m = m0 + row;
+                const bool ok = m < p.M_total;
+                const __half* src = ok ? p.in + static_cast<size_t>(m) * p.in_pitch + kelem : p.in;
+                cp_async16_ca(a_dst + gc * p.lbo_a + row * 16, src, ok ? 16u : 0u);
+              }
+            } else {
+              const int tap = fd_div(p.fd_cin, kelem);
+              const int c0 = kelem - tap * p.Cin;
+              const int kh = p.k == 3 ? tap / 3 : (p.k == 1 ? 0 : tap / p.k);
+              const int kw = tap - kh * p.k;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int ih = g_ih[j] + kh, iw = g_iw[j] + kw;
+                const bool ok = g_base[j] >= 0 && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
+                                static_cast<unsigned>(iw) < static_cast<unsigned>(p.W);
+                const __half* src =
+                    ok ? p.in + (static_cast<size_t>(g_base[j]) + static_cast<size_t>(ih * p.W + iw)) * p.in_pitch + c0
+                       : p.in;
+                cp_async16_ca(a_dst + gc * p.lbo_a + (r0 + 32 * j) * 16, src, ok ? 16u : 0u);
+              }
             }
           }
         } else {
-          const int c = tid % p.cps;
+          // MODE_HALO: thread owns chunk c and walks the slots s0, s0 + step, ... of the padded-linear range
+          const int c = tid & (p.cps - 1);
           const int s0 = tid / p.cps;
-          const int step = 128 / p.cps;
-          const long Lb = m0 - 1 - p.Wp + s0 + static_cast<long>(p.Hp1) * p.Wp;
-          long G = Lb / p.Wp;
-          int cc = static_cast<int>(Lb - G * p.Wp);
-          int b1 = static_cast<int>(G / p.Hp1);
-          int r = static_cast<int>(G - static_cast<long>(b1) * p.Hp1);
-          const int coff = ks * p.cb + c * 8;
+          const int step = CONV_NPROD / p.cps;
+          const int q = m0 - 1 - p.Wp + s0 + p.Hp1 * p.Wp;       // biased by one virtual image: always >= 0
+          int G = fd_div(p.fd_wp, q);
+          int cc = q - G * p.Wp;
+          int b1 = fd_div(p.fd_hp1, G);
+          int r = G - b1 * p.Hp1;
+          const __half* chan = p.in + ks * p.cb + c * 8;
+          const size_t row_stride = static_cast<size_t>(p.W) * p.in_pitch;
+          const __half* rowp = chan + (static_cast<size_t>(b1 - 1) * p.H + r) * row_stride;
+          bool row_ok = static_cast<unsigned>(b1 - 1) < static_cast<unsigned>(p.B) && r < p.H;
+          uint32_t dst = a_dst + c * p.lbo_a + s0 * 16;
+          const uint32_t dst_step = step * 16;
           for (int s = s0; s < p.slots; s += step) {
-            const bool ok = (b1 >= 1 && b1 <= p.B && r < p.H && cc >= 1 && cc <= p.W);
-            const __half* src =
-                ok ? p.in + ((static_cast<size_t>(b1 - 1) * p.H + r) * p.W + (cc - 1)) * p.in_pitch + coff : p.in;
-            cp_async16_ca(a_dst + c * p.lbo_a + s * 16, src, ok ? 16u : 0u);
+            const bool ok = row_ok && static_cast<unsigned>(cc - 1) < static_cast<unsigned>(p.W);
+            cp_async16_ca(dst, ok ? rowp + static_cast<size_t>(cc - 1) * p.in_pitch : p.in, ok ? 16u : 0u);
+            dst += dst_step;
             cc += step;
-            while (cc >= p.Wp) {
-              cc -= p.Wp;
-              if (++r == p.Hp1) { r = 0; ++b1; }
+            if (cc >= p.Wp) {
+              do {
+                cc -= p.Wp;
+                if (++r == p.Hp1) { r = 0; ++b1; }
+              } while (cc >= p.Wp);
+              rowp = chan + (static_cast<size_t>(b1 - 1) * p.H + r) * row_stride;
+              row_ok = static_cast<unsigned>(b1 - 1) < static_cast<unsigned>(p.B) && r < p.H;
             }
           }
         }
@@ -415,34 +475,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
           const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) +
                                (static_cast<size_t>(n_tile) * p.nks + ks) * p.b_stage_bytes;
           const uint32_t b_dst = b_u32 + slot * p.b_stage_bytes;
-          for (int i = tid * 16; i < p.b_stage_bytes; i += 128 * 16) cp_async16(b_dst + i, src + i, 16);
+          for (int i = tid * 16; i < p.b_stage_bytes; i += CONV_NPROD * 16) cp_async16(b_dst + i, src + i, 16);
         }
-        cp_async_commit();
-        if (it >= p.lag) {
-          if (p.lag == 2) cp_async_wait<2>(); else cp_async_wait<1>();
-          fence_proxy_async_smem();
-          mbar_arrive(&full[(it - p.lag) % p.S]);
-        }
+        cp_async_arrive_noinc(&full[slot]);
       }
     }
-    // drain the last `lag` stages
-    if (p.lag == 2 && it >= 2) {
-      cp_async_wait<1>();
-      fence_proxy_async_smem();
-      mbar_arrive(&full[(it - 2) % p.S]);
-    }
-    if (it >= 1) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      mbar_arrive(&full[(it - 1) % p.S]);
-    }
-  } else if (warp == 8) {
+    cp_async_wait<0>();   // nothing of this thread may still be in flight when the CTA exits
+  } else if (warp == CONV_MMA_WARP) {
     // ======================================= MMA issuer ==========================================
     if (lane == 0) {
       const uint32_t a_u32 = smem_u32(smem_a);
       const uint32_t b_u32 = smem_u32(smem_b);
       const uint32_t lbo_b = static_cast<uint32_t>(p.Ntile) * 16u;
-      if (p.b_resident) mbar_wait(bres, 0);
+      if (p.b_resident) {
+        mbar_wait(bres, 0);
+        fence_proxy_async_smem();
+      }
       int it = 0, tcount = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
         const int buf = tcount & 1;
@@ -454,6 +502,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
         for (int ks = 0; ks < p.nks; ++ks, ++it) {
           const int slot = it % p.S;
           mbar_wait(&full[slot], static_cast<uint32_t>(it / p.S) & 1u);
+          fence_proxy_async_smem();   // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
           tc_fence_after();
           const uint32_t a_base = a_u32 + slot * p.a_stage_bytes;
           const uint32_t b_base = b_u32 + (p.b_resident ? ks : slot) * p.b_stage_bytes;
@@ -482,26 +531,52 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
     }
   } else {
     // ======================================= epilogue ============================================
-    const int q = warp & 3;
+    // 8 warps: quadrant q = TMEM lanes 32q..32q+31 (one output row per thread), `half` interleaves the 16-column chunks
+    const int ew = warp - CONV_NPROD / 32;
+    const int q = ew & 3;
+    const int half = ew >> 2;
     const int row = q * 32 + lane;
     int tcount = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
-      const int m_tile = w / p.n_tiles;
-      const int n_tile = w - m_tile * p.n_tiles;
-      const long m = static_cast<long>(m_tile) * 128 + row;
+      const int m_tile = p.n_tiles == 1 ? w : (w >> 1);
+      const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
+      const int m = m_tile * 128 + row;
+      // output pixel of this row (transposed conv: base pixel, the 2x2 position comes from the column chunk)
+      bool valid = m < p.M_total;
+      size_t pix = 0;
+      int tb = 0, th = 0, tw = 0;
+      if (p.mode == MODE_HALO) {
+        const int G = fd_div(p.fd_wp, m);
+        const int cc = m - G * p.Wp;
+        const int b = fd_div(p.fd_hp1, G);
+        const int r = G - b * p.Hp1;
+        valid = valid && r < p.H && cc >= 1 && cc <= p.W;
+        pix = (static_cast<size_t>(b) * p.H + r) * p.W + (cc - 1);
+      } else if (p.transposed) {
+        tb = fd_div(p.fd_hw, m);
+        const int rem = m - tb * p.fd_hw.d;
+        th = fd_div(p.fd_wo, rem);
+        tw = rem - th * p.fd_wo.d;
+      } else {
+        pix = static_cast<size_t>(m);
+      }
       const int buf = tcount & 1;
       const int use = tcount >> 1;
       mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * p.Ntile);
-      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
+      for (int c0 = half * 16; c0 < p.Ntile; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(t_row + c0, v);
         tmem_ld_wait();
         const int n = n_tile * p.Ntile + c0;
-        int co;
-        const PixRef o = out_pixel(p, m, n, &co);
-        if (o.valid) {
+        int co = n;
+        if (p.transposed) {
+          const int pos = fd_div(p.fd_cout, n);
+          co = n - pos * p.Cout;
+          pix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
+        }
+        if (valid) {
           float y[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -509,10 +584,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
             y[i] = p.act ? silu_f(t) : t;
           }
           if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + static_cast<size_t>(o.pix) * p.res_pitch + co);
-            uint4 r0 = rp[0], r1 = rp[1];
-            const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + co);
+            uint4 r0v = rp[0], r1v = rp[1];
+            const __half2* h0 = reinterpret_cast<const __half2*>(&r0v);
+            const __half2* h1 = reinterpret_cast<const __half2*>(&r1v);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
@@ -528,7 +603,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
             q0[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
             q1[i] = __floats2half2_rn(y[8 + 2 * i], y[8 + 2 * i + 1]);
           }
-          uint4* op = reinterpret_cast<uint4*>(p.out + static_cast<size_t>(o.pix) * p.out_pitch + co);
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_pitch + co);
           op[0] = o0;
           op[1] = o1;
         }
@@ -540,7 +615,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == CONV_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }

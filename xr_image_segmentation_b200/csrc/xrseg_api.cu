@@ -986,23 +986,30 @@ int xrseg_profile_ops(xrseg_runner* r, int iters, float* ms, char* names, double
     std::vector<Launch> ls;
     build_chunk_launches(r, 0, nb, ls);
     if (static_cast<int>(ls.size()) > cap) { r->err = "profile buffers too small"; return XRSEG_ERR_CAPACITY; }
-    cudaEvent_t a, b;
-    XR_CUDA(cudaEventCreate(&a));
-    XR_CUDA(cudaEventCreate(&b));
-    int total_det = r->h_offsets[r->batch];
-    for (size_t i = 0; i < ls.size(); ++i) {
-      if (ls[i].name == "post.decode") reset_counters(r, nb, r->stream);
-      ls[i].fn(r->stream);  // warm
-      XR_CUDA(cudaEventRecord(a, r->stream));
-      for (int it = 0; it < iters; ++it) {
-        if (ls[i].name == "post.decode") reset_counters(r, nb, r->stream);
+    // One event pair per launch, whole pipeline per pass: every kernel sees exactly the data of a normal run
+    // (replaying a single launch in a loop would re-apply the in-place residual convolutions of C2PSA).
+    const size_t n = ls.size();
+    std::vector<cudaEvent_t> ev(2 * n);
+    for (auto& e : ev) XR_CUDA(cudaEventCreate(&e));
+    std::vector<double> acc(n, 0.0);
+    const int total_det = r->h_offsets[r->batch];
+    for (int it = -1; it < iters; ++it) {   // pass -1 warms up
+      reset_counters(r, nb, r->stream);
+      for (size_t i = 0; i < n; ++i) {
+        XR_CUDA(cudaEventRecord(ev[2 * i], r->stream));
         ls[i].fn(r->stream);
+        XR_CUDA(cudaEventRecord(ev[2 * i + 1], r->stream));
       }
-      XR_CUDA(cudaEventRecord(b, r->stream));
-      XR_CUDA(cudaEventSynchronize(b));
-      float t = 0;
-      XR_CUDA(cudaEventElapsedTime(&t, a, b));
-      ms[i] = t / iters;
+      XR_CUDA(cudaStreamSynchronize(r->stream));
+      if (it < 0) continue;
+      for (size_t i = 0; i < n; ++i) {
+        float t = 0;
+        XR_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+        acc[i] += t;
+      }
+    }
+    for (size_t i = 0; i < n; ++i) {
+      ms[i] = static_cast<float>(acc[i] / iters);
       if (names) { memset(names + i * 32, 0, 32); strncpy(names + i * 32, ls[i].name.c_str(), 31); }
       double by = ls[i].bytes;
       if (ls[i].name == "post.mask_prob") by += static_cast<double>(total_det) * PROTO_PIX * 4;
@@ -1010,8 +1017,7 @@ int xrseg_profile_ops(xrseg_runner* r, int iters, float* ms, char* names, double
       if (bytes) bytes[i] = by;
     }
     XR_CUDA(cudaGetLastError());
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
+    for (auto& e : ev) cudaEventDestroy(e);
     return static_cast<int>(ls.size());
   } catch (const CudaError& e) {
     r->err = e.msg;

@@ -53,6 +53,64 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ float silu_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
 
+// SiLU of two values in packed fp16: silu(y) = h*tanh(h) + h with h = y/2 -- one MUFU (tanh.approx.f16x2) and two
+// half2 ops per PAIR of outputs, against two MUFUs and five fp32 ops per output for y / (1 + exp(-y)).  The epilogues
+// are issue-bound at N <= 128, so this is what lets them keep up with the tensor pipe.  The result is fp16 anyway.
+__device__ __forceinline__ uint32_t silu_pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(0.5f * a, 0.5f * b);
+  uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));
+  __half2 r = __hfma2(h, *reinterpret_cast<__half2*>(&tu), h);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// Epilogue of 16 consecutive output channels of one pixel: accumulator + bias -> (SiLU) -> (+ residual) -> fp16 -> two
+// 16-byte stores.  bias16: shared memory, 64-byte aligned.  res / out: global, 32-byte aligned.
+__device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const float* bias16, int act, const __half* res,
+                                                 __half* out) {
+  float y[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b4 = reinterpret_cast<const float4*>(bias16)[i];
+    y[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
+    y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+    y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+    y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+  }
+  uint32_t o[8];
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = silu_pack_h2(y[2 * i], y[2 * i + 1]);
+    if (res) {
+      const uint4 r0 = reinterpret_cast<const uint4*>(res)[0], r1 = reinterpret_cast<const uint4*>(res)[1];
+      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __half2 s = __hadd2(*reinterpret_cast<__half2*>(&o[i]), *reinterpret_cast<const __half2*>(&rr[i]));
+        o[i] = *reinterpret_cast<uint32_t*>(&s);
+      }
+    }
+  } else {
+    if (res) {
+      const uint4 r0 = reinterpret_cast<const uint4*>(res)[0], r1 = reinterpret_cast<const uint4*>(res)[1];
+      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
+        y[2 * i] += f.x;
+        y[2 * i + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __half2 h = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+      o[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -114,6 +172,14 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a fully converged warp.  The MMA-issuing warp runs its loop with all 32 lanes (so the compiler keeps the
+// descriptor arithmetic in uniform registers) and predicates only the tcgen05 instructions on the elected lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; kind::f16 covers fp16 and bf16 operands with fp32 accumulation.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -121,7 +187,24 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));   // ordered by the volatile barrier asm around it
+}
+// Same, executed by every lane of the warp but issued only where `issue` != 0: no branch around the instruction.
+__device__ __forceinline__ void umma_f16_pred(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue));
+}
+__device__ __forceinline__ void umma_commit_pred(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(issue)
       : "memory");
 }
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.

@@ -1,0 +1,586 @@
+// conv_tma.cuh -- 3x3 stride-1 convolution on tcgen05 with the input halo fetched by TMA (cp.async.bulk.tensor).
+//
+// Same GEMM view and shared-memory operand layout as conv_umma.cuh (K-major, SWIZZLE_NONE: element (row r, K-chunk c)
+// at base + c*LBO + r*16 B), but the A operand is no longer gathered by threads:
+//   * a work item is R full rows of one image (all W columns) -- R*(W+2) "positions" in padded-row order, split into
+//     nsub <= 4 sub-tiles of 128 positions, each with its own TMEM accumulator;
+//   * per 8-channel K-chunk ONE 4-D TMA box (8 ch, x = -1..W, y = y0-1..y0+R, image b) lands the whole halo:
+//     out-of-bounds coordinates are zero-filled by the TMA unit, which IS the convolution's zero padding;
+//   * the box arrives as [y][x][8 ch] = consecutive 16-byte rows, so tap (kh,kw) of position j is row
+//     j + kh*(W+2) + kw - 1 of the chunk column: nine MMAs per 16 channels whose descriptors merely start at
+//     different rows.  The input is read ~(R+2)/R times instead of 9x (im2col) or 3.5x (linear halo).
+// One thread issues the TMA loads, one thread issues the MMAs, eight warps run the epilogue (TMEM -> +bias -> SiLU ->
+// +residual -> fp16 NHWC).  Weights stay resident in shared memory when they fit, else stream per K-stage by bulk copy.
+#pragma once
+
+#include <cuda.h>
+
+#include "conv_umma.cuh"
+
+namespace xrseg {
+
+enum { MODE_HALO_TMA = 2 };
+enum { TMA_THREADS = 320, TMA_TAIL_PAD = 4096 };
+
+struct TmaPlanExtra {
+  int R, nsub, tpi, hbox, slots_box;
+};
+
+// ---- tensor map (driver entry point fetched through the runtime: no link dependency on libcuda) ----------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    XR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    XR_CHECK(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 4-D view (C, W, H, B) of an NHWC fp16 tensor slice; box = (8 channels, W+2, R+2, 1).
+static inline CUtensorMap make_halo_tensor_map(const __half* base, int B, int H, int W, int C, int pitch, int box_w,
+                                               int box_h, int box_c = 8, int sw = 0) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 2, static_cast<cuuint64_t>(W) * pitch * 2,
+                           static_cast<cuuint64_t>(H) * W * pitch * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_c), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+  const CUtensorMapSwizzle swz = sw == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : sw == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : sw == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for [%d,%d,%d,%d] pitch %d box %dx%d", (int)r, B, H, W,
+           C, pitch, box_w, box_h);
+  return m;
+}
+
+// ---- planning --------------------------------------------------------------------------------------------------
+// Returns false when the layer does not fit this kernel (caller falls back to the thread-gather kernel).
+static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true) {
+  if (!(d.k == 3 && d.stride == 1 && !d.transposed)) return false;
+  p = ConvParams{};
+  p.B = d.B; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.in_pitch = d.in_pitch;
+  p.Cout = d.Cout; p.out_pitch = d.out_pitch; p.res_pitch = d.res_pitch;
+  p.k = 3; p.stride = 1; p.pad = 1; p.act = d.act; p.transposed = 0;
+  p.Ho = d.H; p.Wo = d.W;
+  p.Ntile = d.Cout <= 256 ? d.Cout : 256;
+  if (d.Cout % p.Ntile) return false;
+  p.n_tiles = d.Cout / p.Ntile;
+  p.idesc = umma_idesc_f16(p.Ntile, 0);
+  p.mode = MODE_HALO_TMA;
+  p.Wp = d.W + 2;
+  p.Hp1 = d.H + 1;
+  int nsub_max = 256 / p.Ntile;
+  if (nsub_max > 4) nsub_max = 4;
+  if (nsub_max < 1 || p.Wp > 256) return false;
+  int R = (128 * nsub_max) / p.Wp;
+  if (R > d.H) R = d.H;
+  if (R < 1 || R + 2 > 256) return false;
+  p.R = R;
+  p.nsub = ceil_div(R * p.Wp, 128);
+  p.tpi = ceil_div(d.H, R);
+  p.hbox = R + 2;
+  p.slots = p.hbox * p.Wp;
+  p.lbo_a = round_up(p.slots * 16, 128);
+  if (swizzled) {
+    // Swizzled operands: one smem row = one K-block of cb = min(Cin, 64) channels (32 / 64 / 128 bytes), stored with the
+    // TMA / UMMA hardware swizzle of that width.  A whole K-block of the halo is ONE TMA box; a tap is still a row shift.
+    int best_cb = 0, best_S = 0;
+    for (int cb = 64; cb >= 16; cb >>= 1) {
+      if (cb > d.Cin || d.Cin % cb) continue;
+      const int rb = cb * 2;
+      const int a_stage = round_up(p.slots * rb, 1024);
+      const int b_stage = 9 * p.Ntile * rb;
+      const long total_b = static_cast<long>(d.Cin / cb) * b_stage;
+      const bool res = (p.n_tiles == 1 && total_b <= 98304);
+      const int fixed = round_up(CONV_HDR_BYTES, 1024) + 1024 + 128 * rb + 1024 +
+                        (res ? round_up(static_cast<int>(total_b), 1024) : 0);
+      int S = (CONV_SMEM_MAX - fixed) / (a_stage + (res ? 0 : round_up(b_stage, 1024)));
+      if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
+      if (S > 2 * (d.Cin / cb) + 2) S = 2 * (d.Cin / cb) + 2;
+      if (S >= 3 || (S == 2 && best_S < 2)) {
+        best_cb = cb;
+        best_S = S;
+        if (S >= 3) break;
+      }
+    }
+    if (best_S < 2) return false;
+    const int cb = best_cb;
+    p.sw = cb == 64 ? 3 : (cb == 32 ? 2 : 1);
+    const int rb = cb * 2;
+    p.cb = cb; p.cps = cb / 8; p.nks = d.Cin / cb;
+    p.taps = 9; p.K_total = 9 * d.Cin;
+    p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
+    p.a_stage_bytes = round_up(p.slots * rb, 1024);
+    p.b_stage_bytes = 9 * p.Ntile * rb;
+    const long total_b = static_cast<long>(p.nks) * p.b_stage_bytes;
+    p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
+    const int resident = p.b_resident ? static_cast<int>(total_b) : 0;
+    const int S = best_S;
+    p.S = S;
+    p.M_total = d.B * p.tpi;
+    p.m_tiles = p.M_total;
+    p.smem_off_b = round_up(CONV_HDR_BYTES, 1024);
+    const int b_region = p.b_resident ? resident : S * round_up(p.b_stage_bytes, 1024);
+    // one tail pad BEFORE the A stages too: tap (0,0) of position 0 reads the row before the stage
+    p.smem_off_a = p.smem_off_b + round_up(b_region, 1024) + 1024;
+    p.smem_bytes = p.smem_off_a + S * p.a_stage_bytes + 128 * rb + 1024;
+    if (p.smem_bytes > CONV_SMEM_MAX) return false;
+    const int work = p.m_tiles * p.n_tiles;
+    p.grid = work < num_sms ? work : num_sms;
+    p.fd_wp = make_fastdiv(p.Wp);
+    p.fd_hp1 = make_fastdiv(p.tpi);
+    p.fd_hw = make_fastdiv(1);
+    p.fd_wo = make_fastdiv(1);
+    p.fd_cin = make_fastdiv(d.Cin);
+    p.fd_cout = make_fastdiv(d.Cout);
+    return true;
+  }
+  p.taps = 9;
+  p.K_total = 9 * d.Cin;
+  p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
+  const int budget = CONV_SMEM_MAX - CONV_HDR_BYTES - TMA_TAIL_PAD;
+  const long total_b = 9L * d.Cin * p.Ntile * 2;
+  p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
+  int best_cb = 0, best_S = 0;
+  for (int cb = 64; cb >= 16; cb >>= 1) {
+    if (d.Cin % cb) continue;
+    const int a_stage = (cb / 8) * p.lbo_a;
+    const int b_stage = 9 * cb * p.Ntile * 2;
+    const int resident = p.b_resident ? static_cast<int>(total_b) : 0;
+    int S = (budget - resident) / (a_stage + (p.b_resident ? 0 : b_stage));
+    const int nks = d.Cin / cb;
+    if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
+    if (S >= 3 || (S == 2 && best_S < 2)) {
+      if (S > 2 * nks + 2) S = 2 * nks + 2;
+      best_cb = cb;
+      best_S = S;
+      if (S >= 3) break;
+    }
+  }
+  if (best_S < 2) return false;
+  p.cb = best_cb;
+  p.cps = best_cb / 8;
+  p.nks = d.Cin / best_cb;
+  p.S = best_S;
+  p.a_stage_bytes = p.cps * p.lbo_a;
+  p.b_stage_bytes = 9 * best_cb * p.Ntile * 2;
+  p.M_total = d.B * p.tpi;                      // number of (image, row-block) tiles
+  p.m_tiles = p.M_total;
+  p.smem_off_b = CONV_HDR_BYTES;
+  const int b_region = p.b_resident ? p.nks * p.b_stage_bytes : p.S * p.b_stage_bytes;
+  p.smem_off_a = CONV_HDR_BYTES + round_up(b_region, 128);
+  p.smem_bytes = p.smem_off_a + p.S * p.a_stage_bytes + TMA_TAIL_PAD;
+  if (p.smem_bytes > CONV_SMEM_MAX) return false;
+  const int work = p.m_tiles * p.n_tiles;
+  p.grid = work < num_sms ? work : num_sms;
+  p.fd_wp = make_fastdiv(p.Wp);
+  p.fd_hp1 = make_fastdiv(p.tpi);               // reused: tile -> (image, row block)
+  p.fd_hw = make_fastdiv(1);
+  p.fd_wo = make_fastdiv(1);
+  p.fd_cin = make_fastdiv(d.Cin);
+  p.fd_cout = make_fastdiv(d.Cout);
+  return true;
+}
+
+// Physical byte offset of logical offset `off` inside a pattern-aligned swizzled buffer (Swizzle<sw,4,3>): the 16-byte
+// chunk index (address bits 4..6) is XORed with address bits 7..9, masked to the swizzle width.
+static inline size_t sw_phys(size_t off, int sw) {
+  const size_t mask = (static_cast<size_t>(1) << sw) - 1;
+  return off ^ (((off >> 7) & mask) << 4);
+}
+
+// Swizzled weight image: [n_tile][K-block ks][tap][n][cb channels], each (tap) tile swizzled like the A rows.
+template <typename HalfT>
+static inline void pack_conv_weights_sw(const ConvParams& p, const float* w, const float* bias, int cin_real, int cout_real,
+                                        std::vector<HalfT>& wp, std::vector<float>& bp) {
+  const size_t stage_elems = static_cast<size_t>(p.b_stage_bytes) / 2;
+  wp.assign(static_cast<size_t>(p.n_tiles) * p.nks * stage_elems, HalfT(0.0f));
+  bp.assign(static_cast<size_t>(p.n_tiles) * p.Ntile, 0.0f);
+  const int rb = p.cb * 2;
+  for (int nt = 0; nt < p.n_tiles; ++nt)
+    for (int ks = 0; ks < p.nks; ++ks)
+      for (int t = 0; t < 9; ++t)
+        for (int n = 0; n < p.Ntile; ++n)
+          for (int c = 0; c < p.cb; ++c) {
+            const int ng = nt * p.Ntile + n, ci = ks * p.cb + c;
+            if (ng >= cout_real || ci >= cin_real) continue;
+            const float v = w[((static_cast<size_t>(ng) * cin_real + ci) * 3 + t / 3) * 3 + t % 3];
+            const size_t off = (static_cast<size_t>(t) * p.Ntile + n) * rb + static_cast<size_t>(c) * 2;
+            wp[(static_cast<size_t>(nt) * p.nks + ks) * stage_elems + sw_phys(off, p.sw) / 2] = HalfT(v);
+          }
+  for (int ng = 0; ng < p.n_tiles * p.Ntile; ++ng)
+    if (ng < cout_real && bias) bp[ng] = bias[ng];
+}
+
+#ifdef __CUDACC__
+// ---- PTX: TMA + bulk copy ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// ---- the kernel --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
+  uint64_t* empty = full + 8;                               // [8]
+  uint64_t* tfull = empty + 8;                              // [2]
+  uint64_t* tempty = tfull + 2;                             // [2]
+  uint64_t* bres = tempty + 2;                              // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + 256);     // [<=512]
+  uint8_t* smem_b = smem + p.smem_off_b;
+  uint8_t* smem_a = smem + p.smem_off_a;
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code uses the uniform datapath
+  const int lane = tid & 31;
+  const int total_work = p.m_tiles * p.n_tiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < CONV_MAX_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 256);
+    }
+    mbar_init(bres, 1);
+    mbar_fence_init();
+    prefetch_tensormap(&tmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
+    tmem_relinquish();
+  }
+  for (int i = tid; i < p.n_tiles * p.Ntile; i += TMA_THREADS) bias_s[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================================= TMA producer ========================================
+    if (lane == 0) {
+      const uint32_t a_u32 = smem_u32(smem_a);
+      const uint32_t b_u32 = smem_u32(smem_b);
+      const uint32_t a_tx = static_cast<uint32_t>(p.cps) * p.slots * 16u;     // = slots * row bytes when swizzled
+      const uint32_t b_stride = p.sw ? static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023) : static_cast<uint32_t>(p.b_stage_bytes);
+      if (p.b_resident) {
+        const uint32_t bytes = static_cast<uint32_t>(p.nks) * p.b_stage_bytes;
+        mbar_arrive_expect_tx(bres, bytes);
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+          const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+          bulk_copy_g2s(b_u32 + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, bres);
+        }
+      }
+      int it = 0;
+      long long t_wait = 0, t0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int tile = p.n_tiles == 1 ? w : (w >> 1);
+        const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
+        const int b = fd_div(p.fd_hp1, tile);
+        const int y0 = (tile - b * p.tpi) * p.R;
+        for (int ks = 0; ks < p.nks; ++ks, ++it) {
+          const int slot = it % p.S;
+          t0 = clock64();
+          if (it >= p.S) mbar_wait(&empty[slot], static_cast<uint32_t>((it / p.S) - 1) & 1u);
+          t_wait += clock64() - t0;
+          if (p.dbg_skip & 4) { mbar_arrive(&full[slot]); continue; }
+          mbar_arrive_expect_tx(&full[slot], a_tx + (p.b_resident ? 0u : static_cast<uint32_t>(p.b_stage_bytes)));
+          const uint32_t a_dst = a_u32 + slot * p.a_stage_bytes;
+          if (p.sw) {
+            tma_load_4d(a_dst, &tmap, &full[slot], ks * p.cb, -1, y0 - 1, b);     // the whole K-block in one box
+          } else {
+            for (int c = 0; c < p.cps; ++c)
+              tma_load_4d(a_dst + c * p.lbo_a, &tmap, &full[slot], ks * p.cb + c * 8, -1, y0 - 1, b);
+          }
+          if (!p.b_resident) {
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wpack) +
+                                 (static_cast<size_t>(n_tile) * p.nks + ks) * p.b_stage_bytes;
+            const uint32_t b_dst = b_u32 + slot * b_stride;
+            for (uint32_t off = 0; off < static_cast<uint32_t>(p.b_stage_bytes); off += 32768u) {
+              const uint32_t n = p.b_stage_bytes - off < 32768u ? p.b_stage_bytes - off : 32768u;
+              bulk_copy_g2s(b_dst + off, src + off, n, &full[slot]);
+            }
+          }
+        }
+      }
+      if (p.dbg_clk) p.dbg_clk[blockIdx.x * 8 + 0] = t_wait;
+    }
+  } else if (warp == 1) {
+    // ======================================= MMA issuer ==========================================
+    // all 32 lanes run the loop (uniform control flow); one elected lane issues the tcgen05 instructions
+    {
+      const uint32_t a_u32 = smem_u32(smem_a);
+      const uint32_t b_u32 = smem_u32(smem_b);
+      const uint32_t lbo_a16 = static_cast<uint32_t>(p.lbo_a) >> 4;
+      const uint32_t lbo_b16 = static_cast<uint32_t>(p.Ntile);
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+      const int kj = p.cb >> 4;
+      const int nsub = p.nsub;
+      const uint32_t idesc = p.idesc;
+      const uint32_t ntile_u = static_cast<uint32_t>(p.Ntile);
+      const uint32_t rb = static_cast<uint32_t>(p.cb) * 2u;                 // swizzled row bytes
+      const uint32_t row16 = rb >> 4;                                        // one row in 16-byte units
+      const uint32_t sub16 = 128u * row16;                                   // one 128-row sub-tile
+      const uint32_t tap16 = (ntile_u * rb) >> 4;                            // one tap's weight tile
+      const uint32_t b_stride_sw = static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023);
+      const uint32_t layout = p.sw == 3 ? 2u : (p.sw == 2 ? 4u : 6u);
+      const uint64_t hi_sw = static_cast<uint64_t>(((8u * rb) >> 4) | (1u << 14) | (layout << 29)) << 32;
+      const bool mma_on = !(p.dbg_skip & 1);
+      long long t_start = clock64(), t_bres, t_tempty = 0, t_full = 0, t_issue = 0, t0;
+      if (p.b_resident) mbar_wait(bres, 0);
+      t_bres = clock64() - t_start;
+      int it = 0, tcount = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+        const int buf = tcount & 1;
+        const int use = tcount >> 1;
+        t0 = clock64();
+        if (use >= 1) mbar_wait(&tempty[buf], static_cast<uint32_t>(use - 1) & 1u);
+        t_tempty += clock64() - t0;
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + static_cast<uint32_t>(buf * p.nsub * p.Ntile);
+        for (int ks = 0; ks < p.nks; ++ks, ++it) {
+          const int slot = it % p.S;
+          t0 = clock64();
+          mbar_wait(&full[slot], static_cast<uint32_t>(it / p.S) & 1u);
+          t_full += clock64() - t0;
+          t0 = clock64();
+          tc_fence_after();
+          const uint32_t a_base = a_u32 + slot * p.a_stage_bytes;
+          if (p.sw) {
+            // swizzled operands: row = K-block of cb channels (rb bytes); tap = row shift; k16 step = +32 bytes.
+            // Measured on B200: the UMMA swizzle is a function of the ABSOLUTE shared-memory address bits (like the
+            // TMA write side), so a descriptor may start at any row with the base-offset field left 0; filling that
+            // field with (addr >> 7) & 7 for unaligned starts produces wrong results.
+            const uint32_t b_base = b_u32 + (p.b_resident ? ks * p.b_stage_bytes : slot * b_stride_sw);
+            // descriptor low words: start address >> 4 plus offsets in 16-byte units (never carries out of bits 0-13)
+            const uint32_t a_lo_stage = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
+            uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (1u << 16);
+            // Loop order: sub-tile innermost, so that consecutive MMAs target different accumulators.  Everything is
+            // unrolled with guards folded into the issue predicate: a handful of uniform adds per MMA, no branches.
+            if (elect_one()) {   // one branch per stage; inside, a single lane issues the whole MMA batch
+              uint32_t acc = ks > 0 ? 1u : 0u;
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh) {
+                const uint32_t a_kh = a_lo_stage + static_cast<uint32_t>(kh * p.Wp - 1) * row16;
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                  const uint32_t a_tap = a_kh + static_cast<uint32_t>(kw) * row16;
+                  for (int j = 0; j < kj; ++j) {
+                    {
+                      const uint64_t bd = hi_sw | (b_lo + 2u * j);
+#pragma unroll
+                      for (int u = 0; u < 4; ++u) {
+                        if (u < nsub && mma_on) {
+                          const uint64_t ad = hi_sw | (a_tap + static_cast<uint32_t>(u) * sub16 + 2u * j);
+                          umma_f16(d_base + static_cast<uint32_t>(u) * ntile_u, ad, bd, idesc, acc);
+                        }
+                      }
+                      acc = 1;
+                    }
+                  }
+                  b_lo += tap16;   // next tap's weight tile
+                }
+              }
+              umma_commit(&empty[slot]);
+            }
+            __syncwarp();
+            t_issue += clock64() - t0;
+            continue;
+          }
+          const uint32_t b_base = b_u32 + (p.b_resident ? ks : slot) * p.b_stage_bytes;
+          const uint32_t a_lo0 = ((a_base >> 4) & 0x3FFFu) | (lbo_a16 << 16);
+          const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFFu) | (lbo_b16 << 16);
+          for (int u = 0; u < p.nsub; ++u) {
+            const uint32_t d_tmem = d_base + static_cast<uint32_t>(u * p.Ntile);
+            uint32_t b_lo = b_lo0;
+            uint32_t acc = ks > 0 ? 1u : 0u;
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                // row of tap (kh,kw) for position j = 128u + i:  j + kh*(W+2) + kw - 1   (one row = one 16-byte unit)
+                uint32_t a_lo = a_lo0 + static_cast<uint32_t>(128 * u + kh * p.Wp + kw - 1);
+                for (int j = 0; j < kj; ++j) {
+                  if (elect_one()) umma_f16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | a_lo,
+                           (static_cast<uint64_t>(desc_hi) << 32) | b_lo, p.idesc, acc);
+                  acc = 1;
+                  a_lo += 2 * lbo_a16;
+                  b_lo += 2 * lbo_b16;
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (elect_one()) umma_commit(&empty[slot]);
+        }
+        if (elect_one()) umma_commit(&tfull[buf]);
+      }
+      if (p.dbg_clk && lane == 0) {
+        p.dbg_clk[blockIdx.x * 8 + 1] = t_bres;
+        p.dbg_clk[blockIdx.x * 8 + 2] = t_tempty;
+        p.dbg_clk[blockIdx.x * 8 + 3] = t_full;
+        p.dbg_clk[blockIdx.x * 8 + 4] = t_issue;
+        p.dbg_clk[blockIdx.x * 8 + 5] = clock64() - t_start;
+      }
+    }
+  } else {
+    // ======================================= epilogue ============================================
+    const int ew = warp - 2;
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;
+    int tcount = 0;
+    long long e_wait = 0, e_work = 0, t0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+      const int tile = p.n_tiles == 1 ? w : (w >> 1);
+      const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
+      const int b = fd_div(p.fd_hp1, tile);
+      const int y0 = (tile - b * p.tpi) * p.R;
+      const int buf = tcount & 1;
+      const int use = tcount >> 1;
+      t0 = clock64();
+      mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
+      e_wait += clock64() - t0;
+      t0 = clock64();
+      tc_fence_after();
+      for (int u = 0; u < p.nsub; ++u) {
+        const int j = 128 * u + q * 32 + lane;
+        const int yy = fd_div(p.fd_wp, j);
+        const int cc = j - yy * p.Wp;
+        const int y = y0 + yy;
+        const bool valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
+        const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               static_cast<uint32_t>((buf * p.nsub + u) * p.Ntile);
+        for (int c0 = half * 16; c0 < p.Ntile; c0 += 32) {
+          uint32_t v[16];
+          tmem_ld16(t_row + c0, v);
+          tmem_ld_wait();
+          if (valid && !(p.dbg_skip & 2)) {
+            const int n = n_tile * p.Ntile + c0;
+            epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
+                             p.out + pix * p.out_pitch + n);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[buf]);
+      e_work += clock64() - t0;
+    }
+    if (p.dbg_clk && warp == 2 && lane == 0) {
+      p.dbg_clk[blockIdx.x * 8 + 6] = e_wait;
+      p.dbg_clk[blockIdx.x * 8 + 7] = e_work;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+  }
+}
+
+static inline void conv_tma_prepare_device() {
+  XR_CUDA(cudaFuncSetAttribute(conv_halo_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
+}
+
+static inline void launch_conv_halo_tma(const ConvParams& p, const CUtensorMap& map, cudaStream_t stream) {
+  conv_halo_tma_kernel<<<p.grid, TMA_THREADS, p.smem_bytes, stream>>>(p, map);
+  XR_CUDA(cudaGetLastError());
+}
+#endif  // __CUDACC__
+
+// ---- host emulation of this kernel's data movement (fp32; test infrastructure only) -------------------------------
+static inline void emulate_conv_halo_tma(const ConvParams& p, const float* in, const float* wpack_f, const float* bias,
+                                         const float* res, float* out) {
+  const int bchunks = p.b_stage_bytes / (p.Ntile * 16);
+  const int lbo_slots = p.lbo_a / 16;
+  const int pre = 8;  // rows readable before the stage buffer (the kernel reads row -1 for invalid positions)
+  std::vector<float> a((static_cast<size_t>(p.cps) * lbo_slots + 2 * 128 + pre) * 8);
+  std::vector<float> acc(static_cast<size_t>(p.nsub) * 128 * p.Ntile);
+  for (int w = 0; w < p.m_tiles * p.n_tiles; ++w) {
+    const int tile = w / p.n_tiles, n_tile = w % p.n_tiles;
+    const int b = tile / p.tpi;
+    const int y0 = (tile % p.tpi) * p.R;
+    std::fill(acc.begin(), acc.end(), 0.f);
+    for (int ks = 0; ks < p.nks; ++ks) {
+      std::fill(a.begin(), a.end(), 0.f);
+      for (int c = 0; c < p.cps; ++c)          // one TMA box per chunk: coords (ks*cb + 8c, -1, y0-1, b)
+        for (int by = 0; by < p.hbox; ++by)
+          for (int bx = 0; bx < p.Wp; ++bx) {
+            const int y = y0 - 1 + by, x = -1 + bx;
+            if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;   // OOB -> zero fill
+            const size_t pixi = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+            for (int e = 0; e < 8; ++e)
+              a[(pre + static_cast<size_t>(c) * lbo_slots + by * p.Wp + bx) * 8 + e] =
+                  in[pixi * p.in_pitch + ks * p.cb + c * 8 + e];
+          }
+      const float* bst = wpack_f + (p.sw ? (static_cast<size_t>(n_tile) * p.nks + ks) * (p.b_stage_bytes / 2)
+                                         : (static_cast<size_t>(n_tile) * p.nks + ks) * bchunks * p.Ntile * 8);
+      for (int u = 0; u < p.nsub; ++u)
+        for (int t = 0; t < 9; ++t) {
+          const int shift = 128 * u + (t / 3) * p.Wp + (t % 3) - 1;
+          for (int j = 0; j < p.cb / 16; ++j)
+            for (int hk = 0; hk < 2; ++hk) {
+              const int ac = 2 * j + hk, bc = t * p.cps + 2 * j + hk;
+              for (int i = 0; i < 128; ++i)
+                for (int n = 0; n < p.Ntile; ++n) {
+                  float sacc = 0.f;
+                  for (int e = 0; e < 8; ++e) {
+                    const float bv = p.sw ? bst[sw_phys((static_cast<size_t>(t) * p.Ntile + n) * (p.cb * 2) + (ac * 8 + e) * 2, p.sw) / 2]
+                                          : bst[(static_cast<size_t>(bc) * p.Ntile + n) * 8 + e];
+                    sacc += a[(pre + static_cast<size_t>(ac) * lbo_slots + i + shift) * 8 + e] * bv;
+                  }
+                  acc[(static_cast<size_t>(u) * 128 + i) * p.Ntile + n] += sacc;
+                }
+            }
+        }
+    }
+    for (int u = 0; u < p.nsub; ++u)
+      for (int i = 0; i < 128; ++i) {
+        const int j = 128 * u + i;
+        const int yy = j / p.Wp, cc = j % p.Wp, y = y0 + yy;
+        if (!(yy < p.R && y < p.H && cc >= 1 && cc <= p.W)) continue;
+        const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
+        for (int n = 0; n < p.Ntile; ++n) {
+          const int ng = n_tile * p.Ntile + n;
+          float yv = acc[(static_cast<size_t>(u) * 128 + i) * p.Ntile + n] + bias[ng];
+          if (p.act) yv = yv / (1.0f + expf(-yv));
+          if (res) yv += res[pix * p.res_pitch + ng];
+          out[pix * p.out_pitch + ng] = yv;
+        }
+      }
+  }
+}
+
+}  // namespace xrseg

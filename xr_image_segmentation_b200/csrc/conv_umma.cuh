@@ -79,6 +79,10 @@ struct ConvParams {
   int smem_off_b, smem_off_a, smem_bytes;
   int grid;
   FastDiv fd_wp, fd_hp1, fd_hw, fd_wo, fd_cin, fd_cout;
+  int R, nsub, tpi, hbox;           // MODE_HALO_TMA (conv_tma.cuh): rows per tile, sub-tiles, tiles per image, box rows
+  long long* dbg_clk;               // optional [grid][8] cycle counters per role phase (debug builds of the probe)
+  int dbg_skip;                     // profiling experiment: 1 skip MMA issue, 2 skip epilogue math+stores, 4 skip loads
+  int sw;                           // operand swizzle: 0 none, 1/2/3 = 32/64/128-byte (row = 16/32/64 channels)
 };
 
 struct ConvDesc {
@@ -179,7 +183,7 @@ static inline int pow2_ceil(int v) {
   return r;
 }
 
-// variant: 0 = auto (halo for 3x3 s1), 1 = force MODE_GATHER (cross-check path)
+// variant: 0 / 2 = thread-loaded halo for 3x3 s1, 1 = force MODE_GATHER (cross-check path)
 static inline ConvParams plan_conv(const ConvDesc& d, int num_sms, int variant = 0) {
   ConvParams p{};
   XR_CHECK(d.Cin % 16 == 0 && d.Cout % 16 == 0, "channels must be padded to 16 (cin %d cout %d)", d.Cin, d.Cout);
@@ -272,7 +276,7 @@ static inline size_t conv_wpack_elems(const ConvParams& p) {
 
 // K element consumed at (stage ks, B-chunk bc, element e) -> (tap, input channel); returns false for K padding.
 static inline bool conv_k_index(const ConvParams& p, int ks, int bc, int e, int* tap, int* ci) {
-  if (p.mode == MODE_HALO) {
+  if (p.mode != MODE_GATHER) {
     *tap = bc / p.cps;
     *ci = ks * p.cb + (bc % p.cps) * 8 + e;
     return true;
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   uint8_t* smem_a = smem + p.smem_off_a;
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code uses the uniform datapath
   const int lane = tid & 31;
   const int total_work = p.m_tiles * p.n_tiles;
 
@@ -483,10 +487,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
     cp_async_wait<0>();   // nothing of this thread may still be in flight when the CTA exits
   } else if (warp == CONV_MMA_WARP) {
     // ======================================= MMA issuer ==========================================
-    if (lane == 0) {
+    // all 32 lanes run the loop (uniform control flow); one elected lane issues the tcgen05 instructions
+    {
       const uint32_t a_u32 = smem_u32(smem_a);
       const uint32_t b_u32 = smem_u32(smem_b);
-      const uint32_t lbo_b = static_cast<uint32_t>(p.Ntile) * 16u;
+      const uint32_t lbo_a16 = static_cast<uint32_t>(p.lbo_a) >> 4;
+      const uint32_t lbo_b16 = static_cast<uint32_t>(p.Ntile);            // (Ntile * 16 B) >> 4
+      const uint32_t desc_hi = (128u >> 4) | (1u << 14);                  // SBO = 128 B, descriptor version 1
       if (p.b_resident) {
         mbar_wait(bres, 0);
         fence_proxy_async_smem();
@@ -506,27 +513,42 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
           tc_fence_after();
           const uint32_t a_base = a_u32 + slot * p.a_stage_bytes;
           const uint32_t b_base = b_u32 + (p.b_resident ? ks : slot) * p.b_stage_bytes;
-          int kj;
+          // Descriptors are advanced by adding 16-byte units to their low word (start address field, bits 0-13);
+          // the issue loop is a single thread, so it is kept to a handful of instructions per MMA.
+          const uint32_t a_lo0 = ((a_base >> 4) & 0x3FFFu) | (lbo_a16 << 16);
+          const uint32_t b_lo0 = ((b_base >> 4) & 0x3FFFu) | (lbo_b16 << 16);
           if (p.mode == MODE_GATHER) {
-            kj = (p.K_total - ks * 64) / 16;
+            int kj = (p.K_total - ks * 64) >> 4;
             if (kj > 4) kj = 4;
-          } else {
-            kj = p.cb / 16;
-          }
-          for (int t = 0; t < p.taps; ++t) {
-            const uint32_t shift = (p.mode == MODE_HALO) ? static_cast<uint32_t>((t / 3) * p.Wp + (t % 3)) * 16u : 0u;
+            uint32_t a_lo = a_lo0, b_lo = b_lo0;
             for (int j = 0; j < kj; ++j) {
-              // LBO = distance between the two K-adjacent core matrices of this k16 step, SBO = 128 B between
-              // 8-row groups (verified on B200: the swapped assignment produces wrong results)
-              const uint64_t ad = umma_desc_kmajor_noswz(a_base + 2 * j * p.lbo_a + shift, p.lbo_a, 128);
-              const uint64_t bd = umma_desc_kmajor_noswz(b_base + (t * p.cps + 2 * j) * lbo_b, lbo_b, 128);
-              umma_f16(d_tmem, ad, bd, p.idesc, acc);
+              if (elect_one()) umma_f16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | a_lo, (static_cast<uint64_t>(desc_hi) << 32) | b_lo,
+                       p.idesc, acc);
               acc = 1;
+              a_lo += 2 * lbo_a16;
+              b_lo += 2 * lbo_b16;
+            }
+          } else {
+            const int kj = p.cb >> 4;
+            uint32_t b_lo = b_lo0;
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                uint32_t a_lo = a_lo0 + static_cast<uint32_t>(kh * p.Wp + kw);   // tap shift: one slot = one 16-byte unit
+                for (int j = 0; j < kj; ++j) {
+                  if (elect_one()) umma_f16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | a_lo,
+                           (static_cast<uint64_t>(desc_hi) << 32) | b_lo, p.idesc, acc);
+                  acc = 1;
+                  a_lo += 2 * lbo_a16;
+                  b_lo += 2 * lbo_b16;
+                }
+              }
             }
           }
-          umma_commit(&empty[slot]);
+          __syncwarp();
+          if (elect_one()) umma_commit(&empty[slot]);
         }
-        umma_commit(&tfull[buf]);
+        if (elect_one()) umma_commit(&tfull[buf]);
       }
     }
   } else {
@@ -576,37 +598,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
           co = n - pos * p.Cout;
           pix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
         }
-        if (valid) {
-          float y[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float t = __uint_as_float(v[i]) + bias_s[n + i];
-            y[i] = p.act ? silu_f(t) : t;
-          }
-          if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + co);
-            uint4 r0v = rp[0], r1v = rp[1];
-            const __half2* h0 = reinterpret_cast<const __half2*>(&r0v);
-            const __half2* h1 = reinterpret_cast<const __half2*>(&r1v);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float2 f0 = __half22float2(h0[i]), f1 = __half22float2(h1[i]);
-              y[2 * i] += f0.x; y[2 * i + 1] += f0.y;
-              y[8 + 2 * i] += f1.x; y[8 + 2 * i + 1] += f1.y;
-            }
-          }
-          uint4 o0, o1;
-          __half2* q0 = reinterpret_cast<__half2*>(&o0);
-          __half2* q1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            q0[i] = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
-            q1[i] = __floats2half2_rn(y[8 + 2 * i], y[8 + 2 * i + 1]);
-          }
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_pitch + co);
-          op[0] = o0;
-          op[1] = o1;
-        }
+        if (valid)
+          epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + co : nullptr,
+                           p.out + pix * p.out_pitch + co);
       }
       tc_fence_before();
       mbar_arrive(&tempty[buf]);

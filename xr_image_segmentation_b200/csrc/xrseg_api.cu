@@ -5,11 +5,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
 
 #include "common.cuh"
+#include "conv_tma.cuh"
 #include "conv_umma.cuh"
 #include "kernels_misc.cuh"
 #include "model.cuh"
@@ -24,6 +26,8 @@ thread_local std::string g_create_error;
 struct DevLayer {
   // OP_CONV (UMMA)
   ConvParams cp{};
+  bool use_tma = false;            // 3x3 stride-1 layers: halo fetched by TMA (conv_tma.cuh)
+  CUtensorMap tmap{};
   __half* wpack = nullptr;
   float* bias = nullptr;
   // OP_CONV (direct) / OP_DW / OP_STEM
@@ -87,6 +91,8 @@ struct xrseg_runner {
 
 namespace {
 
+inline __half* ptr_of(xrseg_runner* r, const TV& t) { return r->arena + t.off; }
+
 // ------------------------------------------------------------------------------------------------
 // weights -> device, per layer kind
 // ------------------------------------------------------------------------------------------------
@@ -123,11 +129,17 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch;
       cd.k = o.k; cd.stride = o.stride; cd.act = o.act; cd.transposed = o.transposed;
       cd.res_pitch = o.has_res ? o.res.pitch : 0;
-      d.cp = plan_conv(cd, r->num_sms, 0);
+      d.use_tma = r->cfg.conv_impl == XRSEG_CONV_UMMA && plan_conv_halo_tma(cd, r->num_sms, d.cp);
+      if (d.use_tma)
+        d.tmap = make_halo_tensor_map(ptr_of(r, o.x), r->mb, o.x.H, o.x.W, o.x.Cp, o.x.pitch, d.cp.Wp, d.cp.hbox,
+                                      d.cp.sw ? d.cp.cb : 8, d.cp.sw);
+      else
+        d.cp = plan_conv(cd, r->num_sms, 0);
       if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
         std::vector<__half> wp;
         std::vector<float> bp;
-        pack_conv_weights<__half>(d.cp, w.w.data(), w.b.data(), l.cin, l.cout, wp, bp);
+        if (d.use_tma && d.cp.sw) pack_conv_weights_sw<__half>(d.cp, w.w.data(), w.b.data(), l.cin, l.cout, wp, bp);
+        else pack_conv_weights<__half>(d.cp, w.w.data(), w.b.data(), l.cin, l.cout, wp, bp);
         d.wpack = dev_upload(wp);
         d.bias = dev_upload(bp);
       } else {
@@ -154,8 +166,6 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
     }
   }
 }
-
-inline __half* ptr_of(xrseg_runner* r, const TV& t) { return r->arena + t.off; }
 
 // ------------------------------------------------------------------------------------------------
 // A run is a flat list of kernel launches (network, then post-processing); the normal path enqueues them in order,
@@ -199,12 +209,18 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
             cd.B = nb; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
             cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch; cd.k = o.k; cd.stride = o.stride; cd.act = o.act;
             cd.transposed = o.transposed; cd.res_pitch = o.has_res ? o.res.pitch : 0;
-            p = plan_conv(cd, r->num_sms, 0);
+            if (d.use_tma) plan_conv_halo_tma(cd, r->num_sms, p, d.cp.sw != 0);
+            else p = plan_conv(cd, r->num_sms, 0);
           }
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
           p.res = o.has_res ? ptr_of(r, o.res) : nullptr;
           p.wpack = d.wpack; p.bias = d.bias;
-          L.fn = [p](cudaStream_t st) { launch_conv_umma(p, st); };
+          if (d.use_tma) {
+            const CUtensorMap map = d.tmap;
+            L.fn = [p, map](cudaStream_t st) { launch_conv_halo_tma(p, map, st); };
+          } else {
+            L.fn = [p](cudaStream_t st) { launch_conv_umma(p, st); };
+          }
         } else {
           DirectParams p{};
           p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
@@ -706,6 +722,7 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     XR_CUDA(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
     for (auto& e : r->ev) XR_CUDA(cudaEventCreate(&e));
     conv_umma_prepare_device();
+    conv_tma_prepare_device();
     XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     XR_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 65 * 8));
@@ -1211,14 +1228,60 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
     float* d_b = nullptr;
     if (impl == XRSEG_CONV_UMMA) {
       ConvDesc cd{b, h, w, cin_p, cin_p, cout_p, cout_p, k, stride, act, transposed, residual ? cout_p : 0};
-      ConvParams p = plan_conv(cd, prop.multiProcessorCount, variant & 1);
+      ConvParams p;
+      const bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, prop.multiProcessorCount, p, variant == 0);
+      if (!tma) p = plan_conv(cd, prop.multiProcessorCount, variant & 1);
       std::vector<__half> wp;
       std::vector<float> bp;
-      pack_conv_weights<__half>(p, wgt, hb, cin, cout, wp, bp);
+      if (tma && p.sw) pack_conv_weights_sw<__half>(p, wgt, hb, cin, cout, wp, bp);
+      else pack_conv_weights<__half>(p, wgt, hb, cin, cout, wp, bp);
       d_w = dev_upload(wp);
       d_b = dev_upload(bp);
       p.in = d_x; p.out = d_y; p.res = d_r; p.wpack = d_w; p.bias = d_b;
-      launch_conv_umma(p, 0);
+      const char* dbg = getenv("XRSEG_DBG_SKIP");
+      if (dbg) p.dbg_skip = atoi(dbg);
+      long long* d_clk = nullptr;
+      if (getenv("XRSEG_DBG_TIME") && tma) {
+        d_clk = dev_alloc<long long>(static_cast<size_t>(p.grid) * 8);
+        XR_CUDA(cudaMemset(d_clk, 0, sizeof(long long) * p.grid * 8));
+        p.dbg_clk = d_clk;
+      }
+      const int reps = getenv("XRSEG_DBG_TIME") ? 5 : 1;
+      cudaEvent_t e0, e1;
+      XR_CUDA(cudaEventCreate(&e0));
+      XR_CUDA(cudaEventCreate(&e1));
+      for (int rep = 0; rep < reps; ++rep) {
+        if (rep == reps - 1) XR_CUDA(cudaEventRecord(e0, 0));
+        if (tma) {
+          conv_tma_prepare_device();
+          const CUtensorMap map = make_halo_tensor_map(d_x, b, h, w, cin_p, cin_p, p.Wp, p.hbox, p.sw ? p.cb : 8, p.sw);
+          launch_conv_halo_tma(p, map, 0);
+        } else {
+          launch_conv_umma(p, 0);
+        }
+      }
+      XR_CUDA(cudaEventRecord(e1, 0));
+      XR_CUDA(cudaEventSynchronize(e1));
+      if (reps > 1) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        fprintf(stderr, "xrseg_debug_conv: mode %d sw %d cb %d S %d nsub %d R %d grid %d smem %d skip %d: %.1f us\n", p.mode, p.sw, p.cb,
+                p.S, p.nsub, p.R, p.grid, p.smem_bytes, p.dbg_skip, ms * 1e3f);
+        if (d_clk) {
+          std::vector<long long> h(static_cast<size_t>(p.grid) * 8);
+          XR_CUDA(cudaMemcpy(h.data(), d_clk, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+          const char* nm[8] = {"prod_wait_empty", "mma_wait_bres", "mma_wait_tempty", "mma_wait_full", "mma_issue", "mma_total",
+                               "epi_wait_tfull", "epi_work"};
+          for (int k = 0; k < 8; ++k) {
+            double sum = 0;
+            for (int c = 0; c < p.grid; ++c) sum += static_cast<double>(h[c * 8 + k]);
+            fprintf(stderr, "   %-16s avg %.0f cycles per CTA (x%d launches)\n", nm[k], sum / p.grid, reps);
+          }
+          cudaFree(d_clk);
+        }
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
     } else {
       const int taps = transposed ? 4 : k * k;
       std::vector<__half> wd(static_cast<size_t>(cout_p) * taps * cin_p, __half(0.f));
@@ -1259,10 +1322,13 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
     const int ho = transposed ? h * 2 : (h + 2 * (k / 2) - k) / stride + 1;
     const int wo = transposed ? w * 2 : (w + 2 * (k / 2) - k) / stride + 1;
     ConvDesc cd{b, h, w, cin_p, cin_p, cout_p, cout_p, k, stride, act, transposed, residual ? cout_p : 0};
-    ConvParams p = plan_conv(cd, 148, variant & 1);
+    ConvParams p;
+    const bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, 148, p, variant == 0);
+    if (!tma) p = plan_conv(cd, 148, variant & 1);
     std::vector<float> wp, bp;
     std::vector<float> zero_bias(cout, 0.f);
-    pack_conv_weights<float>(p, wgt, bias ? bias : zero_bias.data(), cin, cout, wp, bp);
+    if (tma && p.sw) pack_conv_weights_sw<float>(p, wgt, bias ? bias : zero_bias.data(), cin, cout, wp, bp);
+    else pack_conv_weights<float>(p, wgt, bias ? bias : zero_bias.data(), cin, cout, wp, bp);
     std::vector<float> xin(static_cast<size_t>(b) * h * w * cin_p, 0.f), yo(static_cast<size_t>(b) * ho * wo * cout_p, 0.f), rr;
     for (int n = 0; n < b; ++n)
       for (int c = 0; c < cin; ++c)
@@ -1273,7 +1339,8 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
         for (int c = 0; c < cout; ++c)
           for (int i = 0; i < ho * wo; ++i) rr[(static_cast<size_t>(n) * ho * wo + i) * cout_p + c] = residual[(static_cast<size_t>(n) * cout + c) * ho * wo + i];
     }
-    emulate_conv_umma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
+    if (tma) emulate_conv_halo_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
+    else emulate_conv_umma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
     for (int n = 0; n < b; ++n)
       for (int c = 0; c < cout; ++c)
         for (int i = 0; i < ho * wo; ++i) y[(static_cast<size_t>(n) * cout + c) * ho * wo + i] = yo[(static_cast<size_t>(n) * ho * wo + i) * cout_p + c];

@@ -138,6 +138,69 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// fused preprocess + stem for frames that already are 640x640 (no resample needed): reads the uint8 RGB / RGBA frame
+// directly (u8 / 255 is folded into the weights), 3x3 stride-2 conv + bias + SiLU -> fp16 NHWC.  Saves the fp16 image
+// round trip of the two-kernel path.  Block = 16x16 output pixels; the 33x33 input patch is staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct StemU8Params {
+  const uint8_t* src; int stride_bytes, bpp;   // [B,H,W,bpp]
+  __half* out; int out_pitch;
+  const float* w;      // [9][4][Cout], already divided by 255
+  const float* bias;
+  int B, H, W, Cout;
+};
+
+__global__ void __launch_bounds__(256) stem_u8_kernel(const StemU8Params p) {
+  extern __shared__ float sw[];                 // 36*Cout weights + Cout bias, then the u8 patch
+  uint8_t* patch = reinterpret_cast<uint8_t*>(sw + 37 * p.Cout);   // [33][33][4]
+  for (int i = threadIdx.x; i < 36 * p.Cout; i += 256) sw[i] = p.w[i];
+  for (int i = threadIdx.x; i < p.Cout; i += 256) sw[36 * p.Cout + i] = p.bias[i];
+  const int Ho = p.H / 2, Wo = p.W / 2;
+  const int ox0 = blockIdx.x * 16, oy0 = blockIdx.y * 16, b = blockIdx.z;
+  const uint8_t* img = p.src + static_cast<size_t>(b) * p.H * p.stride_bytes;
+  const int ix0 = ox0 * 2 - 1, iy0 = oy0 * 2 - 1;
+  for (int i = threadIdx.x; i < 33 * 33; i += 256) {
+    const int py = i / 33, px = i - py * 33;
+    const int iy = iy0 + py, ix = ix0 + px;
+    uint32_t v = 0;
+    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+      const uint8_t* s = img + static_cast<size_t>(iy) * p.stride_bytes + ix * p.bpp;
+      v = s[0] | (s[1] << 8) | (s[2] << 16);
+    }
+    reinterpret_cast<uint32_t*>(patch)[i] = v;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int ox = ox0 + tx, oy = oy0 + ty;
+  if (ox >= Wo || oy >= Ho) return;
+  const size_t pix = (static_cast<size_t>(b) * Ho + oy) * Wo + ox;
+  for (int g = 0; g < p.Cout / 16; ++g) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = sw[36 * p.Cout + g * 16 + i];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const uint32_t v = reinterpret_cast<const uint32_t*>(patch)[(2 * ty + kh) * 33 + 2 * tx + kw];
+        const float xin[3] = {static_cast<float>(v & 0xFF), static_cast<float>((v >> 8) & 0xFF),
+                              static_cast<float>((v >> 16) & 0xFF)};
+        const float* wt = sw + (kh * 3 + kw) * 4 * p.Cout + g * 16;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = fmaf(xin[ci], wt[ci * p.Cout + i], acc[i]);
+      }
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = silu_pack_h2(acc[2 * i], acc[2 * i + 1]);
+    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_pitch + g * 16);
+    op[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    op[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // depthwise 3x3 stride-1 pad-1 conv (+bias, optional SiLU, optional residual add), 8 channels per thread.
 // weights fp32 [9][C], bias fp32 [C].
 // ------------------------------------------------------------------------------------------------
@@ -298,87 +361,147 @@ struct AttnParams {
   float scale;
 };
 
-constexpr int ATT_KD = 32, ATT_HD = 64, ATT_THREADS = 128;
+constexpr int ATT_KD = 32, ATT_HD = 64;
+constexpr int ATT_KSTRIDE = 40;   // halves per K row in smem (80 B: conflict-free 32-bit fragment loads)
+constexpr int ATT_VSTRIDE = 72;   // halves per V row in smem (144 B: conflict-free ldmatrix)
+constexpr int ATT_CHUNK = 80;     // keys per online-softmax step (400 = 5 x 80)
 
-__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams p) {
+__device__ __forceinline__ void hmma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Two CTAs per (image, head), 13 warps each; one warp per 16 queries (N must be a multiple of 16 and of ATT_CHUNK).  S = Q K^T and
+// O = P V run on the tensor cores (mma.sync m16n8k16, fp32 accumulate) with a register-level online softmax: the
+// accumulator fragment of S is re-used directly as the A fragment of P V.  The whole working set of a head is 77 KB
+// of shared memory and 0.06 GFLOP per frame -- too small for a TMEM/tcgen05 pipeline to pay off.
+__global__ void __launch_bounds__(416) attention_kernel(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t att_smem[];
-  __half* ks = reinterpret_cast<__half*>(att_smem);                 // [N][32]
-  __half* vs = ks + static_cast<size_t>(p.N) * ATT_KD;              // [N][64]
+  __half* ks = reinterpret_cast<__half*>(att_smem);                       // [N][ATT_KSTRIDE]
+  __half* vs = ks + static_cast<size_t>(p.N) * ATT_KSTRIDE;               // [N][ATT_VSTRIDE]
   const int bh = blockIdx.x;
   const int h = bh % p.heads;
   const int b = bh / p.heads;
   const int per_head = 2 * ATT_KD + ATT_HD;
   const __half* base = p.qkv + static_cast<size_t>(b) * p.N * p.qkv_pitch + h * per_head;
-  // stage K (4 x 16 B per token) and V (8 x 16 B per token)
   for (int i = threadIdx.x; i < p.N * 12; i += blockDim.x) {
     const int tok = i / 12, part = i - tok * 12;
-    const uint4 v = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(tok) * p.qkv_pitch + ATT_KD + part * 8);
-    if (part < 4) reinterpret_cast<uint4*>(ks)[tok * 4 + part] = v;
-    else reinterpret_cast<uint4*>(vs)[tok * 8 + (part - 4)] = v;
+    const __half* src = base + static_cast<size_t>(tok) * p.qkv_pitch + ATT_KD + part * 8;
+    const uint32_t dst = part < 4 ? smem_u32(ks + tok * ATT_KSTRIDE + part * 8) : smem_u32(vs + tok * ATT_VSTRIDE + (part - 4) * 8);
+    cp_async16(dst, src, 16);
   }
-  __syncthreads();
-  const int qi = blockIdx.y * blockDim.x + threadIdx.x;
-  if (qi >= p.N) return;
-  float q[ATT_KD];
+  cp_async_commit();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = (blockIdx.y * (blockDim.x >> 5) + warp) * 16;
+  const bool active = q0 < p.N;     // the last CTA of a head may have idle warps (they still helped stage K / V)
+  // Q fragments (pre-scaled): 2 k-steps x 4 registers
+  uint32_t qa[2][4];
   {
-    const uint4* qp = reinterpret_cast<const uint4*>(base + static_cast<size_t>(qi) * p.qkv_pitch);
+    const __half2 sc = __float2half2_rn(p.scale);
+    const int qs = active ? q0 : 0;
+    const __half* qr0 = base + static_cast<size_t>(qs + g) * p.qkv_pitch;
+    const __half* qr1 = base + static_cast<size_t>(qs + g + 8) * p.qkv_pitch;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 raw = qp[i];
-      const __half2* hh = reinterpret_cast<const __half2*>(&raw);
+    for (int kk = 0; kk < 2; ++kk) {
+      const int c = kk * 16 + 2 * t;
+      __half2 v0 = __hmul2(*reinterpret_cast<const __half2*>(qr0 + c), sc);
+      __half2 v1 = __hmul2(*reinterpret_cast<const __half2*>(qr1 + c), sc);
+      __half2 v2 = __hmul2(*reinterpret_cast<const __half2*>(qr0 + c + 8), sc);
+      __half2 v3 = __hmul2(*reinterpret_cast<const __half2*>(qr1 + c + 8), sc);
+      qa[kk][0] = *reinterpret_cast<uint32_t*>(&v0);
+      qa[kk][1] = *reinterpret_cast<uint32_t*>(&v1);
+      qa[kk][2] = *reinterpret_cast<uint32_t*>(&v2);
+      qa[kk][3] = *reinterpret_cast<uint32_t*>(&v3);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  if (!active) return;
+
+  float o[8][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(hh[j]);
-        q[i * 8 + 2 * j] = f.x * p.scale;
-        q[i * 8 + 2 * j + 1] = f.y * p.scale;
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float mx0 = -1e30f, mx1 = -1e30f, sum0 = 0.f, sum1 = 0.f;
+  const float LOG2E = 1.4426950408889634f;
+
+  for (int k0 = 0; k0 < p.N; k0 += ATT_CHUNK) {
+    float s[ATT_CHUNK / 8][4];
+#pragma unroll
+    for (int n = 0; n < ATT_CHUNK / 8; ++n) {
+      s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+      const __half* kr = ks + (k0 + n * 8 + g) * ATT_KSTRIDE + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kk * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8);
+        hmma_16816(s[n], qa[kk], b0, b1);
+      }
+    }
+    // online softmax over this chunk (rows g and g+8 of the warp's 16 queries)
+    float cm0 = -1e30f, cm1 = -1e30f;
+#pragma unroll
+    for (int n = 0; n < ATT_CHUNK / 8; ++n) {
+      cm0 = fmaxf(cm0, fmaxf(s[n][0], s[n][1]));
+      cm1 = fmaxf(cm1, fmaxf(s[n][2], s[n][3]));
+    }
+    cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+    cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+    const float nm0 = fmaxf(mx0, cm0), nm1 = fmaxf(mx1, cm1);
+    const float corr0 = exp2f((mx0 - nm0) * LOG2E), corr1 = exp2f((mx1 - nm1) * LOG2E);
+    mx0 = nm0; mx1 = nm1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < ATT_CHUNK / 8; ++n) {
+      s[n][0] = exp2f((s[n][0] - nm0) * LOG2E); s[n][1] = exp2f((s[n][1] - nm0) * LOG2E);
+      s[n][2] = exp2f((s[n][2] - nm1) * LOG2E); s[n][3] = exp2f((s[n][3] - nm1) * LOG2E);
+      ps0 += s[n][0] + s[n][1];
+      ps1 += s[n][2] + s[n][3];
+    }
+    sum0 = sum0 * corr0 + ps0;
+    sum1 = sum1 * corr1 + ps1;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      o[n][0] *= corr0; o[n][1] *= corr0;
+      o[n][2] *= corr1; o[n][3] *= corr1;
+    }
+    // O += P V : 16 keys per k-step; the S accumulator fragments of two adjacent key tiles form the A fragment
+#pragma unroll
+    for (int kk = 0; kk < ATT_CHUNK / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_h2(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_h2(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      const int key = k0 + kk * 16 + (lane & 15);
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {          // two 8-wide dim tiles per ldmatrix.x4
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, smem_u32(vs + key * ATT_VSTRIDE + n2 * 16 + (lane >> 4) * 8));
+        hmma_16816(o[2 * n2], pa, vb[0], vb[1]);
+        hmma_16816(o[2 * n2 + 1], pa, vb[2], vb[3]);
       }
     }
   }
-  float mx = -1e30f, sum = 0.f;
-  float acc[ATT_HD];
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+  __half* o0 = p.out + (static_cast<size_t>(b) * p.N + q0 + g) * p.out_pitch + h * ATT_HD + 2 * t;
+  __half* o1 = o0 + static_cast<size_t>(8) * p.out_pitch;
 #pragma unroll
-  for (int i = 0; i < ATT_HD; ++i) acc[i] = 0.f;
-  for (int j = 0; j < p.N; ++j) {
-    float s = 0.f;
-    const uint4* kp = reinterpret_cast<const uint4*>(ks + j * ATT_KD);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 raw = kp[i];
-      const __half2* hh = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(hh[t]);
-        s = fmaf(q[i * 8 + 2 * t], f.x, s);
-        s = fmaf(q[i * 8 + 2 * t + 1], f.y, s);
-      }
-    }
-    const float nm = fmaxf(mx, s);
-    const float corr = __expf(mx - nm);
-    const float pj = __expf(s - nm);
-    sum = sum * corr + pj;
-    mx = nm;
-    const uint4* vp = reinterpret_cast<const uint4*>(vs + j * ATT_HD);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 raw = vp[i];
-      const __half2* hh = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 f = __half22float2(hh[t]);
-        acc[i * 8 + 2 * t] = fmaf(pj, f.x, acc[i * 8 + 2 * t] * corr);
-        acc[i * 8 + 2 * t + 1] = fmaf(pj, f.y, acc[i * 8 + 2 * t + 1] * corr);
-      }
-    }
-  }
-  const float inv = 1.0f / sum;
-  __half* op = p.out + (static_cast<size_t>(b) * p.N + qi) * p.out_pitch + h * ATT_HD;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    uint4 o;
-    __half2* qo = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) qo[t] = __floats2half2_rn(acc[i * 8 + 2 * t] * inv, acc[i * 8 + 2 * t + 1] * inv);
-    reinterpret_cast<uint4*>(op)[i] = o;
+  for (int n = 0; n < 8; ++n) {
+    *reinterpret_cast<uint32_t*>(o0 + n * 8) = pack_h2(o[n][0] * inv0, o[n][1] * inv0);
+    *reinterpret_cast<uint32_t*>(o1 + n * 8) = pack_h2(o[n][2] * inv1, o[n][3] * inv1);
   }
 }
 

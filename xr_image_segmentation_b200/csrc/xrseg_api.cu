@@ -33,6 +33,7 @@ struct DevLayer {
   // OP_CONV (direct) / OP_DW / OP_STEM
   __half* w16 = nullptr;
   float* w32 = nullptr;
+  float* w32_u8 = nullptr;         // stem weights / 255 for the fused uint8 path
 };
 
 template <typename T>
@@ -85,6 +86,9 @@ struct xrseg_runner {
   int launches = 0;
   float timings[5] = {};
   bool timed = false;
+  // fused preprocess + stem: set by do_schedule when the frames are 640x640 (no resample), consumed by OP_STEM
+  const uint8_t* fused_src = nullptr;
+  int fused_stride = 0, fused_bpp = 0;
 
   ~xrseg_runner();
 };
@@ -114,6 +118,8 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       }
       d.w32 = dev_upload(ws);
       d.bias = dev_upload(bs);
+      for (float& v : ws) v = v / 255.0f;
+      d.w32_u8 = dev_upload(ws);
     } else if (o.kind == OP_DW) {
       const int c = o.y.Cp;
       std::vector<float> ws(9 * c, 0.f), bs(c, 0.f);
@@ -192,7 +198,20 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.name = l.name;
         L.flops = 2.0 * px_out * l.cout * 27;
         L.bytes = px_in * 8 + px_out * l.cout * 2;
-        L.fn = [p, total, smem](cudaStream_t st) { stem_conv_kernel<<<grid_for(total), 256, smem, st>>>(p); };
+        StemU8Params q{};
+        q.out = ptr_of(r, o.y); q.out_pitch = o.y.pitch; q.w = r->dl[o.layer].w32_u8; q.bias = r->dl[o.layer].bias;
+        q.B = nb; q.H = o.x.H; q.W = o.x.W; q.Cout = o.y.Cp;
+        const size_t smem_u8 = smem + 33 * 33 * 4;
+        // b0_off: frame offset of this chunk inside the scheduled batch (fused path reads the caller's frames directly)
+        L.fn = [r, p, q, total, smem, smem_u8, nb](cudaStream_t st) {
+          if (r->fused_src) {
+            StemU8Params u = q;
+            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
+            stem_u8_kernel<<<dim3(ceil_div(u.W / 2, 16), ceil_div(u.H / 2, 16), nb), 256, smem_u8, st>>>(u);
+          } else {
+            stem_conv_kernel<<<grid_for(total), 256, smem, st>>>(p);
+          }
+        };
         break;
       }
       case OP_CONV: {
@@ -266,12 +285,14 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
       case OP_ATTN: {
         AttnParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, nb, o.x.H * o.x.W, o.heads,
                      1.0f / sqrtf(static_cast<float>(ATT_KD))};
-        const size_t smem = static_cast<size_t>(p.N) * (ATT_KD + ATT_HD) * sizeof(__half);
-        dim3 g(nb * o.heads, ceil_div(p.N, ATT_THREADS));
+        const size_t smem = static_cast<size_t>(p.N) * (ATT_KSTRIDE + ATT_VSTRIDE) * sizeof(__half);
+        XR_CHECK(p.N % 16 == 0 && p.N % ATT_CHUNK == 0 && p.N / 16 <= 26, "attention kernel needs N %% 80 == 0 and N <= 416 (N = %d)", p.N);
+        const int threads = 13 * 32;
+        dim3 g(nb * o.heads, ceil_div(p.N / 16, 13));
         L.name = "c2psa.attention";
         L.flops = 2.0 * nb * o.heads * static_cast<double>(p.N) * p.N * (ATT_KD + ATT_HD);
         L.bytes = px_in * (o.x.C + o.y.C) * 2;
-        L.fn = [p, g, smem](cudaStream_t st) { attention_kernel<<<g, ATT_THREADS, smem, st>>>(p); };
+        L.fn = [p, g, smem, threads](cudaStream_t st) { attention_kernel<<<g, threads, smem, st>>>(p); };
         break;
       }
       case OP_VGATHER: {
@@ -481,12 +502,15 @@ void build_chunk_launches(xrseg_runner* r, int b0, int nb, std::vector<Launch>& 
   out.push_back(std::move(L));
 }
 
-int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st) {
+// part: 0 = everything, 1 = only the first launch (the stem, whose source pointer may change per call),
+//       2 = everything after the first launch (what the CUDA graph captures)
+int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st, int part = 0) {
   std::vector<Launch> ls;
   build_chunk_launches(r, b0, nb, ls);
-  for (Launch& l : ls) l.fn(st);
+  const size_t lo = part == 2 ? 1 : 0, hi = part == 1 ? 1 : ls.size();
+  for (size_t i = lo; i < hi; ++i) ls[i].fn(st);
   XR_CUDA(cudaGetLastError());
-  return static_cast<int>(ls.size());
+  return static_cast<int>(hi - lo);
 }
 
 void reset_counters(xrseg_runner* r, int batch, cudaStream_t st) {
@@ -521,16 +545,22 @@ int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, 
     if (r->timed) XR_CUDA(cudaEventRecord(r->ev[0], st));
     reset_counters(r, batch, st);
     const bool single_chunk = batch <= r->mb;
+    const bool fused = (w == 640 && h == 640);     // no resample needed: the stem reads the uint8 frames directly
+    r->fused_stride = stride_bytes;
+    r->fused_bpp = fmt == XRSEG_FMT_RGBA8 ? 4 : 3;
     if (r->cfg.use_cuda_graph && single_chunk) {
-      // graph = network + post for one chunk of `batch` frames; preprocessing stays outside (source pointer varies)
-      preprocess(r, d_src, w, h, stride_bytes, fmt, batch, st);
+      // graph = everything after the stem for one chunk of `batch` frames; preprocessing and the stem stay outside
+      // because their source pointer varies from call to call
+      r->fused_src = fused ? d_src : nullptr;
+      if (!fused) preprocess(r, d_src, w, h, stride_bytes, fmt, batch, st);
+      pipeline_chunk(r, 0, batch, st, 1);
       if (!r->graph || r->graph_batch != batch) {
         if (r->graph) { cudaGraphExecDestroy(r->graph); r->graph = nullptr; }
         cudaGraph_t g = nullptr;
         XR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         int launches = 0;
         try {
-          launches = pipeline_chunk(r, 0, batch, st);
+          launches = pipeline_chunk(r, 0, batch, st, 2);
         } catch (...) {
           cudaStreamEndCapture(st, &g);
           if (g) cudaGraphDestroy(g);
@@ -540,16 +570,18 @@ int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, 
         XR_CUDA(cudaGraphInstantiate(&r->graph, g, 0));
         XR_CUDA(cudaGraphDestroy(g));
         r->graph_batch = batch;
-        r->launches = launches + 1;
+        r->launches = launches + 1 + (fused ? 0 : 1);
       }
       XR_CUDA(cudaGraphLaunch(r->graph, st));
     } else {
       int launches = 0;
       for (int b0 = 0; b0 < batch; b0 += r->mb) {
         const int nb = std::min(r->mb, batch - b0);
-        preprocess(r, d_src + static_cast<size_t>(b0) * frame_bytes, w, h, stride_bytes, fmt, nb, st);
+        const uint8_t* chunk_src = d_src + static_cast<size_t>(b0) * frame_bytes;
+        r->fused_src = fused ? chunk_src : nullptr;
+        if (!fused) preprocess(r, chunk_src, w, h, stride_bytes, fmt, nb, st);
         if (r->timed && b0 == 0) XR_CUDA(cudaEventRecord(r->ev[1], st));
-        launches += 1 + pipeline_chunk(r, b0, nb, st);
+        launches += (fused ? 0 : 1) + pipeline_chunk(r, b0, nb, st);
       }
       r->launches = launches;
     }
@@ -607,7 +639,7 @@ xrseg_runner::~xrseg_runner() {
   if (stream) cudaStreamSynchronize(stream);
   if (graph) cudaGraphExecDestroy(graph);
   for (DevLayer& d : dl) {
-    cudaFree(d.wpack); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32);
+    cudaFree(d.wpack); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
   void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx,
                   d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,

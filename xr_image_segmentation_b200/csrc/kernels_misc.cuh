@@ -213,6 +213,9 @@ struct DwParams {
 };
 
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
+  extern __shared__ float dw_s[];   // [9][C] weights + [C] bias
+  for (int i = threadIdx.x; i < 10 * p.C; i += 256) dw_s[i] = i < 9 * p.C ? p.w[i] : p.bias[i - 9 * p.C];
+  __syncthreads();
   const int cg = p.C / 8;
   const long total = static_cast<long>(p.B) * p.H * p.W * cg;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
@@ -223,8 +226,12 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
     const int y = static_cast<int>((pix / p.W) % p.H);
     const long b = pix / (static_cast<long>(p.W) * p.H);
     float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = p.bias[g * 8 + i];
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(dw_s + 9 * p.C + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(dw_s + 9 * p.C + g * 8 + 4);
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int iy = y - 1 + kh;
@@ -236,8 +243,8 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
         const uint4 raw =
             *reinterpret_cast<const uint4*>(p.in + ((b * p.H + iy) * p.W + ix) * p.in_pitch + g * 8);
         const __half2* h = reinterpret_cast<const __half2*>(&raw);
-        const float4 w0 = *reinterpret_cast<const float4*>(p.w + (kh * 3 + kw) * p.C + g * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(p.w + (kh * 3 + kw) * p.C + g * 8 + 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(dw_s + (kh * 3 + kw) * p.C + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(dw_s + (kh * 3 + kw) * p.C + g * 8 + 4);
         const float2 a = __half22float2(h[0]), bb = __half22float2(h[1]), c = __half22float2(h[2]),
                      d = __half22float2(h[3]);
         acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.y, w0.y, acc[1]);
@@ -246,25 +253,27 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
         acc[6] = fmaf(d.x, w1.z, acc[6]); acc[7] = fmaf(d.y, w1.w, acc[7]);
       }
     }
+    uint32_t o[4];
     if (p.act) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = silu_f(acc[i]);
+      for (int i = 0; i < 4; ++i) o[i] = silu_pack_h2(acc[2 * i], acc[2 * i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __half2 hh = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
+        o[i] = *reinterpret_cast<uint32_t*>(&hh);
+      }
     }
     if (p.res) {
       const uint4 raw = *reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + g * 8);
-      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+      const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        acc[2 * i] += f.x;
-        acc[2 * i + 1] += f.y;
+        __half2 sum = __hadd2(*reinterpret_cast<__half2*>(&o[i]), *reinterpret_cast<const __half2*>(&rr[i]));
+        o[i] = *reinterpret_cast<uint32_t*>(&sum);
       }
     }
-    uint4 o;
-    __half2* q = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p.out + pix * p.out_pitch + g * 8) = o;
+    *reinterpret_cast<uint4*>(p.out + pix * p.out_pitch + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -279,47 +288,43 @@ struct SppfParams {
 };
 
 __global__ void __launch_bounds__(256) sppf_pool_kernel(const SppfParams p) {
-  extern __shared__ __half2 sp[];  // [H*W][4] half2 = 8 channels
+  extern __shared__ uint4 sp4[];    // two ping-pong maps of [H*W] x 8 channels
   const int cg = p.C / 8;
   const int g = blockIdx.x % cg;
   const int b = blockIdx.x / cg;
   const int n = p.H * p.W;
+  uint4* cur = sp4;
+  uint4* tmp = sp4 + n;
   __half* base = p.buf + static_cast<size_t>(b) * n * p.pitch + g * 8;
-  uint4* s4 = reinterpret_cast<uint4*>(sp);
   for (int i = threadIdx.x; i < n; i += blockDim.x)
-    s4[i] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i) * p.pitch);
+    cur[i] = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(i) * p.pitch);
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int y = i / p.W, x = i - y * p.W;
-    __half2 m[3][4];
+  auto max4 = [](uint4 a, const uint4 c) {
+    __half2* x = reinterpret_cast<__half2*>(&a);
+    const __half2* y = reinterpret_cast<const __half2*>(&c);
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) m[r][c] = __float2half2_rn(-65504.0f);
-    for (int dy = -6; dy <= 6; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= p.H) continue;
-      for (int dx = -6; dx <= 6; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= p.W) continue;
-        const int rad = max(abs(dx), abs(dy));
-        const __half2* v = sp + (yy * p.W + xx) * 4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          m[2][c] = __hmax2(m[2][c], v[c]);
-          if (rad <= 4) m[1][c] = __hmax2(m[1][c], v[c]);
-          if (rad <= 2) m[0][c] = __hmax2(m[0][c], v[c]);
-        }
-      }
+    for (int k = 0; k < 4; ++k) x[k] = __hmax2(x[k], y[k]);
+    return a;
+  };
+  // three chained 5x5 stride-1 pools (pad 2 = window clipped at the border), each done separably: rows, then columns
+  for (int r = 0; r < 3; ++r) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int y = i / p.W, x = i - y * p.W;
+      uint4 m = cur[i];
+      for (int dx = -2; dx <= 2; ++dx)
+        if (dx != 0 && x + dx >= 0 && x + dx < p.W) m = max4(m, cur[i + dx]);
+      tmp[i] = m;
     }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      uint4 o;
-      __half2* q = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) q[c] = m[r][c];
-      *reinterpret_cast<uint4*>(base + static_cast<size_t>(i) * p.pitch + (r + 1) * p.C) = o;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int y = i / p.W;
+      uint4 m = tmp[i];
+      for (int dy = -2; dy <= 2; ++dy)
+        if (dy != 0 && y + dy >= 0 && y + dy < p.H) m = max4(m, tmp[i + dy * p.W]);
+      cur[i] = m;   // safe: the column pass only reads tmp
+      *reinterpret_cast<uint4*>(base + static_cast<size_t>(i) * p.pitch + (r + 1) * p.C) = m;
     }
+    __syncthreads();
   }
 }
 

@@ -46,6 +46,28 @@ struct DecodeParams {
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
 
+// 16 consecutive values (64-byte aligned fp32 / 32-byte aligned fp16) with 128-bit loads
+__device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 f = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = f.x; v[4 * i + 1] = f.y; v[4 * i + 2] = f.z; v[4 * i + 3] = f.w;
+  }
+}
+__device__ __forceinline__ void load16(const __half* p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint4 raw = reinterpret_cast<const uint4*>(p)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      v[8 * i + 2 * j] = f.x;
+      v[8 * i + 2 * j + 1] = f.y;
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams<T> p) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -65,12 +87,10 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams<T> p) {
 #pragma unroll
   for (int side = 0; side < 4; ++side) {
     float l[16];
+    load16(bl + side * 16, l);
     float mx = -3.0e38f;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      l[k] = ldf(bl + side * 16 + k);
-      mx = fmaxf(mx, l[k]);
-    }
+    for (int k = 0; k < 16; ++k) mx = fmaxf(mx, l[k]);
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -90,15 +110,22 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams<T> p) {
   const float bw = __fmul_rn(__fsub_rn(x2, x1), s.stride);
   const float bh = __fmul_rn(__fsub_rn(y2, y1), s.stride);
 
-  // ---- class sigmoid + max / first argmax (chains 416, 464, 471)
+  // ---- class sigmoid + max / first argmax (chains 416, 464, 471): like the graph, the maximum is taken over the
+  // fp32 PROBABILITIES (two different logits can round to the same probability; the first index then wins).
   const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(al) * s.cls_pitch;
   float best = -1.f;
   int besti = 0;
-  for (int c = 0; c < NC; ++c) {
-    const float pr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-ldf(cl + c))));
-    if (pr > best) {
-      best = pr;
-      besti = c;
+#pragma unroll
+  for (int c0 = 0; c0 < NC; c0 += 16) {
+    float l[16];
+    load16(cl + c0, l);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float pr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-l[k])));
+      if (pr > best) {
+        best = pr;
+        besti = c0 + k;
+      }
     }
   }
   const long o = static_cast<long>(b) * p.A + a;

@@ -81,9 +81,15 @@ struct xrseg_runner {
   int batch = 0;                   // batch of the scheduled / finished run
   int state = 0;                   // 0 idle, 1 scheduled, 2 done
   int words = 0, max_cand = 0, max_det = 0;
-  cudaGraphExec_t graph = nullptr;
-  int graph_batch = 0;
-  int launches = 0;
+  struct ChunkGraph { int b0, nb; cudaGraphExec_t exec; };
+  std::vector<ChunkGraph> graphs;     // one captured pipeline per (first frame, frame count) chunk
+  cudaStream_t copy_stream = nullptr; // host->device frame copies, overlapped chunk by chunk with compute
+  std::vector<cudaEvent_t> ev_copy;
+  struct ChunkLaunches { int b0, nb; void* list; };   // list: std::vector<Launch>* (type local to this file)
+  std::vector<ChunkLaunches> launch_cache;
+  void* scratch = nullptr;            // grow-only device scratch for xrseg_decode / xrseg_masks results
+  size_t scratch_cap = 0;
+  int launches = 0, chunk_launches = 0;
   float timings[5] = {};
   bool timed = false;
   // fused preprocess + stem: set by do_schedule when the frames are 640x640 (no resample), consumed by OP_STEM
@@ -263,12 +269,13 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.name = l.name;
         L.flops = 2.0 * px_out * l.cout * 9;
         L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1)) * 2;
-        L.fn = [p, total](cudaStream_t st) { dwconv3x3_kernel<<<grid_for(total), 256, 0, st>>>(p); };
+        const size_t smem = static_cast<size_t>(10) * p.C * sizeof(float);
+        L.fn = [p, total, smem](cudaStream_t st) { dwconv3x3_kernel<<<grid_for(total), 256, smem, st>>>(p); };
         break;
       }
       case OP_SPPF: {
         SppfParams p{ptr_of(r, o.x), nb, o.x.H, o.x.W, o.x.Cp / 4, o.x.pitch};
-        const size_t smem = static_cast<size_t>(o.x.H) * o.x.W * 16;
+        const size_t smem = static_cast<size_t>(o.x.H) * o.x.W * 32;
         L.name = "sppf.pool";
         L.bytes = px_in * p.C * 4 * 2;
         L.fn = [p, nb, smem](cudaStream_t st) { sppf_pool_kernel<<<nb * (p.C / 8), 256, smem, st>>>(p); };
@@ -505,12 +512,35 @@ void build_chunk_launches(xrseg_runner* r, int b0, int nb, std::vector<Launch>& 
 // part: 0 = everything, 1 = only the first launch (the stem, whose source pointer may change per call),
 //       2 = everything after the first launch (what the CUDA graph captures)
 int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st, int part = 0) {
-  std::vector<Launch> ls;
-  build_chunk_launches(r, b0, nb, ls);
-  const size_t lo = part == 2 ? 1 : 0, hi = part == 1 ? 1 : ls.size();
-  for (size_t i = lo; i < hi; ++i) ls[i].fn(st);
+  std::vector<Launch>* ls = nullptr;
+  for (auto& c : r->launch_cache)
+    if (c.b0 == b0 && c.nb == nb) ls = static_cast<std::vector<Launch>*>(c.list);
+  if (!ls) {
+    ls = new std::vector<Launch>();
+    build_chunk_launches(r, b0, nb, *ls);
+    r->launch_cache.push_back({b0, nb, ls});
+  }
+  const size_t lo = part == 2 ? 1 : 0, hi = part == 1 ? 1 : ls->size();
+  for (size_t i = lo; i < hi; ++i) (*ls)[i].fn(st);
   XR_CUDA(cudaGetLastError());
   return static_cast<int>(hi - lo);
+}
+
+}  // namespace
+void free_launch_cache(xrseg_runner* r) {
+  for (auto& c : r->launch_cache) delete static_cast<std::vector<Launch>*>(c.list);
+  r->launch_cache.clear();
+}
+namespace {
+
+void* ensure_scratch(xrseg_runner* r, size_t bytes) {
+  if (bytes > r->scratch_cap) {
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+    if (r->scratch) XR_CUDA(cudaFree(r->scratch));
+    r->scratch_cap = bytes + bytes / 2 + 4096;
+    XR_CUDA(cudaMalloc(&r->scratch, r->scratch_cap));
+  }
+  return r->scratch;
 }
 
 void reset_counters(xrseg_runner* r, int batch, cudaStream_t st) {
@@ -531,60 +561,74 @@ int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, 
     cudaStream_t st = r->stream;
     const size_t frame_bytes = static_cast<size_t>(h) * stride_bytes;
     const uint8_t* d_src = src;
+    const int n_chunks = ceil_div(batch, r->mb);
     if (!src_on_device) {
       if (frame_bytes * batch > r->d_frames_cap) {
+        XR_CUDA(cudaStreamSynchronize(st));
         if (r->d_frames) XR_CUDA(cudaFree(r->d_frames));
         r->d_frames_cap = frame_bytes * r->cfg.max_batch;
         XR_CUDA(cudaMalloc(&r->d_frames, r->d_frames_cap));
       }
-      XR_CUDA(cudaMemcpyAsync(r->d_frames, src, frame_bytes * batch, cudaMemcpyHostToDevice, st));
+      while (static_cast<int>(r->ev_copy.size()) < n_chunks + 1) {
+        cudaEvent_t e;
+        XR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        r->ev_copy.push_back(e);
+      }
+      // the staging buffer may still be read by the previous run: order the copies after everything enqueued so far
+      XR_CUDA(cudaEventRecord(r->ev_copy[n_chunks], st));
+      XR_CUDA(cudaStreamWaitEvent(r->copy_stream, r->ev_copy[n_chunks], 0));
+      for (int k = 0; k < n_chunks; ++k) {
+        const int b0 = k * r->mb, nb = std::min(r->mb, batch - b0);
+        XR_CUDA(cudaMemcpyAsync(r->d_frames + b0 * frame_bytes, src + b0 * frame_bytes, frame_bytes * nb,
+                                cudaMemcpyHostToDevice, r->copy_stream));
+        XR_CUDA(cudaEventRecord(r->ev_copy[k], r->copy_stream));
+      }
       d_src = r->d_frames;
     }
     r->batch = batch;
     r->timed = !r->cfg.use_cuda_graph;
     if (r->timed) XR_CUDA(cudaEventRecord(r->ev[0], st));
     reset_counters(r, batch, st);
-    const bool single_chunk = batch <= r->mb;
     const bool fused = (w == 640 && h == 640);     // no resample needed: the stem reads the uint8 frames directly
     r->fused_stride = stride_bytes;
     r->fused_bpp = fmt == XRSEG_FMT_RGBA8 ? 4 : 3;
-    if (r->cfg.use_cuda_graph && single_chunk) {
-      // graph = everything after the stem for one chunk of `batch` frames; preprocessing and the stem stay outside
-      // because their source pointer varies from call to call
-      r->fused_src = fused ? d_src : nullptr;
-      if (!fused) preprocess(r, d_src, w, h, stride_bytes, fmt, batch, st);
-      pipeline_chunk(r, 0, batch, st, 1);
-      if (!r->graph || r->graph_batch != batch) {
-        if (r->graph) { cudaGraphExecDestroy(r->graph); r->graph = nullptr; }
-        cudaGraph_t g = nullptr;
-        XR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        int launches = 0;
-        try {
-          launches = pipeline_chunk(r, 0, batch, st, 2);
-        } catch (...) {
-          cudaStreamEndCapture(st, &g);
-          if (g) cudaGraphDestroy(g);
-          throw;
+    int launches = 0;
+    for (int k = 0; k < n_chunks; ++k) {
+      const int b0 = k * r->mb, nb = std::min(r->mb, batch - b0);
+      const uint8_t* chunk_src = d_src + static_cast<size_t>(b0) * frame_bytes;
+      if (!src_on_device) XR_CUDA(cudaStreamWaitEvent(st, r->ev_copy[k], 0));   // chunk k+1 copies while chunk k computes
+      r->fused_src = fused ? chunk_src : nullptr;
+      if (!fused) preprocess(r, chunk_src, w, h, stride_bytes, fmt, nb, st);
+      if (r->timed && k == 0) XR_CUDA(cudaEventRecord(r->ev[1], st));
+      launches += fused ? 0 : 1;
+      if (r->cfg.use_cuda_graph) {
+        // the stem stays outside the graph (its source pointer varies from call to call); the rest is replayed
+        launches += pipeline_chunk(r, b0, nb, st, 1);
+        cudaGraphExec_t exec = nullptr;
+        for (auto& g : r->graphs)
+          if (g.b0 == b0 && g.nb == nb) exec = g.exec;
+        if (!exec) {
+          cudaGraph_t g = nullptr;
+          XR_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+          try {
+            r->chunk_launches = pipeline_chunk(r, b0, nb, st, 2);
+          } catch (...) {
+            cudaStreamEndCapture(st, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+          }
+          XR_CUDA(cudaStreamEndCapture(st, &g));
+          XR_CUDA(cudaGraphInstantiate(&exec, g, 0));
+          XR_CUDA(cudaGraphDestroy(g));
+          r->graphs.push_back({b0, nb, exec});
         }
-        XR_CUDA(cudaStreamEndCapture(st, &g));
-        XR_CUDA(cudaGraphInstantiate(&r->graph, g, 0));
-        XR_CUDA(cudaGraphDestroy(g));
-        r->graph_batch = batch;
-        r->launches = launches + 1 + (fused ? 0 : 1);
+        XR_CUDA(cudaGraphLaunch(exec, st));
+        launches += r->chunk_launches;
+      } else {
+        launches += pipeline_chunk(r, b0, nb, st);
       }
-      XR_CUDA(cudaGraphLaunch(r->graph, st));
-    } else {
-      int launches = 0;
-      for (int b0 = 0; b0 < batch; b0 += r->mb) {
-        const int nb = std::min(r->mb, batch - b0);
-        const uint8_t* chunk_src = d_src + static_cast<size_t>(b0) * frame_bytes;
-        r->fused_src = fused ? chunk_src : nullptr;
-        if (!fused) preprocess(r, chunk_src, w, h, stride_bytes, fmt, nb, st);
-        if (r->timed && b0 == 0) XR_CUDA(cudaEventRecord(r->ev[1], st));
-        launches += (fused ? 0 : 1) + pipeline_chunk(r, b0, nb, st);
-      }
-      r->launches = launches;
     }
+    r->launches = launches;
     if (r->timed) XR_CUDA(cudaEventRecord(r->ev[2], st));
     XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
@@ -634,10 +678,16 @@ const void* out_ptr(xrseg_runner* r, int idx) {
 
 }  // namespace
 
+void free_launch_cache(xrseg_runner* r);
+
 xrseg_runner::~xrseg_runner() {
   cudaSetDevice(device);
   if (stream) cudaStreamSynchronize(stream);
-  if (graph) cudaGraphExecDestroy(graph);
+  for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
+  free_launch_cache(this);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
+  for (cudaEvent_t e : ev_copy) cudaEventDestroy(e);
+  cudaFree(scratch);
   for (DevLayer& d : dl) {
     cudaFree(d.wpack); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
@@ -751,6 +801,7 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     r->num_sms = prop.multiProcessorCount;
     XR_CUDA(cudaSetDevice(c.device));
     XR_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+    XR_CUDA(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
     XR_CUDA(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
     for (auto& e : r->ev) XR_CUDA(cudaEventCreate(&e));
     conv_umma_prepare_device();
@@ -915,14 +966,12 @@ int xrseg_decode(xrseg_runner* r, float screen_w, float screen_h, int convention
   if (cap < total) { r->err = "box buffer too small"; return XRSEG_ERR_CAPACITY; }
   try {
     XR_CUDA(cudaSetDevice(r->device));
-    BoxOut* d_out = dev_alloc<BoxOut>(total);
-    int* d_n = dev_alloc<int>(1);
+    BoxOut* d_out = static_cast<BoxOut*>(ensure_scratch(r, sizeof(BoxOut) * total + 16));
+    int* d_n = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(d_out) + sizeof(BoxOut) * total);
     boxes_to_screen_kernel<<<1, 32, 0, r->stream>>>(r->o_boxes, r->o_labels, r->d_keep_n, r->d_offsets, r->batch,
                                                     convention, screen_w, screen_h, per_frame_cap, d_out, d_n);
     XR_CUDA(cudaMemcpyAsync(out, d_out, sizeof(BoxOut) * total, cudaMemcpyDeviceToHost, r->stream));
     XR_CUDA(cudaStreamSynchronize(r->stream));
-    cudaFree(d_out);
-    cudaFree(d_n);
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;
@@ -950,13 +999,12 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
   if (cap_bytes < per * count) { r->err = "mask buffer too small"; return XRSEG_ERR_CAPACITY; }
   try {
     XR_CUDA(cudaSetDevice(r->device));
-    uint8_t* d_out = dev_alloc<uint8_t>(per * count);
+    uint8_t* d_out = static_cast<uint8_t*>(ensure_scratch(r, per * count));
     if (mp->mode == XRSEG_MASK_UPSAMPLE_640) {
       const TV& pr = r->net->protos;
       Mask640Params p{ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch, pr.pitch, r->o_coefs, r->o_boxes,
                       r->o_frame, first, d_out};
       if (r->batch > r->mb) {
-        cudaFree(d_out);
         r->err = "640-px masks need the prototypes of every frame resident: use micro_batch >= batch";
         return XRSEG_ERR_STATE;
       }
@@ -975,7 +1023,6 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
     XR_CUDA(cudaGetLastError());
     XR_CUDA(cudaMemcpyAsync(out, d_out, per * count, cudaMemcpyDeviceToHost, r->stream));
     XR_CUDA(cudaStreamSynchronize(r->stream));
-    cudaFree(d_out);
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;

@@ -73,7 +73,7 @@ def step_conv(impl, variant):
 
 
 def load_golden():
-    g = os.path.join(HERE, "golden")
+    g = os.path.join(HERE, "..", "tests", "golden")
     model = I.ModelLoader.Load(os.path.join(g, "yolo11n_seg.xrsw"))
     inputs = np.load(os.path.join(g, "inputs.npz"))
     exp = np.load(os.path.join(g, "expected.npz"))

@@ -201,8 +201,13 @@ __global__ void __launch_bounds__(256) stem_u8_kernel(const StemU8Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3 stride-1 pad-1 conv (+bias, optional SiLU, optional residual add), 8 channels per thread.
-// weights fp32 [9][C], bias fp32 [C].
+// depthwise 3x3 stride-1 pad-1 conv (+bias, optional SiLU, optional residual add).  weights fp32 [9][C], bias [C].
+// A thread owns one (x, 8-channel group) column and walks DOWN a strip of rows with a 3x3 register window: per
+// output it issues three coalesced 16-byte loads (x-1, x, x+1 of the incoming row; the side columns are L1 hits of
+// the neighbouring threads' centre loads) instead of nine, and its 72 weights live in registers.  32-bit index math,
+// one block = 128 consecutive (x, group) columns of one image strip.
+// Channel remap: input channel of output channel c is (c / in_grp) * in_grp_stride + in_grp_off + c % in_grp when
+// in_grp > 0 -- lets the C2PSA positional-encoding conv read V straight out of the interleaved qkv tensor.
 // ------------------------------------------------------------------------------------------------
 struct DwParams {
   const __half* in; int in_pitch;
@@ -210,49 +215,71 @@ struct DwParams {
   const __half* res; int res_pitch;   // optional, added after activation
   const float* w; const float* bias;
   int B, H, W, C, act;
+  int rows;                           // rows per strip (grid.y = ceil(H / rows))
+  int in_grp, in_grp_stride, in_grp_off;
 };
 
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
-  extern __shared__ float dw_s[];   // [9][C] weights + [C] bias
-  for (int i = threadIdx.x; i < 10 * p.C; i += 256) dw_s[i] = i < 9 * p.C ? p.w[i] : p.bias[i - 9 * p.C];
-  __syncthreads();
-  const int cg = p.C / 8;
-  const long total = static_cast<long>(p.B) * p.H * p.W * cg;
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % cg);
-    const long pix = idx / cg;
-    const int x = static_cast<int>(pix % p.W);
-    const int y = static_cast<int>((pix / p.W) % p.H);
-    const long b = pix / (static_cast<long>(p.W) * p.H);
+__device__ __forceinline__ void dw_fma8(float (&acc)[8], const uint4 v, const float (&w)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    acc[2 * i] = fmaf(f.x, w[2 * i], acc[2 * i]);
+    acc[2 * i + 1] = fmaf(f.y, w[2 * i + 1], acc[2 * i + 1]);
+  }
+}
+
+__global__ void __launch_bounds__(128, 4) dwconv3x3_kernel(const DwParams p) {
+  const int cgs = p.C >> 3;
+  const int col = blockIdx.x * 128 + threadIdx.x;       // (x, group) column, group fastest
+  if (col >= p.W * cgs) return;
+  const int x = col / cgs, g = col - x * cgs;
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * p.rows;
+  const int y1 = min(y0 + p.rows, p.H);
+  const int c = g * 8;
+  const int cin = p.in_grp > 0 ? (c / p.in_grp) * p.in_grp_stride + p.in_grp_off + c % p.in_grp : c;
+  float w[9][8], bias[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = *reinterpret_cast<const float4*>(p.w + t * p.C + c);
+    const float4 w1 = *reinterpret_cast<const float4*>(p.w + t * p.C + c + 4);
+    w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w;
+    w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+  }
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+    bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+  }
+  const bool has_l = x > 0, has_r = x + 1 < p.W;
+  const size_t row_elems = static_cast<size_t>(p.W) * p.in_pitch;
+  const __half* src = p.in + static_cast<size_t>(b) * p.H * row_elems + static_cast<size_t>(x) * p.in_pitch + cin;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  auto load_row = [&](int y, uint4 (&r)[3]) {
+    if (y < 0 || y >= p.H) {
+      r[0] = r[1] = r[2] = zero;
+      return;
+    }
+    const __half* q = src + static_cast<size_t>(y) * row_elems;
+    r[1] = *reinterpret_cast<const uint4*>(q);
+    r[0] = has_l ? *reinterpret_cast<const uint4*>(q - p.in_pitch) : zero;
+    r[2] = has_r ? *reinterpret_cast<const uint4*>(q + p.in_pitch) : zero;
+  };
+  uint4 win[3][3];
+  load_row(y0 - 1, win[0]);
+  load_row(y0, win[1]);
+  size_t opix = (static_cast<size_t>(b) * p.H + y0) * p.W + x;
+  for (int y = y0; y < y1; ++y, opix += p.W) {
+    load_row(y + 1, win[2]);
     float acc[8];
-    {
-      const float4 b0 = *reinterpret_cast<const float4*>(dw_s + 9 * p.C + g * 8);
-      const float4 b1 = *reinterpret_cast<const float4*>(dw_s + 9 * p.C + g * 8 + 4);
-      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
-      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    }
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int iy = y - 1 + kh;
-      if (iy < 0 || iy >= p.H) continue;
+    for (int i = 0; i < 8; ++i) acc[i] = bias[i];
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int ix = x - 1 + kw;
-        if (ix < 0 || ix >= p.W) continue;
-        const uint4 raw =
-            *reinterpret_cast<const uint4*>(p.in + ((b * p.H + iy) * p.W + ix) * p.in_pitch + g * 8);
-        const __half2* h = reinterpret_cast<const __half2*>(&raw);
-        const float4 w0 = *reinterpret_cast<const float4*>(dw_s + (kh * 3 + kw) * p.C + g * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(dw_s + (kh * 3 + kw) * p.C + g * 8 + 4);
-        const float2 a = __half22float2(h[0]), bb = __half22float2(h[1]), c = __half22float2(h[2]),
-                     d = __half22float2(h[3]);
-        acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.y, w0.y, acc[1]);
-        acc[2] = fmaf(bb.x, w0.z, acc[2]); acc[3] = fmaf(bb.y, w0.w, acc[3]);
-        acc[4] = fmaf(c.x, w1.x, acc[4]); acc[5] = fmaf(c.y, w1.y, acc[5]);
-        acc[6] = fmaf(d.x, w1.z, acc[6]); acc[7] = fmaf(d.y, w1.w, acc[7]);
-      }
-    }
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) dw_fma8(acc, win[kh][kw], w[kh * 3 + kw]);
     uint32_t o[4];
     if (p.act) {
 #pragma unroll
@@ -265,7 +292,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
       }
     }
     if (p.res) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch + g * 8);
+      const uint4 raw = *reinterpret_cast<const uint4*>(p.res + opix * p.res_pitch + c);
       const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -273,7 +300,12 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const DwParams p) {
         o[i] = *reinterpret_cast<uint32_t*>(&sum);
       }
     }
-    *reinterpret_cast<uint4*>(p.out + pix * p.out_pitch + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(p.out + opix * p.out_pitch + c) = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      win[0][k] = win[1][k];
+      win[1][k] = win[2][k];
+    }
   }
 }
 
@@ -510,23 +542,127 @@ __global__ void __launch_bounds__(416) attention_kernel(const AttnParams p) {
   }
 }
 
-// Copy the V part of qkv ([B,N,heads*(2kd+hd)]) into a dense [B,N,heads*hd] tensor (input of the PE depthwise conv).
-struct VGatherParams {
-  const __half* qkv; int qkv_pitch;
-  __half* out; int out_pitch;
-  long tokens; int heads;
+// ------------------------------------------------------------------------------------------------
+// Stem on the tensor cores (↔ TextureConverter.ToTensor + graph chain 002, IEExecutor.cs:370-371): 3x3 stride-2 conv
+// straight from the uint8 frame, + bias + SiLU -> fp16 NHWC.  K = 27 is too thin for a tcgen05 pipeline (one UMMA of
+// K = 16 per 2 KB of output), so this is a register-level implicit GEMM on mma.sync m16n8k16: the K axis is laid out
+// as (tap, RGBX) = 12 x 4 = 48 (taps 9..11 and channel X carry zero weights), so an A-fragment register is exactly two
+// bytes of ONE pixel word of the staged RGBX patch -- one LDS + PRMT + HSUB2 ("0x6400 | byte" is the fp16 1024 + byte).
+// Bytes stay exact integers in fp16; the 1/255 of ToTensor is applied to the fp32 accumulator.
+// Block = 8 output rows x 32 output columns (one row per warp, two 16-pixel m-tiles); NT = Cout / 8 n-tiles.
+// ------------------------------------------------------------------------------------------------
+struct StemMmaParams {
+  const uint8_t* src; int stride_bytes, bpp;   // [B,H,W,bpp] uint8, rows 4-byte aligned
+  __half* out; int out_pitch;                  // [B,H/2,W/2,Cout]
+  const __half* w16;                           // [Cout][12 taps][4] fp16, zero padded
+  const float* bias;                           // [Cout]
+  int B, H, W;
+  float in_scale;                              // 1/255
 };
-__global__ void __launch_bounds__(256) gather_v_kernel(const VGatherParams p) {
-  const int per_tok = p.heads * 8;  // 16-byte pieces of V per token
-  const long total = p.tokens * per_tok;
-  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long>(gridDim.x) * blockDim.x) {
-    const int piece = static_cast<int>(idx % per_tok);
-    const long tok = idx / per_tok;
-    const int h = piece / 8, part = piece - h * 8;
-    const uint4 v = *reinterpret_cast<const uint4*>(p.qkv + tok * p.qkv_pitch + h * (2 * ATT_KD + ATT_HD) + 2 * ATT_KD +
-                                                    part * 8);
-    *reinterpret_cast<uint4*>(p.out + tok * p.out_pitch + h * ATT_HD + part * 8) = v;
+
+constexpr int STEM_PW = 65, STEM_PH = 17, STEM_RAW_WORDS = 52;
+
+template <int NT>
+__global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
+  __shared__ uint32_t raw[STEM_PH][STEM_RAW_WORDS];
+  __shared__ uint32_t patch[STEM_PH * STEM_PW];
+  const int Ho = p.H >> 1, Wo = p.W >> 1;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * 8, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const uint8_t* img = p.src + static_cast<size_t>(b) * p.H * p.stride_bytes;
+  const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy0 - 1;
+  const int c_lo = max(ix0, 0), c_hi = min(ix0 + STEM_PW - 1, p.W - 1);
+  if (p.bpp == 4) {
+    for (int i = tid; i < STEM_PH * STEM_PW; i += 256) {
+      const int r = i / STEM_PW, c = i - r * STEM_PW;
+      const int iy = iy0 + r, ix = ix0 + c;
+      uint32_t v = 0;
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        v = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(iy) * p.stride_bytes + ix * 4) & 0x00FFFFFFu;
+      patch[i] = v;
+    }
+  } else {
+    // pass 1: aligned 4-byte words covering bytes [3 c_lo, 3 (c_hi + 1)) of each patch row
+    const int a0 = (c_lo * 3) & ~3;
+    const int nwords = ((c_hi + 1) * 3 - a0 + 3) >> 2;
+    for (int i = tid; i < STEM_PH * STEM_RAW_WORDS; i += 256) {
+      const int r = i / STEM_RAW_WORDS, j = i - r * STEM_RAW_WORDS;
+      const int iy = iy0 + r;
+      if (j < nwords && iy >= 0 && iy < p.H)
+        raw[r][j] = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(iy) * p.stride_bytes + a0 + 4 * j);
+    }
+    __syncthreads();
+    // pass 2: RGB bytes -> one RGBX word per pixel (zero outside the image = the conv's zero padding)
+    for (int i = tid; i < STEM_PH * STEM_PW; i += 256) {
+      const int r = i / STEM_PW, c = i - r * STEM_PW;
+      const int iy = iy0 + r, ix = ix0 + c;
+      uint32_t v = 0;
+      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
+        const uint8_t* q = reinterpret_cast<const uint8_t*>(raw[r]) + (ix * 3 - a0);
+        v = q[0] | (q[1] << 8) | (q[2] << 16);
+      }
+      patch[i] = v;
+    }
+  }
+  // weights + bias -> registers (constant for the whole block)
+  uint32_t wb[3][NT][2];
+  int off[3][2];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int tap = 4 * s + 2 * h + (t >> 1);
+      const int tc = min(tap, 8);
+      off[s][h] = (tc / 3) * STEM_PW + tc % 3;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        wb[s][nt][h] = *reinterpret_cast<const uint32_t*>(p.w16 + ((nt * 8 + g) * 12 + tap) * 4 + (t & 1) * 2);
+    }
+  float bs[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    bs[nt][0] = p.bias[nt * 8 + 2 * t];
+    bs[nt][1] = p.bias[nt * 8 + 2 * t + 1];
+  }
+  __syncthreads();
+  const uint32_t sel = (t & 1) ? 0x4342u : 0x4140u;
+  const int oy = oy0 + warp;
+  const uint32_t* prow = patch + 2 * warp * STEM_PW;
+  auto cvt = [&](uint32_t word) {
+    uint32_t v = __byte_perm(word, 0x64646464u, sel);
+    const uint32_t k1024 = 0x64006400u;
+    __half2 r = __hsub2(*reinterpret_cast<__half2*>(&v), *reinterpret_cast<const __half2*>(&k1024));
+    return *reinterpret_cast<uint32_t*>(&r);
+  };
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    float c[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+    const int px = mt * 16 + g;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      uint32_t a[4];
+      a[0] = cvt(prow[2 * px + off[s][0]]);
+      a[1] = cvt(prow[2 * (px + 8) + off[s][0]]);
+      a[2] = cvt(prow[2 * px + off[s][1]]);
+      a[3] = cvt(prow[2 * (px + 8) + off[s][1]]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) hmma_16816(c[nt], a, wb[s][nt][0], wb[s][nt][1]);
+    }
+    if (oy < Ho) {
+      __half* o0 = p.out + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox0 + px) * p.out_pitch + 2 * t;
+      __half* o1 = o0 + static_cast<size_t>(8) * p.out_pitch;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (ox0 + px < Wo)
+          *reinterpret_cast<uint32_t*>(o0 + nt * 8) =
+              silu_pack_h2(fmaf(c[nt][0], p.in_scale, bs[nt][0]), fmaf(c[nt][1], p.in_scale, bs[nt][1]));
+        if (ox0 + px + 8 < Wo)
+          *reinterpret_cast<uint32_t*>(o1 + nt * 8) =
+              silu_pack_h2(fmaf(c[nt][2], p.in_scale, bs[nt][0]), fmaf(c[nt][3], p.in_scale, bs[nt][1]));
+      }
+    }
   }
 }
 

@@ -28,7 +28,7 @@ struct LayerRec {
   int cin, cout, k, stride, groups, act, transposed, h_in, w_in;
 };
 
-enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN, OP_VGATHER };
+enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN };
 
 struct Op {
   OpKind kind;
@@ -36,6 +36,7 @@ struct Op {
   TV x, y, res;
   bool has_res = false;
   int k = 1, stride = 1, act = 0, transposed = 0, heads = 0;
+  int in_grp = 0, in_grp_stride = 0, in_grp_off = 0;   // OP_DW channel remap (see DwParams)
 };
 
 struct Spec {
@@ -110,14 +111,18 @@ class Net {
     named[name] = y;
     return y;
   }
-  TV dw(const TV& x, bool act, const std::string& name, const TV* res = nullptr) {
-    LayerRec l{name, x.C, x.C, 3, 1, x.C, act ? 1 : 0, 0, x.H, x.W};
+  // grp > 0: the conv's C = n_grp * grp input channels are read from x at (c / grp) * grp_stride + grp_off + c % grp
+  TV dw(const TV& x, bool act, const std::string& name, const TV* res = nullptr, int grp = 0, int grp_stride = 0,
+        int grp_off = 0, int n_grp = 0) {
+    const int C = grp > 0 ? grp * n_grp : x.C;
+    LayerRec l{name, C, C, 3, 1, C, act ? 1 : 0, 0, x.H, x.W};
     layers.push_back(l);
-    TV y = alloc(x.H, x.W, x.C);
+    TV y = alloc(x.H, x.W, C);
     Op o;
     o.kind = OP_DW;
     o.layer = static_cast<int>(layers.size()) - 1;
     o.x = x; o.y = y; o.k = 3; o.act = act;
+    o.in_grp = grp; o.in_grp_stride = grp_stride; o.in_grp_off = grp_off;
     if (res) { o.res = *res; o.has_res = true; }
     ops.push_back(o);
     named[name] = y;
@@ -211,11 +216,8 @@ class Net {
       Op oa;
       oa.kind = OP_ATTN; oa.x = qkv; oa.y = ao; oa.heads = sp.heads;
       ops.push_back(oa);
-      TV vb = alloc(h32, h32, c);
-      Op ov;
-      ov.kind = OP_VGATHER; ov.x = qkv; ov.y = vb; ov.heads = sp.heads;
-      ops.push_back(ov);
-      TV s = dw(vb, false, "b10.attn.pe", &ao);                       // pe(v) + attention output
+      // pe(v) + attention output; V is read in place from qkv (per head: kd query, kd key, hd value channels)
+      TV s = dw(qkv, false, "b10.attn.pe", &ao, hd, 2 * kd + hd, 2 * kd, sp.heads);
       conv(s, c, 1, 1, false, "b10.attn.proj", &b, &b);              // b += proj(...)
       TV f = conv(b, 2 * c, 1, 1, true, "b10.ffn.0");
       conv(f, c, 1, 1, false, "b10.ffn.1", &b, &b);                  // b += ffn(b)

@@ -34,7 +34,8 @@ struct DecodeParams {
   ScaleSrc<T> s[3];
   int B, A;
   float score_thr;
-  float* boxes;              // [B,A,4] cx,cy,w,h
+  float logit_floor;         // anchors whose largest class logit is <= this cannot reach score_thr
+  float* boxes;              // [B,A,4] cx,cy,w,h  (rows of candidates only; the rest is never read)
   float* scores;             // [B,A]
   int* labels;               // [B,A]
   unsigned long long* keys;  // [B,A] candidate sort keys
@@ -68,11 +69,39 @@ __device__ __forceinline__ void load16(const __half* p, float (&v)[16]) {
   }
 }
 
+// Block = 256 consecutive anchors of one frame.  Phase 1 (every thread): stream the anchor's 80 class logits and
+// keep the largest; an anchor whose largest LOGIT is below logit(score_thr) - 0.01 cannot pass the probability test
+// and is dropped there -- nothing downstream reads non-candidates.  Phase 2: the survivors (1-2 % of the anchors) are
+// compacted through shared memory so that the expensive exact arithmetic runs in dense warps.
 template <typename T>
-__global__ void __launch_bounds__(128) decode_kernel(const DecodeParams<T> p) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) decode_kernel(const DecodeParams<T> p) {
+  __shared__ int s_list[256];
+  __shared__ int s_n;
   const int b = blockIdx.y;
-  if (a >= p.A) return;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  {
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    if (a < p.A) {
+      int si = 0;
+      if (a >= p.s[1].a_off) si = 1;
+      if (a >= p.s[2].a_off) si = 2;
+      const ScaleSrc<T>& s = p.s[si];
+      const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(a - s.a_off) * s.cls_pitch;
+      float lmax = -3.0e38f;
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 16) {
+        float l[16];
+        load16(cl + c0, l);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) lmax = fmaxf(lmax, l[k]);
+      }
+      if (lmax > p.logit_floor) s_list[atomicAdd(&s_n, 1)] = a;
+    }
+  }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) >= s_n) return;
+  const int a = s_list[threadIdx.x];
   int si = 0;
   if (a >= p.s[1].a_off) si = 1;
   if (a >= p.s[2].a_off) si = 2;
@@ -80,6 +109,26 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams<T> p) {
   const int al = a - s.a_off;
   const int gy = al / s.w, gx = al - gy * s.w;
   const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+
+  // ---- class sigmoid + max / first argmax (chains 416, 464, 471): like the graph, the maximum is taken over the
+  // fp32 PROBABILITIES (two different logits can round to the same probability; the first index then wins).
+  const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(al) * s.cls_pitch;
+  float best = -1.f;
+  int besti = 0;
+#pragma unroll
+  for (int c0 = 0; c0 < NC; c0 += 16) {
+    float l[16];
+    load16(cl + c0, l);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float pr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-l[k])));
+      if (pr > best) {
+        best = pr;
+        besti = c0 + k;
+      }
+    }
+  }
+  if (!(best > p.score_thr)) return;
 
   // ---- DFL (chains 401-406): softmax over 16 bins, expectation with weights 0..15
   const T* bl = s.box + b * s.box_bstride + static_cast<long>(al) * s.box_pitch;
@@ -110,34 +159,14 @@ __global__ void __launch_bounds__(128) decode_kernel(const DecodeParams<T> p) {
   const float bw = __fmul_rn(__fsub_rn(x2, x1), s.stride);
   const float bh = __fmul_rn(__fsub_rn(y2, y1), s.stride);
 
-  // ---- class sigmoid + max / first argmax (chains 416, 464, 471): like the graph, the maximum is taken over the
-  // fp32 PROBABILITIES (two different logits can round to the same probability; the first index then wins).
-  const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(al) * s.cls_pitch;
-  float best = -1.f;
-  int besti = 0;
-#pragma unroll
-  for (int c0 = 0; c0 < NC; c0 += 16) {
-    float l[16];
-    load16(cl + c0, l);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float pr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-l[k])));
-      if (pr > best) {
-        best = pr;
-        besti = c0 + k;
-      }
-    }
-  }
   const long o = static_cast<long>(b) * p.A + a;
   reinterpret_cast<float4*>(p.boxes)[o] = make_float4(cx, cy, bw, bh);
   p.scores[o] = best;
   p.labels[o] = besti;
-  if (best > p.score_thr) {
-    const int slot = atomicAdd(&p.cand_count[b], 1);
-    const unsigned long long key =
-        (static_cast<unsigned long long>(0xFFFFFFFFu - __float_as_uint(best)) << 32) | static_cast<unsigned>(a);
-    p.keys[static_cast<long>(b) * p.A + slot] = key;
-  }
+  const int slot = atomicAdd(&p.cand_count[b], 1);
+  const unsigned long long key =
+      (static_cast<unsigned long long>(0xFFFFFFFFu - __float_as_uint(best)) << 32) | static_cast<unsigned>(a);
+  p.keys[static_cast<long>(b) * p.A + slot] = key;
 }
 
 // Candidate keys straight from caller-provided scores (xrseg_debug_nms).
@@ -226,7 +255,8 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
 }
 
 // ------------------------------------------------------------------------------------------------
-// bitmask: block (cb, rb, frame), 64 threads.  Row i = rb*64 + t against columns cb*64..+63 staged in smem;
+// bitmask: block (rb, frame), 64 threads, loops over the column blocks cb >= rb.  Row i = rb*64 + t against columns
+// cb*64..+63 staged in smem;
 // bit j is set when column candidate (cb*64 + j) comes later in the order and overlaps row i by more than thr.
 // ------------------------------------------------------------------------------------------------
 struct MaskBitsParams {
@@ -238,24 +268,28 @@ struct MaskBitsParams {
 };
 
 __global__ void __launch_bounds__(64) nms_bitmask_kernel(const MaskBitsParams p) {
-  const int cb = blockIdx.x, rb = blockIdx.y, b = blockIdx.z;
+  const int rb = blockIdx.x, b = blockIdx.y;
   const int n = p.n_cand[b];
-  if (cb < rb || rb * 64 >= n || cb * 64 >= n) return;
+  if (rb * 64 >= n) return;
   __shared__ float4 cols[64];
   const int t = threadIdx.x;
-  const int cj = cb * 64 + t;
-  if (cj < n) cols[t] = p.sorted_corners[static_cast<long>(b) * p.max_cand + cj];
-  __syncthreads();
   const int i = rb * 64 + t;
-  if (i >= n) return;
-  const float4 me = p.sorted_corners[static_cast<long>(b) * p.max_cand + i];
-  unsigned long long bits = 0;
-  const int jn = min(64, n - cb * 64);
-  for (int j = 0; j < jn; ++j) {
-    const int gj = cb * 64 + j;
-    if (gj > i && iou_gt(me, cols[j], p.iou_thr)) bits |= 1ull << j;
+  const float4 me = p.sorted_corners[static_cast<long>(b) * p.max_cand + min(i, n - 1)];
+  const int nw = (n + 63) >> 6;
+  for (int cb = rb; cb < nw; ++cb) {
+    const int cj = cb * 64 + t;
+    __syncthreads();
+    if (cj < n) cols[t] = p.sorted_corners[static_cast<long>(b) * p.max_cand + cj];
+    __syncthreads();
+    if (i >= n) continue;
+    unsigned long long bits = 0;
+    const int jn = min(64, n - cb * 64);
+    for (int j = 0; j < jn; ++j) {
+      const int gj = cb * 64 + j;
+      if (gj > i && iou_gt(me, cols[j], p.iou_thr)) bits |= 1ull << j;
+    }
+    p.mask[(static_cast<long>(b) * p.max_cand + i) * p.words + cb] = bits;
   }
-  p.mask[(static_cast<long>(b) * p.max_cand + i) * p.words + cb] = bits;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -124,6 +124,11 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       }
       d.w32 = dev_upload(ws);
       d.bias = dev_upload(bs);
+      std::vector<__half> wt(static_cast<size_t>(co) * 48, __half(0.f));     // [Cout][12 taps][RGBX] for stem_mma_kernel
+      for (int n = 0; n < l.cout; ++n)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int t = 0; t < 9; ++t) wt[(static_cast<size_t>(n) * 12 + t) * 4 + ci] = __half(w.w[(static_cast<size_t>(n) * 3 + ci) * 9 + t]);
+      d.w16 = dev_upload(wt);
       for (float& v : ws) v = v / 255.0f;
       d.w32_u8 = dev_upload(ws);
     } else if (o.kind == OP_DW) {
@@ -209,8 +214,19 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         q.B = nb; q.H = o.x.H; q.W = o.x.W; q.Cout = o.y.Cp;
         const size_t smem_u8 = smem + 33 * 33 * 4;
         // b0_off: frame offset of this chunk inside the scheduled batch (fused path reads the caller's frames directly)
-        L.fn = [r, p, q, total, smem, smem_u8, nb](cudaStream_t st) {
-          if (r->fused_src) {
+        StemMmaParams mq{};
+        mq.out = q.out; mq.out_pitch = q.out_pitch; mq.w16 = r->dl[o.layer].w16; mq.bias = q.bias;
+        mq.B = nb; mq.H = o.x.H; mq.W = o.x.W; mq.in_scale = 1.0f / 255.0f;
+        const int nt = o.y.Cp / 8;
+        L.fn = [r, p, q, mq, nt, total, smem, smem_u8, nb](cudaStream_t st) {
+          const bool aligned = (reinterpret_cast<uintptr_t>(r->fused_src) % 4 == 0) && (r->fused_stride % 4 == 0);
+          if (r->fused_src && aligned && (nt == 2 || nt == 4) && r->cfg.conv_impl == XRSEG_CONV_UMMA) {
+            StemMmaParams u = mq;
+            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
+            const dim3 grid(ceil_div(u.W / 2, 32), ceil_div(u.H / 2, 8), nb);
+            if (nt == 2) stem_mma_kernel<2><<<grid, 256, 0, st>>>(u);
+            else stem_mma_kernel<4><<<grid, 256, 0, st>>>(u);
+          } else if (r->fused_src) {
             StemU8Params u = q;
             u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
             stem_u8_kernel<<<dim3(ceil_div(u.W / 2, 16), ceil_div(u.H / 2, 16), nb), 256, smem_u8, st>>>(u);
@@ -264,13 +280,14 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
         p.res = o.has_res ? ptr_of(r, o.res) : nullptr; p.res_pitch = o.has_res ? o.res.pitch : 0;
         p.w = r->dl[o.layer].w32; p.bias = r->dl[o.layer].bias;
-        p.B = nb; p.H = o.x.H; p.W = o.x.W; p.C = o.x.Cp; p.act = o.act;
-        const long total = static_cast<long>(nb) * o.x.H * o.x.W * (o.x.Cp / 8);
+        p.B = nb; p.H = o.x.H; p.W = o.x.W; p.C = o.y.Cp; p.act = o.act;
+        p.in_grp = o.in_grp; p.in_grp_stride = o.in_grp_stride; p.in_grp_off = o.in_grp_off;
+        p.rows = o.x.H >= 40 ? 16 : 10;
         L.name = l.name;
         L.flops = 2.0 * px_out * l.cout * 9;
         L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1)) * 2;
-        const size_t smem = static_cast<size_t>(10) * p.C * sizeof(float);
-        L.fn = [p, total, smem](cudaStream_t st) { dwconv3x3_kernel<<<grid_for(total), 256, smem, st>>>(p); };
+        const dim3 grid(ceil_div(p.W * (p.C / 8), 128), ceil_div(p.H, p.rows), nb);
+        L.fn = [p, grid](cudaStream_t st) { dwconv3x3_kernel<<<grid, 128, 0, st>>>(p); };
         break;
       }
       case OP_SPPF: {
@@ -300,15 +317,6 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.flops = 2.0 * nb * o.heads * static_cast<double>(p.N) * p.N * (ATT_KD + ATT_HD);
         L.bytes = px_in * (o.x.C + o.y.C) * 2;
         L.fn = [p, g, smem, threads](cudaStream_t st) { attention_kernel<<<g, threads, smem, st>>>(p); };
-        break;
-      }
-      case OP_VGATHER: {
-        VGatherParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, static_cast<long>(nb) * o.x.H * o.x.W,
-                        o.heads};
-        const long total = p.tokens * o.heads * 8;
-        L.name = "c2psa.gather_v";
-        L.bytes = px_in * o.y.C * 2 * 2;
-        L.fn = [p, total](cudaStream_t st) { gather_v_kernel<<<grid_for(total), 256, 0, st>>>(p); };
         break;
       }
     }
@@ -373,6 +381,10 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     DecodeParams<T> dp{};
     for (int i = 0; i < 3; ++i) dp.s[i] = src[i];
     dp.B = nb; dp.A = A; dp.score_thr = r->cfg.score_threshold;
+    {
+      const double t = r->cfg.score_threshold;
+      dp.logit_floor = t <= 0.0 ? -3.0e38f : (t >= 1.0 ? 3.0e38f : static_cast<float>(std::log(t / (1.0 - t)) - 0.01));
+    }
     dp.boxes = r->d_boxes + static_cast<long>(b0) * A * 4;
     dp.scores = r->d_scores + static_cast<long>(b0) * A;
     dp.labels = r->d_labels + static_cast<long>(b0) * A;
@@ -380,8 +392,8 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     dp.cand_count = r->d_cand_count + b0;
     Launch L;
     L.name = "post.decode";
-    L.bytes = static_cast<double>(nb) * A * ((64 + NC) * sizeof(T) + 24);
-    L.fn = [dp, A, nb](cudaStream_t st) { decode_kernel<T><<<dim3(ceil_div(A, 128), nb), 128, 0, st>>>(dp); };
+    L.bytes = static_cast<double>(nb) * A * NC * sizeof(T);   // every anchor's class logits; box logits only for candidates
+    L.fn = [dp, A, nb](cudaStream_t st) { decode_kernel<T><<<dim3(ceil_div(A, 256), nb), 256, 0, st>>>(dp); };
     out.push_back(std::move(L));
   }
   SortParams sp{};
@@ -414,7 +426,7 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
   {
     Launch L;
     L.name = "post.nms_bitmask";
-    L.fn = [mp, words, nb](cudaStream_t st) { nms_bitmask_kernel<<<dim3(words, words, nb), 64, 0, st>>>(mp); };
+    L.fn = [mp, words, nb](cudaStream_t st) { nms_bitmask_kernel<<<dim3(words, nb), 64, 0, st>>>(mp); };
     out.push_back(std::move(L));
   }
   {

@@ -88,7 +88,7 @@ class ClockSampler:
         return out
 
 
-def cpu_oracle_fps(ws, frames, threads, budget_s=12.0, chunk=4):
+def cpu_oracle_fps(ws, frames, threads, budget_s=12.0, chunk=4, max_frames=64):
     """The oracle (CPU restatement of the reference path) on a bounded sample of the same workload."""
     import torch
 
@@ -104,7 +104,7 @@ def cpu_oracle_fps(ws, frames, threads, budget_s=12.0, chunk=4):
         Y.run_model(ws, x, "n")
         done += x.shape[0]
         dt = time.perf_counter() - t0
-        if dt >= budget_s or done >= 2 * len(frames):
+        if dt >= budget_s or done >= max_frames:
             return done / dt, done, dt
 
 
@@ -151,7 +151,8 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-micro-batch", type=int, default=16)
+    ap.add_argument("--e2e-micro-batch", type=int, default=0, help="frames per network pass of the e2e leg (0 = whole batch)")
+    ap.add_argument("--latency-iters", type=int, default=300, help="batch-1 latency samples (0 = skip)")
     ap.add_argument("--profile-ops", type=int, default=5, help="iterations for the per-launch timing pass (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -178,9 +179,11 @@ def main():
     layers, ws = W.random_weights("n", SEED_WEIGHTS, CLS_BIAS)
     model = I.Model(W.write_pack("n", layers, ws), "n")
     runner = I.Runner(model, device=local_rank, max_batch=B)
-    # end-to-end leg: frames are pushed in micro-batches of 16 so that the host->device copy of chunk k+1 overlaps the
-    # compute of chunk k (xrseg_schedule does this internally on a copy stream)
-    runner_e2e = I.Runner(model, device=local_rank, max_batch=B, micro_batch=args.e2e_micro_batch)
+    # end-to-end leg: two runners in ping-pong (inference.PipelinedRunner): the host->device copy and the network pass of
+    # step i+1 overlap the readback of step i; every step still copies its frames from pinned host memory and reads
+    # its detections back
+    pipe = I.PipelinedRunner(model, device=local_rank, max_batch=B, depth=2, micro_batch=args.e2e_micro_batch)
+    runner_e2e = pipe.runners[0]
     # 4 distinct frame sets (4 x 78.6 MB > 126 MB L2) so no step finds its input in L2; every rank has its own frames
     NSETS = 4
     nbytes = B * 640 * 640 * 3
@@ -219,26 +222,52 @@ def main():
     # ---------------- end-to-end leg: host frames in, detections out, every step ----------------
     d2h = 0
 
-    def e2e_step(i):
+    def collect():
         nonlocal d2h
-        runner_e2e.schedule_ptr(host[i % NSETS], B, 640, 640, 3)
-        runner_e2e.wait()
-        boxes = runner_e2e.readback(0)
-        labels = runner_e2e.readback(1)
-        bits = runner_e2e.masks(_lib.MASK_BITS_160)
+        counts, boxes, labels, bits = pipe.collect(_lib.MASK_BITS_160)
         d2h = boxes.nbytes + labels.nbytes + bits.nbytes + 4 * B
-        return boxes, labels, bits
+        return counts
 
-    for i in range(min(args.warmup, 3)):
-        e2e_step(i)
+    for i in range(min(args.warmup, 4)):
+        pipe.submit_ptr(host[i % NSETS], B, 640, 640, 3)
+        collect()
     barrier()
+    for r_ in pipe.runners:
+        r_.sync()
     runner_e2e.event_record(2)
-    for i in range(args.steps):
-        e2e_step(i)
-    runner_e2e.event_record(3)
+    pipe.submit_ptr(host[0], B, 640, 640, 3)
+    for i in range(1, args.steps + 1):
+        if i < args.steps:
+            pipe.submit_ptr(host[i % NSETS], B, 640, 640, 3)
+        collect()
+    for r_ in pipe.runners:
+        r_.sync()
+    runner_e2e.event_record(3)          # everything of both runners has completed before this record
     runner_e2e.sync()
     ms_e2e = runner_e2e.event_elapsed_ms(2, 3)
     barrier()
+
+    # ---------------- batch-1 streaming latency (BASELINE.json configs[3]): 1280x960 -> letterbox -> detections on the host
+    lat = None
+    if rank == 0 and args.latency_iters > 0:
+        r1 = I.Runner(model, device=local_rank, max_batch=1, resize_mode=_lib.RESIZE_LETTERBOX)
+        fb = 960 * 1280 * 3
+        hf = lib.xrseg_host_alloc(fb)
+        C.memmove(hf, np.random.default_rng(4).integers(0, 256, fb, dtype=np.uint8).ctypes.data, fb)
+        ts = []
+        for i in range(args.latency_iters + 20):
+            t0 = time.perf_counter()
+            r1.schedule_ptr(hf, 1, 960, 1280, 3)
+            r1.wait()
+            r1.readback(0)
+            r1.readback(1)
+            r1.masks(_lib.MASK_BITS_160)
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts[20:]) * 1e3
+        lat = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "iters": int(len(ts)),
+               "config": "YOLO11n-seg batch 1, 1280x960 RGB host frame -> letterbox 640 -> boxes+labels+bit masks on the host"}
+        lib.xrseg_host_free(hf)
+        r1.close()
     clocks = sampler.stop() if sampler else None
 
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -260,31 +289,49 @@ def main():
                        "l2": "inputs rotate over 4 distinct 78.6 MB frame sets (> 126 MB L2); each step streams ~3 GB of activations",
                        "parallelism": f"frame-parallel x{world}, no collective"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps, "micro_batch": args.e2e_micro_batch},
+                    "ms_per_step": ms_e2e / args.steps, "pipeline": "2 runners in ping-pong, one run in flight each"},
             "gpu_launches": (launches + launches_e2e + 1) * args.steps,
             "clocks": clocks,
         }
+        if lat:
+            out["latency"] = lat
         # ---------------- roofline of the dominant kernel, timed live per launch ----------------
         if args.profile_ops > 0:
             runner.schedule_device(dev[0].data_ptr(), B, 640, 640, 3)
             runner.wait()
             ops = runner.profile_ops(args.profile_ops)
             tot = sum(o[1] for o in ops)
+            ridge = tf_sust * 1e12 / (hbm * 1e9)                      # FLOP/B above which a kernel is tensor-bound
+            traffic_tab = {}
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tpath):
+                traffic_tab = json.load(open(tpath)).get("launches", {})
+
+            def roof(o):
+                name, ms, fl, by = o
+                tensor = fl > 0 and by > 0 and fl / by > ridge
+                ach = fl / (ms * 1e-3) / 1e12 if tensor else by / (ms * 1e-3) / 1e9
+                peak = tf_sust if tensor else hbm
+                t = traffic_tab.get(name, {}).get("dram_bytes")
+                return {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
+                        "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak, "traffic": t,
+                        "ms_per_launch": ms, "share_of_step": ms / tot, "flop_per_byte": fl / by if by else None}
+
             conv = [o for o in ops if o[2] > 0 and not o[0].startswith("post.")]
             top = max(ops, key=lambda o: o[1])
             conv_ms, conv_fl = sum(o[1] for o in conv), sum(o[2] for o in conv)
             post = [o for o in ops if o[0] in ("post.decode", "post.mask_prob")]
-            out["roofline"] = {
-                "kernel": f"conv_umma_kernel[{top[0]}]" if top[2] > 0 else top[0],
-                "bound": "tensor", "achieved": top[2] / (top[1] * 1e-3) / 1e12, "peak": tf_burst, "unit": "TFLOP/s",
-                "frac": top[2] / (top[1] * 1e-3) / 1e12 / tf_burst, "traffic": None, "peak_source": how,
-                "ms_per_launch": top[1], "share_of_step": top[1] / tot,
-                "hbm_view": {"achieved_gbs": top[3] / (top[1] * 1e-3) / 1e9, "frac_of_hbm_peak": top[3] / (top[1] * 1e-3) / 1e9 / hbm},
-                "conv_stack": {"tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / tf_sust,
-                               "gbs": sum(o[3] for o in conv) / (conv_ms * 1e-3) / 1e9, "ms": conv_ms},
+            out["roofline"] = roof(top)
+            out["roofline"].update({
+                "peak_source": how + (" (sustained bf16 cuBLAS)" if out["roofline"]["bound"] == "tensor" else " (copy bandwidth)"),
+                "algorithmic": "flops = 2*M*Cout*Cin*k*k, bytes = (in + out (+res) + weights) * 2 B, real channel counts (DESIGN.md 4)",
+                "top5": [roof(o) for o in sorted(ops, key=lambda o: -o[1])[:5]],
+                "conv_stack": {"tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "frac_of_tensor_peak": conv_fl / (conv_ms * 1e-3) / 1e12 / tf_sust,
+                               "gbs": sum(o[3] for o in conv) / (conv_ms * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": sum(o[3] for o in conv) / (conv_ms * 1e-3) / 1e9 / hbm, "ms": conv_ms},
                 "post": {o[0]: {"ms": o[1], "gbs": o[3] / (o[1] * 1e-3) / 1e9, "frac_of_hbm_peak": o[3] / (o[1] * 1e-3) / 1e9 / hbm} for o in post},
                 "sum_launch_ms": tot,
-            }
+            })
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "ops_profile.json"), "w") as f:
                 json.dump([{"name": o[0], "ms": o[1], "gflop": o[2] / 1e9, "mbytes": o[3] / 1e6} for o in ops], f, indent=0)
@@ -297,7 +344,7 @@ def main():
     for h in host:
         lib.xrseg_host_free(h)
     runner.close()
-    runner_e2e.close()
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -6,8 +6,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
+#include <utility>
 
 namespace xrseg {
 
@@ -64,6 +66,19 @@ __device__ __forceinline__ uint32_t silu_pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per lane and instruction.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&o)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(ptr)
+               : "memory");
+}
+
 // Epilogue of 16 consecutive output channels of one pixel: accumulator + bias -> (SiLU) -> (+ residual) -> fp16 -> two
 // 16-byte stores.  bias16: shared memory, 64-byte aligned.  res / out: global, 32-byte aligned.
 __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const float* bias16, int act, const __half* res,
@@ -82,8 +97,8 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const 
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = silu_pack_h2(y[2 * i], y[2 * i + 1]);
     if (res) {
-      const uint4 r0 = reinterpret_cast<const uint4*>(res)[0], r1 = reinterpret_cast<const uint4*>(res)[1];
-      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t rr[8];
+      ld_global_256(res, rr);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         __half2 s = __hadd2(*reinterpret_cast<__half2*>(&o[i]), *reinterpret_cast<const __half2*>(&rr[i]));
@@ -92,8 +107,8 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const 
     }
   } else {
     if (res) {
-      const uint4 r0 = reinterpret_cast<const uint4*>(res)[0], r1 = reinterpret_cast<const uint4*>(res)[1];
-      const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      uint32_t rr[8];
+      ld_global_256(res, rr);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
@@ -107,9 +122,22 @@ __device__ __forceinline__ void epilogue_chunk16(const uint32_t (&v)[16], const 
       o[i] = *reinterpret_cast<uint32_t*>(&h);
     }
   }
-  reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-  reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  st_global_256(out, o);
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the per-frame pipeline is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so its
+// CTAs may become resident while the previous kernel drains.  pdl_launch_dependents(): this CTA no longer objects to
+// the next kernel starting; pdl_wait(): block until the previous kernel has fully completed and its writes are
+// visible -- must precede the first access to anything a previous kernel wrote (or still reads, if we write it).
+// Both are no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#define XR_PDL_ENTRY()         \
+  do {                         \
+    pdl_launch_dependents();   \
+    pdl_wait();                \
+  } while (0)
 
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -154,6 +182,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {   // wait until at most n groups of this thread are pending
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    case 6: cp_async_wait<6>(); break;
+    default: cp_async_wait<7>(); break;
+  }
 }
 // generic-proxy writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -247,6 +287,30 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_f16(int n, int is_bf16) 
   d |= static_cast<uint32_t>(n >> 3) << 17;
   d |= static_cast<uint32_t>(128 >> 4) << 24;
   return d;
+}
+
+// Launch with programmatic stream serialization (PDL): only for kernels that call pdl_wait() before touching data
+// produced by earlier kernels.  XRSEG_PDL=0 in the environment turns the attribute off (A/B measurements).
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("XRSEG_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  XR_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
 #endif  // __CUDACC__

@@ -19,7 +19,7 @@
 
 namespace xrseg {
 
-enum { MODE_HALO_TMA = 2 };
+enum { MODE_HALO_TMA = 2, MODE_FLAT_TMA = 3 };
 enum { TMA_THREADS = 320, TMA_TAIL_PAD = 4096 };
 
 struct TmaPlanExtra {
@@ -192,6 +192,92 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
   return true;
 }
 
+
+// 1x1 stride-1 convolution = plain GEMM over the flattened [B*H*W, C] activation matrix ("flat" mode of the same
+// kernel): a work item is 128*nsub consecutive pixels, its A operand ONE (or two) 2-D TMA boxes of cb channels x <= 256
+// rows per K-block, swizzled like the halo boxes; taps = 1.  One mbarrier arrival per stage instead of one per producer
+// thread is what makes the thin layers (K <= 128, N <= 64) run at memory speed: the thread-gather kernel spends most of
+// its time in its own arrive/wait traffic there (tools/probe_umma.py).  Channels beyond Cin inside the last K-block are
+// out of bounds for the tensor map and arrive as zeros, so Cin only has to be a multiple of 16 (e.g. the 48-channel
+// C3k2 concat).
+static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+  if (!(d.k == 1 && d.stride == 1 && !d.transposed)) return false;
+  p = ConvParams{};
+  p.B = d.B; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.in_pitch = d.in_pitch;
+  p.Cout = d.Cout; p.out_pitch = d.out_pitch; p.res_pitch = d.res_pitch;
+  p.k = 1; p.stride = 1; p.pad = 0; p.act = d.act; p.transposed = 0;
+  p.Ho = d.H; p.Wo = d.W;
+  p.Ntile = d.Cout <= 256 ? d.Cout : 256;
+  if (d.Cout % p.Ntile) return false;
+  p.n_tiles = d.Cout / p.Ntile;
+  p.idesc = umma_idesc_f16(p.Ntile, 0);
+  p.mode = MODE_FLAT_TMA;
+  p.taps = 1;
+  const long rows = static_cast<long>(d.B) * d.H * d.W;
+  if (rows >= (1L << 31)) return false;
+  p.flat_rows = static_cast<int>(rows);
+  const int cb = d.Cin > 32 ? 64 : d.Cin;          // 16, 32 or 64 channels per K-block (row = 32 / 64 / 128 bytes)
+  p.cb = cb; p.cps = cb / 8;
+  p.sw = cb == 64 ? 3 : (cb == 32 ? 2 : 1);
+  const int nkb = ceil_div(d.Cin, cb);             // K-blocks
+  p.K_total = nkb * cb;
+  const int rb = cb * 2;
+  const int b_block = p.Ntile * rb;
+  const long total_b = static_cast<long>(nkb) * b_block;
+  p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
+  const int resident = p.b_resident ? static_cast<int>(total_b) : 0;
+  const int tiles128 = ceil_div(p.flat_rows, 128);
+  int nsub = 256 / p.Ntile;
+  if (nsub > 4) nsub = 4;
+  if (nsub < 1) nsub = 1;
+  while (nsub > 1 && ceil_div(tiles128, nsub) < 8 * num_sms) nsub >>= 1;    // keep >= 8 items per CTA for balance
+  for (;; nsub >>= 1) {
+    p.nsub = nsub;
+    p.slots = 128 * nsub;
+    p.hbox = p.slots < 256 ? p.slots : 256;          // rows per TMA box
+    // A stage holds kps K-blocks (each slots x rb bytes, its own swizzled sub-buffer): the MMA warp pays a fixed
+    // ~500 cycles per stage hand-over (tools/probe_tma.py), so thin layers put their whole K into one stage.
+    int kps = nkb;
+    while (kps > 1 && (nkb % kps != 0 || kps * p.slots * rb > 49152)) --kps;
+    p.kps = kps;
+    p.nks = nkb / kps;
+    p.a_stage_bytes = kps * p.slots * rb;            // multiple of 1024 for every cb
+    p.b_stage_bytes = kps * b_block;
+    const int fixed = round_up(CONV_HDR_BYTES, 1024) + (p.b_resident ? round_up(resident, 1024) : 0);
+    int S = (CONV_SMEM_MAX - fixed) / (p.a_stage_bytes + (p.b_resident ? 0 : round_up(p.b_stage_bytes, 1024)));
+    if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
+    if (S >= 3 || nsub == 1) {
+      if (S < 2) return false;
+      p.S = S;
+      break;
+    }
+  }
+  p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
+  p.lbo_a = p.a_stage_bytes;
+  p.M_total = ceil_div(p.flat_rows, p.slots);
+  p.m_tiles = p.M_total;
+  p.smem_off_b = round_up(CONV_HDR_BYTES, 1024);
+  const int b_region = p.b_resident ? resident : p.S * round_up(p.b_stage_bytes, 1024);
+  p.smem_off_a = p.smem_off_b + round_up(b_region, 1024);
+  p.smem_bytes = p.smem_off_a + p.S * p.a_stage_bytes;
+  if (p.smem_bytes > CONV_SMEM_MAX) return false;
+  const int work = p.m_tiles * p.n_tiles;
+  p.grid = work < num_sms ? work : num_sms;
+  p.Wp = 1; p.Hp1 = 1; p.R = 0; p.tpi = 1;
+  p.fd_wp = make_fastdiv(1);
+  p.fd_hp1 = make_fastdiv(1);
+  p.fd_hw = make_fastdiv(1);
+  p.fd_wo = make_fastdiv(1);
+  p.fd_cin = make_fastdiv(d.Cin);
+  p.fd_cout = make_fastdiv(d.Cout);
+  return true;
+}
+
+// Tensor map of the flat mode: the activation matrix [rows, C] (pixel pitch `pitch`) as (C, rows, 1, 1).
+static inline CUtensorMap make_flat_tensor_map(const __half* base, long rows, int C, int pitch, const ConvParams& p) {
+  return make_halo_tensor_map(base, 1, 1, static_cast<int>(rows), C, pitch, p.hbox, 1, p.cb, p.sw);
+}
+
 // Physical byte offset of logical offset `off` inside a pattern-aligned swizzled buffer (Swizzle<sw,4,3>): the 16-byte
 // chunk index (address bits 4..6) is XORed with address bits 7..9, masked to the swizzle width.
 static inline size_t sw_phys(size_t off, int sw) {
@@ -203,20 +289,22 @@ static inline size_t sw_phys(size_t off, int sw) {
 template <typename HalfT>
 static inline void pack_conv_weights_sw(const ConvParams& p, const float* w, const float* bias, int cin_real, int cout_real,
                                         std::vector<HalfT>& wp, std::vector<float>& bp) {
-  const size_t stage_elems = static_cast<size_t>(p.b_stage_bytes) / 2;
-  wp.assign(static_cast<size_t>(p.n_tiles) * p.nks * stage_elems, HalfT(0.0f));
+  const int kps = p.kps > 1 ? p.kps : 1;
+  const int nkb = p.nks * kps;                                      // K-blocks; a stage holds kps consecutive ones
+  const size_t stage_elems = static_cast<size_t>(p.b_stage_bytes) / 2 / kps;
+  wp.assign(static_cast<size_t>(p.n_tiles) * nkb * stage_elems, HalfT(0.0f));
   bp.assign(static_cast<size_t>(p.n_tiles) * p.Ntile, 0.0f);
   const int rb = p.cb * 2;
   for (int nt = 0; nt < p.n_tiles; ++nt)
-    for (int ks = 0; ks < p.nks; ++ks)
-      for (int t = 0; t < 9; ++t)
+    for (int ks = 0; ks < nkb; ++ks)
+      for (int t = 0; t < p.taps; ++t)
         for (int n = 0; n < p.Ntile; ++n)
           for (int c = 0; c < p.cb; ++c) {
             const int ng = nt * p.Ntile + n, ci = ks * p.cb + c;
             if (ng >= cout_real || ci >= cin_real) continue;
-            const float v = w[((static_cast<size_t>(ng) * cin_real + ci) * 3 + t / 3) * 3 + t % 3];
+            const float v = w[(static_cast<size_t>(ng) * cin_real + ci) * p.taps + t];   // [cout][cin][kh][kw], t = kh*3+kw
             const size_t off = (static_cast<size_t>(t) * p.Ntile + n) * rb + static_cast<size_t>(c) * 2;
-            wp[(static_cast<size_t>(nt) * p.nks + ks) * stage_elems + sw_phys(off, p.sw) / 2] = HalfT(v);
+            wp[(static_cast<size_t>(nt) * nkb + ks) * stage_elems + sw_phys(off, p.sw) / 2] = HalfT(v);
           }
   for (int ng = 0; ng < p.n_tiles * p.Ntile; ++ng)
     if (ng < cout_real && bias) bp[ng] = bias[ng];
@@ -263,6 +351,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code uses the uniform datapath
   const int lane = tid & 31;
   const int total_work = p.m_tiles * p.n_tiles;
+  pdl_launch_dependents();
 
   if (tid == 0) {
     for (int i = 0; i < CONV_MAX_STAGES; ++i) {
@@ -271,7 +360,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);
+      mbar_init(&tempty[i], 8);              // one arrival per epilogue warp
     }
     mbar_init(bres, 1);
     mbar_fence_init();
@@ -292,7 +381,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     if (lane == 0) {
       const uint32_t a_u32 = smem_u32(smem_a);
       const uint32_t b_u32 = smem_u32(smem_b);
-      const uint32_t a_tx = static_cast<uint32_t>(p.cps) * p.slots * 16u;     // = slots * row bytes when swizzled
+      const uint32_t a_tx = static_cast<uint32_t>(p.cps) * p.slots * 16u * (p.kps > 1 ? p.kps : 1);   // slots * row bytes (* K-blocks)
       const uint32_t b_stride = p.sw ? static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023) : static_cast<uint32_t>(p.b_stage_bytes);
       if (p.b_resident) {
         const uint32_t bytes = static_cast<uint32_t>(p.nks) * p.b_stage_bytes;
@@ -302,8 +391,10 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           bulk_copy_g2s(b_u32 + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, bres);
         }
       }
+      pdl_wait();   // the weights above are constants; the activations below are the previous kernels' output
       int it = 0;
       long long t_wait = 0, t0;
+      const bool flat = p.mode == MODE_FLAT_TMA;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int tile = p.n_tiles == 1 ? w : (w >> 1);
         const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
@@ -317,7 +408,15 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           if (p.dbg_skip & 4) { mbar_arrive(&full[slot]); continue; }
           mbar_arrive_expect_tx(&full[slot], a_tx + (p.b_resident ? 0u : static_cast<uint32_t>(p.b_stage_bytes)));
           const uint32_t a_dst = a_u32 + slot * p.a_stage_bytes;
-          if (p.sw) {
+          if (flat) {
+            // rows [tile*slots, +slots) of the activation matrix, hbox rows per box, kps K-blocks per stage; rows past
+            // the end and channels past Cin arrive as zeros
+            const uint32_t box_bytes = static_cast<uint32_t>(p.hbox) * p.cb * 2u;
+            uint32_t dst = a_dst;
+            for (int kb = 0; kb < p.kps; ++kb)
+              for (int r0 = 0; r0 < p.slots; r0 += p.hbox, dst += box_bytes)
+                tma_load_4d(dst, &tmap, &full[slot], (ks * p.kps + kb) * p.cb, tile * p.slots + r0, 0, 0);
+          } else if (p.sw) {
             tma_load_4d(a_dst, &tmap, &full[slot], ks * p.cb, -1, y0 - 1, b);     // the whole K-block in one box
           } else {
             for (int c = 0; c < p.cps; ++c)
@@ -390,11 +489,18 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             // unrolled with guards folded into the issue predicate: a handful of uniform adds per MMA, no branches.
             if (elect_one()) {   // one branch per stage; inside, a single lane issues the whole MMA batch
               uint32_t acc = ks > 0 ? 1u : 0u;
+              const int kdim = p.taps == 9 ? 3 : 1;             // flat (1x1) mode: a single tap, no row shift
+              const int tap_bias = p.taps == 9 ? 1 : 0;
+              const int kps = p.kps > 1 ? p.kps : 1;
+              const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;   // one K-block sub-buffer of the stage
+              for (int kb = 0; kb < kps; ++kb)
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
-                const uint32_t a_kh = a_lo_stage + static_cast<uint32_t>(kh * p.Wp - 1) * row16;
+                if (kh >= kdim) break;
+                const uint32_t a_kh = a_lo_stage + kb * blk16 + static_cast<uint32_t>(kh * p.Wp - tap_bias) * row16;
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
+                  if (kw >= kdim) break;
                   const uint32_t a_tap = a_kh + static_cast<uint32_t>(kw) * row16;
                   for (int j = 0; j < kj; ++j) {
                     {
@@ -460,6 +566,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     const int half = ew >> 2;
     int tcount = 0;
     long long e_wait = 0, e_work = 0, t0;
+    pdl_wait();   // before the first residual read / output store
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
       const int tile = p.n_tiles == 1 ? w : (w >> 1);
       const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
@@ -474,11 +581,19 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       tc_fence_after();
       for (int u = 0; u < p.nsub; ++u) {
         const int j = 128 * u + q * 32 + lane;
-        const int yy = fd_div(p.fd_wp, j);
-        const int cc = j - yy * p.Wp;
-        const int y = y0 + yy;
-        const bool valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
-        const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
+        bool valid;
+        size_t pix;
+        if (p.mode == MODE_FLAT_TMA) {
+          const int m = tile * p.slots + j;
+          valid = m < p.flat_rows;
+          pix = static_cast<size_t>(m);
+        } else {
+          const int yy = fd_div(p.fd_wp, j);
+          const int cc = j - yy * p.Wp;
+          const int y = y0 + yy;
+          valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
+          pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
+        }
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                static_cast<uint32_t>((buf * p.nsub + u) * p.Ntile);
         for (int c0 = half * 16; c0 < p.Ntile; c0 += 32) {
@@ -493,7 +608,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
       e_work += clock64() - t0;
     }
     if (p.dbg_clk && warp == 2 && lane == 0) {
@@ -515,8 +631,7 @@ static inline void conv_tma_prepare_device() {
 }
 
 static inline void launch_conv_halo_tma(const ConvParams& p, const CUtensorMap& map, cudaStream_t stream) {
-  conv_halo_tma_kernel<<<p.grid, TMA_THREADS, p.smem_bytes, stream>>>(p, map);
-  XR_CUDA(cudaGetLastError());
+  launch_k(conv_halo_tma_kernel, p.grid, TMA_THREADS, p.smem_bytes, stream, p, map);
 }
 #endif  // __CUDACC__
 
@@ -580,6 +695,49 @@ static inline void emulate_conv_halo_tma(const ConvParams& p, const float* in, c
           out[pix * p.out_pitch + ng] = yv;
         }
       }
+  }
+}
+
+// ---- host emulation of the flat (1x1) mode ---------------------------------------------------------------------------
+static inline void emulate_conv_flat_tma(const ConvParams& p, const float* in, const float* wpack_f, const float* bias,
+                                         const float* res, float* out) {
+  const int rb = p.cb * 2;
+  std::vector<float> a(static_cast<size_t>(p.slots) * p.cb);
+  std::vector<float> acc(static_cast<size_t>(p.slots) * p.Ntile);
+  for (int w = 0; w < p.m_tiles * p.n_tiles; ++w) {
+    const int tile = w / p.n_tiles, n_tile = w % p.n_tiles;
+    std::fill(acc.begin(), acc.end(), 0.f);
+    const int nkb = p.nks * (p.kps > 1 ? p.kps : 1);
+    for (int ks = 0; ks < nkb; ++ks) {
+      std::fill(a.begin(), a.end(), 0.f);
+      for (int r = 0; r < p.slots; ++r) {            // TMA boxes: rows past flat_rows and channels past Cin are zero
+        const long m = static_cast<long>(tile) * p.slots + r;
+        if (m >= p.flat_rows) continue;
+        for (int c = 0; c < p.cb; ++c) {
+          const int ci = ks * p.cb + c;
+          if (ci < p.Cin) a[static_cast<size_t>(r) * p.cb + c] = in[static_cast<size_t>(m) * p.in_pitch + ci];
+        }
+      }
+      const float* bst = wpack_f + (static_cast<size_t>(n_tile) * nkb + ks) * (static_cast<size_t>(p.Ntile) * p.cb);
+      for (int r = 0; r < p.slots; ++r)
+        for (int n = 0; n < p.Ntile; ++n) {
+          float sacc = 0.f;
+          for (int c = 0; c < p.cb; ++c)
+            sacc += a[static_cast<size_t>(r) * p.cb + c] * bst[sw_phys(static_cast<size_t>(n) * rb + c * 2, p.sw) / 2];
+          acc[static_cast<size_t>(r) * p.Ntile + n] += sacc;
+        }
+    }
+    for (int r = 0; r < p.slots; ++r) {
+      const long m = static_cast<long>(tile) * p.slots + r;
+      if (m >= p.flat_rows) continue;
+      for (int n = 0; n < p.Ntile; ++n) {
+        const int ng = n_tile * p.Ntile + n;
+        float yv = acc[static_cast<size_t>(r) * p.Ntile + n] + bias[ng];
+        if (p.act) yv = yv / (1.0f + expf(-yv));
+        if (res) yv += res[static_cast<size_t>(m) * p.res_pitch + ng];
+        out[static_cast<size_t>(m) * p.out_pitch + ng] = yv;
+      }
+    }
   }
 }
 

@@ -83,6 +83,8 @@ struct ConvParams {
   long long* dbg_clk;               // optional [grid][8] cycle counters per role phase (debug builds of the probe)
   int dbg_skip;                     // profiling experiment: 1 skip MMA issue, 2 skip epilogue math+stores, 4 skip loads
   int sw;                           // operand swizzle: 0 none, 1/2/3 = 32/64/128-byte (row = 16/32/64 channels)
+  int flat_rows;                    // MODE_FLAT_TMA: B*H*W rows of the activation matrix
+  int kps;                          // MODE_FLAT_TMA: K-blocks (of cb channels) per pipeline stage; 0 / 1 elsewhere
 };
 
 struct ConvDesc {
@@ -243,6 +245,7 @@ static inline ConvParams plan_conv(const ConvDesc& d, int num_sms, int variant =
     p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
   }
   p.m_tiles = ceil_div(p.M_total, 128);
+  XR_CHECK(static_cast<long>(d.B) * d.H * d.W * d.in_pitch < (1L << 31), "input tensor too large for 32-bit gather offsets");
   const int resident_bytes = p.b_resident ? p.nks * p.b_stage_bytes : 0;
   const int per_stage = p.a_stage_bytes + (p.b_resident ? 0 : p.b_stage_bytes);
   int S = (budget - resident_bytes) / per_stage;
@@ -352,6 +355,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code uses the uniform datapath
   const int lane = tid & 31;
   const int total_work = p.m_tiles * p.n_tiles;
+  pdl_launch_dependents();   // the next kernel's CTAs may take this SM as soon as we leave it (its prologue overlaps our tail)
 
   if (tid == 0) {
     for (int i = 0; i < CONV_MAX_STAGES; ++i) {
@@ -385,6 +389,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
       for (int i = tid * 16; i < bytes; i += CONV_NPROD * 16) cp_async16(b_u32 + i, src + i, 16);
       cp_async_arrive_noinc(bres);
     }
+    pdl_wait();   // weights / bias are constants (loaded above); activations are the previous kernels' output
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int m_tile = p.n_tiles == 1 ? w : (w >> 1);
@@ -394,18 +399,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
       // per-tile row bookkeeping for the general MODE_GATHER path (4 rows per thread: r0 + 32 j)
       const int gc = tid & 7;
       const int r0 = tid >> 3;
-      int g_base[4], g_ih[4], g_iw[4];
+      int g_pre[4], g_ih[4], g_iw[4];
       const bool fast1x1 = (p.mode == MODE_GATHER && p.k == 1 && p.stride == 1) || p.transposed;
+      // K walk of this thread's chunk column (general gather): K element gc*8 + 64*ks -> (kh, kw, channel c0), advanced
+      // incrementally per stage -- no division in the stage loop.  All offsets are 32-bit element offsets (plan checks).
+      int w_c0 = gc * 8, w_kh = 0, w_kw = 0;
       if (p.mode == MODE_GATHER && !fast1x1) {
+        while (w_c0 >= p.Cin) {
+          w_c0 -= p.Cin;
+          if (++w_kw == p.k) { w_kw = 0; ++w_kh; }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int m = m0 + r0 + 32 * j;
           const int b = fd_div(p.fd_hw, m);
           const int rem = m - b * p.fd_hw.d;
           const int oh = fd_div(p.fd_wo, rem), ow = rem - oh * p.fd_wo.d;
-          g_base[j] = m < p.M_total ? b * p.H * p.W : -0x40000000;   // invalid rows fail the bounds test below
-          g_ih[j] = oh * p.stride - p.pad;
+          g_ih[j] = m < p.M_total ? oh * p.stride - p.pad : -0x40000000;   // invalid rows fail the bounds test below
           g_iw[j] = ow * p.stride - p.pad;
+          g_pre[j] = ((b * p.H + oh * p.stride - p.pad) * p.W + g_iw[j]) * p.in_pitch;   // element offset of tap (0,0)
         }
       }
 
@@ -416,7 +428,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
 
         if (p.mode == MODE_GATHER) {
           const int kelem = (ks * 8 + gc) * 8;
-          if (kelem < p.K_total) {
+          if (kelem < p.K_total && !(p.dbg_skip & 4)) {
             if (fast1x1) {
               // A is the activation matrix itself: row m, channels kelem..kelem+7
 #pragma unroll
@@ -428,20 +440,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
                 cp_async16_ca(a_dst + gc * p.lbo_a + row * 16, src, ok ? 16u : 0u);
               }
             } else {
-              const int tap = fd_div(p.fd_cin, kelem);
-              const int c0 = kelem - tap * p.Cin;
-              const int kh = p.k == 3 ? tap / 3 : (p.k == 1 ? 0 : tap / p.k);
-              const int kw = tap - kh * p.k;
+              const uint32_t dst0 = a_dst + gc * p.lbo_a + r0 * 16;
+              const int tap_off = (w_kh * p.W + w_kw) * p.in_pitch + w_c0;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const int ih = g_ih[j] + kh, iw = g_iw[j] + kw;
-                const bool ok = g_base[j] >= 0 && static_cast<unsigned>(ih) < static_cast<unsigned>(p.H) &&
-                                static_cast<unsigned>(iw) < static_cast<unsigned>(p.W);
-                const __half* src =
-                    ok ? p.in + (static_cast<size_t>(g_base[j]) + static_cast<size_t>(ih * p.W + iw)) * p.in_pitch + c0
-                       : p.in;
-                cp_async16_ca(a_dst + gc * p.lbo_a + (r0 + 32 * j) * 16, src, ok ? 16u : 0u);
+                const bool ok = static_cast<unsigned>(g_ih[j] + w_kh) < static_cast<unsigned>(p.H) &&
+                                static_cast<unsigned>(g_iw[j] + w_kw) < static_cast<unsigned>(p.W);
+                const int off = ok ? g_pre[j] + tap_off : 0;
+                cp_async16_ca(dst0 + j * 512, p.in + off, ok ? 16u : 0u);
               }
+            }
+          }
+          if (!fast1x1) {   // advance the K walk by one stage (64 K elements)
+            w_c0 += 64;
+            while (w_c0 >= p.Cin) {
+              w_c0 -= p.Cin;
+              if (++w_kw == p.k) { w_kw = 0; ++w_kh; }
             }
           }
         } else {
@@ -522,7 +536,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
             if (kj > 4) kj = 4;
             uint32_t a_lo = a_lo0, b_lo = b_lo0;
             for (int j = 0; j < kj; ++j) {
-              if (elect_one()) umma_f16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | a_lo, (static_cast<uint64_t>(desc_hi) << 32) | b_lo,
+              if (elect_one() && !(p.dbg_skip & 1)) umma_f16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | a_lo, (static_cast<uint64_t>(desc_hi) << 32) | b_lo,
                        p.idesc, acc);
               acc = 1;
               a_lo += 2 * lbo_a16;
@@ -559,6 +573,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
     const int half = ew >> 2;
     const int row = q * 32 + lane;
     int tcount = 0;
+    pdl_wait();   // before the first residual read / output store
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
       const int m_tile = p.n_tiles == 1 ? w : (w >> 1);
       const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
@@ -598,7 +613,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
           co = n - pos * p.Cout;
           pix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
         }
-        if (valid)
+        if (valid && !(p.dbg_skip & 2))
           epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + co : nullptr,
                            p.out + pix * p.out_pitch + co);
       }
@@ -621,8 +636,7 @@ static inline void conv_umma_prepare_device() {
 }
 
 static inline void launch_conv_umma(const ConvParams& p, cudaStream_t stream) {
-  conv_umma_kernel<<<p.grid, CONV_THREADS, p.smem_bytes, stream>>>(p);
-  XR_CUDA(cudaGetLastError());
+  launch_k(conv_umma_kernel, p.grid, CONV_THREADS, p.smem_bytes, stream, p);
 }
 #endif  // __CUDACC__
 

@@ -30,6 +30,7 @@ struct PreParams {
 };
 
 __global__ void preprocess_kernel(const PreParams p) {
+  XR_PDL_ENTRY();
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int b = blockIdx.z;
@@ -87,6 +88,7 @@ struct StemParams {
 };
 
 __global__ void __launch_bounds__(256) stem_conv_kernel(const StemParams p) {
+  XR_PDL_ENTRY();
   extern __shared__ float sw[];  // 36*Cout weights + Cout bias
   for (int i = threadIdx.x; i < 36 * p.Cout; i += blockDim.x) sw[i] = p.w[i];
   for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) sw[36 * p.Cout + i] = p.bias[i];
@@ -151,6 +153,7 @@ struct StemU8Params {
 };
 
 __global__ void __launch_bounds__(256) stem_u8_kernel(const StemU8Params p) {
+  XR_PDL_ENTRY();
   extern __shared__ float sw[];                 // 36*Cout weights + Cout bias, then the u8 patch
   uint8_t* patch = reinterpret_cast<uint8_t*>(sw + 37 * p.Cout);   // [33][33][4]
   for (int i = threadIdx.x; i < 36 * p.Cout; i += 256) sw[i] = p.w[i];
@@ -230,6 +233,7 @@ __device__ __forceinline__ void dw_fma8(float (&acc)[8], const uint4 v, const fl
 }
 
 __global__ void __launch_bounds__(128, 4) dwconv3x3_kernel(const DwParams p) {
+  XR_PDL_ENTRY();
   const int cgs = p.C >> 3;
   const int col = blockIdx.x * 128 + threadIdx.x;       // (x, group) column, group fastest
   if (col >= p.W * cgs) return;
@@ -320,6 +324,7 @@ struct SppfParams {
 };
 
 __global__ void __launch_bounds__(256) sppf_pool_kernel(const SppfParams p) {
+  XR_PDL_ENTRY();
   extern __shared__ uint4 sp4[];    // two ping-pong maps of [H*W] x 8 channels
   const int cg = p.C / 8;
   const int g = blockIdx.x % cg;
@@ -370,6 +375,7 @@ struct UpParams {
 };
 
 __global__ void __launch_bounds__(256) upsample2x_kernel(const UpParams p) {
+  XR_PDL_ENTRY();
   const int cg = p.C / 8;
   const int Ho = p.H * 2, Wo = p.W * 2;
   const long total = static_cast<long>(p.B) * Ho * Wo * cg;
@@ -423,6 +429,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // accumulator fragment of S is re-used directly as the A fragment of P V.  The whole working set of a head is 77 KB
 // of shared memory and 0.06 GFLOP per frame -- too small for a TMEM/tcgen05 pipeline to pay off.
 __global__ void __launch_bounds__(416) attention_kernel(const AttnParams p) {
+  XR_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t att_smem[];
   __half* ks = reinterpret_cast<__half*>(att_smem);                       // [N][ATT_KSTRIDE]
   __half* vs = ks + static_cast<size_t>(p.N) * ATT_KSTRIDE;               // [N][ATT_VSTRIDE]
@@ -564,6 +571,7 @@ constexpr int STEM_PW = 65, STEM_PH = 17, STEM_RAW_WORDS = 52;
 
 template <int NT>
 __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
+  XR_PDL_ENTRY();
   __shared__ uint32_t raw[STEM_PH][STEM_RAW_WORDS];
   __shared__ uint32_t patch[STEM_PH * STEM_PW];
   const int Ho = p.H >> 1, Wo = p.W >> 1;

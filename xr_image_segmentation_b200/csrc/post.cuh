@@ -75,6 +75,7 @@ __device__ __forceinline__ void load16(const __half* p, float (&v)[16]) {
 // compacted through shared memory so that the expensive exact arithmetic runs in dense warps.
 template <typename T>
 __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams<T> p) {
+  XR_PDL_ENTRY();
   __shared__ int s_list[256];
   __shared__ int s_n;
   const int b = blockIdx.y;
@@ -200,6 +201,7 @@ struct SortParams {
 };
 
 __global__ void __launch_bounds__(1024) nms_sort_kernel(const SortParams p) {
+  XR_PDL_ENTRY();
   extern __shared__ unsigned long long skeys[];
   const int b = blockIdx.x;
   const int cnt = min(p.cand_count[b], p.A);
@@ -268,6 +270,7 @@ struct MaskBitsParams {
 };
 
 __global__ void __launch_bounds__(64) nms_bitmask_kernel(const MaskBitsParams p) {
+  XR_PDL_ENTRY();
   const int rb = blockIdx.x, b = blockIdx.y;
   const int n = p.n_cand[b];
   if (rb * 64 >= n) return;
@@ -307,6 +310,7 @@ struct ReduceParams {
 };
 
 __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
+  XR_PDL_ENTRY();
   extern __shared__ unsigned long long rsm[];  // remv[words] + chunk[64*words]
   unsigned long long* remv = rsm;
   unsigned long long* chunk = rsm + p.words;
@@ -351,6 +355,7 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
 
 // exclusive scan of keep_n over frames -> offsets[B+1]
 __global__ void offsets_kernel(const int* keep_n, int B, int* offsets) {
+  XR_PDL_ENTRY();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int acc = 0;
     for (int b = 0; b < B; ++b) {
@@ -376,6 +381,7 @@ struct GatherParams {
 
 template <typename T>
 __global__ void __launch_bounds__(128) gather_kernel(const GatherParams<T> p) {
+  XR_PDL_ENTRY();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int b = warp / p.max_det;
@@ -415,6 +421,7 @@ struct MaskParams {
 
 template <typename T, bool PLANAR>
 __global__ void __launch_bounds__(256) mask_prob_kernel(const MaskParams<T, PLANAR> p) {
+  XR_PDL_ENTRY();
   __shared__ float sc[32][NM + 1];
   const int b = blockIdx.y;
   const int n = p.keep_n[b];

@@ -36,6 +36,12 @@ struct DevLayer {
   float* w32_u8 = nullptr;         // stem weights / 255 for the fused uint8 path
 };
 
+// XRSEG_FLAT_TMA=0: keep the 1x1 convolutions on the thread-gather kernel (A/B measurements only)
+bool flat_tma_disabled() {
+  const char* e = getenv("XRSEG_FLAT_TMA");
+  return e && e[0] == '0';
+}
+
 template <typename T>
 T* dev_alloc(size_t n) {
   T* p = nullptr;
@@ -147,11 +153,15 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       cd.k = o.k; cd.stride = o.stride; cd.act = o.act; cd.transposed = o.transposed;
       cd.res_pitch = o.has_res ? o.res.pitch : 0;
       d.use_tma = r->cfg.conv_impl == XRSEG_CONV_UMMA && plan_conv_halo_tma(cd, r->num_sms, d.cp);
-      if (d.use_tma)
+      if (d.use_tma) {
         d.tmap = make_halo_tensor_map(ptr_of(r, o.x), r->mb, o.x.H, o.x.W, o.x.Cp, o.x.pitch, d.cp.Wp, d.cp.hbox,
                                       d.cp.sw ? d.cp.cb : 8, d.cp.sw);
-      else
+      } else if (r->cfg.conv_impl == XRSEG_CONV_UMMA && !flat_tma_disabled() && plan_conv_flat_tma(cd, r->num_sms, d.cp)) {
+        d.use_tma = true;
+        d.tmap = make_flat_tensor_map(ptr_of(r, o.x), static_cast<long>(r->mb) * o.x.H * o.x.W, o.x.Cp, o.x.pitch, d.cp);
+      } else {
         d.cp = plan_conv(cd, r->num_sms, 0);
+      }
       if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
         std::vector<__half> wp;
         std::vector<float> bp;
@@ -224,14 +234,14 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
             StemMmaParams u = mq;
             u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
             const dim3 grid(ceil_div(u.W / 2, 32), ceil_div(u.H / 2, 8), nb);
-            if (nt == 2) stem_mma_kernel<2><<<grid, 256, 0, st>>>(u);
-            else stem_mma_kernel<4><<<grid, 256, 0, st>>>(u);
+            if (nt == 2) launch_k(stem_mma_kernel<2>, grid, 256, 0, st, u);
+            else launch_k(stem_mma_kernel<4>, grid, 256, 0, st, u);
           } else if (r->fused_src) {
             StemU8Params u = q;
             u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
-            stem_u8_kernel<<<dim3(ceil_div(u.W / 2, 16), ceil_div(u.H / 2, 16), nb), 256, smem_u8, st>>>(u);
+            launch_k(stem_u8_kernel, dim3(ceil_div(u.W / 2, 16), ceil_div(u.H / 2, 16), nb), 256, smem_u8, st, u);
           } else {
-            stem_conv_kernel<<<grid_for(total), 256, smem, st>>>(p);
+            launch_k(stem_conv_kernel, grid_for(total), 256, smem, st, p);
           }
         };
         break;
@@ -250,7 +260,8 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
             cd.B = nb; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
             cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch; cd.k = o.k; cd.stride = o.stride; cd.act = o.act;
             cd.transposed = o.transposed; cd.res_pitch = o.has_res ? o.res.pitch : 0;
-            if (d.use_tma) plan_conv_halo_tma(cd, r->num_sms, p, d.cp.sw != 0);
+            if (d.use_tma && d.cp.mode == MODE_FLAT_TMA) plan_conv_flat_tma(cd, r->num_sms, p);
+            else if (d.use_tma) plan_conv_halo_tma(cd, r->num_sms, p, d.cp.sw != 0);
             else p = plan_conv(cd, r->num_sms, 0);
           }
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
@@ -287,7 +298,7 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.flops = 2.0 * px_out * l.cout * 9;
         L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1)) * 2;
         const dim3 grid(ceil_div(p.W * (p.C / 8), 128), ceil_div(p.H, p.rows), nb);
-        L.fn = [p, grid](cudaStream_t st) { dwconv3x3_kernel<<<grid, 128, 0, st>>>(p); };
+        L.fn = [p, grid](cudaStream_t st) { launch_k(dwconv3x3_kernel, grid, 128, 0, st, p); };
         break;
       }
       case OP_SPPF: {
@@ -295,7 +306,7 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         const size_t smem = static_cast<size_t>(o.x.H) * o.x.W * 32;
         L.name = "sppf.pool";
         L.bytes = px_in * p.C * 4 * 2;
-        L.fn = [p, nb, smem](cudaStream_t st) { sppf_pool_kernel<<<nb * (p.C / 8), 256, smem, st>>>(p); };
+        L.fn = [p, nb, smem](cudaStream_t st) { launch_k(sppf_pool_kernel, nb * (p.C / 8), 256, smem, st, p); };
         break;
       }
       case OP_UP: {
@@ -303,7 +314,7 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         const long total = static_cast<long>(nb) * o.x.H * o.x.W * 4 * (o.x.Cp / 8);
         L.name = "upsample2x";
         L.bytes = px_in * o.x.C * 5 * 2;
-        L.fn = [p, total](cudaStream_t st) { upsample2x_kernel<<<grid_for(total), 256, 0, st>>>(p); };
+        L.fn = [p, total](cudaStream_t st) { launch_k(upsample2x_kernel, grid_for(total), 256, 0, st, p); };
         break;
       }
       case OP_ATTN: {
@@ -316,7 +327,7 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.name = "c2psa.attention";
         L.flops = 2.0 * nb * o.heads * static_cast<double>(p.N) * p.N * (ATT_KD + ATT_HD);
         L.bytes = px_in * (o.x.C + o.y.C) * 2;
-        L.fn = [p, g, smem, threads](cudaStream_t st) { attention_kernel<<<g, threads, smem, st>>>(p); };
+        L.fn = [p, g, smem, threads](cudaStream_t st) { launch_k(attention_kernel, g, threads, smem, st, p); };
         break;
       }
     }
@@ -393,7 +404,7 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     Launch L;
     L.name = "post.decode";
     L.bytes = static_cast<double>(nb) * A * NC * sizeof(T);   // every anchor's class logits; box logits only for candidates
-    L.fn = [dp, A, nb](cudaStream_t st) { decode_kernel<T><<<dim3(ceil_div(A, 256), nb), 256, 0, st>>>(dp); };
+    L.fn = [dp, A, nb](cudaStream_t st) { launch_k(decode_kernel<T>, dim3(ceil_div(A, 256), nb), 256, 0, st, dp); };
     out.push_back(std::move(L));
   }
   SortParams sp{};
@@ -420,20 +431,20 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
   {
     Launch L;
     L.name = "post.nms_sort";
-    L.fn = [sp, nb](cudaStream_t st) { nms_sort_kernel<<<nb, 1024, 16384 * sizeof(unsigned long long), st>>>(sp); };
+    L.fn = [sp, nb](cudaStream_t st) { launch_k(nms_sort_kernel, nb, 1024, 16384 * sizeof(unsigned long long), st, sp); };
     out.push_back(std::move(L));
   }
   {
     Launch L;
     L.name = "post.nms_bitmask";
-    L.fn = [mp, words, nb](cudaStream_t st) { nms_bitmask_kernel<<<dim3(words, nb), 64, 0, st>>>(mp); };
+    L.fn = [mp, words, nb](cudaStream_t st) { launch_k(nms_bitmask_kernel, dim3(words, nb), 64, 0, st, mp); };
     out.push_back(std::move(L));
   }
   {
     Launch L;
     L.name = "post.nms_reduce";
     L.fn = [rp, words, nb](cudaStream_t st) {
-      nms_reduce_kernel<<<nb, 128, static_cast<size_t>(words) * 65 * sizeof(unsigned long long), st>>>(rp);
+      launch_k(nms_reduce_kernel, nb, 128, static_cast<size_t>(words) * 65 * sizeof(unsigned long long), st, rp);
     };
     out.push_back(std::move(L));
   }
@@ -443,7 +454,7 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     const int* keep_n = r->d_keep_n;
     int* offsets = r->d_offsets;
     const int upto = b0 + nb;
-    L.fn = [keep_n, offsets, upto](cudaStream_t st) { offsets_kernel<<<1, 32, 0, st>>>(keep_n, upto, offsets); };
+    L.fn = [keep_n, offsets, upto](cudaStream_t st) { launch_k(offsets_kernel, 1, 32, 0, st, keep_n, upto, offsets); };
     out.push_back(std::move(L));
   }
   if (!src[0].coef) return;  // NMS-only debug path
@@ -460,7 +471,7 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     Launch L;
     L.name = "post.gather";
     const int blocks = ceil_div(nb * r->max_det * 32, 128);
-    L.fn = [gp, blocks](cudaStream_t st) { gather_kernel<T><<<blocks, 128, 0, st>>>(gp); };
+    L.fn = [gp, blocks](cudaStream_t st) { launch_k(gather_kernel<T>, blocks, 128, 0, st, gp); };
     out.push_back(std::move(L));
   }
   if (protos) {
@@ -471,13 +482,14 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     Launch L;
     L.name = "post.mask_prob";
     L.bytes = static_cast<double>(nb) * NM * PROTO_PIX * sizeof(T);   // + 102400 B per detection, added by the caller
-    L.fn = [kp, nb](cudaStream_t st) { mask_prob_kernel<T, PLANAR><<<dim3(PROTO_PIX / 256, nb), 256, 0, st>>>(kp); };
+    L.fn = [kp, nb](cudaStream_t st) { launch_k(mask_prob_kernel<T, PLANAR>, dim3(PROTO_PIX / 256, nb), 256, 0, st, kp); };
     out.push_back(std::move(L));
   }
 }
 
 // frame offset fix-up: gather/mask kernels index frames relative to b0 but o_frame must be global
 __global__ void add_frame_base_kernel(int* frames, const int* offsets, int b0, int nb) {
+  XR_PDL_ENTRY();
   const int b = blockIdx.x;
   if (b >= nb) return;
   const int lo = offsets[b0 + b], hi = offsets[b0 + b + 1];
@@ -502,7 +514,7 @@ void preprocess(xrseg_runner* r, const uint8_t* d_src, int w, int h, int stride_
     p.scale_x = static_cast<float>(w) / 640.0f;
     p.scale_y = static_cast<float>(h) / 640.0f;
   }
-  preprocess_kernel<<<dim3(5, 640, nb), 128, 0, st>>>(p);
+  launch_k(preprocess_kernel, dim3(5, 640, nb), 128, 0, st, p);
   XR_CUDA(cudaGetLastError());
 }
 
@@ -517,7 +529,7 @@ void build_chunk_launches(xrseg_runner* r, int b0, int nb, std::vector<Launch>& 
   L.name = "post.frame_ids";
   int* frames = r->o_frame;
   const int* offsets = r->d_offsets;
-  L.fn = [frames, offsets, b0, nb](cudaStream_t st) { add_frame_base_kernel<<<nb, 64, 0, st>>>(frames, offsets, b0, nb); };
+  L.fn = [frames, offsets, b0, nb](cudaStream_t st) { launch_k(add_frame_base_kernel, nb, 64, 0, st, frames, offsets, b0, nb); };
   out.push_back(std::move(L));
 }
 
@@ -1199,7 +1211,7 @@ int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_
     std::vector<Launch> ls;
     add_post_launches<float, true>(r, 0, batch, src, r->dbg_proto, static_cast<long>(NM) * PROTO_PIX, 0, true, false, ls);
     for (Launch& l : ls) l.fn(st);
-    add_frame_base_kernel<<<batch, 64, 0, st>>>(r->o_frame, r->d_offsets, 0, batch);
+    launch_k(add_frame_base_kernel, batch, 64, 0, st, r->o_frame, r->d_offsets, 0, batch);
     XR_CUDA(cudaGetLastError());
     XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
@@ -1320,7 +1332,9 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
     if (impl == XRSEG_CONV_UMMA) {
       ConvDesc cd{b, h, w, cin_p, cin_p, cout_p, cout_p, k, stride, act, transposed, residual ? cout_p : 0};
       ConvParams p;
-      const bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, prop.multiProcessorCount, p, variant == 0);
+      bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, prop.multiProcessorCount, p, variant == 0);
+      const bool flat = !tma && variant == 0 && plan_conv_flat_tma(cd, prop.multiProcessorCount, p);
+      tma = tma || flat;
       if (!tma) p = plan_conv(cd, prop.multiProcessorCount, variant & 1);
       std::vector<__half> wp;
       std::vector<float> bp;
@@ -1345,7 +1359,8 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
         if (rep == reps - 1) XR_CUDA(cudaEventRecord(e0, 0));
         if (tma) {
           conv_tma_prepare_device();
-          const CUtensorMap map = make_halo_tensor_map(d_x, b, h, w, cin_p, cin_p, p.Wp, p.hbox, p.sw ? p.cb : 8, p.sw);
+          const CUtensorMap map = flat ? make_flat_tensor_map(d_x, static_cast<long>(b) * h * w, cin_p, cin_p, p)
+                                       : make_halo_tensor_map(d_x, b, h, w, cin_p, cin_p, p.Wp, p.hbox, p.sw ? p.cb : 8, p.sw);
           launch_conv_halo_tma(p, map, 0);
         } else {
           launch_conv_umma(p, 0);
@@ -1356,8 +1371,8 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
       if (reps > 1) {
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        fprintf(stderr, "xrseg_debug_conv: mode %d sw %d cb %d S %d nsub %d R %d grid %d smem %d skip %d: %.1f us\n", p.mode, p.sw, p.cb,
-                p.S, p.nsub, p.R, p.grid, p.smem_bytes, p.dbg_skip, ms * 1e3f);
+        fprintf(stderr, "xrseg_debug_conv: mode %d sw %d cb %d S %d nks %d nsub %d R %d grid %d smem %d tiles %d skip %d: %.1f us\n", p.mode, p.sw, p.cb,
+                p.S, p.nks, p.nsub, p.R, p.grid, p.smem_bytes, p.m_tiles * p.n_tiles, p.dbg_skip, ms * 1e3f);
         if (d_clk) {
           std::vector<long long> h(static_cast<size_t>(p.grid) * 8);
           XR_CUDA(cudaMemcpy(h.data(), d_clk, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
@@ -1414,7 +1429,9 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
     const int wo = transposed ? w * 2 : (w + 2 * (k / 2) - k) / stride + 1;
     ConvDesc cd{b, h, w, cin_p, cin_p, cout_p, cout_p, k, stride, act, transposed, residual ? cout_p : 0};
     ConvParams p;
-    const bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, 148, p, variant == 0);
+    bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, 148, p, variant == 0);
+    const bool flat = !tma && variant == 0 && plan_conv_flat_tma(cd, 148, p);
+    tma = tma || flat;
     if (!tma) p = plan_conv(cd, 148, variant & 1);
     std::vector<float> wp, bp;
     std::vector<float> zero_bias(cout, 0.f);
@@ -1430,7 +1447,8 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
         for (int c = 0; c < cout; ++c)
           for (int i = 0; i < ho * wo; ++i) rr[(static_cast<size_t>(n) * ho * wo + i) * cout_p + c] = residual[(static_cast<size_t>(n) * cout + c) * ho * wo + i];
     }
-    if (tma) emulate_conv_halo_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
+    if (flat) emulate_conv_flat_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
+    else if (tma) emulate_conv_halo_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
     else emulate_conv_umma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
     for (int n = 0; n < b; ++n)
       for (int c = 0; c < cout; ++c)

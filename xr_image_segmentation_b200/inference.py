@@ -222,6 +222,43 @@ class Runner:
         return out
 
 
+class PipelinedRunner:
+    """`depth` runners on one GPU used round-robin: the host->device copy and the network pass of submission i+1
+    overlap the readback of submission i (each runner still has exactly one run in flight, like the reference's
+    `_started` gate, IEE:365).  Throughput-oriented callers use this instead of a single Runner."""
+
+    def __init__(self, model: Model, device: int = 0, max_batch: int = 1, depth: int = 2, **runner_kw):
+        self.runners = [Runner(model, device=device, max_batch=max_batch, **runner_kw) for _ in range(depth)]
+        self._head = 0          # next runner to submit to
+        self._inflight = []     # runner indices in submission order
+
+    def submit_ptr(self, host_ptr: int, b, h, w, c):
+        if len(self._inflight) == len(self.runners):
+            raise XrsegError(_lib.ERR_STATE, "pipeline full: collect() first")
+        self.runners[self._head].schedule_ptr(host_ptr, b, h, w, c)
+        self._inflight.append(self._head)
+        self._head = (self._head + 1) % len(self.runners)
+
+    def submit(self, frames: np.ndarray):
+        if len(self._inflight) == len(self.runners):
+            raise XrsegError(_lib.ERR_STATE, "pipeline full: collect() first")
+        self.runners[self._head].schedule(frames)
+        self._inflight.append(self._head)
+        self._head = (self._head + 1) % len(self.runners)
+
+    def collect(self, mask_mode=_lib.MASK_BITS_160):
+        """Results of the oldest submission: (counts, boxes [N,4], labels [N], masks)."""
+        if not self._inflight:
+            raise XrsegError(_lib.ERR_STATE, "nothing in flight")
+        r = self.runners[self._inflight.pop(0)]
+        r.wait()
+        return r.counts(), r.readback(0), r.readback(1), r.masks(mask_mode)
+
+    def close(self):
+        for r in self.runners:
+            r.close()
+
+
 def debug_conv(x, w, b, k, stride, act, transposed=False, residual=None, impl=_lib.CONV_UMMA, variant=0, device=0):
     """One convolution through the CUDA library (parity tests)."""
     lib = _lib.load_library()

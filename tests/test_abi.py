@@ -76,6 +76,10 @@ CASES = [
     (3, 128, 32, 4, 4, 3, 1, 1, False, True, 0), (1, 16, 8, 3, 170, 3, 1, 1, False, False, 0),
     (1, 256, 512, 3, 3, 1, 1, 1, False, False, 0), (1, 128, 128, 3, 3, 2, 2, 0, True, False, 0),
     (1, 256, 64, 5, 4, 3, 1, 1, False, False, 0),
+    # stride-2 3x3 on even maps -> parity-plane TMA mode (variant 0); flat 1x1 with a partial last K-block / 2 N tiles
+    (1, 16, 32, 12, 10, 3, 2, 1, False, False, 0), (2, 64, 64, 8, 8, 3, 2, 1, False, False, 0),
+    (1, 128, 256, 6, 4, 3, 2, 0, False, False, 0), (1, 32, 16, 40, 6, 3, 2, 1, False, False, 0),
+    (2, 144, 32, 5, 5, 1, 1, 1, False, False, 0), (1, 512, 256, 4, 4, 1, 1, 1, False, True, 0),
 ]
 
 

@@ -35,13 +35,17 @@ CONV_CASES = [
     (1, 64, 64, 20, 160, 3, 1, 1, False, False), (3, 128, 32, 20, 20, 3, 1, 1, False, True),
     (1, 256, 64, 20, 20, 3, 1, 1, False, False), (1, 80, 80, 7, 7, 1, 1, 0, False, False),
     (5, 32, 32, 33, 17, 3, 1, 1, False, False), (1, 512, 256, 10, 10, 1, 1, 1, False, False),
+    # stride-2 3x3 on even maps (parity-plane TMA mode under variant 0) at the network's own shapes, and thin 1x1 layers
+    (2, 16, 32, 64, 64, 3, 2, 1, False, False), (1, 128, 128, 40, 40, 3, 2, 1, False, False),
+    (2, 128, 256, 40, 40, 3, 2, 1, False, False), (1, 64, 64, 160, 160, 3, 2, 1, False, False),
+    (3, 32, 32, 24, 20, 1, 1, 1, False, True), (2, 144, 80, 16, 16, 1, 1, 0, False, False),
 ]
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 4])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_tcgen05_conv_vs_torch(lib, case, variant):
-    """variant 0: product plan (TMA halo for 3x3 s1, gather otherwise); 1: gather everywhere; 2: thread-loaded halo; 4: TMA halo with unswizzled operands."""
+    """variant 0: product plan (TMA halo for 3x3 s1, parity-plane TMA for 3x3 s2 on even maps, flat TMA for 1x1, gather otherwise); 1: gather everywhere; 2: thread-loaded halo; 4: TMA halo with unswizzled operands."""
     B, cin, cout, h, wd, k, s, act, tr, useres = case
     rng = np.random.default_rng(abs(hash(case)) % 2**32)
     x = rng.standard_normal((B, cin, h, wd), dtype=np.float32)

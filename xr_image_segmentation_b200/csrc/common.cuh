@@ -165,7 +165,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
-      printf("xrseg: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      if ((threadIdx.x & 31) == 0)
+        printf("xrseg: mbarrier wait timeout (block %d of %d, thread %d, barrier @%u parity %u)\n", blockIdx.x, gridDim.x,
+               threadIdx.x, smem_u32(bar) & 0xFFFFu, parity);
       __trap();
     }
   }

@@ -19,7 +19,12 @@
 
 namespace xrseg {
 
-enum { MODE_HALO_TMA = 2, MODE_FLAT_TMA = 3 };
+enum { MODE_HALO_TMA = 2, MODE_FLAT_TMA = 3, MODE_S2_TMA = 4 };
+
+// Up to four tensor maps per launch (MODE_S2_TMA reads four parity planes of the input; the other modes use m[0]).
+struct TmapSet {
+  CUtensorMap m[4];
+};
 enum { TMA_THREADS = 320, TMA_TAIL_PAD = 4096 };
 
 struct TmaPlanExtra {
@@ -193,6 +198,128 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
 }
 
 
+// General 4-D tiled map over fp16 data: dims / strides (bytes, dims 1..3) / box given explicitly.
+static inline CUtensorMap make_tensor_map_4d(const __half* base, const cuuint64_t (&dims)[4], const cuuint64_t (&strides)[3],
+                                             const cuuint32_t (&box)[4], int sw) {
+  CUtensorMap m;
+  const CUtensorMapSwizzle swz = sw == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : sw == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : sw == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  XR_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return m;
+}
+
+// 3x3 STRIDE-2 convolution on the same kernel ("s2" mode).  The input is read as four parity planes
+//     plane(py,px)[ys][xs] = X[2 ys + py][2 xs + px]          (four tensor maps: same dims, base shifted by (py W + px) pixels,
+//                                                               x / y strides doubled)
+// so that every tap is again a pure row shift of a plane buffer in position-linear order (position j = yy*(Wo+1) + cc,
+// cc = ox + 1): tap (kh,kw) reads plane (kh != 1, kw != 1) at row j + (kh == 2 ? Wo+1 : 0) - (kw == 0 ? 1 : 0).
+// Per K-block the producer issues four TMA boxes (cb channels, Wo+1 columns from xs = -1, R+1 rows from ys = oy0 - py);
+// out-of-bounds coordinates are the convolution's zero padding.  The input is read ~(R+1)/R times instead of 2.25x by
+// the im2col gather, and nothing but one thread touches addresses.
+// NOTE: p.H / p.W / p.Wp hold the OUTPUT geometry (Ho, Wo, Wo+1) in this mode -- that is what the epilogue indexes.
+static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+  if (!(d.k == 3 && d.stride == 2 && !d.transposed) || (d.H & 1) || (d.W & 1)) return false;
+  p = ConvParams{};
+  const int Ho = d.H / 2, Wo = d.W / 2;
+  p.B = d.B; p.H = Ho; p.W = Wo; p.Cin = d.Cin; p.in_pitch = d.in_pitch;
+  p.Cout = d.Cout; p.out_pitch = d.out_pitch; p.res_pitch = d.res_pitch;
+  p.k = 3; p.stride = 2; p.pad = 1; p.act = d.act; p.transposed = 0;
+  p.Ho = Ho; p.Wo = Wo;
+  p.Ntile = d.Cout <= 256 ? d.Cout : 256;
+  if (d.Cout % p.Ntile) return false;
+  p.n_tiles = d.Cout / p.Ntile;
+  p.idesc = umma_idesc_f16(p.Ntile, 0);
+  p.mode = MODE_S2_TMA;
+  p.taps = 9;
+  p.K_total = 9 * d.Cin;
+  p.Wp = Wo + 1;
+  p.Hp1 = Ho + 1;
+  int nsub_max = 256 / p.Ntile;
+  if (nsub_max > 4) nsub_max = 4;
+  if (nsub_max < 1 || p.Wp > 255) return false;
+  const long total_w = 9L * d.Cin * p.Ntile * 2;
+  p.b_resident = (p.n_tiles == 1 && total_w <= 98304) ? 1 : 0;
+  const int resident = p.b_resident ? static_cast<int>(total_w) : 0;
+  // search (cb, R) for the lowest estimated cycles per output position.  Measured constants (tools/probe_tma.py): one
+  // tcgen05.mma costs the issuing thread ~50 cycles (or its tensor time 128*N/256 if larger), one stage hand-over ~600,
+  // one epilogue pass over 128 rows x 32 columns ~650; a 2-stage ring stalls more than a 3-stage one.
+  int best_cb = 0, best_R = 0, best_S = 0;
+  double best_cost = 1e30;
+  for (int cb = 64; cb >= 16; cb >>= 1) {
+    if (cb > d.Cin || d.Cin % cb) continue;
+    const int rb = cb * 2;
+    for (int R = (128 * nsub_max) / p.Wp; R >= 1; --R) {
+      if (R > Ho) continue;
+      const int plane = round_up((R + 1) * p.Wp * rb, 1024);
+      const int b_stage = 9 * p.Ntile * rb;
+      const int fixed = round_up(CONV_HDR_BYTES, 1024) + 1024 + 128 * rb + 1024 + p.Wp * rb + round_up(resident, 1024);
+      int S = (CONV_SMEM_MAX - fixed) / (4 * plane + (p.b_resident ? 0 : round_up(b_stage, 1024)));
+      if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
+      if (S > 2 * (d.Cin / cb) + 2) S = 2 * (d.Cin / cb) + 2;
+      if (S < 2) continue;
+      const int nks = d.Cin / cb, nsub = ceil_div(R * p.Wp, 128);
+      const double mma_each = p.Ntile / 2.0 > 50.0 ? p.Ntile / 2.0 : 50.0;
+      const double t_mma = nks * 600.0 + 9.0 * (d.Cin / 16) * nsub * mma_each;
+      const double t_epi = nsub * ceil_div(p.Ntile, 32) * 650.0;
+      const double t_mem = 4.0 * (R + 1) * p.Wp * d.Cin * 2 / 40.0;          // smem fill at ~40 B/clk from L2
+      double t = t_mma > t_epi ? t_mma : t_epi;
+      if (t_mem > t) t = t_mem;
+      t = (t + 800.0) * (S >= 3 ? 1.0 : 1.15);
+      const int items = d.B * ceil_div(Ho, R) * p.n_tiles;
+      const double cost = t * ceil_div(items, num_sms);                       // the busiest CTA's time (wave quantization)
+      if (cost < best_cost) { best_cost = cost; best_cb = cb; best_R = R; best_S = S; }
+    }
+  }
+  if (best_S < 2) return false;
+  const int cb = best_cb, rb = cb * 2;
+  p.cb = cb; p.cps = cb / 8; p.nks = d.Cin / cb; p.kps = 1;
+  p.sw = cb == 64 ? 3 : (cb == 32 ? 2 : 1);
+  p.R = best_R;
+  p.S = best_S;
+  p.nsub = ceil_div(p.R * p.Wp, 128);
+  p.tpi = ceil_div(Ho, p.R);
+  p.hbox = p.R + 1;
+  p.slots = p.hbox * p.Wp;                         // rows of ONE plane box
+  p.lbo_a = round_up(p.slots * rb, 1024);          // bytes of one plane buffer
+  p.a_stage_bytes = 4 * p.lbo_a;
+  p.b_stage_bytes = 9 * p.Ntile * rb;
+  p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
+  p.M_total = d.B * p.tpi;
+  p.m_tiles = p.M_total;
+  p.smem_off_b = round_up(CONV_HDR_BYTES, 1024);
+  const int b_region = p.b_resident ? resident : p.S * round_up(p.b_stage_bytes, 1024);
+  p.smem_off_a = p.smem_off_b + round_up(b_region, 1024) + 1024;        // one pad row block before the stages (offset -1)
+  p.smem_bytes = p.smem_off_a + p.S * p.a_stage_bytes + 128 * rb + p.Wp * rb + 1024;   // tail: rows read past the last plane
+  if (p.smem_bytes > CONV_SMEM_MAX) return false;
+  const int work = p.m_tiles * p.n_tiles;
+  p.grid = work < num_sms ? work : num_sms;
+  p.fd_wp = make_fastdiv(p.Wp);
+  p.fd_hp1 = make_fastdiv(p.tpi);
+  p.fd_hw = make_fastdiv(1);
+  p.fd_wo = make_fastdiv(1);
+  p.fd_cin = make_fastdiv(d.Cin);
+  p.fd_cout = make_fastdiv(d.Cout);
+  return true;
+}
+
+// The four parity-plane maps of an NHWC input [B,H,W,C] (pixel pitch `pitch`): index py*2 + px.
+static inline TmapSet make_s2_tensor_maps(const __half* base, int B, int H, int W, int C, int pitch, const ConvParams& p) {
+  TmapSet t{};
+  const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W / 2), static_cast<cuuint64_t>(H / 2),
+                              static_cast<cuuint64_t>(B)};
+  const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 4, static_cast<cuuint64_t>(W) * pitch * 4,
+                                 static_cast<cuuint64_t>(H) * W * pitch * 2};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(p.cb), static_cast<cuuint32_t>(p.Wp), static_cast<cuuint32_t>(p.hbox), 1};
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px)
+      t.m[py * 2 + px] = make_tensor_map_4d(base + (static_cast<size_t>(py) * W + px) * pitch, dims, strides, box, p.sw);
+  return t;
+}
+
 // 1x1 stride-1 convolution = plain GEMM over the flattened [B*H*W, C] activation matrix ("flat" mode of the same
 // kernel): a work item is 128*nsub consecutive pixels, its A operand ONE (or two) 2-D TMA boxes of cb channels x <= 256
 // rows per K-block, swizzled like the halo boxes; taps = 1.  One mbarrier arrival per stage instead of one per producer
@@ -278,6 +405,28 @@ static inline CUtensorMap make_flat_tensor_map(const __half* base, long rows, in
   return make_halo_tensor_map(base, 1, 1, static_cast<int>(rows), C, pitch, p.hbox, 1, p.cb, p.sw);
 }
 
+// Same layer, fewer frames (the last chunk of a batch): keep every layout-determining choice of the full plan (K-block,
+// rows per item, sub-tiles, stages -- the weight image and the tensor-map boxes were built for them) and shrink only the
+// batch-dependent extents.
+static inline ConvParams replan_for_batch(const ConvParams& full, int nb, int num_sms) {
+  ConvParams p = full;
+  p.B = nb;
+  if (p.mode == MODE_FLAT_TMA) {
+    p.flat_rows = nb * p.H * p.W;
+    p.M_total = ceil_div(p.flat_rows, p.slots);
+  } else if (p.mode == MODE_HALO_TMA || p.mode == MODE_S2_TMA) {
+    p.M_total = nb * p.tpi;
+  } else if (p.mode == MODE_HALO) {
+    p.M_total = nb * p.Hp1 * p.Wp;
+  } else {
+    p.M_total = p.transposed ? nb * p.H * p.W : nb * p.Ho * p.Wo;
+  }
+  p.m_tiles = (p.mode == MODE_GATHER || p.mode == MODE_HALO) ? ceil_div(p.M_total, 128) : p.M_total;
+  const int work = p.m_tiles * p.n_tiles;
+  p.grid = work < num_sms ? work : num_sms;
+  return p;
+}
+
 // Physical byte offset of logical offset `off` inside a pattern-aligned swizzled buffer (Swizzle<sw,4,3>): the 16-byte
 // chunk index (address bits 4..6) is XORed with address bits 7..9, masked to the swizzle width.
 static inline size_t sw_phys(size_t off, int sw) {
@@ -335,7 +484,8 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ CUtensorMap tmap) {
+conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ TmapSet tmaps) {
+  const CUtensorMap& tmap = tmaps.m[0];
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
   uint64_t* empty = full + 8;                               // [8]
@@ -351,7 +501,6 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code uses the uniform datapath
   const int lane = tid & 31;
   const int total_work = p.m_tiles * p.n_tiles;
-  pdl_launch_dependents();
 
   if (tid == 0) {
     for (int i = 0; i < CONV_MAX_STAGES; ++i) {
@@ -365,6 +514,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     mbar_init(bres, 1);
     mbar_fence_init();
     prefetch_tensormap(&tmap);
+    if (p.mode == MODE_S2_TMA)
+      for (int i = 1; i < 4; ++i) prefetch_tensormap(&tmaps.m[i]);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
@@ -375,13 +526,17 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Only now may the next kernel's CTAs start (PDL): a dependent CTA that became co-resident and grabbed TMEM columns
+  // before this CTA had its own would wait for this kernel to finish while this CTA waits for its columns -- deadlock.
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ======================================= TMA producer ========================================
     if (lane == 0) {
       const uint32_t a_u32 = smem_u32(smem_a);
       const uint32_t b_u32 = smem_u32(smem_b);
-      const uint32_t a_tx = static_cast<uint32_t>(p.cps) * p.slots * 16u * (p.kps > 1 ? p.kps : 1);   // slots * row bytes (* K-blocks)
+      const uint32_t a_tx = static_cast<uint32_t>(p.cps) * p.slots * 16u * (p.kps > 1 ? p.kps : 1) *   // slots * row bytes (* K-blocks)
+                            (p.mode == MODE_S2_TMA ? 4u : 1u);                                           // (* parity planes)
       const uint32_t b_stride = p.sw ? static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023) : static_cast<uint32_t>(p.b_stage_bytes);
       if (p.b_resident) {
         const uint32_t bytes = static_cast<uint32_t>(p.nks) * p.b_stage_bytes;
@@ -408,7 +563,11 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           if (p.dbg_skip & 4) { mbar_arrive(&full[slot]); continue; }
           mbar_arrive_expect_tx(&full[slot], a_tx + (p.b_resident ? 0u : static_cast<uint32_t>(p.b_stage_bytes)));
           const uint32_t a_dst = a_u32 + slot * p.a_stage_bytes;
-          if (flat) {
+          if (p.mode == MODE_S2_TMA) {
+            // four parity planes: columns xs = -1 .. Wo-1, rows ys = y0 - py .. y0 - py + R  (y0 = first OUTPUT row)
+            for (int pl = 0; pl < 4; ++pl)
+              tma_load_4d(a_dst + pl * p.lbo_a, &tmaps.m[pl], &full[slot], ks * p.cb, -1, y0 - (pl >> 1), b);
+          } else if (flat) {
             // rows [tile*slots, +slots) of the activation matrix, hbox rows per box, kps K-blocks per stage; rows past
             // the end and channels past Cin arrive as zeros
             const uint32_t box_bytes = static_cast<uint32_t>(p.hbox) * p.cb * 2u;
@@ -489,31 +648,30 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             // unrolled with guards folded into the issue predicate: a handful of uniform adds per MMA, no branches.
             if (elect_one()) {   // one branch per stage; inside, a single lane issues the whole MMA batch
               uint32_t acc = ks > 0 ? 1u : 0u;
-              const int kdim = p.taps == 9 ? 3 : 1;             // flat (1x1) mode: a single tap, no row shift
-              const int tap_bias = p.taps == 9 ? 1 : 0;
               const int kps = p.kps > 1 ? p.kps : 1;
-              const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;   // one K-block sub-buffer of the stage
-              for (int kb = 0; kb < kps; ++kb)
+              const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;   // one K-block sub-buffer of the stage (flat)
+              const uint32_t plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;    // one parity-plane buffer (s2)
+              for (int kb = 0; kb < kps; ++kb) {
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh) {
-                if (kh >= kdim) break;
-                const uint32_t a_kh = a_lo_stage + kb * blk16 + static_cast<uint32_t>(kh * p.Wp - tap_bias) * row16;
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                  if (kw >= kdim) break;
-                  const uint32_t a_tap = a_kh + static_cast<uint32_t>(kw) * row16;
+                for (int t = 0; t < 9; ++t) {
+                  if (t >= p.taps) break;
+                  const int kh = t / 3, kw = t - 3 * kh;
+                  // start row of tap t relative to the stage: a pure row shift in every mode
+                  uint32_t a_tap = a_lo_stage + kb * blk16;
+                  if (p.mode == MODE_HALO_TMA) a_tap += static_cast<uint32_t>(kh * p.Wp + kw - 1) * row16;
+                  else if (p.mode == MODE_S2_TMA)
+                    a_tap += static_cast<uint32_t>((kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0)) * plane16 +
+                             static_cast<uint32_t>((kh == 2 ? p.Wp : 0) - (kw == 0 ? 1 : 0)) * row16;
                   for (int j = 0; j < kj; ++j) {
-                    {
-                      const uint64_t bd = hi_sw | (b_lo + 2u * j);
+                    const uint64_t bd = hi_sw | (b_lo + 2u * j);
 #pragma unroll
-                      for (int u = 0; u < 4; ++u) {
-                        if (u < nsub && mma_on) {
-                          const uint64_t ad = hi_sw | (a_tap + static_cast<uint32_t>(u) * sub16 + 2u * j);
-                          umma_f16(d_base + static_cast<uint32_t>(u) * ntile_u, ad, bd, idesc, acc);
-                        }
+                    for (int u = 0; u < 4; ++u) {
+                      if (u < nsub && mma_on) {
+                        const uint64_t ad = hi_sw | (a_tap + static_cast<uint32_t>(u) * sub16 + 2u * j);
+                        umma_f16(d_base + static_cast<uint32_t>(u) * ntile_u, ad, bd, idesc, acc);
                       }
-                      acc = 1;
                     }
+                    acc = 1;
                   }
                   b_lo += tap16;   // next tap's weight tile
                 }
@@ -630,8 +788,13 @@ static inline void conv_tma_prepare_device() {
   XR_CUDA(cudaFuncSetAttribute(conv_halo_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
 }
 
+static inline void launch_conv_halo_tma(const ConvParams& p, const TmapSet& maps, cudaStream_t stream) {
+  launch_k(conv_halo_tma_kernel, p.grid, TMA_THREADS, p.smem_bytes, stream, p, maps);
+}
 static inline void launch_conv_halo_tma(const ConvParams& p, const CUtensorMap& map, cudaStream_t stream) {
-  launch_k(conv_halo_tma_kernel, p.grid, TMA_THREADS, p.smem_bytes, stream, p, map);
+  TmapSet t{};
+  t.m[0] = map;
+  launch_conv_halo_tma(p, t, stream);
 }
 #endif  // __CUDACC__
 
@@ -739,6 +902,68 @@ static inline void emulate_conv_flat_tma(const ConvParams& p, const float* in, c
       }
     }
   }
+}
+
+// ---- host emulation of the stride-2 parity-plane mode ----------------------------------------------------------------
+// `in` is the NHWC input [B, 2*p.H, 2*p.W, in_pitch]; follows the kernel literally: four plane boxes per K-block, taps as
+// row shifts, epilogue on position-linear indices.  Valid outputs must never read outside their plane buffer.
+static inline bool emulate_conv_s2_tma(const ConvParams& p, const float* in, const float* wpack_f, const float* bias,
+                                       const float* res, float* out) {
+  const int H = 2 * p.H, W = 2 * p.W, rb = p.cb * 2;
+  const int plane_rows = p.slots;
+  std::vector<float> a(static_cast<size_t>(4) * plane_rows * p.cb);
+  std::vector<float> acc(static_cast<size_t>(p.nsub) * 128 * p.Ntile);
+  for (int w = 0; w < p.m_tiles * p.n_tiles; ++w) {
+    const int tile = w / p.n_tiles, n_tile = w % p.n_tiles;
+    const int b = tile / p.tpi, y0 = (tile % p.tpi) * p.R;
+    std::fill(acc.begin(), acc.end(), 0.f);
+    for (int ks = 0; ks < p.nks; ++ks) {
+      std::fill(a.begin(), a.end(), 0.f);
+      for (int pl = 0; pl < 4; ++pl) {
+        const int py = pl >> 1, px = pl & 1;
+        for (int by = 0; by < p.hbox; ++by)
+          for (int bx = 0; bx < p.Wp; ++bx) {
+            const int ys = y0 - py + by, xs = -1 + bx;
+            if (ys < 0 || ys >= H / 2 || xs < 0 || xs >= W / 2) continue;     // OOB -> zero fill
+            const size_t pix = (static_cast<size_t>(b) * H + 2 * ys + py) * W + 2 * xs + px;
+            for (int c = 0; c < p.cb; ++c)
+              a[(static_cast<size_t>(pl) * plane_rows + by * p.Wp + bx) * p.cb + c] = in[pix * p.in_pitch + ks * p.cb + c];
+          }
+      }
+      const float* bst = wpack_f + (static_cast<size_t>(n_tile) * p.nks + ks) * (p.b_stage_bytes / 2);
+      for (int j = 0; j < p.nsub * 128; ++j) {
+        const int yy = j / p.Wp, cc = j % p.Wp;
+        const bool valid = yy < p.R && y0 + yy < p.H && cc >= 1;
+        if (!valid) continue;
+        for (int t = 0; t < 9; ++t) {
+          const int kh = t / 3, kw = t % 3;
+          const int pl = (kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0);
+          const int row = j + (kh == 2 ? p.Wp : 0) - (kw == 0 ? 1 : 0);
+          if (row < 0 || row >= plane_rows) return false;                     // a valid output left its plane buffer
+          for (int n = 0; n < p.Ntile; ++n) {
+            float sacc = 0.f;
+            for (int c = 0; c < p.cb; ++c)
+              sacc += a[(static_cast<size_t>(pl) * plane_rows + row) * p.cb + c] *
+                      bst[sw_phys((static_cast<size_t>(t) * p.Ntile + n) * rb + c * 2, p.sw) / 2];
+            acc[static_cast<size_t>(j) * p.Ntile + n] += sacc;
+          }
+        }
+      }
+    }
+    for (int j = 0; j < p.nsub * 128; ++j) {
+      const int yy = j / p.Wp, cc = j % p.Wp, y = y0 + yy;
+      if (!(yy < p.R && y < p.H && cc >= 1 && cc <= p.W)) continue;
+      const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
+      for (int n = 0; n < p.Ntile; ++n) {
+        const int ng = n_tile * p.Ntile + n;
+        float yv = acc[static_cast<size_t>(j) * p.Ntile + n] + bias[ng];
+        if (p.act) yv = yv / (1.0f + expf(-yv));
+        if (res) yv += res[pix * p.res_pitch + ng];
+        out[pix * p.out_pitch + ng] = yv;
+      }
+    }
+  }
+  return true;
 }
 
 }  // namespace xrseg

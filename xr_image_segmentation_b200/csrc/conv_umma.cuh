@@ -355,7 +355,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code uses the uniform datapath
   const int lane = tid & 31;
   const int total_work = p.m_tiles * p.n_tiles;
-  pdl_launch_dependents();   // the next kernel's CTAs may take this SM as soon as we leave it (its prologue overlaps our tail)
 
   if (tid == 0) {
     for (int i = 0; i < CONV_MAX_STAGES; ++i) {
@@ -378,6 +377,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Only now may the next kernel's CTAs start (PDL): a dependent CTA that became co-resident and grabbed TMEM columns
+  // before this CTA had its own would wait for this kernel to finish while this CTA waits for its columns -- deadlock.
+  pdl_launch_dependents();
 
   if (warp < CONV_NPROD / 32) {
     // ======================================= producers ===========================================

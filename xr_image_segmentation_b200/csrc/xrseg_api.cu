@@ -27,7 +27,7 @@ struct DevLayer {
   // OP_CONV (UMMA)
   ConvParams cp{};
   bool use_tma = false;            // 3x3 stride-1 layers: halo fetched by TMA (conv_tma.cuh)
-  CUtensorMap tmap{};
+  TmapSet tmaps{};
   __half* wpack = nullptr;
   float* bias = nullptr;
   // OP_CONV (direct) / OP_DW / OP_STEM
@@ -39,6 +39,11 @@ struct DevLayer {
 // XRSEG_FLAT_TMA=0: keep the 1x1 convolutions on the thread-gather kernel (A/B measurements only)
 bool flat_tma_disabled() {
   const char* e = getenv("XRSEG_FLAT_TMA");
+  return e && e[0] == '0';
+}
+
+bool s2_tma_disabled() {
+  const char* e = getenv("XRSEG_S2_TMA");
   return e && e[0] == '0';
 }
 
@@ -154,11 +159,14 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       cd.res_pitch = o.has_res ? o.res.pitch : 0;
       d.use_tma = r->cfg.conv_impl == XRSEG_CONV_UMMA && plan_conv_halo_tma(cd, r->num_sms, d.cp);
       if (d.use_tma) {
-        d.tmap = make_halo_tensor_map(ptr_of(r, o.x), r->mb, o.x.H, o.x.W, o.x.Cp, o.x.pitch, d.cp.Wp, d.cp.hbox,
-                                      d.cp.sw ? d.cp.cb : 8, d.cp.sw);
+        d.tmaps.m[0] = make_halo_tensor_map(ptr_of(r, o.x), r->mb, o.x.H, o.x.W, o.x.Cp, o.x.pitch, d.cp.Wp, d.cp.hbox,
+                                            d.cp.sw ? d.cp.cb : 8, d.cp.sw);
       } else if (r->cfg.conv_impl == XRSEG_CONV_UMMA && !flat_tma_disabled() && plan_conv_flat_tma(cd, r->num_sms, d.cp)) {
         d.use_tma = true;
-        d.tmap = make_flat_tensor_map(ptr_of(r, o.x), static_cast<long>(r->mb) * o.x.H * o.x.W, o.x.Cp, o.x.pitch, d.cp);
+        d.tmaps.m[0] = make_flat_tensor_map(ptr_of(r, o.x), static_cast<long>(r->mb) * o.x.H * o.x.W, o.x.Cp, o.x.pitch, d.cp);
+      } else if (r->cfg.conv_impl == XRSEG_CONV_UMMA && !s2_tma_disabled() && plan_conv_s2_tma(cd, r->num_sms, d.cp)) {
+        d.use_tma = true;
+        d.tmaps = make_s2_tensor_maps(ptr_of(r, o.x), r->mb, o.x.H, o.x.W, o.x.Cp, o.x.pitch, d.cp);
       } else {
         d.cp = plan_conv(cd, r->num_sms, 0);
       }
@@ -255,21 +263,13 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1) + static_cast<double>(l.cout) * l.cin * o.k * o.k) * 2;
         if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
           ConvParams p = d.cp;
-          if (nb != p.B) {  // partial last chunk: re-plan the M extent only (the weight packing does not depend on B)
-            ConvDesc cd{};
-            cd.B = nb; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
-            cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch; cd.k = o.k; cd.stride = o.stride; cd.act = o.act;
-            cd.transposed = o.transposed; cd.res_pitch = o.has_res ? o.res.pitch : 0;
-            if (d.use_tma && d.cp.mode == MODE_FLAT_TMA) plan_conv_flat_tma(cd, r->num_sms, p);
-            else if (d.use_tma) plan_conv_halo_tma(cd, r->num_sms, p, d.cp.sw != 0);
-            else p = plan_conv(cd, r->num_sms, 0);
-          }
+          if (nb != p.B) p = replan_for_batch(d.cp, nb, r->num_sms);   // partial last chunk: same layout, fewer frames
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
           p.res = o.has_res ? ptr_of(r, o.res) : nullptr;
           p.wpack = d.wpack; p.bias = d.bias;
           if (d.use_tma) {
-            const CUtensorMap map = d.tmap;
-            L.fn = [p, map](cudaStream_t st) { launch_conv_halo_tma(p, map, st); };
+            const TmapSet maps = d.tmaps;
+            L.fn = [p, maps](cudaStream_t st) { launch_conv_halo_tma(p, maps, st); };
           } else {
             L.fn = [p](cudaStream_t st) { launch_conv_umma(p, st); };
           }
@@ -1334,7 +1334,8 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
       ConvParams p;
       bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, prop.multiProcessorCount, p, variant == 0);
       const bool flat = !tma && variant == 0 && plan_conv_flat_tma(cd, prop.multiProcessorCount, p);
-      tma = tma || flat;
+      const bool s2 = !tma && !flat && variant == 0 && plan_conv_s2_tma(cd, prop.multiProcessorCount, p);
+      tma = tma || flat || s2;
       if (!tma) p = plan_conv(cd, prop.multiProcessorCount, variant & 1);
       std::vector<__half> wp;
       std::vector<float> bp;
@@ -1359,9 +1360,11 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
         if (rep == reps - 1) XR_CUDA(cudaEventRecord(e0, 0));
         if (tma) {
           conv_tma_prepare_device();
-          const CUtensorMap map = flat ? make_flat_tensor_map(d_x, static_cast<long>(b) * h * w, cin_p, cin_p, p)
-                                       : make_halo_tensor_map(d_x, b, h, w, cin_p, cin_p, p.Wp, p.hbox, p.sw ? p.cb : 8, p.sw);
-          launch_conv_halo_tma(p, map, 0);
+          TmapSet maps{};
+          if (s2) maps = make_s2_tensor_maps(d_x, b, h, w, cin_p, cin_p, p);
+          else maps.m[0] = flat ? make_flat_tensor_map(d_x, static_cast<long>(b) * h * w, cin_p, cin_p, p)
+                                : make_halo_tensor_map(d_x, b, h, w, cin_p, cin_p, p.Wp, p.hbox, p.sw ? p.cb : 8, p.sw);
+          launch_conv_halo_tma(p, maps, 0);
         } else {
           launch_conv_umma(p, 0);
         }
@@ -1431,7 +1434,8 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
     ConvParams p;
     bool tma = (variant == 0 || variant == 4) && plan_conv_halo_tma(cd, 148, p, variant == 0);
     const bool flat = !tma && variant == 0 && plan_conv_flat_tma(cd, 148, p);
-    tma = tma || flat;
+    const bool s2 = !tma && !flat && variant == 0 && plan_conv_s2_tma(cd, 148, p);
+    tma = tma || flat || s2;
     if (!tma) p = plan_conv(cd, 148, variant & 1);
     std::vector<float> wp, bp;
     std::vector<float> zero_bias(cout, 0.f);
@@ -1447,7 +1451,12 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
         for (int c = 0; c < cout; ++c)
           for (int i = 0; i < ho * wo; ++i) rr[(static_cast<size_t>(n) * ho * wo + i) * cout_p + c] = residual[(static_cast<size_t>(n) * cout + c) * ho * wo + i];
     }
-    if (flat) emulate_conv_flat_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
+    if (s2) {
+      if (!emulate_conv_s2_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data())) {
+        g_create_error = "s2 plan: a valid output reads outside its plane buffer";
+        return XRSEG_ERR_INVALID;
+      }
+    } else if (flat) emulate_conv_flat_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
     else if (tma) emulate_conv_halo_tma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
     else emulate_conv_umma(p, xin.data(), wp.data(), bp.data(), residual ? rr.data() : nullptr, yo.data());
     for (int n = 0; n < b; ++n)

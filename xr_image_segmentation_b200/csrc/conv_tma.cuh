@@ -648,34 +648,44 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             // unrolled with guards folded into the issue predicate: a handful of uniform adds per MMA, no branches.
             if (elect_one()) {   // one branch per stage; inside, a single lane issues the whole MMA batch
               uint32_t acc = ks > 0 ? 1u : 0u;
-              const int kps = p.kps > 1 ? p.kps : 1;
-              const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;   // one K-block sub-buffer of the stage (flat)
-              const uint32_t plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;    // one parity-plane buffer (s2)
-              for (int kb = 0; kb < kps; ++kb) {
+              // one tap: kj k16-steps x nsub sub-tiles (sub-tile innermost: consecutive MMAs hit different accumulators)
+#define XR_ISSUE_TAP(A_TAP)                                                                          \
+  {                                                                                                  \
+    const uint32_t a_tap_ = (A_TAP);                                                                 \
+    for (int j = 0; j < kj; ++j) {                                                                   \
+      const uint64_t bd = hi_sw | (b_lo + 2u * j);                                                   \
+      _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                \
+        if (u < nsub && mma_on) {                                                                    \
+          const uint64_t ad = hi_sw | (a_tap_ + static_cast<uint32_t>(u) * sub16 + 2u * j);          \
+          umma_f16(d_base + static_cast<uint32_t>(u) * ntile_u, ad, bd, idesc, acc);                 \
+        }                                                                                            \
+      }                                                                                              \
+      acc = 1;                                                                                       \
+    }                                                                                                \
+    b_lo += tap16;                                                                                   \
+  }
+              if (p.mode == MODE_HALO_TMA) {          // tap (kh,kw) = row shift kh*Wp + kw - 1
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                  if (t >= p.taps) break;
-                  const int kh = t / 3, kw = t - 3 * kh;
-                  // start row of tap t relative to the stage: a pure row shift in every mode
-                  uint32_t a_tap = a_lo_stage + kb * blk16;
-                  if (p.mode == MODE_HALO_TMA) a_tap += static_cast<uint32_t>(kh * p.Wp + kw - 1) * row16;
-                  else if (p.mode == MODE_S2_TMA)
-                    a_tap += static_cast<uint32_t>((kh != 1 ? 2 : 0) + (kw != 1 ? 1 : 0)) * plane16 +
-                             static_cast<uint32_t>((kh == 2 ? p.Wp : 0) - (kw == 0 ? 1 : 0)) * row16;
-                  for (int j = 0; j < kj; ++j) {
-                    const uint64_t bd = hi_sw | (b_lo + 2u * j);
+                for (int kh = 0; kh < 3; ++kh) {
+                  const uint32_t a_kh = a_lo_stage + static_cast<uint32_t>(kh * p.Wp - 1) * row16;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                      if (u < nsub && mma_on) {
-                        const uint64_t ad = hi_sw | (a_tap + static_cast<uint32_t>(u) * sub16 + 2u * j);
-                        umma_f16(d_base + static_cast<uint32_t>(u) * ntile_u, ad, bd, idesc, acc);
-                      }
-                    }
-                    acc = 1;
-                  }
-                  b_lo += tap16;   // next tap's weight tile
+                  for (int kw = 0; kw < 3; ++kw) XR_ISSUE_TAP(a_kh + static_cast<uint32_t>(kw) * row16)
                 }
+              } else if (p.mode == MODE_S2_TMA) {     // tap (kh,kw) = plane (kh != 1, kw != 1), row shift (kh == 2) Wp - (kw == 0)
+                const uint32_t plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                  const uint32_t a_kh = a_lo_stage + (kh != 1 ? 2u * plane16 : 0u) + (kh == 2 ? static_cast<uint32_t>(p.Wp) * row16 : 0u);
+#pragma unroll
+                  for (int kw = 0; kw < 3; ++kw)
+                    XR_ISSUE_TAP(a_kh + (kw != 1 ? plane16 : 0u) - (kw == 0 ? row16 : 0u))
+                }
+              } else {                                // flat 1x1: kps K-blocks, one tap each
+                const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;
+                const int kps = p.kps > 1 ? p.kps : 1;
+                for (int kb = 0; kb < kps; ++kb) XR_ISSUE_TAP(a_lo_stage + static_cast<uint32_t>(kb) * blk16)
               }
+#undef XR_ISSUE_TAP
               umma_commit(&empty[slot]);
             }
             __syncwarp();
@@ -737,7 +747,22 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       e_wait += clock64() - t0;
       t0 = clock64();
       tc_fence_after();
-      for (int u = 0; u < p.nsub; ++u) {
+      // Work units of this item: (sub-tile u, 16-column chunk c), unit index k = u * nch + c.  The two warp halves take
+      // alternating units (so thin layers with a single chunk per sub-tile still use all eight warps), and the TMEM load
+      // of the next unit is in flight while the current one is converted and stored.
+      const int nch = p.Ntile >> 4;
+      auto first_c = [&](int u) { return (half + u * nch) & 1; };
+      auto advance = [&](int& u, int& c) {     // next unit of this half after (u, c); u == nsub when exhausted
+        c += 2;
+        while (c >= nch) {
+          if (++u >= p.nsub) return;
+          c = first_c(u);
+        }
+      };
+      auto t_addr = [&](int u, int c) {
+        return tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((buf * p.nsub + u) * p.Ntile + c * 16);
+      };
+      auto finish_unit = [&](const uint32_t (&v)[16], int u, int c) {
         const int j = 128 * u + q * 32 + lane;
         bool valid;
         size_t pix;
@@ -752,17 +777,59 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
           pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
         }
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                               static_cast<uint32_t>((buf * p.nsub + u) * p.Ntile);
-        for (int c0 = half * 16; c0 < p.Ntile; c0 += 32) {
-          uint32_t v[16];
-          tmem_ld16(t_row + c0, v);
-          tmem_ld_wait();
-          if (valid && !(p.dbg_skip & 2)) {
-            const int n = n_tile * p.Ntile + c0;
-            epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
-                             p.out + pix * p.out_pitch + n);
+        if (valid && !(p.dbg_skip & 2)) {
+          const int n = n_tile * p.Ntile + c * 16;
+          epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
+                           p.out + pix * p.out_pitch + n);
+        }
+      };
+      if (!(p.dbg_skip & 8)) {
+        // default: per sub-tile the two warp halves take alternating 16-column chunks; with an odd chunk count the
+        // starting chunk alternates with the sub-tile, so single-chunk layers (N = 16) still use all eight warps
+        for (int u = 0; u < p.nsub; ++u) {
+          const int j = 128 * u + q * 32 + lane;
+          bool valid;
+          size_t pix;
+          if (p.mode == MODE_FLAT_TMA) {
+            const int m = tile * p.slots + j;
+            valid = m < p.flat_rows;
+            pix = static_cast<size_t>(m);
+          } else {
+            const int yy = fd_div(p.fd_wp, j);
+            const int cc = j - yy * p.Wp;
+            const int y = y0 + yy;
+            valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
+            pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
           }
+          valid = valid && !(p.dbg_skip & 2);
+          for (int c = first_c(u); c < nch; c += 2) {
+            uint32_t v[16];
+            tmem_ld16(t_addr(u, c), v);
+            tmem_ld_wait();
+            if (valid) {
+              const int n = n_tile * p.Ntile + c * 16;
+              epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
+                               p.out + pix * p.out_pitch + n);
+            }
+          }
+        }
+      } else {   // XRSEG_EPI=1: software-pipelined variant (TMEM load of the next unit in flight), kept for A/B runs
+        int u = 0, c = first_c(0) - 2;
+        advance(u, c);
+        uint32_t va[16], vb[16];
+        if (u < p.nsub) tmem_ld16(t_addr(u, c), va);
+        while (u < p.nsub) {
+          tmem_ld_wait();
+          int u2 = u, c2 = c;
+          advance(u2, c2);
+          if (u2 < p.nsub) tmem_ld16(t_addr(u2, c2), vb);
+          finish_unit(va, u, c);
+          if (u2 >= p.nsub) break;
+          tmem_ld_wait();
+          u = u2; c = c2;
+          advance(u, c);
+          if (u < p.nsub) tmem_ld16(t_addr(u, c), va);
+          finish_unit(vb, u2, c2);
         }
       }
       tc_fence_before();

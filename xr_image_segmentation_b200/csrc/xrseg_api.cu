@@ -170,6 +170,7 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       } else {
         d.cp = plan_conv(cd, r->num_sms, 0);
       }
+      if (const char* e = getenv("XRSEG_EPI")) d.cp.dbg_skip |= (e[0] == '1') ? 8 : 0;   // A/B of the TMA kernel's epilogue
       if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
         std::vector<__half> wp;
         std::vector<float> bp;

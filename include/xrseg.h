@@ -64,7 +64,8 @@ typedef struct xrseg_config {
   int32_t device;              /* CUDA device ordinal */
   int32_t max_batch;           /* frames per schedule call (1 = the reference's behaviour) */
   int32_t model_scale;         /* 'n' or 's' */
-  const void* weights;         /* XRSW weight pack (see weights.py), host memory */
+  const void* weights;         /* host memory: the sample's .sentis asset bytes (yolo11n-seg-sentis.sentis, loaded like
+                                  ModelLoader.Load, IEE:382) or an XRSW weight pack (weights.py) */
   size_t weights_bytes;
   float iou_threshold;         /* 0 -> 0.43 */
   float score_threshold;       /* 0 -> 0.301 */
@@ -150,6 +151,31 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* p, uint8_t* out, size_
 /* Kept anchor indices (0..8399) and scores of the finished run, compacted like output_0. */
 int xrseg_keep_indices(xrseg_runner* r, int32_t* idx, float* scores, int cap);
 
+/* ---- the step after the path ------------------------------------------------ */
+/* ↔ the fields IEExecutor hands to DepthExtractionJob (IEE:623-644): depth texture geometry, sampling step (_samplingStep,
+ * XRScene.unity:1259 = 5), _maxPoints (8000), _confidenceThreshold, Screen size, the depth camera pose and intrinsics. */
+typedef struct xrseg_depth_params {
+  uint32_t struct_size;
+  int32_t detection;           /* row of the compacted outputs (targetIndex of ExtractDepthData, IEE:561) */
+  int32_t depth_w, depth_h;    /* depth texture size; texels are IEEE half floats in metres */
+  int32_t sampling_step;       /* 0 -> 5 */
+  int32_t max_points;          /* 0 -> 8000 */
+  float confidence_threshold;  /* 0 -> the runner's mask threshold (0.5) */
+  float screen_w, screen_h;
+  float camera_position[3];    /* _depthCameraPose */
+  float camera_rotation[4];    /* _depthCameraRot as x, y, z, w */
+  float focal_length[2], principal_point[2], sensor_resolution[2];
+} xrseg_depth_params;
+/* ↔ ExtractDepthData + DepthExtractionJob.Execute + CollectJobResults (IEE:561-667): world-space points of the target's
+ * mask.  depth_host: depth_w*depth_h half floats (host memory); out_xyzd: [cap][4] floats (x, y, z, depth in metres) in
+ * sample order, at most max_points.  The 160x160 mask is read on the device (output_3), never copied to the host. */
+int xrseg_extract_points(xrseg_runner* r, const xrseg_depth_params* p, const uint16_t* depth_host, float* out_xyzd, int cap,
+                         int* n);
+/* ↔ the locked-target re-association of ProcessInferenceResult (IEE:488-507): among the first 50 boxes (ParseBoxes) of
+ * `frame`, the nearest one whose label equals locked_label; *best_index = -1 when none is closer than max_dist (300). */
+int xrseg_associate(xrseg_runner* r, int frame, float locked_center_x, float locked_center_y, int locked_label, float screen_w,
+                    float screen_h, float max_dist, int* best_index, float* best_dist);
+
 /* ---- host helpers ------------------------------------------------------------------------------ */
 /* Page-locked host memory for frame / result buffers (cudaHostAlloc); NULL on failure. */
 void* xrseg_host_alloc(size_t bytes);
@@ -164,6 +190,15 @@ typedef struct xrseg_layer_info {
 } xrseg_layer_info;
 int xrseg_layer_count(int model_scale);
 int xrseg_layer_info_get(int model_scale, int index, xrseg_layer_info* info);
+
+/* ---- .sentis asset introspection (↔ ModelLoader.Load, IEE:382; host only, no GPU needed) --------- */
+/* Number of biased convolutions in the asset and the thresholds baked into its NonMaxSuppression layer
+ * (IEModelEditorConverter.cs:76); 0 thresholds when the graph has no NMS. */
+int xrseg_sentis_info(const void* data, size_t bytes, int32_t* n_convs, float* iou_threshold, float* score_threshold);
+/* Dequantized ((q - zp) * scale, like the graph's DequantizeUint8 layers) weights / bias of convolution `index` in chain
+ * order.  w_shape4: [cout,cin/g,kh,kw] ([cin,cout,kh,kw] when transposed).  Returns the weight element count. */
+int xrseg_sentis_layer(const void* data, size_t bytes, int index, float* w, size_t w_cap, float* b, size_t b_cap,
+                       int32_t* w_shape4, int32_t* transposed);
 
 /* ---- timing ---------------------------------------------------------------------------------- */
 /* Device time (ms, CUDA events on the runner's stream) of the last finished run: [0] whole run,

@@ -273,3 +273,78 @@ def upsample_mask_640(logit: np.ndarray, box_cxcywh: np.ndarray, out_size: int =
     ys, xs = np.meshgrid(np.arange(out_size, dtype=f32), np.arange(out_size, dtype=f32), indexing="ij")
     inside = (xs >= x1) & (xs < x2) & (ys >= y1) & (ys < y2)
     return ((val > f32(0)) & inside).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------------------
+# RGB-D point extraction and target association
+# --------------------------------------------------------------------------------------
+def extract_points(mask_prob: np.ndarray, raw_box, depth_half: np.ndarray, screen_w: float, screen_h: float, cam_pos, cam_rot,
+                   focal, principal, sensor_res, step: int = 5, thr: float = 0.5, max_points: int = 8000) -> np.ndarray:
+    """↔ IEExecutor.ExtractDepthData (IEE:561-651) + DepthExtractionJob.Execute (IEE:86-156) + the in-order compaction of
+    CollectJobResults (IEE:653-667).  mask_prob f32 [160,160] (output_3 row), raw_box = output_0 row (cx,cy,w,h @640),
+    depth_half uint16 [H,W] half floats.  Returns f32 [n,4]: world x, y, z, depth (m).
+
+    fp32, one IEEE operation per step, in the C# expression order; math.normalize = rsqrt(dot(v,v)) * v and
+    math.mul(quaternion, float3) = v + q.w * t + cross(q.xyz, t), t = 2 * cross(q.xyz, v) (Unity.Mathematics)."""
+    sx, sy = f32(screen_w) / f32(640), f32(screen_h) / f32(640)
+    cx, cy, w, h = (f32(v) for v in raw_box)
+    bx, by, bw, bh = (cx - f32(320)) * sx, (f32(320) - cy) * sy, w * sx, h * sy            # ParseBoxes, IEE:548-551
+    rcx, rcy, rw, rh = bx / sx + f32(320), f32(320) - by / sy, bw / sx, bh / sy           # IEE:586-589
+    dh, dw = depth_half.shape
+    depth = depth_half.reshape(-1).view(np.float16).astype(f32)
+    qx, qy, qz, qw = (f32(v) for v in cam_rot)
+    pos = [f32(v) for v in cam_pos]
+    out = []
+    total_x = 160 // step
+    for index in range(total_x * total_x):
+        ly, lx = divmod(index, total_x)
+        y, x = ly * step, lx * step
+        if y >= 160 or x >= 160 or not (mask_prob[y, x] > f32(thr)):
+            continue
+        nx, ny = f32(x) / f32(160), f32(y) / f32(160)
+        ipx = f32(f32(rcx - f32(rw * f32(0.5))) + f32(nx * rw))
+        ipy = f32(f32(rcy - f32(rh * f32(0.5))) + f32(ny * rh))
+        u = min(max(f32(ipx / f32(640)), f32(0)), f32(1))
+        v = min(max(f32(ipy / f32(640)), f32(0)), f32(1))
+        omv = f32(f32(1) - v)
+        dx = int(f32(u * f32(dw - 1)))
+        dy = int(f32(omv * f32(dh - 1)))
+        di = dy * dw + dx
+        if di < 0 or di >= dw * dh:
+            continue
+        d = depth[di]
+        if not (d > f32(0.1) and d < f32(3.0)):
+            continue
+        cpx, cpy = f32(u * f32(sensor_res[0])), f32(omv * f32(sensor_res[1]))
+        vx = f32(f32(cpx - f32(principal[0])) / f32(focal[0]))
+        vy = f32(f32(cpy - f32(principal[1])) / f32(focal[1]))
+        vz = f32(1)
+        dot = f32(f32(f32(vx * vx) + f32(vy * vy)) + f32(vz * vz))
+        inv = f32(f32(1) / np.sqrt(dot, dtype=f32))
+        vx, vy, vz = f32(inv * vx), f32(inv * vy), f32(inv * vz)
+        tx = f32(f32(2) * f32(f32(qy * vz) - f32(qz * vy)))
+        ty = f32(f32(2) * f32(f32(qz * vx) - f32(qx * vz)))
+        tz = f32(f32(2) * f32(f32(qx * vy) - f32(qy * vx)))
+        wx = f32(f32(vx + f32(qw * tx)) + f32(f32(qy * tz) - f32(qz * ty)))
+        wy = f32(f32(vy + f32(qw * ty)) + f32(f32(qz * tx) - f32(qx * tz)))
+        wz = f32(f32(vz + f32(qw * tz)) + f32(f32(qx * ty) - f32(qy * tx)))
+        out.append((f32(pos[0] + f32(wx * d)), f32(pos[1] + f32(wy * d)), f32(pos[2] + f32(wz * d)), d))
+        if len(out) >= max_points:
+            break
+    return np.asarray(out, f32).reshape(-1, 4)
+
+
+def associate(boxes: np.ndarray, label_ids: np.ndarray, locked_cx: float, locked_cy: float, locked_label: int,
+              screen_w: float, screen_h: float, max_dist: float = 300.0):
+    """↔ the locked-target search of IEExecutor.ProcessInferenceResult (IEE:488-507) over ParseBoxes' list (cap 50):
+    nearest box of the same class, strict `<` (first of equal distances); (-1, dist) when not closer than max_dist."""
+    pb, lab = parse_boxes(boxes, label_ids, screen_w, screen_h)
+    best, mind = -1, f32(3.402823466e+38)
+    for i in range(len(pb)):
+        if int(lab[i]) != int(locked_label):
+            continue
+        dx, dy = f32(pb[i, 0] - f32(locked_cx)), f32(pb[i, 1] - f32(locked_cy))
+        dist = np.sqrt(f32(f32(dx * dx) + f32(dy * dy)), dtype=f32)
+        if dist < mind:
+            mind, best = dist, i
+    return (best if best != -1 and mind < f32(max_dist) else -1), float(mind)

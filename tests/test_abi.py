@@ -124,3 +124,64 @@ def test_shard_range_and_merge():
     assert m.counts.tolist() == [1, 0, 2] and m.labels.tolist() == [3, 1, 2] and m.boxes.shape == (3, 4)
     with pytest.raises(ValueError):
         S.merge_detections([a, S.Detections(3, np.array([0]), np.zeros((0, 4), np.float32), np.zeros(0, np.int64))])
+
+
+# ---- .sentis loader inside the library ------------------------------------------------------------
+SENTIS = "/root/reference/Assets/Resources/Model/yolo11n-seg-sentis.sentis"
+
+
+@pytest.mark.skipif(not os.path.exists(SENTIS), reason="the reference asset only exists in the build container")
+def test_sentis_loader_matches_oracle_reader_and_golden_pack(lib, golden):
+    """The C++ FlatBuffer walk + uint8 dequantization (csrc/sentis.cuh) against the oracle's Python reader and the committed
+    XRSW re-container of the same asset: every convolution, bit for bit; thresholds as decoded in SURVEY.md fact 3."""
+    import ctypes as C
+
+    from oracle.sentis import load_sentis
+    from xr_image_segmentation_b200 import weights as W
+    data = open(SENTIS, "rb").read()
+    buf = C.create_string_buffer(data, len(data))
+    ptr = C.cast(buf, C.c_void_p)
+    n, iou, sc = C.c_int32(), C.c_float(), C.c_float()
+    assert lib.xrseg_sentis_info(ptr, len(data), C.byref(n), C.byref(iou), C.byref(sc)) == 0
+    assert n.value == 100 and abs(iou.value - 0.43) < 1e-6 and abs(sc.value - 0.301) < 1e-6
+    # oracle reader: DequantizeUint8 chains feeding Conv / ConvTranspose chains in file order
+    m = load_sentis(data)
+    deq, ref = {}, []
+    for c in m.chains:
+        if c.op == "DequantizeUint8":
+            deq[c.outputs[0]] = W.Tensor8(m.values[c.inputs[0]].data, m.values[c.args[0]], m.values[c.args[1]]).dequant()
+        elif c.op in ("Conv", "ConvTranspose") and len(c.inputs) >= 3 and c.inputs[2] >= 0:
+            ref.append((deq[c.inputs[1]], deq[c.inputs[2]], c.op == "ConvTranspose"))
+    _, packed = W.read_pack(golden["model"].pack)
+    assert len(ref) == 100 == len(packed)
+    for i, (w, b, tr) in enumerate(ref):
+        wb, bb = np.zeros(w.size, np.float32), np.zeros(b.size, np.float32)
+        shp, t = (C.c_int32 * 4)(), C.c_int32()
+        rc = lib.xrseg_sentis_layer(ptr, len(data), i, wb.ctypes.data, wb.size, bb.ctypes.data, bb.size, shp, C.byref(t))
+        assert rc == w.size and list(shp) == list(w.shape) and bool(t.value) == tr
+        assert np.array_equal(wb.reshape(w.shape), w) and np.array_equal(bb, b)
+        assert np.array_equal(w, packed[i][1]) and np.array_equal(b, packed[i][2])
+    # ModelLoader.Load accepts the asset bytes unchanged (IEE:382)
+    from xr_image_segmentation_b200 import inference as I
+    assert I.ModelLoader.Load(data).scale == "n"
+
+
+@pytest.mark.skipif(not os.path.exists(SENTIS), reason="the reference asset only exists in the build container")
+def test_sentis_loader_rejects_corrupt_input(lib):
+    import ctypes as C
+    data = bytearray(open(SENTIS, "rb").read())
+    n = C.c_int32()
+
+    def info(b):
+        buf = C.create_string_buffer(bytes(b), len(b))
+        return lib.xrseg_sentis_info(C.cast(buf, C.c_void_p), len(b), C.byref(n), None, None)
+
+    assert info(data[:1000]) < 0                      # truncated program
+    assert info(data[:len(data) // 2]) < 0            # truncated weight blob
+    assert info(b"XRSW" + bytes(60)) < 0              # not a sentis container
+    rng = np.random.default_rng(0)
+    for _ in range(20):                               # random corruption of the program: an error code, never a crash
+        d = bytearray(data)
+        for p in rng.integers(8, 100000, 16):
+            d[p] = int(rng.integers(0, 256))
+        assert info(d) <= 0

@@ -361,3 +361,65 @@ def test_ieexecutor_mirror_flow(golden):
         seen.append(int(ex._downloadState))
     assert E.InferenceDownloadState.Error in seen
     ex.OnDestroy()
+
+
+@pytest.mark.gpu
+def test_depth_points_and_target_association_vs_oracle(golden, runner):
+    """↔ ExtractDepthData / DepthExtractionJob / CollectJobResults (IEE:561-667, 86-156) and the locked-target
+    search (IEE:488-507), on the detections of a reference frame with a synthetic half-float depth texture and camera."""
+    from oracle import postprocess as pp
+    img = golden["inputs"]["coco139"]
+    runner.schedule(img[None])
+    runner.wait()
+    boxes, labels, masks = runner.readback(0), runner.readback(1), runner.readback(3)
+    assert len(boxes) >= 2
+    rng = np.random.default_rng(7)
+    depth = rng.uniform(0.05, 3.5, (240, 320)).astype(np.float16).view(np.uint16)      # some texels outside (0.1, 3.0)
+    q = rng.standard_normal(4)
+    q = (q / np.linalg.norm(q)).astype(np.float32)
+    cam = dict(camera_position=[0.3, 1.5, -0.2], camera_rotation=q, focal_length=[867.5, 866.9], principal_point=[641.2, 479.6],
+               sensor_resolution=[1280.0, 960.0])
+    screen = (1920.0, 1080.0)
+    for det in range(min(len(boxes), 4)):
+        for step, max_points in ((5, 8000), (1, 8000), (3, 100)):
+            got = runner.extract_points(det, depth, *screen, sampling_step=step, max_points=max_points, **cam)
+            ref = pp.extract_points(masks[det], boxes[det], depth, *screen, cam["camera_position"], cam["camera_rotation"],
+                                    cam["focal_length"], cam["principal_point"], cam["sensor_resolution"], step=step, thr=0.5,
+                                    max_points=max_points)
+            assert got.shape == ref.shape, (det, step, got.shape, ref.shape)
+            assert np.array_equal(got[:, 3], ref[:, 3])                                # same samples, same depths
+            np.testing.assert_allclose(got[:, :3], ref[:, :3], rtol=2e-6, atol=2e-6)
+    assert sum(len(runner.extract_points(d, depth, *screen, **cam)) for d in range(len(boxes))) > 0
+    # target association: lock on each detection's own ParseBoxes position (+ an offset), and on an absent class
+    pb, lab = pp.parse_boxes(boxes, labels, *screen)
+    for i in range(len(pb)):
+        for off in ((0.0, 0.0), (25.0, -40.0), (500.0, 500.0)):
+            got = runner.associate(0, float(pb[i, 0]) + off[0], float(pb[i, 1]) + off[1], int(lab[i]), *screen)
+            ref = pp.associate(boxes, labels, float(pb[i, 0]) + off[0], float(pb[i, 1]) + off[1], int(lab[i]), *screen)
+            assert got[0] == ref[0] and (got[0] == -1 or abs(got[1] - ref[1]) <= 1e-4 * max(1.0, ref[1]))
+    assert runner.associate(0, 0.0, 0.0, 79, *screen)[0] == pp.associate(boxes, labels, 0.0, 0.0, 79, *screen)[0]
+
+
+@pytest.mark.gpu
+def test_pipelined_runner_matches_single_runner(golden):
+    """inference.PipelinedRunner (two runners in ping-pong, the bench's e2e leg) returns exactly what one runner returns."""
+    frames = np.stack([golden["inputs"][n] for n in ("coco139", "coco632", "bus")])
+    single = I.Runner(golden["model"], max_batch=3)
+    pipe = I.PipelinedRunner(golden["model"], max_batch=3, depth=2)
+    want = []
+    for k in range(3):
+        single.schedule(np.ascontiguousarray(np.roll(frames, k, axis=0)))
+        single.wait()
+        want.append((single.counts().copy(), single.readback(0), single.readback(1), single.masks(_lib.MASK_BITS_160)))
+    got = []
+    pipe.submit(np.ascontiguousarray(np.roll(frames, 0, axis=0)))
+    for k in range(1, 4):
+        if k < 3:
+            pipe.submit(np.ascontiguousarray(np.roll(frames, k, axis=0)))
+        got.append(pipe.collect())
+    for (c0, b0, l0, m0), (c1, b1, l1, m1) in zip(want, got):
+        assert np.array_equal(c0, c1) and np.array_equal(b0, b1) and np.array_equal(l0, l1) and np.array_equal(m0, m1)
+    with pytest.raises(_lib.XrsegError):
+        pipe.collect()
+    single.close()
+    pipe.close()

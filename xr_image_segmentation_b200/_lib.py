@@ -48,6 +48,14 @@ class MaskParams(C.Structure):
                 ("first", C.c_int32), ("count", C.c_int32)]
 
 
+class DepthParams(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("detection", C.c_int32), ("depth_w", C.c_int32), ("depth_h", C.c_int32),
+                ("sampling_step", C.c_int32), ("max_points", C.c_int32), ("confidence_threshold", C.c_float),
+                ("screen_w", C.c_float), ("screen_h", C.c_float), ("camera_position", C.c_float * 3),
+                ("camera_rotation", C.c_float * 4), ("focal_length", C.c_float * 2), ("principal_point", C.c_float * 2),
+                ("sensor_resolution", C.c_float * 2)]
+
+
 class LayerInfo(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
                 ("stride", C.c_int32), ("groups", C.c_int32), ("act", C.c_int32), ("transposed", C.c_int32),
@@ -87,6 +95,12 @@ SIGNATURES = {
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "xrseg_debug_emulate_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "xrseg_extract_points": (C.c_int, [C.c_void_p, _P(DepthParams), C.c_void_p, C.c_void_p, C.c_int, _P(C.c_int)]),
+    "xrseg_associate": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                                  _P(C.c_int), _P(C.c_float)]),
+    "xrseg_sentis_info": (C.c_int, [C.c_void_p, C.c_size_t, _P(C.c_int32), _P(C.c_float), _P(C.c_float)]),
+    "xrseg_sentis_layer": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                     _P(C.c_int32), _P(C.c_int32)]),
     "xrseg_host_alloc": (C.c_void_p, [C.c_size_t]),
     "xrseg_host_free": (None, [C.c_void_p]),
     "xrseg_device_count": (C.c_int, []),

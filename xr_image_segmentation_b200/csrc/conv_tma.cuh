@@ -69,6 +69,16 @@ static inline CUtensorMap make_halo_tensor_map(const __half* base, int B, int H,
 }
 
 // ---- planning --------------------------------------------------------------------------------------------------
+// A CTA never has more than ceil(work / grid) * nks stages to fetch: a deeper ring only costs shared memory, and a small
+// footprint is what lets the next kernel's CTAs become co-resident early (programmatic dependent launch) so that their
+// prologue -- barrier init, TMEM allocation, weight fetch -- overlaps this kernel's tail.
+static inline int clamp_stages(int S, int work, int num_sms, int nks) {
+  const int grid = work < num_sms ? work : num_sms;
+  int need = ceil_div(work, grid) * nks;
+  if (need < 2) need = 2;
+  return S < need ? S : need;
+}
+
 // Returns false when the layer does not fit this kernel (caller falls back to the thread-gather kernel).
 static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true) {
   if (!(d.k == 3 && d.stride == 1 && !d.transposed)) return false;
@@ -90,6 +100,21 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
   int R = (128 * nsub_max) / p.Wp;
   if (R > d.H) R = d.H;
   if (R < 1 || R + 2 > 256) return false;
+  {
+    // rows per item: the tallest tile that fits unless a shorter one fills the SMs better (20x20 maps: R = 20 would keep
+    // 64 CTAs busy with four sub-tiles each, R = 10 keeps 128 busy with two).  Cost = rounds of the busiest CTA x
+    // (sub-tiles + fixed item overhead), weighted by the halo re-read (R + 2) / R.
+    int best_R = R;
+    double best_c = 1e30;
+    const bool few_rounds = ceil_div(d.B * ceil_div(d.H, R) * p.n_tiles, num_sms) <= 2;   // only then quantization matters
+    for (int r = R; r >= (few_rounds ? 1 : R); --r) {
+      const int nsub = ceil_div(r * p.Wp, 128);
+      const int items = d.B * ceil_div(d.H, r) * p.n_tiles;
+      const double c = ceil_div(items, num_sms) * (nsub + 0.35) * (1.0 + 0.5 / r);
+      if (c < best_c - 1e-9) { best_c = c; best_R = r; }
+    }
+    R = best_R;
+  }
   p.R = R;
   p.nsub = ceil_div(R * p.Wp, 128);
   p.tpi = ceil_div(d.H, R);
@@ -130,7 +155,7 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
     const long total_b = static_cast<long>(p.nks) * p.b_stage_bytes;
     p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
     const int resident = p.b_resident ? static_cast<int>(total_b) : 0;
-    const int S = best_S;
+    const int S = clamp_stages(best_S, d.B * p.tpi * p.n_tiles, num_sms, p.nks);
     p.S = S;
     p.M_total = d.B * p.tpi;
     p.m_tiles = p.M_total;
@@ -279,9 +304,9 @@ static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& 
   p.cb = cb; p.cps = cb / 8; p.nks = d.Cin / cb; p.kps = 1;
   p.sw = cb == 64 ? 3 : (cb == 32 ? 2 : 1);
   p.R = best_R;
-  p.S = best_S;
   p.nsub = ceil_div(p.R * p.Wp, 128);
   p.tpi = ceil_div(Ho, p.R);
+  p.S = clamp_stages(best_S, d.B * p.tpi * p.n_tiles, num_sms, p.nks);
   p.hbox = p.R + 1;
   p.slots = p.hbox * p.Wp;                         // rows of ONE plane box
   p.lbo_a = round_up(p.slots * rb, 1024);          // bytes of one plane buffer
@@ -364,18 +389,21 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
     p.hbox = p.slots < 256 ? p.slots : 256;          // rows per TMA box
     // A stage holds kps K-blocks (each slots x rb bytes, its own swizzled sub-buffer): the MMA warp pays a fixed
     // ~500 cycles per stage hand-over (tools/probe_tma.py), so thin layers put their whole K into one stage.
-    int kps = nkb;
-    while (kps > 1 && (nkb % kps != 0 || kps * p.slots * rb > 49152)) --kps;
-    p.kps = kps;
-    p.nks = nkb / kps;
-    p.a_stage_bytes = kps * p.slots * rb;            // multiple of 1024 for every cb
-    p.b_stage_bytes = kps * b_block;
-    const int fixed = round_up(CONV_HDR_BYTES, 1024) + (p.b_resident ? round_up(resident, 1024) : 0);
-    int S = (CONV_SMEM_MAX - fixed) / (p.a_stage_bytes + (p.b_resident ? 0 : round_up(p.b_stage_bytes, 1024)));
-    if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
+    int kps = nkb, S = 0;
+    for (; kps >= 1; --kps) {
+      if (nkb % kps != 0 || (kps > 1 && kps * p.slots * rb > 49152)) continue;
+      p.kps = kps;
+      p.nks = nkb / kps;
+      p.a_stage_bytes = kps * p.slots * rb;          // multiple of 1024 for every cb
+      p.b_stage_bytes = kps * b_block;
+      const int fixed = round_up(CONV_HDR_BYTES, 1024) + (p.b_resident ? round_up(resident, 1024) : 0);
+      S = (CONV_SMEM_MAX - fixed) / (p.a_stage_bytes + (p.b_resident ? 0 : round_up(p.b_stage_bytes, 1024)));
+      if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
+      if (S >= 2) break;                             // streamed weights of a wide layer: fewer K-blocks per stage
+    }
     if (S >= 3 || nsub == 1) {
       if (S < 2) return false;
-      p.S = S;
+      p.S = clamp_stages(S, ceil_div(p.flat_rows, p.slots) * p.n_tiles, num_sms, p.nks);
       break;
     }
   }
@@ -483,7 +511,7 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TMA_THREADS, 1)
+__global__ void __launch_bounds__(TMA_THREADS, 2)
 conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ TmapSet tmaps) {
   const CUtensorMap& tmap = tmaps.m[0];
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -516,6 +544,17 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     prefetch_tensormap(&tmap);
     if (p.mode == MODE_S2_TMA)
       for (int i = 1; i < 4; ++i) prefetch_tensormap(&tmaps.m[i]);
+    if (p.b_resident) {
+      // resident weights: fetched first thing (they are constants: no dependence on the previous kernel), so the copy
+      // runs while warp 1 allocates TMEM -- which may have to wait for a co-resident CTA of the previous kernel
+      const uint32_t bytes = static_cast<uint32_t>(p.nks) * p.b_stage_bytes;
+      const uint32_t b_dst = smem_u32(smem_b);
+      mbar_arrive_expect_tx(bres, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u) {
+        const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+        bulk_copy_g2s(b_dst + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, bres);
+      }
+    }
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
@@ -538,14 +577,6 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const uint32_t a_tx = static_cast<uint32_t>(p.cps) * p.slots * 16u * (p.kps > 1 ? p.kps : 1) *   // slots * row bytes (* K-blocks)
                             (p.mode == MODE_S2_TMA ? 4u : 1u);                                           // (* parity planes)
       const uint32_t b_stride = p.sw ? static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023) : static_cast<uint32_t>(p.b_stage_bytes);
-      if (p.b_resident) {
-        const uint32_t bytes = static_cast<uint32_t>(p.nks) * p.b_stage_bytes;
-        mbar_arrive_expect_tx(bres, bytes);
-        for (uint32_t off = 0; off < bytes; off += 32768u) {
-          const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
-          bulk_copy_g2s(b_u32 + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, bres);
-        }
-      }
       pdl_wait();   // the weights above are constants; the activations below are the previous kernels' output
       int it = 0;
       long long t_wait = 0, t0;

@@ -567,6 +567,124 @@ __global__ void __launch_bounds__(160) mask_bits_kernel(const MaskThrParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// RGB-D point extraction: ↔ IEExecutor.ExtractDepthData + DepthExtractionJob.Execute (IEE:561-651,
+// 86-156) and CollectJobResults' in-order compaction (IEE:653-667).  One sample per (160 / step)^2 grid point of the
+// target's mask: mask > thr -> box-relative image position -> depth lookup (half -> float, 0.1 m < d < 3.0 m) ->
+// unproject with the camera intrinsics -> rotate by the depth camera pose.  The reference copies the 160x160 mask to the
+// host and runs a Burst job; here the mask never leaves the device and only the compacted points do.
+// Arithmetic follows the C# expression order with IEEE intrinsics (no FMA contraction); math.normalize / math.mul
+// (quaternion, float3) are restated from Unity.Mathematics (rsqrt(dot) * v; v + q.w * t + cross(q.xyz, t), t = 2 cross(q.xyz, v)).
+// ------------------------------------------------------------------------------------------------
+struct DepthParams {
+  const float* probs;          // output_3 row of the target: [160*160]
+  const float* box;            // output_0 row of the target: raw cx, cy, w, h
+  const uint16_t* depth;       // [depth_h * depth_w] half floats (device copy of the depth texture)
+  int depth_w, depth_h, step, max_points;
+  float thr, screen_w, screen_h;
+  float pos[3], rot[4], focal[2], principal[2], sensor[2];
+  float4* out;                 // [max_points] world x, y, z, depth in metres
+  int* out_n;
+};
+
+__global__ void __launch_bounds__(1024) depth_extract_kernel(const DepthParams p) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  // ParseBoxes box (IEE:529-559) and back to raw 640-space exactly as ExtractDepthData does (IEE:586-589)
+  const float sx = __fdiv_rn(p.screen_w, 640.f), sy = __fdiv_rn(p.screen_h, 640.f);
+  const float bx = __fmul_rn(__fsub_rn(p.box[0], 320.f), sx), by = __fmul_rn(__fsub_rn(320.f, p.box[1]), sy);
+  const float bw = __fmul_rn(p.box[2], sx), bh = __fmul_rn(p.box[3], sy);
+  const float rcx = __fadd_rn(__fdiv_rn(bx, sx), 320.f), rcy = __fsub_rn(320.f, __fdiv_rn(by, sy));
+  const float rw = __fdiv_rn(bw, sx), rh = __fdiv_rn(bh, sy);
+  const int total_x = PROTO_HW / p.step;
+  const int total = total_x * total_x;
+  for (int i0 = 0; i0 < total; i0 += 1024) {
+    const int index = i0 + tid;
+    bool valid = false;
+    float4 res = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (index < total) {
+      const int ly = index / total_x, lx = index - ly * total_x;
+      const int y = ly * p.step, x = lx * p.step;
+      if (y < PROTO_HW && x < PROTO_HW && p.probs[y * PROTO_HW + x] > p.thr) {
+        const float nx = __fdiv_rn(static_cast<float>(x), static_cast<float>(PROTO_HW));
+        const float ny = __fdiv_rn(static_cast<float>(y), static_cast<float>(PROTO_HW));
+        const float ipx = __fadd_rn(__fsub_rn(rcx, __fmul_rn(rw, 0.5f)), __fmul_rn(nx, rw));
+        const float ipy = __fadd_rn(__fsub_rn(rcy, __fmul_rn(rh, 0.5f)), __fmul_rn(ny, rh));
+        const float u = fminf(fmaxf(__fdiv_rn(ipx, 640.f), 0.f), 1.f);
+        const float v = fminf(fmaxf(__fdiv_rn(ipy, 640.f), 0.f), 1.f);
+        const float omv = __fsub_rn(1.0f, v);
+        const int dx = static_cast<int>(__fmul_rn(u, static_cast<float>(p.depth_w - 1)));
+        const int dy = static_cast<int>(__fmul_rn(omv, static_cast<float>(p.depth_h - 1)));
+        const int di = dy * p.depth_w + dx;
+        if (di >= 0 && di < p.depth_w * p.depth_h) {
+          const float d = __half2float(__ushort_as_half(p.depth[di]));
+          if (d > 0.1f && d < 3.0f) {
+            const float cpx = __fmul_rn(u, p.sensor[0]), cpy = __fmul_rn(omv, p.sensor[1]);
+            float dxc = __fdiv_rn(__fsub_rn(cpx, p.principal[0]), p.focal[0]);
+            float dyc = __fdiv_rn(__fsub_rn(cpy, p.principal[1]), p.focal[1]);
+            float dzc = 1.0f;
+            const float dot = __fadd_rn(__fadd_rn(__fmul_rn(dxc, dxc), __fmul_rn(dyc, dyc)), __fmul_rn(dzc, dzc));
+            const float inv = __fdiv_rn(1.0f, __fsqrt_rn(dot));
+            dxc = __fmul_rn(inv, dxc); dyc = __fmul_rn(inv, dyc); dzc = __fmul_rn(inv, dzc);
+            // t = 2 * cross(q.xyz, v)
+            const float qx = p.rot[0], qy = p.rot[1], qz = p.rot[2], qw = p.rot[3];
+            const float tx = __fmul_rn(2.f, __fsub_rn(__fmul_rn(qy, dzc), __fmul_rn(qz, dyc)));
+            const float ty = __fmul_rn(2.f, __fsub_rn(__fmul_rn(qz, dxc), __fmul_rn(qx, dzc)));
+            const float tz = __fmul_rn(2.f, __fsub_rn(__fmul_rn(qx, dyc), __fmul_rn(qy, dxc)));
+            // v + q.w * t + cross(q.xyz, t)
+            const float wx = __fadd_rn(__fadd_rn(dxc, __fmul_rn(qw, tx)), __fsub_rn(__fmul_rn(qy, tz), __fmul_rn(qz, ty)));
+            const float wy = __fadd_rn(__fadd_rn(dyc, __fmul_rn(qw, ty)), __fsub_rn(__fmul_rn(qz, tx), __fmul_rn(qx, tz)));
+            const float wz = __fadd_rn(__fadd_rn(dzc, __fmul_rn(qw, tz)), __fsub_rn(__fmul_rn(qx, ty), __fmul_rn(qy, tx)));
+            res = make_float4(__fadd_rn(p.pos[0], __fmul_rn(wx, d)), __fadd_rn(p.pos[1], __fmul_rn(wy, d)),
+                              __fadd_rn(p.pos[2], __fmul_rn(wz, d)), d);
+            valid = true;
+          }
+        }
+      }
+    }
+    // order-preserving compaction (the C# loop appends valid samples in index order and stops at _maxPoints)
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, chunk_total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      if (w < warp) before += c;
+      chunk_total += c;
+    }
+    const int slot = s_base + before + __popc(bal & ((1u << lane) - 1u));
+    if (valid && slot < p.max_points) p.out[slot] = res;
+    __syncthreads();
+    if (tid == 0) s_base += chunk_total;
+    __syncthreads();
+  }
+  if (tid == 0) *p.out_n = min(s_base, p.max_points);
+}
+
+// Target association (IEE:488-507): nearest box of the locked class (ParseBoxes coordinates) among the first `cap`
+// detections of a frame; strict `<` keeps the first of equal distances; accepted when the distance is below max_dist.
+__global__ void associate_kernel(const float* boxes, const int* labels, int first, int n, int cap, float screen_w, float screen_h,
+                                 float lx, float ly, int llabel, float max_dist, int* best_index, float* best_dist) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float sx = __fdiv_rn(screen_w, 640.f), sy = __fdiv_rn(screen_h, 640.f);
+  int best = -1;
+  float mind = 3.402823466e+38f;
+  const int m = n < cap ? n : cap;
+  for (int i = 0; i < m; ++i) {
+    if (labels[first + i] != llabel) continue;
+    const float cx = __fmul_rn(__fsub_rn(boxes[4 * (first + i)], 320.f), sx);
+    const float cy = __fmul_rn(__fsub_rn(320.f, boxes[4 * (first + i) + 1]), sy);
+    const float dx = __fsub_rn(cx, lx), dy = __fsub_rn(cy, ly);
+    const float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    if (dist < mind) { mind = dist; best = i; }
+  }
+  *best_index = (best != -1 && mind < max_dist) ? best : -1;
+  *best_dist = mind;
+}
+
+// ------------------------------------------------------------------------------------------------
 // mode 2 (extension, BASELINE.json config 5): fused coef x proto -> bilinear 160->640 of the LOGITS -> box crop ->
 // threshold (logit > 0) -> u8 [n,640,640].  Block = one detection x one 64x64 output tile: the 18x18 logit patch it
 // needs is computed once into shared memory from the frame's prototypes.

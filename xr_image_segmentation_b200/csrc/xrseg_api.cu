@@ -16,6 +16,7 @@
 #include "kernels_misc.cuh"
 #include "model.cuh"
 #include "post.cuh"
+#include "sentis.cuh"
 
 using namespace xrseg;
 
@@ -790,6 +791,41 @@ int xrseg_layer_info_get(int model_scale, int index, xrseg_layer_info* info) {
   }
 }
 
+int xrseg_sentis_info(const void* data, size_t bytes, int32_t* n_convs, float* iou_threshold, float* score_threshold) {
+  if (!data) return XRSEG_ERR_INVALID;
+  try {
+    if (!looks_like_sentis(data, bytes)) { g_create_error = "not a .sentis container"; return XRSEG_ERR_WEIGHTS; }
+    SentisWeights sw = sentis_load(data, bytes);
+    if (n_convs) *n_convs = static_cast<int32_t>(sw.convs.size());
+    if (iou_threshold) *iou_threshold = sw.has_nms ? sw.iou_threshold : 0.f;
+    if (score_threshold) *score_threshold = sw.has_nms ? sw.score_threshold : 0.f;
+    return XRSEG_OK;
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_WEIGHTS;
+  }
+}
+
+int xrseg_sentis_layer(const void* data, size_t bytes, int index, float* w, size_t w_cap, float* b, size_t b_cap,
+                       int32_t* w_shape4, int32_t* transposed) {
+  if (!data || index < 0) return XRSEG_ERR_INVALID;
+  try {
+    if (!looks_like_sentis(data, bytes)) { g_create_error = "not a .sentis container"; return XRSEG_ERR_WEIGHTS; }
+    SentisWeights sw = sentis_load(data, bytes);
+    if (static_cast<size_t>(index) >= sw.convs.size()) return XRSEG_ERR_INVALID;
+    const SentisConv& cv = sw.convs[index];
+    if (w_shape4) for (int i = 0; i < 4; ++i) w_shape4[i] = i < static_cast<int>(cv.w_shape.size()) ? cv.w_shape[i] : 1;
+    if (transposed) *transposed = cv.transposed ? 1 : 0;
+    if ((w && w_cap < cv.w.size()) || (b && b_cap < cv.b.size())) return XRSEG_ERR_CAPACITY;
+    if (w) memcpy(w, cv.w.data(), cv.w.size() * sizeof(float));
+    if (b) memcpy(b, cv.b.data(), cv.b.size() * sizeof(float));
+    return static_cast<int>(cv.w.size());
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_WEIGHTS;
+  }
+}
+
 int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
   if (!cfg_in || !out || cfg_in->struct_size != sizeof(xrseg_config)) {
     g_create_error = "xrseg_create: bad config (struct_size mismatch?)";
@@ -841,7 +877,29 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     r->A = net.fh[0] * net.fw[0] + net.fh[1] * net.fw[1] + net.fh[2] * net.fw[2];
     std::vector<HostLayerWeights> hw;
     try {
-      xrsw_load(c.weights, c.weights_bytes, net.layers, c.model_scale, hw);
+      if (looks_like_sentis(c.weights, c.weights_bytes)) {
+        // the sample's own asset (↔ ModelLoader.Load(_sentisModel), IEE:382): dequantize its convolutions in chain order
+        SentisWeights sw = sentis_load(c.weights, c.weights_bytes);
+        XR_CHECK(sw.convs.size() == net.layers.size(), "sentis asset has %zu convolutions, the '%c' topology has %zu",
+                 sw.convs.size(), static_cast<char>(c.model_scale), net.layers.size());
+        hw.resize(sw.convs.size());
+        for (size_t i = 0; i < sw.convs.size(); ++i) {
+          const LayerRec& l = net.layers[i];
+          const SentisConv& cv = sw.convs[i];
+          const int cin_g = l.cin / l.groups;
+          const int d0 = l.transposed ? l.cin : l.cout, d1 = l.transposed ? l.cout : cin_g;
+          XR_CHECK(cv.transposed == (l.transposed != 0) && cv.w_shape.size() == 4 && cv.w_shape[0] == d0 && cv.w_shape[1] == d1 &&
+                       cv.w_shape[2] == l.k && cv.w_shape[3] == l.k && cv.b.size() == static_cast<size_t>(l.cout),
+                   "sentis convolution %zu does not match topology layer %s", i, l.name.c_str());
+          hw[i].w = cv.w;
+          hw[i].b = cv.b;
+        }
+        // thresholds baked into the asset's NonMaxSuppression chain win over the built-in defaults (not over the caller)
+        if (sw.has_nms && cfg_in->iou_threshold == 0.f) c.iou_threshold = sw.iou_threshold;
+        if (sw.has_nms && cfg_in->score_threshold == 0.f) c.score_threshold = sw.score_threshold;
+      } else {
+        xrsw_load(c.weights, c.weights_bytes, net.layers, c.model_scale, hw);
+      }
     } catch (const CudaError& e) {
       g_create_error = e.msg;
       return XRSEG_ERR_WEIGHTS;
@@ -1053,6 +1111,80 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
     return XRSEG_ERR_CUDA;
   }
   return count;
+}
+
+int xrseg_extract_points(xrseg_runner* r, const xrseg_depth_params* dp, const uint16_t* depth_host, float* out_xyzd, int cap,
+                         int* n_out) {
+  if (!r || !dp || !depth_host || !out_xyzd || !n_out || dp->struct_size != sizeof(xrseg_depth_params)) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  const int total = r->h_offsets[r->batch];
+  const int step = dp->sampling_step > 0 ? dp->sampling_step : 5;
+  const int max_points = dp->max_points > 0 ? dp->max_points : 8000;
+  if (dp->detection < 0 || dp->detection >= total || dp->depth_w < 1 || dp->depth_h < 1 || step > PROTO_HW) {
+    r->err = "xrseg_extract_points: bad detection index or depth geometry";
+    return XRSEG_ERR_INVALID;
+  }
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    const size_t depth_bytes = static_cast<size_t>(dp->depth_w) * dp->depth_h * sizeof(uint16_t);
+    const size_t out_bytes = static_cast<size_t>(max_points) * sizeof(float4);
+    uint8_t* base = static_cast<uint8_t*>(ensure_scratch(r, out_bytes + 16 + depth_bytes));
+    DepthParams k{};
+    k.out = reinterpret_cast<float4*>(base);
+    k.out_n = reinterpret_cast<int*>(base + out_bytes);
+    uint16_t* d_depth = reinterpret_cast<uint16_t*>(base + out_bytes + 16);
+    XR_CUDA(cudaMemcpyAsync(d_depth, depth_host, depth_bytes, cudaMemcpyHostToDevice, r->stream));
+    k.probs = r->o_probs + static_cast<size_t>(dp->detection) * PROTO_PIX;
+    k.box = r->o_boxes + static_cast<size_t>(dp->detection) * 4;
+    k.depth = d_depth;
+    k.depth_w = dp->depth_w; k.depth_h = dp->depth_h; k.step = step; k.max_points = max_points;
+    k.thr = dp->confidence_threshold > 0.f ? dp->confidence_threshold : r->cfg.mask_threshold;
+    k.screen_w = dp->screen_w; k.screen_h = dp->screen_h;
+    for (int i = 0; i < 3; ++i) k.pos[i] = dp->camera_position[i];
+    for (int i = 0; i < 4; ++i) k.rot[i] = dp->camera_rotation[i];
+    for (int i = 0; i < 2; ++i) { k.focal[i] = dp->focal_length[i]; k.principal[i] = dp->principal_point[i]; k.sensor[i] = dp->sensor_resolution[i]; }
+    depth_extract_kernel<<<1, 1024, 0, r->stream>>>(k);
+    XR_CUDA(cudaGetLastError());
+    int n = 0;
+    XR_CUDA(cudaMemcpyAsync(&n, k.out_n, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+    *n_out = n;
+    if (n > cap) { r->err = "point buffer too small"; return XRSEG_ERR_CAPACITY; }
+    if (n) XR_CUDA(cudaMemcpy(out_xyzd, k.out, static_cast<size_t>(n) * sizeof(float4), cudaMemcpyDeviceToHost));
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+int xrseg_associate(xrseg_runner* r, int frame, float lx, float ly, int llabel, float screen_w, float screen_h, float max_dist,
+                    int* best_index, float* best_dist) {
+  if (!r || !best_index) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  if (frame < 0 || frame >= r->batch) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    uint8_t* base = static_cast<uint8_t*>(ensure_scratch(r, 16));
+    int* d_idx = reinterpret_cast<int*>(base);
+    float* d_dist = reinterpret_cast<float*>(base + 4);
+    associate_kernel<<<1, 32, 0, r->stream>>>(r->o_boxes, r->o_labels, r->h_offsets[frame], r->h_counts[frame], 50, screen_w,
+                                              screen_h, lx, ly, llabel, max_dist > 0.f ? max_dist : 300.f, d_idx, d_dist);
+    XR_CUDA(cudaGetLastError());
+    int idx = -1;
+    float dist = 0.f;
+    XR_CUDA(cudaMemcpyAsync(&idx, d_idx, sizeof(int), cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaMemcpyAsync(&dist, d_dist, sizeof(float), cudaMemcpyDeviceToHost, r->stream));
+    XR_CUDA(cudaStreamSynchronize(r->stream));
+    *best_index = idx;
+    if (best_dist) *best_dist = dist;
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
 }
 
 int xrseg_last_timings(xrseg_runner* r, float* ms, int n) {

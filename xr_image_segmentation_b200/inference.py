@@ -39,9 +39,19 @@ class ModelLoader:
     def Load(asset) -> Model:
         """↔ ModelLoader.Load(ModelAsset) IEE:382.  `asset`: path to / bytes of an XRSW pack."""
         data = asset if isinstance(asset, (bytes, bytearray)) else open(os.fspath(asset), "rb").read()
-        if data[:4] != b"XRSW":
-            raise XrsegError(_lib.ERR_WEIGHTS, "not an XRSW weight pack (convert the .sentis asset with tests/golden/make_golden.py)")
-        return Model(bytes(data), chr(int.from_bytes(data[12:16], "little")))
+        if data[:4] == b"XRSW":
+            return Model(bytes(data), chr(int.from_bytes(data[12:16], "little")))
+        # the sample's own .sentis asset: parsed (FlatBuffer walk + uint8 dequantization) inside libxrseg.so
+        lib = _lib.load_library()
+        buf = C.create_string_buffer(bytes(data), len(data))
+        n = C.c_int32()
+        rc = lib.xrseg_sentis_info(C.cast(buf, C.c_void_p), len(data), C.byref(n), None, None)
+        if rc < 0:
+            raise XrsegError(_lib.ERR_WEIGHTS, "neither an XRSW weight pack nor a .sentis asset")
+        scale = {100: "n"}.get(n.value)
+        if scale is None:
+            raise XrsegError(_lib.ERR_WEIGHTS, f".sentis asset with {n.value} convolutions does not match a known topology")
+        return Model(bytes(data), scale)
 
 
 class Runner:
@@ -162,6 +172,34 @@ class Runner:
         p = _lib.MaskParams(C.sizeof(_lib.MaskParams), mode, box_convention, screen_w, screen_h, image_w, image_h, first, n)
         self._ck(self.lib.xrseg_masks(self.h, C.byref(p), out.ctypes.data, out.nbytes))
         return out.view(np.uint32).reshape(n, 160, 5) if mode == _lib.MASK_BITS_160 else out
+
+    def extract_points(self, detection: int, depth_half: np.ndarray, screen_w: float, screen_h: float, camera_position,
+                       camera_rotation, focal_length, principal_point, sensor_resolution, sampling_step=5, max_points=8000,
+                       confidence_threshold=0.0) -> np.ndarray:
+        """↔ IEExecutor.ExtractDepthData (IEE:561-667).  depth_half: uint16 [H,W] half floats.  Returns f32 [n,4] x,y,z,depth."""
+        d = np.ascontiguousarray(depth_half, np.uint16)
+        p = _lib.DepthParams()
+        p.struct_size = C.sizeof(_lib.DepthParams)
+        p.detection, p.depth_h, p.depth_w = detection, d.shape[0], d.shape[1]
+        p.sampling_step, p.max_points, p.confidence_threshold = sampling_step, max_points, confidence_threshold
+        p.screen_w, p.screen_h = screen_w, screen_h
+        p.camera_position[:] = [float(v) for v in camera_position]
+        p.camera_rotation[:] = [float(v) for v in camera_rotation]
+        p.focal_length[:] = [float(v) for v in focal_length]
+        p.principal_point[:] = [float(v) for v in principal_point]
+        p.sensor_resolution[:] = [float(v) for v in sensor_resolution]
+        out = np.zeros((max_points, 4), np.float32)
+        n = C.c_int()
+        self._ck(self.lib.xrseg_extract_points(self.h, C.byref(p), d.ctypes.data, out.ctypes.data, max_points, C.byref(n)))
+        return out[:n.value]
+
+    def associate(self, frame: int, locked_cx: float, locked_cy: float, locked_label: int, screen_w: float, screen_h: float,
+                  max_dist: float = 300.0):
+        """↔ the locked-target search of ProcessInferenceResult (IEE:488-507): (index inside the frame or -1, min distance)."""
+        idx, dist = C.c_int(), C.c_float()
+        self._ck(self.lib.xrseg_associate(self.h, frame, locked_cx, locked_cy, locked_label, screen_w, screen_h, max_dist,
+                                          C.byref(idx), C.byref(dist)))
+        return idx.value, dist.value
 
     def timings(self):
         ms = (C.c_float * 5)()

@@ -353,15 +353,18 @@ static inline TmapSet make_s2_tensor_maps(const __half* base, int B, int H, int 
 // out of bounds for the tensor map and arrive as zeros, so Cin only has to be a multiple of 16 (e.g. the 48-channel
 // C3k2 concat).
 static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
-  if (!(d.k == 1 && d.stride == 1 && !d.transposed)) return false;
+  // also the 2x2 stride-2 ConvTranspose: the same GEMM with N = 4 positions x Cout, scattered by the epilogue
+  const bool convt = d.transposed && d.k == 2 && d.stride == 2 && d.res_pitch == 0;
+  if (!((d.k == 1 && d.stride == 1 && !d.transposed) || convt)) return false;
   p = ConvParams{};
   p.B = d.B; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.in_pitch = d.in_pitch;
   p.Cout = d.Cout; p.out_pitch = d.out_pitch; p.res_pitch = d.res_pitch;
-  p.k = 1; p.stride = 1; p.pad = 0; p.act = d.act; p.transposed = 0;
-  p.Ho = d.H; p.Wo = d.W;
-  p.Ntile = d.Cout <= 256 ? d.Cout : 256;
-  if (d.Cout % p.Ntile) return false;
-  p.n_tiles = d.Cout / p.Ntile;
+  p.k = d.k; p.stride = d.stride; p.pad = 0; p.act = d.act; p.transposed = convt ? 1 : 0;
+  p.Ho = convt ? 2 * d.H : d.H; p.Wo = convt ? 2 * d.W : d.W;
+  const int ncols = convt ? 4 * d.Cout : d.Cout;
+  p.Ntile = ncols <= 256 ? ncols : 256;
+  if (ncols % p.Ntile) return false;
+  p.n_tiles = ncols / p.Ntile;
   p.idesc = umma_idesc_f16(p.Ntile, 0);
   p.mode = MODE_FLAT_TMA;
   p.taps = 1;
@@ -421,8 +424,8 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
   p.Wp = 1; p.Hp1 = 1; p.R = 0; p.tpi = 1;
   p.fd_wp = make_fastdiv(1);
   p.fd_hp1 = make_fastdiv(1);
-  p.fd_hw = make_fastdiv(1);
-  p.fd_wo = make_fastdiv(1);
+  p.fd_hw = make_fastdiv(d.H * d.W);           // ConvTranspose epilogue: row -> (image, h, w)
+  p.fd_wo = make_fastdiv(d.W);
   p.fd_cin = make_fastdiv(d.Cin);
   p.fd_cout = make_fastdiv(d.Cout);
   return true;
@@ -478,13 +481,23 @@ static inline void pack_conv_weights_sw(const ConvParams& p, const float* w, con
         for (int n = 0; n < p.Ntile; ++n)
           for (int c = 0; c < p.cb; ++c) {
             const int ng = nt * p.Ntile + n, ci = ks * p.cb + c;
-            if (ng >= cout_real || ci >= cin_real) continue;
-            const float v = w[(static_cast<size_t>(ng) * cin_real + ci) * p.taps + t];   // [cout][cin][kh][kw], t = kh*3+kw
+            if (ci >= cin_real) continue;
+            float v;
+            if (p.transposed) {                    // column = position (kh,kw) x output channel; weights [cin][cout][2][2]
+              const int pos = ng / p.Cout, co = ng - pos * p.Cout;
+              if (co >= cout_real) continue;
+              v = w[((static_cast<size_t>(ci) * cout_real + co) * 2 + (pos >> 1)) * 2 + (pos & 1)];
+            } else {
+              if (ng >= cout_real) continue;
+              v = w[(static_cast<size_t>(ng) * cin_real + ci) * p.taps + t];   // [cout][cin][kh][kw], t = kh*3+kw
+            }
             const size_t off = (static_cast<size_t>(t) * p.Ntile + n) * rb + static_cast<size_t>(c) * 2;
             wp[(static_cast<size_t>(nt) * nkb + ks) * stage_elems + sw_phys(off, p.sw) / 2] = HalfT(v);
           }
-  for (int ng = 0; ng < p.n_tiles * p.Ntile; ++ng)
-    if (ng < cout_real && bias) bp[ng] = bias[ng];
+  for (int ng = 0; ng < p.n_tiles * p.Ntile; ++ng) {
+    const int co = p.transposed ? ng % p.Cout : ng;
+    if (co < cout_real && bias) bp[ng] = bias[co];
+  }
 }
 
 #ifdef __CUDACC__
@@ -814,7 +827,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
                            p.out + pix * p.out_pitch + n);
         }
       };
-      if (!(p.dbg_skip & 8)) {
+      if (!(p.dbg_skip & 8) || p.transposed) {
         // default: per sub-tile the two warp halves take alternating 16-column chunks; with an odd chunk count the
         // starting chunk alternates with the sub-tile, so single-chunk layers (N = 16) still use all eight warps
         for (int u = 0; u < p.nsub; ++u) {
@@ -833,14 +846,29 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
           }
           valid = valid && !(p.dbg_skip & 2);
+          int tb = 0, th = 0, tw = 0;
+          if (p.transposed) {                      // 2x2 stride-2 ConvTranspose: input pixel (image, h, w) of this row
+            const int m = static_cast<int>(pix);
+            tb = fd_div(p.fd_hw, m);
+            const int rem = m - tb * p.fd_hw.d;
+            th = fd_div(p.fd_wo, rem);
+            tw = rem - th * p.fd_wo.d;
+          }
           for (int c = first_c(u); c < nch; c += 2) {
             uint32_t v[16];
             tmem_ld16(t_addr(u, c), v);
             tmem_ld_wait();
             if (valid) {
               const int n = n_tile * p.Ntile + c * 16;
-              epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
-                               p.out + pix * p.out_pitch + n);
+              if (p.transposed) {                  // column chunk -> output position (pos >> 1, pos & 1) and channel
+                const int pos = fd_div(p.fd_cout, n);
+                const int co = n - pos * p.Cout;
+                const size_t opix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
+                epilogue_chunk16(v, bias_s + n, p.act, nullptr, p.out + opix * p.out_pitch + co);
+              } else {
+                epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
+                                 p.out + pix * p.out_pitch + n);
+              }
             }
           }
         }
@@ -995,6 +1023,13 @@ static inline void emulate_conv_flat_tma(const ConvParams& p, const float* in, c
         const int ng = n_tile * p.Ntile + n;
         float yv = acc[static_cast<size_t>(r) * p.Ntile + n] + bias[ng];
         if (p.act) yv = yv / (1.0f + expf(-yv));
+        if (p.transposed) {
+          const int pos = ng / p.Cout, co = ng % p.Cout;
+          const long tb = m / (p.H * p.W), rem = m % (p.H * p.W), th = rem / p.W, tw = rem % p.W;
+          const size_t opix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
+          out[opix * p.out_pitch + co] = yv;
+          continue;
+        }
         if (res) yv += res[static_cast<size_t>(m) * p.res_pitch + ng];
         out[static_cast<size_t>(m) * p.out_pitch + ng] = yv;
       }

@@ -37,6 +37,10 @@ struct Op {
   bool has_res = false;
   int k = 1, stride = 1, act = 0, transposed = 0, heads = 0;
   int in_grp = 0, in_grp_stride = 0, in_grp_off = 0;   // OP_DW channel remap (see DwParams)
+  // Branch concurrency inside the captured graph: ops of branch > 0 (the head / proto chains) run on side streams.  The
+  // first op of a branch segment waits for the event `wait_tag` (3/4/5 = P3/P4/P5 ready); the op producing that feature
+  // map carries `signal_tag`.
+  int branch = 0, wait_tag = 0, signal_tag = 0;
 };
 
 struct Spec {
@@ -69,6 +73,7 @@ class Net {
   std::vector<Op> ops;
   std::map<std::string, TV> named;
   size_t arena_elems = 0;
+  int cur_branch = 0, pending_wait = 0;   // see Op::branch
   TV input;                 // [B,640,640,4] fp16
   TV box[3], cls[3], coef[3], protos;
   int fh[3], fw[3];
@@ -107,6 +112,7 @@ class Net {
     o.layer = static_cast<int>(layers.size()) - 1;
     o.x = x; o.y = y; o.k = k; o.stride = s; o.act = act; o.transposed = transposed;
     if (res) { o.res = *res; o.has_res = true; }
+    o.branch = cur_branch; o.wait_tag = pending_wait; pending_wait = 0;
     ops.push_back(o);
     named[name] = y;
     return y;
@@ -124,6 +130,7 @@ class Net {
     o.x = x; o.y = y; o.k = 3; o.act = act;
     o.in_grp = grp; o.in_grp_stride = grp_stride; o.in_grp_off = grp_off;
     if (res) { o.res = *res; o.has_res = true; }
+    o.branch = cur_branch; o.wait_tag = pending_wait; pending_wait = 0;
     ops.push_back(o);
     named[name] = y;
     return y;
@@ -155,19 +162,24 @@ class Net {
   }
 
   void head_box_cls(const TV& p, int i, const std::string& n) {
+    cur_branch = 1; pending_wait = 3 + i;            // box chain: side stream 1, after P(3+i)
     TV t = conv(p, sp.box_mid, 3, 1, true, n + ".box.0");
     t = conv(t, sp.box_mid, 3, 1, true, n + ".box.1");
     box[i] = conv(t, 64, 1, 1, false, n + ".box.2");
+    cur_branch = 2; pending_wait = 3 + i;            // class chain: side stream 2
     t = dw(p, true, n + ".cls.0dw");
     t = conv(t, sp.cls_mid, 1, 1, true, n + ".cls.0pw");
     t = dw(t, true, n + ".cls.1dw");
     t = conv(t, sp.cls_mid, 1, 1, true, n + ".cls.1pw");
     cls[i] = conv(t, 80, 1, 1, false, n + ".cls.2");
+    cur_branch = 0;
   }
   void head_coef(const TV& p, int i, const std::string& n) {
+    cur_branch = 3; pending_wait = 3 + i;            // coefficient chain: side stream 3
     TV t = conv(p, sp.coef_mid, 3, 1, true, n + ".coef.0");
     t = conv(t, sp.coef_mid, 3, 1, true, n + ".coef.1");
     coef[i] = conv(t, 32, 1, 1, false, n + ".coef.2");
+    cur_branch = 0;
   }
 
   void build(int hw) {
@@ -233,22 +245,27 @@ class Net {
     c3k2(cat13, sp.mid1, sp.mid1 / 2, false, "n13", &f13);
     upsample(f13, slice(cat16, 0, sp.mid1));
     TV p3 = c3k2(cat16, sp.mid0, sp.mid0 / 2, false, "n16");
+    ops.back().signal_tag = 3;
     head_box_cls(p3, 0, "h3");
     TV n17 = slice(cat19, 0, sp.mid0);
     conv(p3, sp.mid0, 3, 2, true, "n17", &n17);
     TV p4 = c3k2(cat19, sp.mid1, sp.mid1 / 2, false, "n19");
+    ops.back().signal_tag = 4;
     head_box_cls(p4, 1, "h4");
     TV n20 = slice(cat22, 0, sp.mid1);
     conv(p4, sp.mid1, 3, 2, true, "n20", &n20);
     TV p5 = c3k2(cat22, c5, c5 / 2, true, "n22");
+    ops.back().signal_tag = 5;
     head_box_cls(p5, 2, "h5");
     head_coef(p3, 0, "h3");
     head_coef(p4, 1, "h4");
     head_coef(p5, 2, "h5");
+    cur_branch = 4; pending_wait = 3;                // prototype chain: side stream 4, after P3
     t = conv(p3, sp.proto_mid, 3, 1, true, "proto.cv1");
     t = conv(t, sp.proto_mid, 2, 2, false, "proto.up", nullptr, nullptr, true);
     t = conv(t, sp.proto_mid, 3, 1, true, "proto.cv2");
     protos = conv(t, 32, 1, 1, true, "proto.cv3");
+    cur_branch = 0;
     named["p3"] = p3; named["p4"] = p4; named["p5"] = p5;
     fh[0] = p3.H; fw[0] = p3.W; fh[1] = p4.H; fw[1] = p4.W; fh[2] = p5.H; fw[2] = p5.W;
   }

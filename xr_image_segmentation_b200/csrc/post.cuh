@@ -250,6 +250,7 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, float thr
   const float iw = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
   const float ih = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
   const float inter = __fmul_rn(iw, ih);
+  if (inter <= 0.f && thr >= 0.f) return false;   // disjoint boxes: 0 / union (or 0 / 0 = NaN) is never > thr -- same answer, no division
   const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
@@ -269,29 +270,37 @@ struct MaskBitsParams {
   unsigned long long* mask;      // [B,max_cand,words]
 };
 
-__global__ void __launch_bounds__(64) nms_bitmask_kernel(const MaskBitsParams p) {
+__global__ void __launch_bounds__(256) nms_bitmask_kernel(const MaskBitsParams p) {
   XR_PDL_ENTRY();
   const int rb = blockIdx.x, b = blockIdx.y;
   const int n = p.n_cand[b];
   if (rb * 64 >= n) return;
   __shared__ float4 cols[64];
-  const int t = threadIdx.x;
+  __shared__ unsigned long long part[4][64];
+  // 256 threads: row t of the block against a quarter (16 columns) of each 64-column tile -- the per-thread chain of
+  // exact divisions is what bounds this latency-bound kernel (~100 candidates per frame), so it is split four ways
+  const int t = threadIdx.x & 63, s = threadIdx.x >> 6;
   const int i = rb * 64 + t;
   const float4 me = p.sorted_corners[static_cast<long>(b) * p.max_cand + min(i, n - 1)];
   const int nw = (n + 63) >> 6;
   for (int cb = rb; cb < nw; ++cb) {
     const int cj = cb * 64 + t;
     __syncthreads();
-    if (cj < n) cols[t] = p.sorted_corners[static_cast<long>(b) * p.max_cand + cj];
+    if (s == 0 && cj < n) cols[t] = p.sorted_corners[static_cast<long>(b) * p.max_cand + cj];
     __syncthreads();
-    if (i >= n) continue;
     unsigned long long bits = 0;
-    const int jn = min(64, n - cb * 64);
-    for (int j = 0; j < jn; ++j) {
-      const int gj = cb * 64 + j;
-      if (gj > i && iou_gt(me, cols[j], p.iou_thr)) bits |= 1ull << j;
+    if (i < n) {
+      const int jn = min(64, n - cb * 64);
+      const int j1 = min(jn, s * 16 + 16);
+      for (int j = s * 16; j < j1; ++j) {
+        const int gj = cb * 64 + j;
+        if (gj > i && iou_gt(me, cols[j], p.iou_thr)) bits |= 1ull << j;
+      }
     }
-    p.mask[(static_cast<long>(b) * p.max_cand + i) * p.words + cb] = bits;
+    part[s][t] = bits;
+    __syncthreads();
+    if (s == 0 && i < n)
+      p.mask[(static_cast<long>(b) * p.max_cand + i) * p.words + cb] = part[0][t] | part[1][t] | part[2][t] | part[3][t];
   }
 }
 

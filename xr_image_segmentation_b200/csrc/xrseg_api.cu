@@ -43,6 +43,10 @@ bool flat_tma_disabled() {
   return e && e[0] == '0';
 }
 
+bool branches_disabled() {   // XRSEG_BRANCHES=0: everything on one stream (A/B measurements)
+  const char* e = getenv("XRSEG_BRANCHES");
+  return e && e[0] == '0';
+}
 bool s2_tma_disabled() {
   const char* e = getenv("XRSEG_S2_TMA");
   return e && e[0] == '0';
@@ -96,6 +100,8 @@ struct xrseg_runner {
   struct ChunkGraph { int b0, nb; cudaGraphExec_t exec; };
   std::vector<ChunkGraph> graphs;     // one captured pipeline per (first frame, frame count) chunk
   cudaStream_t copy_stream = nullptr; // host->device frame copies, overlapped chunk by chunk with compute
+  cudaStream_t side[4] = {};          // head / prototype branches inside the captured graph
+  cudaEvent_t ev_tag[3] = {}, ev_join[4] = {};
   std::vector<cudaEvent_t> ev_copy;
   struct ChunkLaunches { int b0, nb; void* list; };   // list: std::vector<Launch>* (type local to this file)
   std::vector<ChunkLaunches> launch_cache;
@@ -212,6 +218,7 @@ struct Launch {
   std::string name;
   std::function<void(cudaStream_t)> fn;
   double flops = 0, bytes = 0;   // algorithmic work of the launch (real channel counts, fp16 activations)
+  int branch = 0, wait_tag = 0, signal_tag = 0;   // see model.cuh Op::branch
 };
 
 void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
@@ -333,6 +340,7 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         break;
       }
     }
+    L.branch = o.branch; L.wait_tag = o.wait_tag; L.signal_tag = o.signal_tag;
     out.push_back(std::move(L));
   }
 }
@@ -439,7 +447,7 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
   {
     Launch L;
     L.name = "post.nms_bitmask";
-    L.fn = [mp, words, nb](cudaStream_t st) { launch_k(nms_bitmask_kernel, dim3(words, nb), 64, 0, st, mp); };
+    L.fn = [mp, words, nb](cudaStream_t st) { launch_k(nms_bitmask_kernel, dim3(words, nb), 256, 0, st, mp); };
     out.push_back(std::move(L));
   }
   {
@@ -547,7 +555,29 @@ int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st, int part = 
     r->launch_cache.push_back({b0, nb, ls});
   }
   const size_t lo = part == 2 ? 1 : 0, hi = part == 1 ? 1 : ls->size();
-  for (size_t i = lo; i < hi; ++i) (*ls)[i].fn(st);
+  // Branch concurrency (only while capturing the graph, part == 2): the head / prototype chains run on side streams,
+  // forked after the feature map they read (P3 / P4 / P5) and joined before the post-processing.  The small P4 / P5
+  // kernels keep only part of the SMs busy; this lets independent ones share the GPU.
+  const bool fork = part == 2 && r->side[0] != nullptr && r->cfg.use_cuda_graph && !branches_disabled();
+  bool used[5] = {};
+  for (size_t i = lo; i < hi; ++i) {
+    Launch& L = (*ls)[i];
+    cudaStream_t s = st;
+    if (fork && L.branch > 0) {
+      s = r->side[L.branch - 1];
+      if (L.wait_tag) XR_CUDA(cudaStreamWaitEvent(s, r->ev_tag[L.wait_tag - 3], 0));
+      used[L.branch] = true;
+    } else if (fork && L.branch == 0 && (used[1] || used[2] || used[3] || used[4]) && L.name.rfind("post.", 0) == 0) {
+      for (int b = 1; b <= 4; ++b)                       // join before the first post-processing kernel
+        if (used[b]) {
+          XR_CUDA(cudaEventRecord(r->ev_join[b - 1], r->side[b - 1]));
+          XR_CUDA(cudaStreamWaitEvent(st, r->ev_join[b - 1], 0));
+          used[b] = false;
+        }
+    }
+    L.fn(s);
+    if (fork && L.signal_tag) XR_CUDA(cudaEventRecord(r->ev_tag[L.signal_tag - 3], st));
+  }
   XR_CUDA(cudaGetLastError());
   return static_cast<int>(hi - lo);
 }
@@ -712,6 +742,9 @@ xrseg_runner::~xrseg_runner() {
   for (auto& g : graphs) cudaGraphExecDestroy(g.exec);
   free_launch_cache(this);
   if (copy_stream) cudaStreamDestroy(copy_stream);
+  for (cudaStream_t s : side) if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t e : ev_tag) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ev_join) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ev_copy) cudaEventDestroy(e);
   cudaFree(scratch);
   for (DevLayer& d : dl) {
@@ -863,6 +896,9 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     XR_CUDA(cudaSetDevice(c.device));
     XR_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
     XR_CUDA(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+    for (auto& s : r->side) XR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : r->ev_tag) XR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : r->ev_join) XR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     XR_CUDA(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
     for (auto& e : r->ev) XR_CUDA(cudaEventCreate(&e));
     conv_umma_prepare_device();

@@ -25,7 +25,9 @@ enum { MODE_HALO_TMA = 2, MODE_FLAT_TMA = 3, MODE_S2_TMA = 4 };
 struct TmapSet {
   CUtensorMap m[4];
 };
-enum { TMA_THREADS = 320, TMA_TAIL_PAD = 4096 };
+// warp 0: TMA producer; warps 1-4: MMA issuers (one per 128-row sub-tile: a single thread cannot issue tcgen05.mma faster
+// than one per ~50-65 cycles, which bounded every thin layer); warps 5-12: epilogue
+enum { TMA_THREADS = 416, TMA_TAIL_PAD = 4096, TMA_FIRST_EPI_WARP = 5 };
 
 struct TmaPlanExtra {
   int R, nsub, tpi, hbox, slots_box;
@@ -543,13 +545,14 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   const int lane = tid & 31;
   const int total_work = p.m_tiles * p.n_tiles;
 
+  const int n_issuers = p.sw ? p.nsub : 1;    // MMA-issuing warps (swizzled path: one per sub-tile)
   if (tid == 0) {
     for (int i = 0; i < CONV_MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], n_issuers);       // every issuer commits the stage it has consumed
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
+      mbar_init(&tfull[i], n_issuers);       // ... and the accumulators it has finished
       mbar_init(&tempty[i], 8);              // one arrival per epilogue warp
     }
     mbar_init(bres, 1);
@@ -638,8 +641,11 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       }
       if (p.dbg_clk) p.dbg_clk[blockIdx.x * 8 + 0] = t_wait;
     }
-  } else if (warp == 1) {
-    // ======================================= MMA issuer ==========================================
+  } else if (warp < TMA_FIRST_EPI_WARP) {
+    // ======================================= MMA issuers =========================================
+    // warp 1 + u owns sub-tile u (its own TMEM accumulator): same waits, its own MMAs, its own commits
+    const int my_u = warp - 1;
+    if (my_u < n_issuers)
     // all 32 lanes run the loop (uniform control flow); one elected lane issues the tcgen05 instructions
     {
       const uint32_t a_u32 = smem_u32(smem_a);
@@ -692,17 +698,15 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             // unrolled with guards folded into the issue predicate: a handful of uniform adds per MMA, no branches.
             if (elect_one()) {   // one branch per stage; inside, a single lane issues the whole MMA batch
               uint32_t acc = ks > 0 ? 1u : 0u;
-              // one tap: kj k16-steps x nsub sub-tiles (sub-tile innermost: consecutive MMAs hit different accumulators)
+              // one tap of this warp's sub-tile: kj k16-steps
 #define XR_ISSUE_TAP(A_TAP)                                                                          \
   {                                                                                                  \
     const uint32_t a_tap_ = (A_TAP);                                                                 \
     for (int j = 0; j < kj; ++j) {                                                                   \
       const uint64_t bd = hi_sw | (b_lo + 2u * j);                                                   \
-      _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                \
-        if (u < nsub && mma_on) {                                                                    \
-          const uint64_t ad = hi_sw | (a_tap_ + static_cast<uint32_t>(u) * sub16 + 2u * j);          \
-          umma_f16(d_base + static_cast<uint32_t>(u) * ntile_u, ad, bd, idesc, acc);                 \
-        }                                                                                            \
+      if (mma_on) {                                                                                  \
+        const uint64_t ad = hi_sw | (a_tap_ + static_cast<uint32_t>(my_u) * sub16 + 2u * j);         \
+        umma_f16(d_base + static_cast<uint32_t>(my_u) * ntile_u, ad, bd, idesc, acc);                \
       }                                                                                              \
       acc = 1;                                                                                       \
     }                                                                                                \
@@ -763,7 +767,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         }
         if (elect_one()) umma_commit(&tfull[buf]);
       }
-      if (p.dbg_clk && lane == 0) {
+      if (p.dbg_clk && lane == 0 && warp == 1) {
         p.dbg_clk[blockIdx.x * 8 + 1] = t_bres;
         p.dbg_clk[blockIdx.x * 8 + 2] = t_tempty;
         p.dbg_clk[blockIdx.x * 8 + 3] = t_full;
@@ -773,7 +777,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     }
   } else {
     // ======================================= epilogue ============================================
-    const int ew = warp - 2;
+    const int ew = warp - TMA_FIRST_EPI_WARP;
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
     const int half = ew >> 2;
     int tcount = 0;
@@ -896,7 +900,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       if (lane == 0) mbar_arrive(&tempty[buf]);
       e_work += clock64() - t0;
     }
-    if (p.dbg_clk && warp == 2 && lane == 0) {
+    if (p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
       p.dbg_clk[blockIdx.x * 8 + 6] = e_wait;
       p.dbg_clk[blockIdx.x * 8 + 7] = e_work;
     }

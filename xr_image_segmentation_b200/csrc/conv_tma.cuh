@@ -525,6 +525,47 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// MMAs of one pipeline stage for ONE 128-row sub-tile, issued by one thread.  MODE: 0 halo (3x3 s1), 1 parity planes
+// (3x3 s2), 2 flat (1x1 / ConvT, kps K-blocks of one tap).  KJ = k16 steps per K-block.  a_sub / b_lo: low descriptor
+// words (start address >> 4 | LBO field) of the sub-tile's first row and of the stage's first weight tile.
+template <int MODE, int KJ>
+__device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem, uint32_t a_sub, uint32_t b_lo, uint64_t hi_sw,
+                                           uint32_t idesc, uint32_t acc0, uint32_t row16, uint32_t tap16) {
+  uint32_t acc = acc0;
+  if (MODE == 2) {
+    const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;
+    const int kps = p.kps > 1 ? p.kps : 1;
+    for (int kb = 0; kb < kps; ++kb) {
+#pragma unroll
+      for (int j = 0; j < KJ; ++j) {
+        umma_f16(d_tmem, hi_sw | (a_sub + 2u * j), hi_sw | (b_lo + 2u * j), idesc, acc);
+        acc = 1;
+      }
+      a_sub += blk16;
+      b_lo += tap16;
+    }
+    return;
+  }
+  const uint32_t wp16 = static_cast<uint32_t>(p.Wp) * row16;
+  const uint32_t plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      uint32_t a_tap;
+      if (MODE == 0) a_tap = a_sub + kh * wp16 + (kw - 1) * row16;                       // row shift kh*Wp + kw - 1
+      else a_tap = a_sub + (kh != 1 ? 2u : 0u) * plane16 + (kw != 1 ? plane16 : 0u) +    // plane (kh != 1, kw != 1)
+                   (kh == 2 ? wp16 : 0u) - (kw == 0 ? row16 : 0u);                        // row shift (kh == 2) Wp - (kw == 0)
+#pragma unroll
+      for (int j = 0; j < KJ; ++j) {
+        umma_f16(d_tmem, hi_sw | (a_tap + 2u * j), hi_sw | (b_lo + 2u * j), idesc, acc);
+        acc = 1;
+      }
+      b_lo += tap16;
+    }
+  }
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TMA_THREADS, 2)
 conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ TmapSet tmaps) {
@@ -639,7 +680,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           }
         }
       }
-      if (p.dbg_clk) p.dbg_clk[blockIdx.x * 8 + 0] = t_wait;
+      if (p.dbg_clk) p.dbg_clk[blockIdx.x * 12 + 0] = t_wait;
     }
   } else if (warp < TMA_FIRST_EPI_WARP) {
     // ======================================= MMA issuers =========================================
@@ -654,7 +695,6 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const uint32_t lbo_b16 = static_cast<uint32_t>(p.Ntile);
       const uint32_t desc_hi = (128u >> 4) | (1u << 14);
       const int kj = p.cb >> 4;
-      const int nsub = p.nsub;
       const uint32_t idesc = p.idesc;
       const uint32_t ntile_u = static_cast<uint32_t>(p.Ntile);
       const uint32_t rb = static_cast<uint32_t>(p.cb) * 2u;                 // swizzled row bytes
@@ -665,7 +705,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const uint32_t layout = p.sw == 3 ? 2u : (p.sw == 2 ? 4u : 6u);
       const uint64_t hi_sw = static_cast<uint64_t>(((8u * rb) >> 4) | (1u << 14) | (layout << 29)) << 32;
       const bool mma_on = !(p.dbg_skip & 1);
-      long long t_start = clock64(), t_bres, t_tempty = 0, t_full = 0, t_issue = 0, t0;
+      long long t_start = clock64(), t_bres, t_tempty = 0, t_full = 0, t_issue = 0, t_fence = 0, t_commit = 0, t0;
       if (p.b_resident) mbar_wait(bres, 0);
       t_bres = clock64() - t_start;
       int it = 0, tcount = 0;
@@ -684,6 +724,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           t_full += clock64() - t0;
           t0 = clock64();
           tc_fence_after();
+          t_fence += clock64() - t0;
           const uint32_t a_base = a_u32 + slot * p.a_stage_bytes;
           if (p.sw) {
             // swizzled operands: row = K-block of cb channels (rb bytes); tap = row shift; k16 step = +32 bytes.
@@ -697,43 +738,24 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             // Loop order: sub-tile innermost, so that consecutive MMAs target different accumulators.  Everything is
             // unrolled with guards folded into the issue predicate: a handful of uniform adds per MMA, no branches.
             if (elect_one()) {   // one branch per stage; inside, a single lane issues the whole MMA batch
-              uint32_t acc = ks > 0 ? 1u : 0u;
-              // one tap of this warp's sub-tile: kj k16-steps
-#define XR_ISSUE_TAP(A_TAP)                                                                          \
-  {                                                                                                  \
-    const uint32_t a_tap_ = (A_TAP);                                                                 \
-    for (int j = 0; j < kj; ++j) {                                                                   \
-      const uint64_t bd = hi_sw | (b_lo + 2u * j);                                                   \
-      if (mma_on) {                                                                                  \
-        const uint64_t ad = hi_sw | (a_tap_ + static_cast<uint32_t>(my_u) * sub16 + 2u * j);         \
-        umma_f16(d_base + static_cast<uint32_t>(my_u) * ntile_u, ad, bd, idesc, acc);                \
-      }                                                                                              \
-      acc = 1;                                                                                       \
-    }                                                                                                \
-    b_lo += tap16;                                                                                   \
-  }
-              if (p.mode == MODE_HALO_TMA) {          // tap (kh,kw) = row shift kh*Wp + kw - 1
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                  const uint32_t a_kh = a_lo_stage + static_cast<uint32_t>(kh * p.Wp - 1) * row16;
-#pragma unroll
-                  for (int kw = 0; kw < 3; ++kw) XR_ISSUE_TAP(a_kh + static_cast<uint32_t>(kw) * row16)
+              if (mma_on) {
+                const uint32_t a_sub = a_lo_stage + static_cast<uint32_t>(my_u) * sub16;
+                const uint32_t d_tmem = d_base + static_cast<uint32_t>(my_u) * ntile_u;
+                const uint32_t acc0 = ks > 0 ? 1u : 0u;
+                // straight-line issue code per (mode, k16 steps): the issuing thread is the bottleneck of thin layers, so
+                // everything but the two descriptor adds per MMA is resolved at compile time
+                switch ((p.mode == MODE_HALO_TMA ? 0 : p.mode == MODE_S2_TMA ? 4 : 8) + (kj == 4 ? 2 : kj == 2 ? 1 : 0)) {
+                  case 0: issue_taps<0, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 1: issue_taps<0, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 2: issue_taps<0, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 4: issue_taps<1, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 5: issue_taps<1, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 6: issue_taps<1, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 8: issue_taps<2, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 9: issue_taps<2, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  default: issue_taps<2, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
                 }
-              } else if (p.mode == MODE_S2_TMA) {     // tap (kh,kw) = plane (kh != 1, kw != 1), row shift (kh == 2) Wp - (kw == 0)
-                const uint32_t plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-                  const uint32_t a_kh = a_lo_stage + (kh != 1 ? 2u * plane16 : 0u) + (kh == 2 ? static_cast<uint32_t>(p.Wp) * row16 : 0u);
-#pragma unroll
-                  for (int kw = 0; kw < 3; ++kw)
-                    XR_ISSUE_TAP(a_kh + (kw != 1 ? plane16 : 0u) - (kw == 0 ? row16 : 0u))
-                }
-              } else {                                // flat 1x1: kps K-blocks, one tap each
-                const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;
-                const int kps = p.kps > 1 ? p.kps : 1;
-                for (int kb = 0; kb < kps; ++kb) XR_ISSUE_TAP(a_lo_stage + static_cast<uint32_t>(kb) * blk16)
               }
-#undef XR_ISSUE_TAP
               umma_commit(&empty[slot]);
             }
             __syncwarp();
@@ -768,11 +790,13 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         if (elect_one()) umma_commit(&tfull[buf]);
       }
       if (p.dbg_clk && lane == 0 && warp == 1) {
-        p.dbg_clk[blockIdx.x * 8 + 1] = t_bres;
-        p.dbg_clk[blockIdx.x * 8 + 2] = t_tempty;
-        p.dbg_clk[blockIdx.x * 8 + 3] = t_full;
-        p.dbg_clk[blockIdx.x * 8 + 4] = t_issue;
-        p.dbg_clk[blockIdx.x * 8 + 5] = clock64() - t_start;
+        p.dbg_clk[blockIdx.x * 12 + 1] = t_bres;
+        p.dbg_clk[blockIdx.x * 12 + 2] = t_tempty;
+        p.dbg_clk[blockIdx.x * 12 + 3] = t_full;
+        p.dbg_clk[blockIdx.x * 12 + 4] = t_issue;
+        p.dbg_clk[blockIdx.x * 12 + 5] = clock64() - t_start;
+        p.dbg_clk[blockIdx.x * 12 + 8] = t_fence;
+        p.dbg_clk[blockIdx.x * 12 + 9] = t_commit;
       }
     }
   } else {
@@ -901,8 +925,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       e_work += clock64() - t0;
     }
     if (p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
-      p.dbg_clk[blockIdx.x * 8 + 6] = e_wait;
-      p.dbg_clk[blockIdx.x * 8 + 7] = e_work;
+      p.dbg_clk[blockIdx.x * 12 + 6] = e_wait;
+      p.dbg_clk[blockIdx.x * 12 + 7] = e_work;
     }
   }
 

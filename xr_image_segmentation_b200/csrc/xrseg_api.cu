@@ -1517,8 +1517,8 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
       if (dbg) p.dbg_skip = atoi(dbg);
       long long* d_clk = nullptr;
       if (getenv("XRSEG_DBG_TIME") && tma) {
-        d_clk = dev_alloc<long long>(static_cast<size_t>(p.grid) * 8);
-        XR_CUDA(cudaMemset(d_clk, 0, sizeof(long long) * p.grid * 8));
+        d_clk = dev_alloc<long long>(static_cast<size_t>(p.grid) * 12);
+        XR_CUDA(cudaMemset(d_clk, 0, sizeof(long long) * p.grid * 12));
         p.dbg_clk = d_clk;
       }
       const int reps = getenv("XRSEG_DBG_TIME") ? 5 : 1;
@@ -1546,14 +1546,14 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
         fprintf(stderr, "xrseg_debug_conv: mode %d sw %d cb %d S %d nks %d nsub %d R %d grid %d smem %d tiles %d skip %d: %.1f us\n", p.mode, p.sw, p.cb,
                 p.S, p.nks, p.nsub, p.R, p.grid, p.smem_bytes, p.m_tiles * p.n_tiles, p.dbg_skip, ms * 1e3f);
         if (d_clk) {
-          std::vector<long long> h(static_cast<size_t>(p.grid) * 8);
+          std::vector<long long> h(static_cast<size_t>(p.grid) * 12);
           XR_CUDA(cudaMemcpy(h.data(), d_clk, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
-          const char* nm[8] = {"prod_wait_empty", "mma_wait_bres", "mma_wait_tempty", "mma_wait_full", "mma_issue", "mma_total",
-                               "epi_wait_tfull", "epi_work"};
-          for (int k = 0; k < 8; ++k) {
+          const char* nm[12] = {"prod_wait_empty", "mma_wait_bres", "mma_wait_tempty", "mma_wait_full", "mma_issue", "mma_total",
+                                "epi_wait_tfull", "epi_work", "mma_fence", "mma_commit", "-", "-"};
+          for (int k = 0; k < 10; ++k) {
             double sum = 0;
-            for (int c = 0; c < p.grid; ++c) sum += static_cast<double>(h[c * 8 + k]);
-            fprintf(stderr, "   %-16s avg %.0f cycles per CTA (x%d launches)\n", nm[k], sum / p.grid, reps);
+            for (int c = 0; c < p.grid; ++c) sum += static_cast<double>(h[c * 12 + k]);
+            fprintf(stderr, "   %-16s avg %.0f cycles per CTA (last of %d launches)\n", nm[k], sum / p.grid, reps);
           }
           cudaFree(d_clk);
         }

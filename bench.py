@@ -146,13 +146,15 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-micro-batch", type=int, default=0, help="frames per network pass of the e2e leg (0 = whole batch)")
     ap.add_argument("--latency-iters", type=int, default=300, help="batch-1 latency samples (0 = skip)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="runners of the end-to-end leg (submissions in flight + 1)")
+    ap.add_argument("--value-streams", type=int, default=2, help="runners (streams) the device-resident leg alternates over")
     ap.add_argument("--profile-ops", type=int, default=5, help="iterations for the per-launch timing pass (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -179,10 +181,10 @@ def main():
     layers, ws = W.random_weights("n", SEED_WEIGHTS, CLS_BIAS)
     model = I.Model(W.write_pack("n", layers, ws), "n")
     runner = I.Runner(model, device=local_rank, max_batch=B)
-    # end-to-end leg: two runners in ping-pong (inference.PipelinedRunner): the host->device copy and the network pass of
-    # step i+1 overlap the readback of step i; every step still copies its frames from pinned host memory and reads
-    # its detections back
-    pipe = I.PipelinedRunner(model, device=local_rank, max_batch=B, depth=2, micro_batch=args.e2e_micro_batch)
+    # end-to-end leg: runners used round-robin (inference.PipelinedRunner): the host->device copies and the network passes
+    # of the next steps overlap the readback of step i; every step still copies its frames from pinned host memory and
+    # reads its detections back
+    pipe = I.PipelinedRunner(model, device=local_rank, max_batch=B, depth=args.e2e_depth, micro_batch=args.e2e_micro_batch)
     runner_e2e = pipe.runners[0]
     # 4 distinct frame sets (4 x 78.6 MB > 126 MB L2) so no step finds its input in L2; every rank has its own frames
     NSETS = 4
@@ -211,12 +213,21 @@ def main():
     dets_per_frame = float(counts.mean())
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    runner.event_record(0)
+    # Consecutive steps alternate between two runners (own stream, own activation arena each), so the sparse tail of
+    # step i (NMS / gather / masks keep few SMs busy) overlaps the head of step i+1.  --value-streams 1 serialises them.
+    vr = [runner] if args.value_streams <= 1 else [pipe.runners[0], pipe.runners[1]]
+    for r_ in vr:
+        r_.schedule_device(dev[0].data_ptr(), B, 640, 640, 3)      # graph capture / warm-up of every runner used
+        r_.sync()
+    barrier()
+    vr[0].event_record(0)
     for i in range(args.steps):
-        runner.schedule_device(dev[i % NSETS].data_ptr(), B, 640, 640, 3)
-    runner.event_record(1)
-    runner.sync()
-    ms_dev = runner.event_elapsed_ms(0, 1)
+        vr[i % len(vr)].schedule_device(dev[i % NSETS].data_ptr(), B, 640, 640, 3)
+    for r_ in vr:
+        r_.sync()
+    vr[0].event_record(1)               # recorded after every stream has drained
+    vr[0].sync()
+    ms_dev = vr[0].event_elapsed_ms(0, 1)
     barrier()
 
     # ---------------- end-to-end leg: host frames in, detections out, every step ----------------
@@ -235,10 +246,12 @@ def main():
     for r_ in pipe.runners:
         r_.sync()
     runner_e2e.event_record(2)
-    pipe.submit_ptr(host[0], B, 640, 640, 3)
-    for i in range(1, args.steps + 1):
-        if i < args.steps:
-            pipe.submit_ptr(host[i % NSETS], B, 640, 640, 3)
+    ahead = args.e2e_depth - 1                         # submissions in flight while the oldest one is collected
+    for i in range(min(ahead, args.steps)):
+        pipe.submit_ptr(host[i % NSETS], B, 640, 640, 3)
+    for i in range(args.steps):
+        if i + ahead < args.steps:
+            pipe.submit_ptr(host[(i + ahead) % NSETS], B, 640, 640, 3)
         collect()
     for r_ in pipe.runners:
         r_.sync()
@@ -287,9 +300,10 @@ def main():
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "dets_per_frame": dets_per_frame,
                        "l2": "inputs rotate over 4 distinct 78.6 MB frame sets (> 126 MB L2); each step streams ~3 GB of activations",
-                       "parallelism": f"frame-parallel x{world}, no collective"},
+                       "parallelism": f"frame-parallel x{world}, no collective",
+                       "streams_per_gpu": min(max(args.value_streams, 1), 2)},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e / args.steps, "pipeline": "2 runners in ping-pong, one run in flight each"},
+                    "ms_per_step": ms_e2e / args.steps, "pipeline": f"{args.e2e_depth} runners round-robin, one run in flight each"},
             "gpu_launches": (launches + launches_e2e + 1) * args.steps,
             "clocks": clocks,
         }

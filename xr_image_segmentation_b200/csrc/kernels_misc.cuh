@@ -588,12 +588,12 @@ struct StemMmaParams {
   float in_scale;                              // 1/255
 };
 
-constexpr int STEM_PW = 65, STEM_PH = 17, STEM_RAW_WORDS = 52;
+constexpr int STEM_PW = 65, STEM_PH = 17, STEM_RAW_WORDS = 56, STEM_RAW_CHUNKS = 14;
 
 template <int NT>
 __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
   XR_PDL_ENTRY();
-  __shared__ uint32_t raw[STEM_PH][STEM_RAW_WORDS];
+  __shared__ __align__(16) uint32_t raw[STEM_PH][STEM_RAW_WORDS];
   __shared__ uint32_t patch[STEM_PH * STEM_PW];
   const int Ho = p.H >> 1, Wo = p.W >> 1;
   const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * 8, b = blockIdx.z;
@@ -611,14 +611,29 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
       patch[i] = v;
     }
   } else {
-    // pass 1: aligned 4-byte words covering bytes [3 c_lo, 3 (c_hi + 1)) of each patch row
-    const int a0 = (c_lo * 3) & ~3;
-    const int nwords = ((c_hi + 1) * 3 - a0 + 3) >> 2;
-    for (int i = tid; i < STEM_PH * STEM_RAW_WORDS; i += 256) {
-      const int r = i / STEM_RAW_WORDS, j = i - r * STEM_RAW_WORDS;
-      const int iy = iy0 + r;
-      if (j < nwords && iy >= 0 && iy < p.H)
-        raw[r][j] = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(iy) * p.stride_bytes + a0 + 4 * j);
+    // pass 1: the bytes [3 c_lo, 3 (c_hi + 1)) of each patch row into shared memory
+    const bool wide = ((reinterpret_cast<uintptr_t>(p.src) | static_cast<uintptr_t>(p.stride_bytes)) & 15) == 0 &&
+                      ((p.W * 3) & 15) == 0;
+    const int a0 = wide ? (c_lo * 3) & ~15 : (c_lo * 3) & ~3;
+    if (wide) {
+      // 16-byte path (the normal case: 640-wide frames, 16-byte aligned rows): ONE load per thread covers the 17 x 224
+      // bytes of the patch -- staging latency, not arithmetic, bounded the previous 4-byte version
+      if (tid < STEM_PH * STEM_RAW_CHUNKS) {
+        const int r = tid / STEM_RAW_CHUNKS, j = tid - r * STEM_RAW_CHUNKS;
+        const int iy = iy0 + r;
+        const int off = a0 + 16 * j;
+        if (iy >= 0 && iy < p.H && off < p.W * 3 && off < (c_hi + 1) * 3)
+          *reinterpret_cast<uint4*>(&raw[r][4 * j]) =
+              *reinterpret_cast<const uint4*>(img + static_cast<size_t>(iy) * p.stride_bytes + off);
+      }
+    } else {
+      const int nwords = ((c_hi + 1) * 3 - a0 + 3) >> 2;
+      for (int i = tid; i < STEM_PH * STEM_RAW_WORDS; i += 256) {
+        const int r = i / STEM_RAW_WORDS, j = i - r * STEM_RAW_WORDS;
+        const int iy = iy0 + r;
+        if (j < nwords && iy >= 0 && iy < p.H)
+          raw[r][j] = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(iy) * p.stride_bytes + a0 + 4 * j);
+      }
     }
     __syncthreads();
     // pass 2: RGB bytes -> one RGBX word per pixel (zero outside the image = the conv's zero padding)

@@ -431,7 +431,7 @@ struct MaskParams {
 template <typename T, bool PLANAR>
 __global__ void __launch_bounds__(256) mask_prob_kernel(const MaskParams<T, PLANAR> p) {
   XR_PDL_ENTRY();
-  __shared__ float sc[32][NM + 1];
+  __shared__ __align__(16) float sc[32][NM];    // broadcast reads (every thread the same address): 8 LDS.128 per detection
   const int b = blockIdx.y;
   const int n = p.keep_n[b];
   if (n == 0) return;
@@ -463,8 +463,16 @@ __global__ void __launch_bounds__(256) mask_prob_kernel(const MaskParams<T, PLAN
     for (int d = 0; d < nd; ++d) {
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < NM; ++k) acc = __fmaf_rn(sc[d][k], pr[k], acc);
-      const float prob = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-acc)));
+      for (int k4 = 0; k4 < NM / 4; ++k4) {      // sequential fp32 FMA chain k = 0..31 (the oracle's order)
+        const float4 c = reinterpret_cast<const float4*>(sc[d])[k4];
+        acc = __fmaf_rn(c.x, pr[4 * k4], acc);
+        acc = __fmaf_rn(c.y, pr[4 * k4 + 1], acc);
+        acc = __fmaf_rn(c.z, pr[4 * k4 + 2], acc);
+        acc = __fmaf_rn(c.w, pr[4 * k4 + 3], acc);
+      }
+      // PLANAR = the oracle's own fp32 tensors: IEEE sigmoid (probabilities agree to 1e-6, thresholds bit for bit);
+      // network path (fp16 prototypes, tolerance 0.1 % of mask pixels): ex2/rcp approximations, same sign behaviour
+      const float prob = PLANAR ? __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-acc))) : __fdividef(1.0f, 1.0f + __expf(-acc));
       __stcs(p.probs + static_cast<long>(off + d0 + d) * PROTO_PIX + pix, prob);
     }
   }

@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--e2e-micro-batch", type=int, default=0, help="frames per network pass of the e2e leg (0 = whole batch)")
     ap.add_argument("--latency-iters", type=int, default=300, help="batch-1 latency samples (0 = skip)")
     ap.add_argument("--e2e-depth", type=int, default=3, help="runners of the end-to-end leg (submissions in flight + 1)")
-    ap.add_argument("--value-streams", type=int, default=2, help="runners (streams) the device-resident leg alternates over")
+    ap.add_argument("--value-streams", type=int, default=3, help="runners (streams) the device-resident leg alternates over")
     ap.add_argument("--profile-ops", type=int, default=5, help="iterations for the per-launch timing pass (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -215,7 +215,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     # Consecutive steps alternate between two runners (own stream, own activation arena each), so the sparse tail of
     # step i (NMS / gather / masks keep few SMs busy) overlaps the head of step i+1.  --value-streams 1 serialises them.
-    vr = [runner] if args.value_streams <= 1 else [pipe.runners[0], pipe.runners[1]]
+    vr = [runner] if args.value_streams <= 1 else pipe.runners[:min(args.value_streams, len(pipe.runners))]
     for r_ in vr:
         r_.schedule_device(dev[0].data_ptr(), B, 640, 640, 3)      # graph capture / warm-up of every runner used
         r_.sync()
@@ -301,7 +301,7 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_gpu_per_step": B, "dets_per_frame": dets_per_frame,
                        "l2": "inputs rotate over 4 distinct 78.6 MB frame sets (> 126 MB L2); each step streams ~3 GB of activations",
                        "parallelism": f"frame-parallel x{world}, no collective",
-                       "streams_per_gpu": min(max(args.value_streams, 1), 2)},
+                       "streams_per_gpu": len(vr)},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e / args.steps, "pipeline": f"{args.e2e_depth} runners round-robin, one run in flight each"},
             "gpu_launches": (launches + launches_e2e + 1) * args.steps,

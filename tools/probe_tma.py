@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from xr_image_segmentation_b200 import inference as I
 rng = np.random.default_rng(0)
 #        B  cin cout  h    w   k  s
-cases = [(32, 64, 64, 160, 160, 3, 1)]
+cases = [(32, 16, 8, 160, 160, 3, 1), (32, 32, 32, 160, 160, 1, 1), (32, 48, 64, 160, 160, 1, 1)]
 os.environ["XRSEG_DBG_TIME"] = "1"
 for B, cin, cout, h, w, k, s in cases:
     x = rng.standard_normal((B, cin, h, w), dtype=np.float32)

@@ -74,6 +74,20 @@ static inline CUtensorMap make_halo_tensor_map(const __half* base, int B, int H,
 // A CTA never has more than ceil(work / grid) * nks stages to fetch: a deeper ring only costs shared memory, and a small
 // footprint is what lets the next kernel's CTAs become co-resident early (programmatic dependent launch) so that their
 // prologue -- barrier init, TMEM allocation, weight fetch -- overlaps this kernel's tail.
+// Accumulator sets in TMEM: the MMA -> commit -> epilogue -> release round trip of one item is several microseconds, so
+// thin layers (few columns per item) ring up to four sets instead of two; CTAs with little work keep two, which leaves
+// TMEM columns for a co-resident CTA of the next kernel.
+static inline int choose_nbuf(int nsub, int ntile, int work, int num_sms) {
+  const int grid = work < num_sms ? work : num_sms;
+  int nbuf = 512 / (nsub * ntile);
+  if (nbuf > 4) nbuf = 4;
+  if (nbuf < 2) nbuf = 2;
+  if (ceil_div(work, grid) < 4) nbuf = 2;
+  // Measured on B200 (YOLO11n-seg, batch 64): ringing 4 sets instead of 2 changes no layer by more than noise -- the
+  // round trip is not what bounds the thin layers -- so two sets stay the default (XRSEG_NBUF=4 re-enables the ring).
+  static const bool deep = [] { const char* e = getenv("XRSEG_NBUF"); return e && e[0] == '4'; }();
+  return deep ? nbuf : 2;
+}
 static inline int clamp_stages(int S, int work, int num_sms, int nks) {
   const int grid = work < num_sms ? work : num_sms;
   int need = ceil_div(work, grid) * nks;
@@ -151,7 +165,8 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
     const int rb = cb * 2;
     p.cb = cb; p.cps = cb / 8; p.nks = d.Cin / cb;
     p.taps = 9; p.K_total = 9 * d.Cin;
-    p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
+    p.nbuf = choose_nbuf(p.nsub, p.Ntile, d.B * p.tpi * p.n_tiles, num_sms);
+    p.tmem_cols = pow2_ceil(p.nbuf * p.nsub * p.Ntile);
     p.a_stage_bytes = round_up(p.slots * rb, 1024);
     p.b_stage_bytes = 9 * p.Ntile * rb;
     const long total_b = static_cast<long>(p.nks) * p.b_stage_bytes;
@@ -179,6 +194,7 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
   }
   p.taps = 9;
   p.K_total = 9 * d.Cin;
+  p.nbuf = 2;
   p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
   const int budget = CONV_SMEM_MAX - CONV_HDR_BYTES - TMA_TAIL_PAD;
   const long total_b = 9L * d.Cin * p.Ntile * 2;
@@ -314,7 +330,8 @@ static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& 
   p.lbo_a = round_up(p.slots * rb, 1024);          // bytes of one plane buffer
   p.a_stage_bytes = 4 * p.lbo_a;
   p.b_stage_bytes = 9 * p.Ntile * rb;
-  p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
+  p.nbuf = choose_nbuf(p.nsub, p.Ntile, d.B * p.tpi * p.n_tiles, num_sms);
+  p.tmem_cols = pow2_ceil(p.nbuf * p.nsub * p.Ntile);
   p.M_total = d.B * p.tpi;
   p.m_tiles = p.M_total;
   p.smem_off_b = round_up(CONV_HDR_BYTES, 1024);
@@ -412,7 +429,8 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
       break;
     }
   }
-  p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
+  p.nbuf = choose_nbuf(p.nsub, p.Ntile, ceil_div(p.flat_rows, p.slots) * p.n_tiles, num_sms);
+  p.tmem_cols = pow2_ceil(p.nbuf * p.nsub * p.Ntile);
   p.lbo_a = p.a_stage_bytes;
   p.M_total = ceil_div(p.flat_rows, p.slots);
   p.m_tiles = p.M_total;
@@ -574,8 +592,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);       // [8]
   uint64_t* empty = full + 8;                               // [8]
   uint64_t* tfull = empty + 8;                              // [2]
-  uint64_t* tempty = tfull + 2;                             // [2]
-  uint64_t* bres = tempty + 2;                              // [1]
+  uint64_t* tempty = tfull + 4;                             // [4]
+  uint64_t* bres = tempty + 4;                              // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
   float* bias_s = reinterpret_cast<float*>(smem + 256);     // [<=512]
   uint8_t* smem_b = smem + p.smem_off_b;
@@ -587,12 +605,13 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   const int total_work = p.m_tiles * p.n_tiles;
 
   const int n_issuers = p.sw ? p.nsub : 1;    // MMA-issuing warps (swizzled path: one per sub-tile)
+  const int nbuf = p.nbuf > 2 ? p.nbuf : 2;   // TMEM accumulator sets in flight
   if (tid == 0) {
     for (int i = 0; i < CONV_MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], n_issuers);       // every issuer commits the stage it has consumed
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], n_issuers);       // ... and the accumulators it has finished
       mbar_init(&tempty[i], 8);              // one arrival per epilogue warp
     }
@@ -710,8 +729,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       t_bres = clock64() - t_start;
       int it = 0, tcount = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
-        const int buf = tcount & 1;
-        const int use = tcount >> 1;
+        const int buf = tcount % nbuf;
+        const int use = tcount / nbuf;
         t0 = clock64();
         if (use >= 1) mbar_wait(&tempty[buf], static_cast<uint32_t>(use - 1) & 1u);
         t_tempty += clock64() - t0;
@@ -812,8 +831,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
       const int b = fd_div(p.fd_hp1, tile);
       const int y0 = (tile - b * p.tpi) * p.R;
-      const int buf = tcount & 1;
-      const int use = tcount >> 1;
+      const int buf = tcount % nbuf;
+      const int use = tcount / nbuf;
       t0 = clock64();
       mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
       e_wait += clock64() - t0;

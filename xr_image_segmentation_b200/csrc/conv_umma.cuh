@@ -85,6 +85,7 @@ struct ConvParams {
   int sw;                           // operand swizzle: 0 none, 1/2/3 = 32/64/128-byte (row = 16/32/64 channels)
   int flat_rows;                    // MODE_FLAT_TMA: B*H*W rows of the activation matrix
   int kps;                          // MODE_FLAT_TMA: K-blocks (of cb channels) per pipeline stage; 0 / 1 elsewhere
+  int nbuf;                         // TMA kernel: TMEM accumulator sets in flight (0 = 2)
 };
 
 struct ConvDesc {

@@ -71,6 +71,19 @@ static inline CUtensorMap make_halo_tensor_map(const __half* base, int B, int H,
 }
 
 // ---- planning --------------------------------------------------------------------------------------------------
+// Shared-memory budget of the TMA planners.  tma_smem_budget() is CONV_SMEM_MAX unless XRSEG_SMEM_KB asks for a smaller
+// PREFERRED footprint (e.g. 113 = half an SM, so that consecutive kernels can be co-resident under programmatic
+// dependent launch); plan_conv_*_tma first try the preferred budget and fall back to the full one.
+static inline int& tma_budget_ref() {
+  static thread_local int b = CONV_SMEM_MAX;
+  return b;
+}
+static inline int tma_preferred_budget() {
+  static const int kb = [] { const char* e = getenv("XRSEG_SMEM_KB"); return e ? atoi(e) : 0; }();
+  return kb > 0 && kb * 1024 < CONV_SMEM_MAX ? kb * 1024 : CONV_SMEM_MAX;
+}
+#define XR_TMA_BUDGET (tma_budget_ref())
+
 // A CTA never has more than ceil(work / grid) * nks stages to fetch: a deeper ring only costs shared memory, and a small
 // footprint is what lets the next kernel's CTAs become co-resident early (programmatic dependent launch) so that their
 // prologue -- barrier init, TMEM allocation, weight fetch -- overlaps this kernel's tail.
@@ -96,7 +109,7 @@ static inline int clamp_stages(int S, int work, int num_sms, int nks) {
 }
 
 // Returns false when the layer does not fit this kernel (caller falls back to the thread-gather kernel).
-static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true) {
+static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true) {
   if (!(d.k == 3 && d.stride == 1 && !d.transposed)) return false;
   p = ConvParams{};
   p.B = d.B; p.H = d.H; p.W = d.W; p.Cin = d.Cin; p.in_pitch = d.in_pitch;
@@ -150,7 +163,7 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
       const bool res = (p.n_tiles == 1 && total_b <= 98304);
       const int fixed = round_up(CONV_HDR_BYTES, 1024) + 1024 + 128 * rb + 1024 +
                         (res ? round_up(static_cast<int>(total_b), 1024) : 0);
-      int S = (CONV_SMEM_MAX - fixed) / (a_stage + (res ? 0 : round_up(b_stage, 1024)));
+      int S = (XR_TMA_BUDGET - fixed) / (a_stage + (res ? 0 : round_up(b_stage, 1024)));
       if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
       if (S > 2 * (d.Cin / cb) + 2) S = 2 * (d.Cin / cb) + 2;
       if (S >= 3 || (S == 2 && best_S < 2)) {
@@ -181,7 +194,7 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
     // one tail pad BEFORE the A stages too: tap (0,0) of position 0 reads the row before the stage
     p.smem_off_a = p.smem_off_b + round_up(b_region, 1024) + 1024;
     p.smem_bytes = p.smem_off_a + S * p.a_stage_bytes + 128 * rb + 1024;
-    if (p.smem_bytes > CONV_SMEM_MAX) return false;
+    if (p.smem_bytes > XR_TMA_BUDGET) return false;
     const int work = p.m_tiles * p.n_tiles;
     p.grid = work < num_sms ? work : num_sms;
     p.fd_wp = make_fastdiv(p.Wp);
@@ -196,7 +209,7 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
   p.K_total = 9 * d.Cin;
   p.nbuf = 2;
   p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
-  const int budget = CONV_SMEM_MAX - CONV_HDR_BYTES - TMA_TAIL_PAD;
+  const int budget = XR_TMA_BUDGET - CONV_HDR_BYTES - TMA_TAIL_PAD;
   const long total_b = 9L * d.Cin * p.Ntile * 2;
   p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
   int best_cb = 0, best_S = 0;
@@ -228,7 +241,7 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
   const int b_region = p.b_resident ? p.nks * p.b_stage_bytes : p.S * p.b_stage_bytes;
   p.smem_off_a = CONV_HDR_BYTES + round_up(b_region, 128);
   p.smem_bytes = p.smem_off_a + p.S * p.a_stage_bytes + TMA_TAIL_PAD;
-  if (p.smem_bytes > CONV_SMEM_MAX) return false;
+  if (p.smem_bytes > XR_TMA_BUDGET) return false;
   const int work = p.m_tiles * p.n_tiles;
   p.grid = work < num_sms ? work : num_sms;
   p.fd_wp = make_fastdiv(p.Wp);
@@ -264,7 +277,7 @@ static inline CUtensorMap make_tensor_map_4d(const __half* base, const cuuint64_
 // out-of-bounds coordinates are the convolution's zero padding.  The input is read ~(R+1)/R times instead of 2.25x by
 // the im2col gather, and nothing but one thread touches addresses.
 // NOTE: p.H / p.W / p.Wp hold the OUTPUT geometry (Ho, Wo, Wo+1) in this mode -- that is what the epilogue indexes.
-static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvParams& p) {
   if (!(d.k == 3 && d.stride == 2 && !d.transposed) || (d.H & 1) || (d.W & 1)) return false;
   p = ConvParams{};
   const int Ho = d.H / 2, Wo = d.W / 2;
@@ -300,7 +313,7 @@ static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& 
       const int plane = round_up((R + 1) * p.Wp * rb, 1024);
       const int b_stage = 9 * p.Ntile * rb;
       const int fixed = round_up(CONV_HDR_BYTES, 1024) + 1024 + 128 * rb + 1024 + p.Wp * rb + round_up(resident, 1024);
-      int S = (CONV_SMEM_MAX - fixed) / (4 * plane + (p.b_resident ? 0 : round_up(b_stage, 1024)));
+      int S = (XR_TMA_BUDGET - fixed) / (4 * plane + (p.b_resident ? 0 : round_up(b_stage, 1024)));
       if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
       if (S > 2 * (d.Cin / cb) + 2) S = 2 * (d.Cin / cb) + 2;
       if (S < 2) continue;
@@ -338,7 +351,7 @@ static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& 
   const int b_region = p.b_resident ? resident : p.S * round_up(p.b_stage_bytes, 1024);
   p.smem_off_a = p.smem_off_b + round_up(b_region, 1024) + 1024;        // one pad row block before the stages (offset -1)
   p.smem_bytes = p.smem_off_a + p.S * p.a_stage_bytes + 128 * rb + p.Wp * rb + 1024;   // tail: rows read past the last plane
-  if (p.smem_bytes > CONV_SMEM_MAX) return false;
+  if (p.smem_bytes > XR_TMA_BUDGET) return false;
   const int work = p.m_tiles * p.n_tiles;
   p.grid = work < num_sms ? work : num_sms;
   p.fd_wp = make_fastdiv(p.Wp);
@@ -371,7 +384,7 @@ static inline TmapSet make_s2_tensor_maps(const __half* base, int B, int H, int 
 // its time in its own arrive/wait traffic there (tools/probe_umma.py).  Channels beyond Cin inside the last K-block are
 // out of bounds for the tensor map and arrive as zeros, so Cin only has to be a multiple of 16 (e.g. the 48-channel
 // C3k2 concat).
-static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+static inline bool plan_conv_flat_tma_impl(const ConvDesc& d, int num_sms, ConvParams& p) {
   // also the 2x2 stride-2 ConvTranspose: the same GEMM with N = 4 positions x Cout, scattered by the epilogue
   const bool convt = d.transposed && d.k == 2 && d.stride == 2 && d.res_pitch == 0;
   if (!((d.k == 1 && d.stride == 1 && !d.transposed) || convt)) return false;
@@ -419,7 +432,7 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
       p.a_stage_bytes = kps * p.slots * rb;          // multiple of 1024 for every cb
       p.b_stage_bytes = kps * b_block;
       const int fixed = round_up(CONV_HDR_BYTES, 1024) + (p.b_resident ? round_up(resident, 1024) : 0);
-      S = (CONV_SMEM_MAX - fixed) / (p.a_stage_bytes + (p.b_resident ? 0 : round_up(p.b_stage_bytes, 1024)));
+      S = (XR_TMA_BUDGET - fixed) / (p.a_stage_bytes + (p.b_resident ? 0 : round_up(p.b_stage_bytes, 1024)));
       if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
       if (S >= 2) break;                             // streamed weights of a wide layer: fewer K-blocks per stage
     }
@@ -438,7 +451,7 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
   const int b_region = p.b_resident ? resident : p.S * round_up(p.b_stage_bytes, 1024);
   p.smem_off_a = p.smem_off_b + round_up(b_region, 1024);
   p.smem_bytes = p.smem_off_a + p.S * p.a_stage_bytes;
-  if (p.smem_bytes > CONV_SMEM_MAX) return false;
+  if (p.smem_bytes > XR_TMA_BUDGET) return false;
   const int work = p.m_tiles * p.n_tiles;
   p.grid = work < num_sms ? work : num_sms;
   p.Wp = 1; p.Hp1 = 1; p.R = 0; p.tpi = 1;
@@ -448,6 +461,45 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
   p.fd_wo = make_fastdiv(d.W);
   p.fd_cin = make_fastdiv(d.Cin);
   p.fd_cout = make_fastdiv(d.Cout);
+  return true;
+}
+
+// Preferred-budget wrappers (see tma_budget_ref): the smaller footprint is taken only when it costs nothing but ring
+// depth -- same K-block, rows per item, sub-tiles and K-blocks per stage as the unconstrained plan.
+static inline bool same_tiling(const ConvParams& a, const ConvParams& b) {
+  return a.cb == b.cb && a.R == b.R && a.nsub == b.nsub && a.kps == b.kps && a.b_resident == b.b_resident && a.S >= 2;
+}
+static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true) {
+  tma_budget_ref() = CONV_SMEM_MAX;
+  if (!plan_conv_halo_tma_impl(d, num_sms, p, swizzled)) return false;
+  if (tma_preferred_budget() < CONV_SMEM_MAX) {
+    ConvParams q;
+    tma_budget_ref() = tma_preferred_budget();
+    if (plan_conv_halo_tma_impl(d, num_sms, q, swizzled) && same_tiling(q, p)) p = q;
+    tma_budget_ref() = CONV_SMEM_MAX;
+  }
+  return true;
+}
+static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+  tma_budget_ref() = CONV_SMEM_MAX;
+  if (!plan_conv_s2_tma_impl(d, num_sms, p)) return false;
+  if (tma_preferred_budget() < CONV_SMEM_MAX) {
+    ConvParams q;
+    tma_budget_ref() = tma_preferred_budget();
+    if (plan_conv_s2_tma_impl(d, num_sms, q) && same_tiling(q, p)) p = q;
+    tma_budget_ref() = CONV_SMEM_MAX;
+  }
+  return true;
+}
+static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+  tma_budget_ref() = CONV_SMEM_MAX;
+  if (!plan_conv_flat_tma_impl(d, num_sms, p)) return false;
+  if (tma_preferred_budget() < CONV_SMEM_MAX) {
+    ConvParams q;
+    tma_budget_ref() = tma_preferred_budget();
+    if (plan_conv_flat_tma_impl(d, num_sms, q) && same_tiling(q, p)) p = q;
+    tma_budget_ref() = CONV_SMEM_MAX;
+  }
   return true;
 }
 

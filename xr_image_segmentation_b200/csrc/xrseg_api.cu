@@ -535,6 +535,7 @@ void build_chunk_launches(xrseg_runner* r, int b0, int nb, std::vector<Launch>& 
   const TV& pr = r->net->protos;
   add_post_launches<__half, false>(r, b0, nb, src, ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch, pr.pitch,
                                    true, false, out);
+  if (b0 == 0) return;   // gather already wrote chunk-relative frame ids, which are global for the first chunk
   Launch L;
   L.name = "post.frame_ids";
   int* frames = r->o_frame;

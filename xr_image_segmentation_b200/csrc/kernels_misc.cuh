@@ -236,7 +236,7 @@ __device__ __forceinline__ void dw_fma8(float (&acc)[8], const uint4 v, const fl
 // added in fp32.  Against a full fp32 accumulation this adds ~1e-3 relative error (the output is rounded to fp16 anyway)
 // and cuts the instruction count per 8 outputs from ~150 (72 conversions + 72 FMAs) to ~50; with the weights held as
 // 36 half2 registers the kernel also fits 5 blocks per SM instead of 4.
-__global__ void __launch_bounds__(128, 5) dwconv3x3_kernel(const DwParams p) {
+__global__ void __launch_bounds__(128, 4) dwconv3x3_kernel(const DwParams p) {
   XR_PDL_ENTRY();
   const int cgs = p.C >> 3;
   const int col = blockIdx.x * 128 + threadIdx.x;       // (x, group) column, group fastest
@@ -269,16 +269,18 @@ __global__ void __launch_bounds__(128, 5) dwconv3x3_kernel(const DwParams p) {
   // Output row y needs input rows y-1, y, y+1 against kernel rows 0, 1, 2.  An input row is loaded ONCE and its three
   // row sums (against kh = 0, 1, 2) are kept in a rolling window: rs[kh] of input rows y-1+kh.
   __half2 s_up0[4], s_mid1[4], s_mid0[4], s_dn2[4], s_dn1[4], s_dn0[4];
-  auto row_sums3 = [&](int y, __half2 (&a0)[4], __half2 (&a1)[4], __half2 (&a2)[4]) {
+  // raw input row (left / centre / right pixel, 8 channels each); rows outside the image are zero
+  auto load_raw = [&](int y, uint4& vl, uint4& vc, uint4& vr) {
     if (y < 0 || y >= p.H) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a0[i] = a1[i] = a2[i] = __float2half2_rn(0.f);
+      vl = vc = vr = zero;
       return;
     }
     const __half* q = src + static_cast<size_t>(y) * row_elems;
-    const uint4 vc = *reinterpret_cast<const uint4*>(q);
-    const uint4 vl = has_l ? *reinterpret_cast<const uint4*>(q - p.in_pitch) : zero;
-    const uint4 vr = has_r ? *reinterpret_cast<const uint4*>(q + p.in_pitch) : zero;
+    vc = *reinterpret_cast<const uint4*>(q);
+    vl = has_l ? *reinterpret_cast<const uint4*>(q - p.in_pitch) : zero;
+    vr = has_r ? *reinterpret_cast<const uint4*>(q + p.in_pitch) : zero;
+  };
+  auto sums_of = [&](const uint4& vl, const uint4& vc, const uint4& vr, __half2 (&a0)[4], __half2 (&a1)[4], __half2 (&a2)[4]) {
     const __half2* hl = reinterpret_cast<const __half2*>(&vl);
     const __half2* hc = reinterpret_cast<const __half2*>(&vc);
     const __half2* hr = reinterpret_cast<const __half2*>(&vr);
@@ -290,12 +292,19 @@ __global__ void __launch_bounds__(128, 5) dwconv3x3_kernel(const DwParams p) {
     }
   };
   __half2 dummy[4];
+  uint4 rl, rc, rr;
   // prologue: input row y0-1 contributes kernel row 0 to output y0; input row y0 contributes row 1 to y0 and row 0 to y0+1
-  row_sums3(y0 - 1, s_up0, dummy, dummy);
-  row_sums3(y0, s_mid0, s_mid1, dummy);
+  load_raw(y0 - 1, rl, rc, rr);
+  sums_of(rl, rc, rr, s_up0, dummy, dummy);
+  load_raw(y0, rl, rc, rr);
+  sums_of(rl, rc, rr, s_mid0, s_mid1, dummy);
+  load_raw(y0 + 1, rl, rc, rr);                  // the loop always has the NEXT input row's loads in flight
   size_t opix = (static_cast<size_t>(b) * p.H + y0) * p.W + x;
   for (int y = y0; y < y1; ++y, opix += p.W) {
-    row_sums3(y + 1, s_dn0, s_dn1, s_dn2);     // input row y+1: kernel row 2 for output y, row 1 for y+1, row 0 for y+2
+    uint4 nl, nc, nr;
+    load_raw(y + 2, nl, nc, nr);                 // prefetch for the next iteration (clamped to zero rows past the image)
+    sums_of(rl, rc, rr, s_dn0, s_dn1, s_dn2);    // input row y+1: kernel row 2 for output y, row 1 for y+1, row 0 for y+2
+    rl = nl; rc = nc; rr = nr;
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

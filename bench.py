@@ -9,9 +9,13 @@ Workload (BASELINE.json configs[1]): YOLO11n-seg, 640x640, batch 64 synthetic ui
 A step = one pass of the whole path (preprocess -> backbone/neck/head -> decode -> NMS -> gather -> masks) over one
 batch of 64 frames per GPU.  Frames are sharded over ranks with no collective (weak scaling: 64 frames per GPU).
 
-  value : frames/s with the frames already resident in HBM (xrseg_schedule_device), CUDA events on the runner's stream
-  e2e   : the same through the reference-facing call with HOST buffers: H2D of the frames from pinned memory and D2H of
-          boxes + labels + bit-packed masks inside the timed region, every step
+  value   : frames/s with the frames already resident in HBM (xrseg_schedule_device), CUDA events on the runners' streams;
+            consecutive steps alternate over --value-streams runners so that the sparse tail of one step overlaps the head
+            of the next (every step is still a full pass over its own 64 frames)
+  e2e     : the same through the reference-facing call with HOST buffers: H2D of the frames from pinned memory and D2H of
+            boxes + labels + bit-packed masks inside the timed region, every step (--e2e-depth runners round-robin)
+  latency : batch-1 1280x960 frame -> letterbox -> detections on the host, p50 / p99 (BASELINE.json configs[3])
+  roofline / cpu_baseline : see DESIGN.md section 5
 """
 import argparse
 import json

@@ -235,64 +235,73 @@ __device__ __forceinline__ void dw_fma8(float (&acc)[8], const uint4 v, const fl
 // Arithmetic: each kernel ROW (three taps) is a packed-half HMUL2 + 2 HFMA2 chain, the three row sums and the bias are
 // added in fp32.  Against a full fp32 accumulation this adds ~1e-3 relative error (the output is rounded to fp16 anyway)
 // and cuts the instruction count per 8 outputs from ~150 (72 conversions + 72 FMAs) to ~50; with the weights held as
-// 36 half2 registers the kernel also fits 5 blocks per SM instead of 4.
-__global__ void __launch_bounds__(128, 4) dwconv3x3_kernel(const DwParams p) {
+// 36 half2 registers the kernel also fits more blocks per SM.
+// NV = half2 lanes per thread: a thread owns 2*NV channels of one pixel column.  NV = 2 (four channels, 8-byte accesses)
+// halves the per-thread state (~60 registers) and doubles the threads: the kernel is latency-bound at the 25 %
+// occupancy the 8-channel version reaches.
+template <int NV>
+struct alignas(NV * 4) DwVec {
+  uint32_t v[NV];
+};
+
+template <int NV>
+__global__ void __launch_bounds__(128, NV == 2 ? 8 : 4) dwconv3x3_kernel(const DwParams p) {
   XR_PDL_ENTRY();
-  const int cgs = p.C >> 3;
+  constexpr int CPT = 2 * NV;                           // channels per thread
+  using Vec = DwVec<NV>;
+  const int cgs = p.C / CPT;
   const int col = blockIdx.x * 128 + threadIdx.x;       // (x, group) column, group fastest
   if (col >= p.W * cgs) return;
   const int x = col / cgs, g = col - x * cgs;
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * p.rows;
   const int y1 = min(y0 + p.rows, p.H);
-  const int c = g * 8;
+  const int c = g * CPT;
   const int cin = p.in_grp > 0 ? (c / p.in_grp) * p.in_grp_stride + p.in_grp_off + c % p.in_grp : c;
-  __half2 w[9][4];
-  float bias[8];
+  __half2 w[9][NV];
+  float bias[CPT];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) {
-    const float4 w0 = *reinterpret_cast<const float4*>(p.w + t * p.C + c);
-    const float4 w1 = *reinterpret_cast<const float4*>(p.w + t * p.C + c + 4);
-    w[t][0] = __floats2half2_rn(w0.x, w0.y); w[t][1] = __floats2half2_rn(w0.z, w0.w);
-    w[t][2] = __floats2half2_rn(w1.x, w1.y); w[t][3] = __floats2half2_rn(w1.z, w1.w);
-  }
-  {
-    const float4 b0 = *reinterpret_cast<const float4*>(p.bias + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(p.bias + c + 4);
-    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
-    bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
-  }
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float2 wf = *reinterpret_cast<const float2*>(p.w + t * p.C + c + 2 * i);
+      w[t][i] = __floats2half2_rn(wf.x, wf.y);
+    }
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) bias[i] = p.bias[c + i];
   const bool has_l = x > 0, has_r = x + 1 < p.W;
   const size_t row_elems = static_cast<size_t>(p.W) * p.in_pitch;
   const __half* src = p.in + static_cast<size_t>(b) * p.H * row_elems + static_cast<size_t>(x) * p.in_pitch + cin;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  Vec zero;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) zero.v[i] = 0u;
   // Output row y needs input rows y-1, y, y+1 against kernel rows 0, 1, 2.  An input row is loaded ONCE and its three
   // row sums (against kh = 0, 1, 2) are kept in a rolling window: rs[kh] of input rows y-1+kh.
-  __half2 s_up0[4], s_mid1[4], s_mid0[4], s_dn2[4], s_dn1[4], s_dn0[4];
-  // raw input row (left / centre / right pixel, 8 channels each); rows outside the image are zero
-  auto load_raw = [&](int y, uint4& vl, uint4& vc, uint4& vr) {
+  __half2 s_up0[NV], s_mid1[NV], s_mid0[NV], s_dn2[NV], s_dn1[NV], s_dn0[NV];
+  // raw input row (left / centre / right pixel); rows outside the image are zero
+  auto load_raw = [&](int y, Vec& vl, Vec& vc, Vec& vr) {
     if (y < 0 || y >= p.H) {
       vl = vc = vr = zero;
       return;
     }
     const __half* q = src + static_cast<size_t>(y) * row_elems;
-    vc = *reinterpret_cast<const uint4*>(q);
-    vl = has_l ? *reinterpret_cast<const uint4*>(q - p.in_pitch) : zero;
-    vr = has_r ? *reinterpret_cast<const uint4*>(q + p.in_pitch) : zero;
+    vc = *reinterpret_cast<const Vec*>(q);
+    vl = has_l ? *reinterpret_cast<const Vec*>(q - p.in_pitch) : zero;
+    vr = has_r ? *reinterpret_cast<const Vec*>(q + p.in_pitch) : zero;
   };
-  auto sums_of = [&](const uint4& vl, const uint4& vc, const uint4& vr, __half2 (&a0)[4], __half2 (&a1)[4], __half2 (&a2)[4]) {
-    const __half2* hl = reinterpret_cast<const __half2*>(&vl);
-    const __half2* hc = reinterpret_cast<const __half2*>(&vc);
-    const __half2* hr = reinterpret_cast<const __half2*>(&vr);
+  auto sums_of = [&](const Vec& vl, const Vec& vc, const Vec& vr, __half2 (&a0)[NV], __half2 (&a1)[NV], __half2 (&a2)[NV]) {
+    const __half2* hl = reinterpret_cast<const __half2*>(vl.v);
+    const __half2* hc = reinterpret_cast<const __half2*>(vc.v);
+    const __half2* hr = reinterpret_cast<const __half2*>(vr.v);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       a0[i] = __hfma2(hr[i], w[2][i], __hfma2(hc[i], w[1][i], __hmul2(hl[i], w[0][i])));
       a1[i] = __hfma2(hr[i], w[5][i], __hfma2(hc[i], w[4][i], __hmul2(hl[i], w[3][i])));
       a2[i] = __hfma2(hr[i], w[8][i], __hfma2(hc[i], w[7][i], __hmul2(hl[i], w[6][i])));
     }
   };
-  __half2 dummy[4];
-  uint4 rl, rc, rr;
+  __half2 dummy[NV];
+  Vec rl, rc, rr;
   // prologue: input row y0-1 contributes kernel row 0 to output y0; input row y0 contributes row 1 to y0 and row 0 to y0+1
   load_raw(y0 - 1, rl, rc, rr);
   sums_of(rl, rc, rr, s_up0, dummy, dummy);
@@ -301,41 +310,40 @@ __global__ void __launch_bounds__(128, 4) dwconv3x3_kernel(const DwParams p) {
   load_raw(y0 + 1, rl, rc, rr);                  // the loop always has the NEXT input row's loads in flight
   size_t opix = (static_cast<size_t>(b) * p.H + y0) * p.W + x;
   for (int y = y0; y < y1; ++y, opix += p.W) {
-    uint4 nl, nc, nr;
-    load_raw(y + 2, nl, nc, nr);                 // prefetch for the next iteration (clamped to zero rows past the image)
+    Vec nl, nc, nr;
+    load_raw(y + 2, nl, nc, nr);                 // prefetch for the next iteration (zero rows past the image)
     sums_of(rl, rc, rr, s_dn0, s_dn1, s_dn2);    // input row y+1: kernel row 2 for output y, row 1 for y+1, row 0 for y+2
     rl = nl; rc = nc; rr = nr;
-    float acc[8];
+    float acc[CPT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const float2 a = __half22float2(s_up0[i]), m = __half22float2(s_mid1[i]), d = __half22float2(s_dn2[i]);
       acc[2 * i] = bias[2 * i] + a.x + m.x + d.x;
       acc[2 * i + 1] = bias[2 * i + 1] + a.y + m.y + d.y;
     }
-    uint32_t o[4];
+    Vec o;
     if (p.act) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) o[i] = silu_pack_h2(acc[2 * i], acc[2 * i + 1]);
+      for (int i = 0; i < NV; ++i) o.v[i] = silu_pack_h2(acc[2 * i], acc[2 * i + 1]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         __half2 hh = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]);
-        o[i] = *reinterpret_cast<uint32_t*>(&hh);
+        o.v[i] = *reinterpret_cast<uint32_t*>(&hh);
       }
     }
     if (p.res) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(p.res + opix * p.res_pitch + c);
-      const uint32_t rr[4] = {raw.x, raw.y, raw.z, raw.w};
+      const Vec raw = *reinterpret_cast<const Vec*>(p.res + opix * p.res_pitch + c);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        __half2 sum = __hadd2(*reinterpret_cast<__half2*>(&o[i]), *reinterpret_cast<const __half2*>(&rr[i]));
-        o[i] = *reinterpret_cast<uint32_t*>(&sum);
+      for (int i = 0; i < NV; ++i) {
+        __half2 sum = __hadd2(*reinterpret_cast<__half2*>(&o.v[i]), *reinterpret_cast<const __half2*>(&raw.v[i]));
+        o.v[i] = *reinterpret_cast<uint32_t*>(&sum);
       }
     }
-    *reinterpret_cast<uint4*>(p.out + opix * p.out_pitch + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<Vec*>(p.out + opix * p.out_pitch + c) = o;
     // roll: the row below becomes the middle row, the middle row becomes the row above
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < NV; ++i) {
       s_up0[i] = s_mid0[i];
       s_mid0[i] = s_dn0[i];
       s_mid1[i] = s_dn1[i];

@@ -47,6 +47,10 @@ bool branches_disabled() {   // XRSEG_BRANCHES=0: everything on one stream (A/B 
   const char* e = getenv("XRSEG_BRANCHES");
   return e && e[0] == '0';
 }
+bool dw_wide() {   // 8 channels per thread unless XRSEG_DW_NARROW=1 (4 channels, twice the occupancy: measured equal)
+  const char* e = getenv("XRSEG_DW_NARROW");
+  return !(e && e[0] == '1');
+}
 bool s2_tma_disabled() {
   const char* e = getenv("XRSEG_S2_TMA");
   return e && e[0] == '0';
@@ -306,8 +310,10 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.name = l.name;
         L.flops = 2.0 * px_out * l.cout * 9;
         L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1)) * 2;
-        const dim3 grid(ceil_div(p.W * (p.C / 8), 128), ceil_div(p.H, p.rows), nb);
-        L.fn = [p, grid](cudaStream_t st) { launch_k(dwconv3x3_kernel, grid, 128, 0, st, p); };
+        const bool narrow = !dw_wide();             // 8 channels per thread (default) or 4 (XRSEG_DW_NARROW=1)
+        const dim3 grid(ceil_div(p.W * (p.C / (narrow ? 4 : 8)), 128), ceil_div(p.H, p.rows), nb);
+        if (narrow) L.fn = [p, grid](cudaStream_t st) { launch_k(dwconv3x3_kernel<2>, grid, 128, 0, st, p); };
+        else L.fn = [p, grid](cudaStream_t st) { launch_k(dwconv3x3_kernel<4>, grid, 128, 0, st, p); };
         break;
       }
       case OP_SPPF: {

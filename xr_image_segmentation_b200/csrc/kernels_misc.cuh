@@ -653,16 +653,34 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
       }
     }
     __syncthreads();
-    // pass 2: RGB bytes -> one RGBX word per pixel (zero outside the image = the conv's zero padding)
-    for (int i = tid; i < STEM_PH * STEM_PW; i += 256) {
-      const int r = i / STEM_PW, c = i - r * STEM_PW;
-      const int iy = iy0 + r, ix = ix0 + c;
-      uint32_t v = 0;
-      if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-        const uint8_t* q = reinterpret_cast<const uint8_t*>(raw[r]) + (ix * 3 - a0);
-        v = q[0] | (q[1] << 8) | (q[2] << 16);
+    // pass 2: RGB bytes -> one RGBX word per pixel (zero outside the image = the conv's zero padding).  A thread expands
+    // five consecutive pixels (15 bytes): five word loads and one funnel shift per pixel instead of three byte loads.
+    static_assert(STEM_PW % 5 == 0 && STEM_PH * (STEM_PW / 5) <= 256, "one (row, 5-pixel group) unit per thread");
+    if (tid < STEM_PH * (STEM_PW / 5)) {
+      const int r = tid / (STEM_PW / 5), q5 = tid - r * (STEM_PW / 5);
+      const int iy = iy0 + r;
+      const bool row_ok = iy >= 0 && iy < p.H;
+      const int ob = 3 * (ix0 + 5 * q5) - a0;              // byte offset of the group's first pixel in raw[r] (may be < 0)
+      const int wi = max(ob, 0) >> 2;
+      uint32_t w5[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w5[k] = (wi + k < STEM_RAW_WORDS) ? raw[r][wi + k] : 0u;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int ix = ix0 + 5 * q5 + k;
+        const int rel = ob + 3 * k - 4 * wi;               // >= 0 for every pixel inside the image
+        uint32_t v = 0;
+        if (row_ok && ix >= 0 && ix < p.W) {
+          const int j = rel >> 2;                          // 0..4
+          uint32_t lo = w5[0], hi = w5[1];
+          if (j == 1) { lo = w5[1]; hi = w5[2]; }
+          if (j == 2) { lo = w5[2]; hi = w5[3]; }
+          if (j == 3) { lo = w5[3]; hi = w5[4]; }
+          if (j == 4) { lo = w5[4]; hi = w5[5]; }
+          v = __funnelshift_r(lo, hi, 8 * (rel & 3)) & 0x00FFFFFFu;
+        }
+        patch[r * STEM_PW + 5 * q5 + k] = v;
       }
-      patch[i] = v;
     }
   }
   // weights + bias -> registers (constant for the whole block)

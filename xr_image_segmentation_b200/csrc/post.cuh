@@ -479,6 +479,73 @@ __global__ void __launch_bounds__(256) mask_prob_kernel(const MaskParams<T, PLAN
 }
 
 // ------------------------------------------------------------------------------------------------
+// masks on the network path (fp16 prototypes, NHWC [B,P,32]): the same product as mask_prob_kernel, on mma.sync.
+// The scalar kernel is bound by its own 32-FMA chain per output (issue slots, not HBM); here one m16n8k16 pair does
+// 16 detections x 8 pixels x 32 prototypes with fp32 accumulation, coefficients rounded to fp16 (the prototypes already
+// are).  The exact fp32 FMA-chain kernel stays the one fed with the oracle's tensors (PLANAR) -- this one is covered by the
+// end-to-end tolerance (<= 0.1 % of mask pixels).
+// Block = 8 warps x MASK_MMA_GROUPS groups of 8 consecutive pixels of one frame; detections in tiles of 16.
+// ------------------------------------------------------------------------------------------------
+constexpr int MASK_MMA_GROUPS = 16;                          // 8-pixel groups per warp
+constexpr int MASK_MMA_PIX = 8 * 8 * MASK_MMA_GROUPS;        // pixels per block (1024)
+
+__device__ __forceinline__ void mask_hmma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) mask_prob_mma_kernel(const MaskParams<__half, false> p) {
+  XR_PDL_ENTRY();
+  __shared__ __align__(16) __half sc[16][NM + 8];            // one tile of 16 detections x 32 coefficients (fp16), padded rows
+  const int b = blockIdx.y;
+  const int n = p.keep_n[b];
+  if (n == 0) return;
+  const int off = p.offsets[b];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int pix_base = blockIdx.x * MASK_MMA_PIX + warp * (8 * MASK_MMA_GROUPS);
+  const __half* pr = p.protos + b * p.proto_bstride;
+  for (int d0 = 0; d0 < n; d0 += 16) {
+    const int nd = min(16, n - d0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 16 * NM; i += 256) {
+      const int r = i / NM, k = i - r * NM;
+      sc[r][k] = __float2half_rn(r < nd ? p.coefs[static_cast<long>(off + d0 + r) * NM + k] : 0.f);
+    }
+    __syncthreads();
+    // A fragments (row-major 16 x 16, two k-steps): a0 = A[g][2t..], a1 = A[g+8][2t..], a2 = A[g][2t+8..], a3 = A[g+8][2t+8..]
+    uint32_t a[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      a[ks][0] = *reinterpret_cast<const uint32_t*>(&sc[g][16 * ks + 2 * t]);
+      a[ks][1] = *reinterpret_cast<const uint32_t*>(&sc[g + 8][16 * ks + 2 * t]);
+      a[ks][2] = *reinterpret_cast<const uint32_t*>(&sc[g][16 * ks + 2 * t + 8]);
+      a[ks][3] = *reinterpret_cast<const uint32_t*>(&sc[g + 8][16 * ks + 2 * t + 8]);
+    }
+    float* out0 = p.probs + static_cast<long>(off + d0 + g) * PROTO_PIX;
+    float* out1 = out0 + static_cast<long>(8) * PROTO_PIX;
+#pragma unroll 4
+    for (int grp = 0; grp < MASK_MMA_GROUPS; ++grp) {
+      const int pix0 = pix_base + grp * 8;
+      // B fragments (col-major 16 x 8): column = pixel pix0 + g, rows = prototypes; b0 = B[2t..2t+1], b1 = B[2t+8..2t+9]
+      const __half* q = pr + static_cast<long>(pix0 + g) * p.proto_pitch + 2 * t;
+      const uint32_t b00 = *reinterpret_cast<const uint32_t*>(q), b01 = *reinterpret_cast<const uint32_t*>(q + 8);
+      const uint32_t b10 = *reinterpret_cast<const uint32_t*>(q + 16), b11 = *reinterpret_cast<const uint32_t*>(q + 24);
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      mask_hmma(c, a[0], b00, b01);
+      mask_hmma(c, a[1], b10, b11);
+      // c0,c1 = detection g, pixels pix0 + 2t, +1;  c2,c3 = detection g + 8
+      if (g < nd)
+        __stcs(reinterpret_cast<float2*>(out0 + pix0 + 2 * t),
+               make_float2(__fdividef(1.0f, 1.0f + __expf(-c[0])), __fdividef(1.0f, 1.0f + __expf(-c[1]))));
+      if (g + 8 < nd)
+        __stcs(reinterpret_cast<float2*>(out1 + pix0 + 2 * t),
+               make_float2(__fdividef(1.0f, 1.0f + __expf(-c[2])), __fdividef(1.0f, 1.0f + __expf(-c[3]))));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // C# box conventions (IEExecutor.ParseBoxes IEE:529-559, IEBoxer.DrawBoxes IEB:37-81)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 box_convention(const float4 raw, int conv, float sw, float sh) {

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <type_traits>
 
 #include "common.cuh"
 #include "conv_tma.cuh"
@@ -50,6 +51,10 @@ bool branches_disabled() {   // XRSEG_BRANCHES=0: everything on one stream (A/B 
 bool dw_wide() {   // 8 channels per thread unless XRSEG_DW_NARROW=1 (4 channels, twice the occupancy: measured equal)
   const char* e = getenv("XRSEG_DW_NARROW");
   return !(e && e[0] == '1');
+}
+bool mask_mma_enabled() {
+  const char* e = getenv("XRSEG_MASK_MMA");
+  return !(e && e[0] == '0');
 }
 bool s2_tma_disabled() {
   const char* e = getenv("XRSEG_S2_TMA");
@@ -498,7 +503,16 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     Launch L;
     L.name = "post.mask_prob";
     L.bytes = static_cast<double>(nb) * NM * PROTO_PIX * sizeof(T);   // + 102400 B per detection, added by the caller
-    L.fn = [kp, nb](cudaStream_t st) { launch_k(mask_prob_kernel<T, PLANAR>, dim3(PROTO_PIX / 256, nb), 256, 0, st, kp); };
+    if constexpr (!PLANAR && std::is_same<T, __half>::value) {
+      // network path: tensor-core variant (XRSEG_MASK_MMA=0 keeps the scalar FMA-chain kernel)
+      if (mask_mma_enabled()) {
+        L.fn = [kp, nb](cudaStream_t st) { launch_k(mask_prob_mma_kernel, dim3(PROTO_PIX / MASK_MMA_PIX, nb), 256, 0, st, kp); };
+      } else {
+        L.fn = [kp, nb](cudaStream_t st) { launch_k(mask_prob_kernel<T, PLANAR>, dim3(PROTO_PIX / 256, nb), 256, 0, st, kp); };
+      }
+    } else {
+      L.fn = [kp, nb](cudaStream_t st) { launch_k(mask_prob_kernel<T, PLANAR>, dim3(PROTO_PIX / 256, nb), 256, 0, st, kp); };
+    }
     out.push_back(std::move(L));
   }
 }

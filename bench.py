@@ -338,7 +338,7 @@ def main():
             conv = [o for o in ops if o[2] > 0 and not o[0].startswith("post.")]
             top = max(ops, key=lambda o: o[1])
             conv_ms, conv_fl = sum(o[1] for o in conv), sum(o[2] for o in conv)
-            post = [o for o in ops if o[0] in ("post.decode", "post.mask_prob")]
+            post = [o for o in ops if o[0] in ("post.decode", "post.decode_exact", "post.mask_prob")]
             out["roofline"] = roof(top)
             out["roofline"].update({
                 "peak_source": how + (" (sustained bf16 cuBLAS)" if out["roofline"]["bound"] == "tensor" else " (copy bandwidth)"),

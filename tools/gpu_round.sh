@@ -23,6 +23,6 @@ full s2_b1 conv_halo_tma $((91 + 0)) 1         # b1 (3x3 stride 2, parity-plane 
 full flat_b2cv1 conv_halo_tma $((91 + 1)) 1    # b2.cv1 (1x1, flat TMA) of pass 2
 full halo_protocv2 conv_halo_tma $((91 + 89)) 1  # proto.cv2 (3x3 stride 1, halo TMA) of pass 2
 full dw dwconv3x3 $((7 + 1)) 1                 # h3.cls.1dw of pass 2
-full decode decode_kernel 1 1
+full decode decode_filter 1 1
 full maskprob mask_prob 1 1
 ls -la gpurun_out/${T}_*.ncu-rep

@@ -40,6 +40,8 @@ struct DecodeParams {
   int* labels;               // [B,A]
   unsigned long long* keys;  // [B,A] candidate sort keys
   int* cand_count;           // [B]
+  int* filt_list;            // [B,A] anchors that survived the logit filter (unordered)
+  int* filt_count;           // [B]
 };
 
 #ifdef __CUDACC__
@@ -69,27 +71,70 @@ __device__ __forceinline__ void load16(const __half* p, float (&v)[16]) {
   }
 }
 
-// Block = 256 consecutive anchors of one frame.  Phase 1 (every thread): stream the anchor's 80 class logits and
-// keep the largest; an anchor whose largest LOGIT is below logit(score_thr) - 0.01 cannot pass the probability test
-// and is dropped there -- nothing downstream reads non-candidates.  Phase 2: the survivors (1-2 % of the anchors) are
-// compacted through shared memory so that the expensive exact arithmetic runs in dense warps.
+// ---- decode, kernel 1 of 2: the streaming filter ---------------------------------------------------------------------
+// Block = 256 consecutive anchors of one frame; every anchor's 80 class logits are read once and reduced to their
+// maximum; an anchor whose largest LOGIT is below logit(score_thr) - 0.01 cannot pass the probability test and is
+// dropped -- nothing downstream reads non-candidates.  Survivors (1-2 % of the anchors) are appended to the frame's list.
+// Loads are warp-coalesced: a warp owns 32 consecutive anchors = one contiguous run of 32*NC logits, lane l reads the
+// 16-byte chunks l, l+32, ... of the run and the per-anchor maximum is a segmented reduction through shared memory (a
+// thread-per-anchor walk touches 32 different sectors per load instruction and was bound by the load/store unit).
 template <typename T>
-__global__ void __launch_bounds__(256) decode_kernel(const DecodeParams<T> p) {
+__global__ void __launch_bounds__(256) decode_filter_kernel(const DecodeParams<T> p) {
   XR_PDL_ENTRY();
+  constexpr int EPC = 16 / static_cast<int>(sizeof(T));          // logits per 16-byte chunk
+  constexpr int CPA = NC / EPC;                                   // chunks per anchor (10 fp16, 20 fp32)
+  __shared__ float s_max[8][32 * CPA];
   __shared__ int s_list[256];
-  __shared__ int s_n;
+  __shared__ int s_n, s_base;
   const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  {
-    const int a = blockIdx.x * 256 + threadIdx.x;
-    if (a < p.A) {
-      int si = 0;
-      if (a >= p.s[1].a_off) si = 1;
-      if (a >= p.s[2].a_off) si = 2;
+  const int a0 = blockIdx.x * 256 + warp * 32;                    // first anchor of this warp
+  const int a = a0 + lane;
+  if (a0 < p.A) {
+    const int a_last = min(a0 + 31, p.A - 1);
+    int si = 0;
+    if (a0 >= p.s[1].a_off) si = 1;
+    if (a0 >= p.s[2].a_off) si = 2;
+    int sl = 0;
+    if (a_last >= p.s[1].a_off) sl = 1;
+    if (a_last >= p.s[2].a_off) sl = 2;
+    float lmax = -3.0e38f;
+    if (si == sl && p.s[si].cls_pitch == NC) {
+      // coalesced run: anchors a0 .. a_last of scale si
       const ScaleSrc<T>& s = p.s[si];
+      const T* run = s.cls + b * s.cls_bstride + static_cast<long>(a0 - s.a_off) * NC;
+      const int n_chunks = (a_last - a0 + 1) * CPA;
+#pragma unroll
+      for (int it = 0; it < CPA; ++it) {
+        const int gi = it * 32 + lane;
+        float m = -3.0e38f;
+        if (gi < n_chunks) {
+          const uint4 raw = reinterpret_cast<const uint4*>(run)[gi];
+          if (sizeof(T) == 2) {
+            const __half2* h = reinterpret_cast<const __half2*>(&raw);
+            const __half2 m2 = __hmax2(__hmax2(h[0], h[1]), __hmax2(h[2], h[3]));
+            m = fmaxf(__low2float(m2), __high2float(m2));
+          } else {
+            const float* f = reinterpret_cast<const float*>(&raw);
+            m = fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3]));
+          }
+        }
+        s_max[warp][gi] = m;
+      }
+      __syncwarp();
+      if (a <= a_last) {
+#pragma unroll
+        for (int k = 0; k < CPA; ++k) lmax = fmaxf(lmax, s_max[warp][lane * CPA + k]);
+      }
+    } else if (a < p.A) {
+      // generic walk (a warp straddling two scales, or a padded class tensor)
+      int sa = 0;
+      if (a >= p.s[1].a_off) sa = 1;
+      if (a >= p.s[2].a_off) sa = 2;
+      const ScaleSrc<T>& s = p.s[sa];
       const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(a - s.a_off) * s.cls_pitch;
-      float lmax = -3.0e38f;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 16) {
         float l[16];
@@ -97,77 +142,101 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeParams<T> p) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) lmax = fmaxf(lmax, l[k]);
       }
-      if (lmax > p.logit_floor) s_list[atomicAdd(&s_n, 1)] = a;
     }
+    if (a < p.A && lmax > p.logit_floor) s_list[atomicAdd(&s_n, 1)] = a;
   }
   __syncthreads();
-  if (static_cast<int>(threadIdx.x) >= s_n) return;
-  const int a = s_list[threadIdx.x];
-  int si = 0;
-  if (a >= p.s[1].a_off) si = 1;
-  if (a >= p.s[2].a_off) si = 2;
-  const ScaleSrc<T>& s = p.s[si];
-  const int al = a - s.a_off;
-  const int gy = al / s.w, gx = al - gy * s.w;
-  const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+  const int n = s_n;
+  if (n == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&p.filt_count[b], n);   // one global atomic per block
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < n) p.filt_list[static_cast<long>(b) * p.A + s_base + threadIdx.x] = s_list[threadIdx.x];
+}
 
-  // ---- class sigmoid + max / first argmax (chains 416, 464, 471): like the graph, the maximum is taken over the
-  // fp32 PROBABILITIES (two different logits can round to the same probability; the first index then wins).
-  const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(al) * s.cls_pitch;
-  float best = -1.f;
-  int besti = 0;
-#pragma unroll
-  for (int c0 = 0; c0 < NC; c0 += 16) {
-    float l[16];
-    load16(cl + c0, l);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float pr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-l[k])));
+// ---- decode, kernel 2 of 2: exact arithmetic on the survivors ----------------------------------------------------------
+// One WARP per listed anchor: the 80 class sigmoids are spread over the lanes and reduced with the graph's first-maximum
+// rule (max probability, lowest index on ties); the four DFL sides go to four lanes, each keeping the sequential 16-bin
+// order; lane 0 does the anchor / stride decode.  IEEE intrinsics in the oracle's operation order throughout.
+template <typename T>
+__global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams<T> p) {
+  XR_PDL_ENTRY();
+  const int b = blockIdx.y;
+  const int n_list = min(p.filt_count[b], p.A);
+  const int lane = threadIdx.x & 31;
+  const int warps = gridDim.x * 8;
+  for (int li = blockIdx.x * 8 + (threadIdx.x >> 5); li < n_list; li += warps) {
+    const int a = p.filt_list[static_cast<long>(b) * p.A + li];
+    int si = 0;
+    if (a >= p.s[1].a_off) si = 1;
+    if (a >= p.s[2].a_off) si = 2;
+    const ScaleSrc<T>& s = p.s[si];
+    const int al = a - s.a_off;
+    const int gy = al / s.w, gx = al - gy * s.w;
+    const float ax = static_cast<float>(gx) + 0.5f, ay = static_cast<float>(gy) + 0.5f;
+
+    // ---- class sigmoid + max / first argmax (chains 416, 464, 471): like the graph, the maximum is taken over the
+    // fp32 PROBABILITIES (two different logits can round to the same probability; the first index then wins).
+    const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(al) * s.cls_pitch;
+    float best = -1.f;
+    int besti = 0;
+    for (int c = lane; c < NC; c += 32) {
+      const float pr = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-ldf(cl + c))));
       if (pr > best) {
         best = pr;
-        besti = c0 + k;
+        besti = c;
       }
     }
-  }
-  if (!(best > p.score_thr)) return;
-
-  // ---- DFL (chains 401-406): softmax over 16 bins, expectation with weights 0..15
-  const T* bl = s.box + b * s.box_bstride + static_cast<long>(al) * s.box_pitch;
-  float d[4];
 #pragma unroll
-  for (int side = 0; side < 4; ++side) {
-    float l[16];
-    load16(bl + side * 16, l);
-    float mx = -3.0e38f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) mx = fmaxf(mx, l[k]);
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      l[k] = expf(__fsub_rn(l[k], mx));
-      sum = __fadd_rn(sum, l[k]);
+    for (int o = 16; o >= 1; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) {
+        best = ob;
+        besti = oi;
+      }
     }
-    float e = 0.f;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) e = __fadd_rn(e, __fmul_rn(__fdiv_rn(l[k], sum), static_cast<float>(k)));
-    d[side] = e;
-  }
-  // chains 407-415
-  const float x1 = __fsub_rn(ax, d[0]), y1 = __fsub_rn(ay, d[1]);
-  const float x2 = __fadd_rn(ax, d[2]), y2 = __fadd_rn(ay, d[3]);
-  const float cx = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), s.stride);
-  const float cy = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), s.stride);
-  const float bw = __fmul_rn(__fsub_rn(x2, x1), s.stride);
-  const float bh = __fmul_rn(__fsub_rn(y2, y1), s.stride);
+    if (!(best > p.score_thr)) continue;     // warp-uniform after the reduction
 
-  const long o = static_cast<long>(b) * p.A + a;
-  reinterpret_cast<float4*>(p.boxes)[o] = make_float4(cx, cy, bw, bh);
-  p.scores[o] = best;
-  p.labels[o] = besti;
-  const int slot = atomicAdd(&p.cand_count[b], 1);
-  const unsigned long long key =
-      (static_cast<unsigned long long>(0xFFFFFFFFu - __float_as_uint(best)) << 32) | static_cast<unsigned>(a);
-  p.keys[static_cast<long>(b) * p.A + slot] = key;
+    // ---- DFL (chains 401-406): softmax over 16 bins, expectation with weights 0..15; lane = side
+    float dv = 0.f;
+    if (lane < 4) {
+      const T* bl = s.box + b * s.box_bstride + static_cast<long>(al) * s.box_pitch;
+      float l[16];
+      load16(bl + lane * 16, l);
+      float mx = -3.0e38f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) mx = fmaxf(mx, l[k]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        l[k] = expf(__fsub_rn(l[k], mx));
+        sum = __fadd_rn(sum, l[k]);
+      }
+      float e = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) e = __fadd_rn(e, __fmul_rn(__fdiv_rn(l[k], sum), static_cast<float>(k)));
+      dv = e;
+    }
+    const float d0 = __shfl_sync(0xffffffffu, dv, 0), d1 = __shfl_sync(0xffffffffu, dv, 1);
+    const float d2 = __shfl_sync(0xffffffffu, dv, 2), d3 = __shfl_sync(0xffffffffu, dv, 3);
+    if (lane != 0) continue;
+    // chains 407-415
+    const float x1 = __fsub_rn(ax, d0), y1 = __fsub_rn(ay, d1);
+    const float x2 = __fadd_rn(ax, d2), y2 = __fadd_rn(ay, d3);
+    const float cx = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), s.stride);
+    const float cy = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), s.stride);
+    const float bw = __fmul_rn(__fsub_rn(x2, x1), s.stride);
+    const float bh = __fmul_rn(__fsub_rn(y2, y1), s.stride);
+
+    const long o = static_cast<long>(b) * p.A + a;
+    reinterpret_cast<float4*>(p.boxes)[o] = make_float4(cx, cy, bw, bh);
+    p.scores[o] = best;
+    p.labels[o] = besti;
+    const int slot = atomicAdd(&p.cand_count[b], 1);
+    const unsigned long long key =
+        (static_cast<unsigned long long>(0xFFFFFFFFu - __float_as_uint(best)) << 32) | static_cast<unsigned>(a);
+    p.keys[static_cast<long>(b) * p.A + slot] = key;
+  }
 }
 
 // Candidate keys straight from caller-provided scores (xrseg_debug_nms).

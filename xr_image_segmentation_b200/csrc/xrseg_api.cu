@@ -93,7 +93,7 @@ struct xrseg_runner {
   float *d_boxes = nullptr, *d_scores = nullptr;
   int* d_labels = nullptr;
   unsigned long long* d_keys = nullptr;
-  int *d_cand_count = nullptr, *d_n_cand = nullptr, *d_sorted_idx = nullptr, *d_overflow = nullptr;
+  int *d_cand_count = nullptr, *d_n_cand = nullptr, *d_sorted_idx = nullptr, *d_overflow = nullptr, *d_filt_list = nullptr;
   float4* d_sorted_corners = nullptr;
   unsigned long long* d_mask = nullptr;
   int *d_keep_idx = nullptr, *d_keep_n = nullptr, *d_offsets = nullptr;
@@ -422,11 +422,17 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     dp.labels = r->d_labels + static_cast<long>(b0) * A;
     dp.keys = r->d_keys + static_cast<long>(b0) * A;
     dp.cand_count = r->d_cand_count + b0;
+    dp.filt_count = r->d_cand_count + r->cfg.max_batch + b0;
+    dp.filt_list = r->d_filt_list + static_cast<long>(b0) * A;
     Launch L;
     L.name = "post.decode";
     L.bytes = static_cast<double>(nb) * A * NC * sizeof(T);   // every anchor's class logits; box logits only for candidates
-    L.fn = [dp, A, nb](cudaStream_t st) { launch_k(decode_kernel<T>, dim3(ceil_div(A, 256), nb), 256, 0, st, dp); };
+    L.fn = [dp, A, nb](cudaStream_t st) { launch_k(decode_filter_kernel<T>, dim3(ceil_div(A, 256), nb), 256, 0, st, dp); };
     out.push_back(std::move(L));
+    Launch L2;
+    L2.name = "post.decode_exact";
+    L2.fn = [dp, nb](cudaStream_t st) { launch_k(decode_exact_kernel<T>, dim3(8, nb), 256, 0, st, dp); };
+    out.push_back(std::move(L2));
   }
   SortParams sp{};
   sp.keys = r->d_keys + static_cast<long>(b0) * A;
@@ -621,7 +627,7 @@ void* ensure_scratch(xrseg_runner* r, size_t bytes) {
 }
 
 void reset_counters(xrseg_runner* r, int batch, cudaStream_t st) {
-  XR_CUDA(cudaMemsetAsync(r->d_cand_count, 0, sizeof(int) * batch, st));
+  XR_CUDA(cudaMemsetAsync(r->d_cand_count, 0, sizeof(int) * 2 * r->cfg.max_batch, st));   // candidate + filter counters
   XR_CUDA(cudaMemsetAsync(r->d_overflow, 0, sizeof(int), st));
 }
 
@@ -771,7 +777,7 @@ xrseg_runner::~xrseg_runner() {
   for (DevLayer& d : dl) {
     cudaFree(d.wpack); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
-  void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx,
+  void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx, d_filt_list,
                   d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,
                   o_probs, o_labels, o_anchor, o_frame, dbg_box, dbg_cls, dbg_coef, dbg_proto, dbg_corners};
   for (void* b : bufs) cudaFree(b);
@@ -973,7 +979,8 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     r->d_scores = dev_alloc<float>(static_cast<size_t>(B) * A);
     r->d_labels = dev_alloc<int>(static_cast<size_t>(B) * A);
     r->d_keys = dev_alloc<unsigned long long>(static_cast<size_t>(B) * A);
-    r->d_cand_count = dev_alloc<int>(B);
+    r->d_cand_count = dev_alloc<int>(2 * B);               // [0,B) candidates per frame, [B,2B) logit-filter survivors
+    r->d_filt_list = dev_alloc<int>(static_cast<size_t>(B) * A);
     r->d_n_cand = dev_alloc<int>(B);
     r->d_sorted_idx = dev_alloc<int>(static_cast<size_t>(B) * r->max_cand);
     r->d_sorted_corners = dev_alloc<float4>(static_cast<size_t>(B) * r->max_cand);

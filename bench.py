@@ -169,6 +169,15 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    # bind this rank to the CPUs (and therefore the host memory) next to its GPU before anything allocates pinned
+    # buffers: eight ranks streaming frames from one NUMA node would share that node's memory and PCIe root
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+    except Exception:
+        pass
+
     import torch
     import torch.distributed as dist
 

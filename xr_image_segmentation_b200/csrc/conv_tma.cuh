@@ -1,16 +1,22 @@
-// conv_tma.cuh -- 3x3 stride-1 convolution on tcgen05 with the input halo fetched by TMA (cp.async.bulk.tensor).
+// conv_tma.cuh -- the TMA-fed tcgen05 convolution kernel: every convolution of the network except the K = 27 stem.
 //
-// Same GEMM view and shared-memory operand layout as conv_umma.cuh (K-major, SWIZZLE_NONE: element (row r, K-chunk c)
-// at base + c*LBO + r*16 B), but the A operand is no longer gathered by threads:
-//   * a work item is R full rows of one image (all W columns) -- R*(W+2) "positions" in padded-row order, split into
-//     nsub <= 4 sub-tiles of 128 positions, each with its own TMEM accumulator;
-//   * per 8-channel K-chunk ONE 4-D TMA box (8 ch, x = -1..W, y = y0-1..y0+R, image b) lands the whole halo:
-//     out-of-bounds coordinates are zero-filled by the TMA unit, which IS the convolution's zero padding;
-//   * the box arrives as [y][x][8 ch] = consecutive 16-byte rows, so tap (kh,kw) of position j is row
-//     j + kh*(W+2) + kw - 1 of the chunk column: nine MMAs per 16 channels whose descriptors merely start at
-//     different rows.  The input is read ~(R+2)/R times instead of 9x (im2col) or 3.5x (linear halo).
-// One thread issues the TMA loads, one thread issues the MMAs, eight warps run the epilogue (TMEM -> +bias -> SiLU ->
-// +residual -> fp16 NHWC).  Weights stay resident in shared memory when they fit, else stream per K-stage by bulk copy.
+// Same GEMM view as conv_umma.cuh (D[M = output positions, N = Cout] = A[M, K] * W[N, K]^T, fp16 operands, fp32 accumulators
+// in TMEM), but nothing except ONE thread ever touches an address: the A operand is fetched by cp.async.bulk.tensor into
+// hardware-swizzled shared memory (row = one K-block of 16 / 32 / 64 channels = 32 / 64 / 128 bytes) and a tap is a pure
+// ROW SHIFT of the operand descriptor.  Three modes share the kernel:
+//   * halo  (3x3 stride 1): a work item is R full rows of one image; per K-block one 4-D box (channels, x = -1..W,
+//     y = y0-1..y0+R, image) lands the whole halo, out-of-bounds coordinates are zero-filled by the TMA unit -- which IS the
+//     convolution's padding.  Tap (kh,kw) of position j is row j + kh*(W+2) + kw - 1: nine MMAs per 16 channels whose
+//     descriptors merely start at different rows.  The input is read ~(R+2)/R times instead of 9x (im2col).
+//   * s2    (3x3 stride 2): the input is read as four parity planes X[2ys+py][2xs+px] (four tensor maps), so taps are row
+//     shifts again: tap (kh,kw) = plane (kh != 1, kw != 1) at row j + (kh == 2)(Wo+1) - (kw == 0).
+//   * flat  (1x1 and the 2x2 stride-2 ConvTranspose): plain GEMM over the flattened [B*H*W, C] matrix, the whole K of a
+//     thin layer in one stage; ConvTranspose = N = 4 positions x Cout, scattered by the epilogue.
+// Warp roles (416 threads): warp 0 = TMA producer (one lane), warps 1-4 = MMA issuers, ONE PER 128-ROW SUB-TILE (a single
+// thread cannot issue tcgen05.mma faster than one per ~50-65 cycles, which bounded every thin layer), warps 5-12 = epilogue
+// (tcgen05.ld -> +bias -> SiLU -> +residual -> one 256-bit store per 16 channels into the concat slice).  Accumulators are
+// double-buffered in TMEM; weights stay resident in shared memory when they fit, else stream per stage by bulk copy.
+// Every launch uses programmatic dependent launch: weights are fetched and TMEM allocated before griddepcontrol.wait.
 #pragma once
 
 #include <cuda.h>

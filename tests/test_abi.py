@@ -185,3 +185,37 @@ def test_sentis_loader_rejects_corrupt_input(lib):
         for p in rng.integers(8, 100000, 16):
             d[p] = int(rng.integers(0, 256))
         assert info(d) <= 0
+
+
+# ---- launch planner invariants (host-only: tools/plan_dump.cu compiles the planners without a GPU) --------------------
+@pytest.fixture(scope="module")
+def plan_dump(tmp_path_factory):
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path_factory.mktemp("plan") / "plan_dump")
+    r = subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr", "-o", exe,
+                        os.path.join(ROOT, "tools", "plan_dump.cu"), "-lcuda"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return exe
+
+
+@pytest.mark.parametrize("batch,scale", [(1, "n"), (3, "n"), (64, "n"), (64, "s"), (5, "s")])
+def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
+    """Every convolution of the network gets a TMA plan (no thread-gather fallback at 640x640) that fits the SM:
+    <= 227 KB shared memory, <= 512 TMEM columns, >= 2 pipeline stages, <= 4 sub-tiles, and covers all its work."""
+    import subprocess
+    out = subprocess.run([plan_dump, str(batch), scale], capture_output=True, text=True, check=True).stdout
+    rows = [l for l in out.splitlines() if " smem " in l]
+    assert len(rows) == 92                       # 100 layers - stem - 7 depthwise
+    for l in rows:
+        tok = l.split()
+        f = {tok[i]: tok[i + 1] for i in range(len(tok) - 1)}
+        mode = tok[5]
+        assert mode in ("halo_tma", "flat_tma", "s2_tma"), l
+        assert int(f["smem"]) <= 232448 and int(f["tmem"]) <= 512 and int(f["S"]) >= 2, l
+        assert 1 <= int(f["nsub"]) <= 4 and int(f["items"]) >= 1, l
+        if mode != "flat_tma":
+            assert int(f["R"]) >= 1, l

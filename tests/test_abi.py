@@ -209,7 +209,7 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
     import subprocess
     out = subprocess.run([plan_dump, str(batch), scale], capture_output=True, text=True, check=True).stdout
     rows = [l for l in out.splitlines() if " smem " in l]
-    assert len(rows) == 92                       # 100 layers - stem - 7 depthwise
+    assert len(rows) == 86                       # 100 layers - stem - 7 depthwise - 6 fused siblings
     for l in rows:
         tok = l.split()
         f = {tok[i]: tok[i + 1] for i in range(len(tok) - 1)}

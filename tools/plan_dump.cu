@@ -14,13 +14,14 @@ int main(int argc, char** argv) {
     if (o.kind != OP_CONV) continue;
     const LayerRec& l = net.layers[o.layer];
     ConvDesc cd{};
-    cd.B = B; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch; cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch;
+    cd.B = B; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch; cd.Cout = o.y.Cp + (o.layer2 >= 0 ? o.y2.Cp : 0); cd.out_pitch = o.y.pitch;
     cd.k = o.k; cd.stride = o.stride; cd.act = o.act; cd.transposed = o.transposed; cd.res_pitch = o.has_res ? o.res.pitch : 0;
     ConvParams p;
     if (!plan_conv_halo_tma(cd, 148, p) && !plan_conv_flat_tma(cd, 148, p) && !plan_conv_s2_tma(cd, 148, p)) p = plan_conv(cd, 148, 0);
     const int work = p.m_tiles * p.n_tiles;
     printf("%-16s %3dx%-3d %3d->%-3d k%d s%d %-8s cb %2d kps %d nks %2d R %2d nsub %d S %d smem %6d tmem %3d items %5d (%.1f/CTA) bres %d\n",
-           l.name.c_str(), o.x.H, o.x.W, l.cin, l.cout, o.k, o.stride, mode_name[p.mode], p.cb, p.kps, p.nks, p.R, p.nsub, p.S,
+           (o.layer2 >= 0 ? l.name + "+" : l.name).c_str(), o.x.H, o.x.W, l.cin,
+           l.cout + (o.layer2 >= 0 ? net.layers[o.layer2].cout : 0), o.k, o.stride, mode_name[p.mode], p.cb, p.kps, p.nks, p.R, p.nsub, p.S,
            p.smem_bytes, p.tmem_cols, work, static_cast<double>(work) / p.grid, p.b_resident);
     if (p.smem_bytes <= 113 * 1024) ++total_smem_small;
   }

@@ -166,7 +166,7 @@ static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvP
       const int a_stage = round_up(p.slots * rb, 1024);
       const int b_stage = 9 * p.Ntile * rb;
       const long total_b = static_cast<long>(d.Cin / cb) * b_stage;
-      const bool res = (p.n_tiles == 1 && total_b <= 98304);
+      const bool res = (p.n_tiles == 1 && total_b <= 114688);
       const int fixed = round_up(CONV_HDR_BYTES, 1024) + 1024 + 128 * rb + 1024 +
                         (res ? round_up(static_cast<int>(total_b), 1024) : 0);
       int S = (XR_TMA_BUDGET - fixed) / (a_stage + (res ? 0 : round_up(b_stage, 1024)));
@@ -189,7 +189,7 @@ static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvP
     p.a_stage_bytes = round_up(p.slots * rb, 1024);
     p.b_stage_bytes = 9 * p.Ntile * rb;
     const long total_b = static_cast<long>(p.nks) * p.b_stage_bytes;
-    p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
+    p.b_resident = (p.n_tiles == 1 && total_b <= 114688) ? 1 : 0;
     const int resident = p.b_resident ? static_cast<int>(total_b) : 0;
     const int S = clamp_stages(best_S, d.B * p.tpi * p.n_tiles, num_sms, p.nks);
     p.S = S;
@@ -217,7 +217,7 @@ static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvP
   p.tmem_cols = pow2_ceil(2 * p.nsub * p.Ntile);
   const int budget = XR_TMA_BUDGET - CONV_HDR_BYTES - TMA_TAIL_PAD;
   const long total_b = 9L * d.Cin * p.Ntile * 2;
-  p.b_resident = (p.n_tiles == 1 && total_b <= 98304) ? 1 : 0;
+  p.b_resident = (p.n_tiles == 1 && total_b <= 114688) ? 1 : 0;
   int best_cb = 0, best_S = 0;
   for (int cb = 64; cb >= 16; cb >>= 1) {
     if (d.Cin % cb) continue;
@@ -928,8 +928,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         }
         if (valid && !(p.dbg_skip & 2)) {
           const int n = n_tile * p.Ntile + c * 16;
-          epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
-                           p.out + pix * p.out_pitch + n);
+          __half* dst = (p.split_n && n >= p.split_n) ? p.out2 + pix * p.out2_pitch + (n - p.split_n) : p.out + pix * p.out_pitch + n;
+          epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr, dst);
         }
       };
       if (!(p.dbg_skip & 8) || p.transposed) {
@@ -971,8 +971,9 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
                 const size_t opix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
                 epilogue_chunk16(v, bias_s + n, p.act, nullptr, p.out + opix * p.out_pitch + co);
               } else {
-                epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr,
-                                 p.out + pix * p.out_pitch + n);
+                __half* dst = (p.split_n && n >= p.split_n) ? p.out2 + pix * p.out2_pitch + (n - p.split_n)
+                                                             : p.out + pix * p.out_pitch + n;
+                epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr, dst);
               }
             }
           }

@@ -41,6 +41,9 @@ struct Op {
   // first op of a branch segment waits for the event `wait_tag` (3/4/5 = P3/P4/P5 ready); the op producing that feature
   // map carries `signal_tag`.
   int branch = 0, wait_tag = 0, signal_tag = 0;
+  // sibling fusion: a second convolution of the same input / kernel / stride / activation computed by the same launch
+  int layer2 = -1;
+  TV y2;
 };
 
 struct Spec {
@@ -74,11 +77,12 @@ class Net {
   std::map<std::string, TV> named;
   size_t arena_elems = 0;
   int cur_branch = 0, pending_wait = 0;   // see Op::branch
+  bool fuse_enabled = true;               // sibling fusion (fuse_siblings); off for the direct-convolution cross-check
   TV input;                 // [B,640,640,4] fp16
   TV box[3], cls[3], coef[3], protos;
   int fh[3], fw[3];
 
-  Net(int scale, int batch, int in_hw = 640) : B(batch), sp(make_spec(scale)) { build(in_hw); }
+  Net(int scale, int batch, int in_hw = 640, bool fuse = true) : B(batch), sp(make_spec(scale)), fuse_enabled(fuse) { build(in_hw); }
 
   TV alloc(int H, int W, int C, int pitch_override = 0) {
     TV t;
@@ -182,6 +186,46 @@ class Net {
     cur_branch = 0;
   }
 
+  // Two convolutions that read the same tensor with the same kernel / stride / activation and no residual become one
+  // launch with N = Cout_a + Cout_b (the input is read once, one launch less): the two 1x1 convs at the head of every
+  // C3k block (m0.cv1 | m0.cv2) and the first 3x3 of the box and coefficient branches of every scale (box.0 | coef.0).
+  // The second op disappears from `ops`; its consumers wait for the fused launch through event tag 6 + pair index.
+  void fuse_siblings() {
+    if (!fuse_enabled) return;
+    auto find = [&](const std::string& nm) {
+      for (size_t i = 0; i < ops.size(); ++i)
+        if (ops[i].layer >= 0 && layers[ops[i].layer].name == nm) return static_cast<int>(i);
+      return -1;
+    };
+    std::vector<std::pair<std::string, std::string>> pairs;
+    for (const char* blk : {"b6", "b8", "n22"}) pairs.push_back({std::string(blk) + ".m0.cv1", std::string(blk) + ".m0.cv2"});
+    for (const char* h : {"h3", "h4", "h5"}) pairs.push_back({std::string(h) + ".box.0", std::string(h) + ".coef.0"});
+    int tag = 6;
+    for (const auto& pr : pairs) {
+      const int ia = find(pr.first), ib = find(pr.second);
+      if (ia < 0 || ib < 0) continue;
+      Op& a = ops[ia];
+      const Op b = ops[ib];
+      const bool same = a.kind == OP_CONV && b.kind == OP_CONV && a.x.off == b.x.off && a.x.C == b.x.C && a.x.pitch == b.x.pitch &&
+                        a.k == b.k && a.stride == b.stride && a.act == b.act && !a.has_res && !b.has_res && !a.transposed &&
+                        !b.transposed && a.layer2 < 0 && a.y.Cp + b.y.Cp <= 256;
+      if (!same) continue;
+      a.layer2 = b.layer;
+      a.y2 = b.y;
+      if (a.branch != b.branch) {
+        // the consumer chain of b runs on another stream: it must wait for the fused launch (which runs on a's stream)
+        a.signal_tag = tag;
+        for (size_t j = ib + 1; j < ops.size(); ++j)
+          if (ops[j].branch == b.branch) {           // first later op of b's branch = b's consumer
+            if (ops[j].wait_tag == 0) ops[j].wait_tag = tag;
+            break;
+          }
+        ++tag;
+      }
+      ops.erase(ops.begin() + ib);
+    }
+  }
+
   void build(int hw) {
     const int c1 = sp.ch[0], c2 = sp.ch[1], c5 = sp.ch[4];
     input = alloc(hw, hw, 3, 4);
@@ -267,6 +311,7 @@ class Net {
     protos = conv(t, 32, 1, 1, true, "proto.cv3");
     cur_branch = 0;
     named["p3"] = p3; named["p4"] = p4; named["p5"] = p5;
+    fuse_siblings();
     fh[0] = p3.H; fw[0] = p3.W; fh[1] = p4.H; fw[1] = p4.W; fh[2] = p5.H; fw[2] = p5.W;
   }
 };

@@ -110,7 +110,7 @@ struct xrseg_runner {
   std::vector<ChunkGraph> graphs;     // one captured pipeline per (first frame, frame count) chunk
   cudaStream_t copy_stream = nullptr; // host->device frame copies, overlapped chunk by chunk with compute
   cudaStream_t side[4] = {};          // head / prototype branches inside the captured graph
-  cudaEvent_t ev_tag[3] = {}, ev_join[4] = {};
+  cudaEvent_t ev_tag[16] = {}, ev_join[4] = {};
   std::vector<cudaEvent_t> ev_copy;
   struct ChunkLaunches { int b0, nb; void* list; };   // list: std::vector<Launch>* (type local to this file)
   std::vector<ChunkLaunches> launch_cache;
@@ -168,9 +168,25 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       d.w32 = dev_upload(ws);
       d.bias = dev_upload(bs);
     } else if (o.kind == OP_CONV) {
+      // sibling fusion: one weight matrix [Cout_a padded to 16 | Cout_b] x Cin x k x k, one bias vector
+      HostLayerWeights fused;
+      int cout_real = l.cout;
+      if (o.layer2 >= 0) {
+        const LayerRec& l2 = net.layers[o.layer2];
+        const HostLayerWeights& w2 = hw[o.layer2];
+        const size_t per = static_cast<size_t>(l.cin) * l.k * l.k;
+        fused.w.assign((static_cast<size_t>(o.y.Cp) + l2.cout) * per, 0.f);
+        fused.b.assign(static_cast<size_t>(o.y.Cp) + l2.cout, 0.f);
+        std::copy(w.w.begin(), w.w.end(), fused.w.begin());
+        std::copy(w.b.begin(), w.b.end(), fused.b.begin());
+        std::copy(w2.w.begin(), w2.w.end(), fused.w.begin() + static_cast<size_t>(o.y.Cp) * per);
+        std::copy(w2.b.begin(), w2.b.end(), fused.b.begin() + o.y.Cp);
+        cout_real = o.y.Cp + l2.cout;
+      }
+      const HostLayerWeights& wsrc = o.layer2 >= 0 ? fused : w;
       ConvDesc cd{};
       cd.B = r->mb; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
-      cd.Cout = o.y.Cp; cd.out_pitch = o.y.pitch;
+      cd.Cout = o.y.Cp + (o.layer2 >= 0 ? o.y2.Cp : 0); cd.out_pitch = o.y.pitch;
       cd.k = o.k; cd.stride = o.stride; cd.act = o.act; cd.transposed = o.transposed;
       cd.res_pitch = o.has_res ? o.res.pitch : 0;
       d.use_tma = r->cfg.conv_impl == XRSEG_CONV_UMMA && plan_conv_halo_tma(cd, r->num_sms, d.cp);
@@ -190,8 +206,9 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
         std::vector<__half> wp;
         std::vector<float> bp;
-        if (d.use_tma && d.cp.sw) pack_conv_weights_sw<__half>(d.cp, w.w.data(), w.b.data(), l.cin, l.cout, wp, bp);
-        else pack_conv_weights<__half>(d.cp, w.w.data(), w.b.data(), l.cin, l.cout, wp, bp);
+        XR_CHECK(o.layer2 < 0 || (d.use_tma && d.cp.sw), "fused siblings need the TMA kernel (%s)", l.name.c_str());
+        if (d.use_tma && d.cp.sw) pack_conv_weights_sw<__half>(d.cp, wsrc.w.data(), wsrc.b.data(), l.cin, cout_real, wp, bp);
+        else pack_conv_weights<__half>(d.cp, wsrc.w.data(), wsrc.b.data(), l.cin, cout_real, wp, bp);
         d.wpack = dev_upload(wp);
         d.bias = dev_upload(bp);
       } else {
@@ -277,12 +294,19 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         DevLayer& d = r->dl[o.layer];
         L.name = l.name;
         const double taps = o.transposed ? 1.0 : static_cast<double>(o.k) * o.k;
-        L.flops = 2.0 * (o.transposed ? px_in * 4 : px_out) * l.cout * l.cin * taps;
-        L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1) + static_cast<double>(l.cout) * l.cin * o.k * o.k) * 2;
+        int cout_alg = l.cout;                       // algorithmic output channels (both siblings of a fused launch)
+        if (o.layer2 >= 0) {
+          cout_alg += net.layers[o.layer2].cout;
+          L.name = l.name + "+" + net.layers[o.layer2].name.substr(net.layers[o.layer2].name.find('.') + 1);
+          if (L.name.size() > 31) L.name.resize(31);
+        }
+        L.flops = 2.0 * (o.transposed ? px_in * 4 : px_out) * cout_alg * l.cin * taps;
+        L.bytes = (px_in * l.cin + px_out * cout_alg * (o.has_res ? 2 : 1) + static_cast<double>(cout_alg) * l.cin * o.k * o.k) * 2;
         if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
           ConvParams p = d.cp;
           if (nb != p.B) p = replan_for_batch(d.cp, nb, r->num_sms);   // partial last chunk: same layout, fewer frames
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
+          if (o.layer2 >= 0) { p.out2 = ptr_of(r, o.y2); p.split_n = o.y.Cp; p.out2_pitch = o.y2.pitch; }
           p.res = o.has_res ? ptr_of(r, o.res) : nullptr;
           p.wpack = d.wpack; p.bias = d.bias;
           if (d.use_tma) {
@@ -603,7 +627,7 @@ int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st, int part = 
         }
     }
     L.fn(s);
-    if (fork && L.signal_tag) XR_CUDA(cudaEventRecord(r->ev_tag[L.signal_tag - 3], st));
+    if (fork && L.signal_tag) XR_CUDA(cudaEventRecord(r->ev_tag[L.signal_tag - 3], s));
   }
   XR_CUDA(cudaGetLastError());
   return static_cast<int>(hi - lo);
@@ -935,7 +959,9 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 65 * 8));
 
     r->mb = c.micro_batch > 0 ? std::min(c.micro_batch, c.max_batch) : c.max_batch;
-    r->net.reset(new Net(c.model_scale, r->mb));
+    const char* fuse_env = getenv("XRSEG_FUSE");
+    const bool fuse = c.conv_impl == XRSEG_CONV_UMMA && !(fuse_env && fuse_env[0] == '0');
+    r->net.reset(new Net(c.model_scale, r->mb, 640, fuse));
     Net& net = *r->net;
     r->A = net.fh[0] * net.fw[0] + net.fh[1] * net.fw[1] + net.fh[2] * net.fw[2];
     std::vector<HostLayerWeights> hw;

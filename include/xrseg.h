@@ -236,6 +236,11 @@ int xrseg_debug_mask_threshold(xrseg_runner* r, const float* probs, const float*
 int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h, int w, const float* wgt,
                      const float* bias, int cout, int k, int stride, int groups, int act, int transposed,
                      const float* residual, float* y, int variant);
+/* The fused Bottleneck kernel (Conv3x3+SiLU -> Conv3x3+SiLU (+ x), graph chains X.m0.cv1 / X.m0.cv2 of the C3k2 blocks,
+ * SURVEY.md Appendix A) on caller tensors: x f32 NCHW [b,c1,h,w], w1 [cm,c1,3,3], w2 [c2,cm,3,3]; y f32 NCHW out.
+ * Channel triples: 16-8-16 and 32-16-32 (after padding). */
+int xrseg_debug_bottleneck(int device, const float* x, int b, int c1, int h, int w, const float* w1, const float* b1,
+                           int cm, const float* w2, const float* b2, int c2, int residual, float* y);
 /* Host-side emulation of the UMMA conv kernel's data movement (slot mapping, weight packing, tap shifts)
  * in fp32 -- used by CPU tests to validate index math without a GPU.  NOT a product path. */
 int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const float* wgt, const float* bias,

@@ -66,6 +66,38 @@ def test_tcgen05_conv_vs_torch(lib, case, variant):
     np.testing.assert_allclose(y, ref, atol=2e-3 * max(1.0, float(np.abs(ref).max())), rtol=2e-3)
 
 
+BNECK_CASES = [   # (batch, c1, cm, c2, h, w, residual): full tiles, ragged tiles, maps smaller than one tile
+    (2, 16, 8, 16, 32, 64, True), (1, 16, 8, 16, 37, 45, True), (1, 16, 8, 16, 5, 7, False), (1, 16, 8, 16, 160, 160, True),
+    (2, 32, 16, 32, 20, 80, True), (1, 32, 16, 32, 23, 51, False), (1, 32, 16, 32, 3, 3, True), (1, 32, 16, 32, 80, 80, True),
+    (1, 32, 16, 32, 160, 160, True),
+]
+
+
+@pytest.mark.parametrize("case", BNECK_CASES)
+def test_fused_bottleneck_vs_torch(lib, case):
+    """Conv3x3+SiLU -> Conv3x3+SiLU (+ x) in one launch (graph chains X.m0.cv1 / X.m0.cv2) against torch fp32 with the
+    intermediate rounded to fp16 like the kernel's shared-memory copy."""
+    B, c1, cm, c2, h, wd, res = case
+    rng = np.random.default_rng(abs(hash(case)) % 2**32)
+    x = rng.standard_normal((B, c1, h, wd), dtype=np.float32)
+    w1 = rng.standard_normal((cm, c1, 3, 3), dtype=np.float32) * np.float32(1.5 / np.sqrt(c1 * 9))
+    w2 = rng.standard_normal((c2, cm, 3, 3), dtype=np.float32) * np.float32(1.5 / np.sqrt(cm * 9))
+    b1 = rng.standard_normal(cm, dtype=np.float32)
+    b2 = rng.standard_normal(c2, dtype=np.float32)
+    h16 = lambda a: torch.from_numpy(a).half().float()
+    xt = h16(x)
+    t = F.conv2d(xt, h16(w1), torch.from_numpy(b1), padding=1)
+    t = (t * torch.sigmoid(t)).half().float()
+    ref = F.conv2d(t, h16(w2), torch.from_numpy(b2), padding=1)
+    ref = ref * torch.sigmoid(ref)
+    if res:
+        ref = ref + xt
+    y = I.debug_bottleneck(x, w1, b1, w2, b2, residual=res)
+    ref = ref.numpy()
+    # the fp16 intermediate may round differently by one ulp (2^-11 relative) where tanh.approx differs from exp
+    np.testing.assert_allclose(y, ref, atol=4e-3 * max(1.0, float(np.abs(ref).max())), rtol=4e-3)
+
+
 # ---- whole path on the reference's frames ------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def runner(golden):

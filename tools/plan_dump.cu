@@ -7,7 +7,7 @@ using namespace xrseg;
 int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 64;
   const int scale = argc > 2 ? argv[2][0] : 'n';
-  Net net(scale, B);
+  Net net(scale, B, 640, true, false);   // Bottleneck fusion off: every convolution keeps its own plan
   const char* mode_name[] = {"gather", "halo", "halo_tma", "flat_tma", "s2_tma"};
   long total_smem_small = 0;
   for (const Op& o : net.ops) {

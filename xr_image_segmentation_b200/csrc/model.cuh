@@ -28,7 +28,7 @@ struct LayerRec {
   int cin, cout, k, stride, groups, act, transposed, h_in, w_in;
 };
 
-enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN };
+enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN, OP_BNECK };
 
 struct Op {
   OpKind kind;
@@ -42,9 +42,16 @@ struct Op {
   // map carries `signal_tag`.
   int branch = 0, wait_tag = 0, signal_tag = 0;
   // sibling fusion: a second convolution of the same input / kernel / stride / activation computed by the same launch
+  // (OP_BNECK: the second 3x3 convolution of the fused Bottleneck, whose output is y)
   int layer2 = -1;
   TV y2;
 };
+
+// Channel triples (input, middle, output; as laid out in shared memory) the fused Bottleneck kernel is built for
+// (bottleneck.cuh).  Anything else keeps its two tcgen05 launches.
+static inline bool bneck_supported(int c1, int cm, int c2) {
+  return (c1 == 16 && cm == 8 && c2 == 16) || (c1 == 32 && cm == 16 && c2 == 32);
+}
 
 struct Spec {
   int ch[5];
@@ -78,11 +85,13 @@ class Net {
   size_t arena_elems = 0;
   int cur_branch = 0, pending_wait = 0;   // see Op::branch
   bool fuse_enabled = true;               // sibling fusion (fuse_siblings); off for the direct-convolution cross-check
+  bool fuse_bneck = true;                 // Bottleneck fusion (fuse_bottlenecks)
   TV input;                 // [B,640,640,4] fp16
   TV box[3], cls[3], coef[3], protos;
   int fh[3], fw[3];
 
-  Net(int scale, int batch, int in_hw = 640, bool fuse = true) : B(batch), sp(make_spec(scale)), fuse_enabled(fuse) { build(in_hw); }
+  Net(int scale, int batch, int in_hw = 640, bool fuse = true, bool bneck = true)
+      : B(batch), sp(make_spec(scale)), fuse_enabled(fuse), fuse_bneck(fuse && bneck) { build(in_hw); }
 
   TV alloc(int H, int W, int C, int pitch_override = 0) {
     TV t;
@@ -226,6 +235,33 @@ class Net {
     }
   }
 
+  // The Bottleneck of a C3k2 block without C3k (X.m0.cv1 -> X.m0.cv2 (+ x)): two dependent 3x3 convolutions over 8..32
+  // channels become one launch whose intermediate stays in shared memory (bottleneck.cuh).  The pair collapses into one
+  // OP_BNECK op: layer = cv1, layer2 = cv2, x = the block input (also the residual), y = cv2's destination.
+  void fuse_bottlenecks() {
+    if (!fuse_bneck) return;
+    for (size_t i = 0; i + 1 < ops.size(); ++i) {
+      Op& a = ops[i];
+      const Op b = ops[i + 1];
+      if (a.kind != OP_CONV || b.kind != OP_CONV || a.layer2 >= 0 || b.layer2 >= 0) continue;
+      const std::string &na = layers[a.layer].name, &nb = layers[b.layer].name;
+      const bool names = na.size() > 7 && na.compare(na.size() - 7, 7, ".m0.cv1") == 0 && nb == na.substr(0, na.size() - 1) + "2";
+      if (!names) continue;
+      const bool chain = a.k == 3 && b.k == 3 && a.stride == 1 && b.stride == 1 && a.act && b.act && !a.has_res &&
+                         !a.transposed && !b.transposed && b.x.off == a.y.off && a.branch == b.branch && b.wait_tag == 0 &&
+                         a.signal_tag == 0 && (!b.has_res || (b.res.off == a.x.off && b.res.pitch == a.x.pitch));
+      const int cm = round_up(layers[a.layer].cout, 8);
+      if (!chain || !bneck_supported(a.x.Cp, cm, b.y.Cp) || (b.has_res && a.x.Cp != b.y.Cp)) continue;
+      a.kind = OP_BNECK;
+      a.layer2 = b.layer;
+      a.y = b.y;
+      a.has_res = b.has_res;
+      a.res = b.res;
+      a.signal_tag = b.signal_tag;
+      ops.erase(ops.begin() + i + 1);
+    }
+  }
+
   void build(int hw) {
     const int c1 = sp.ch[0], c2 = sp.ch[1], c5 = sp.ch[4];
     input = alloc(hw, hw, 3, 4);
@@ -312,6 +348,7 @@ class Net {
     cur_branch = 0;
     named["p3"] = p3; named["p4"] = p4; named["p5"] = p5;
     fuse_siblings();
+    fuse_bottlenecks();
     fh[0] = p3.H; fw[0] = p3.W; fh[1] = p4.H; fw[1] = p4.W; fh[2] = p5.H; fw[2] = p5.W;
   }
 };

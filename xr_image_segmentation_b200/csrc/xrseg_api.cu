@@ -18,6 +18,7 @@
 #include "model.cuh"
 #include "post.cuh"
 #include "sentis.cuh"
+#include "bottleneck.cuh"
 
 using namespace xrseg;
 
@@ -36,7 +37,32 @@ struct DevLayer {
   __half* w16 = nullptr;
   float* w32 = nullptr;
   float* w32_u8 = nullptr;         // stem weights / 255 for the fused uint8 path
+  uint2* wfrag = nullptr;          // OP_BNECK: mma.sync B-fragment order (bottleneck.cuh)
 };
+
+// ---- fused Bottleneck (bottleneck.cuh): one instantiation per supported channel triple ---------------------------------
+template <int C1, int CM, int C2, int TH>
+void bneck_launch_t(const BneckParams& p, bool res, cudaStream_t st) {
+  using Cfg = BneckCfg<C1, CM, C2, TH>;
+  const dim3 grid(ceil_div(p.W, BNECK_TW), ceil_div(p.H, TH), p.B);
+  if (res) launch_k(bottleneck_mma_kernel<C1, CM, C2, TH, true>, grid, 256, Cfg::SMEM_BYTES, st, p);
+  else launch_k(bottleneck_mma_kernel<C1, CM, C2, TH, false>, grid, 256, Cfg::SMEM_BYTES, st, p);
+}
+template <int C1, int CM, int C2, int TH>
+void bneck_prepare_t() {
+  using Cfg = BneckCfg<C1, CM, C2, TH>;
+  XR_CUDA(cudaFuncSetAttribute(bottleneck_mma_kernel<C1, CM, C2, TH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  XR_CUDA(cudaFuncSetAttribute(bottleneck_mma_kernel<C1, CM, C2, TH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+}
+void bneck_prepare_device() {
+  bneck_prepare_t<16, 8, 16, 14>();
+  bneck_prepare_t<32, 16, 32, 14>();
+}
+void launch_bneck(int c1, int cm, int c2, const BneckParams& p, bool res, cudaStream_t st) {
+  if (c1 == 16 && cm == 8 && c2 == 16) bneck_launch_t<16, 8, 16, 14>(p, res, st);
+  else if (c1 == 32 && cm == 16 && c2 == 32) bneck_launch_t<32, 16, 32, 14>(p, res, st);
+  else XR_CHECK(false, "no fused Bottleneck kernel for %d-%d-%d channels", c1, cm, c2);
+}
 
 // XRSEG_FLAT_TMA=0: keep the 1x1 convolutions on the thread-gather kernel (A/B measurements only)
 bool flat_tma_disabled() {
@@ -167,6 +193,21 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       }
       d.w32 = dev_upload(ws);
       d.bias = dev_upload(bs);
+    } else if (o.kind == OP_BNECK) {
+      const LayerRec& l2 = net.layers[o.layer2];
+      const HostLayerWeights& w2 = hw[o.layer2];
+      DevLayer& d2 = r->dl[o.layer2];
+      const int cm = round_up(l.cout, 8);
+      std::vector<uint32_t> f1, f2;
+      pack_bneck_weights(w.w.data(), l.cin, l.cout, o.x.Cp, cm, f1);
+      pack_bneck_weights(w2.w.data(), l2.cin, l2.cout, cm, o.y.Cp, f2);
+      std::vector<float> b1(cm, 0.f), b2(o.y.Cp, 0.f);
+      std::copy(w.b.begin(), w.b.end(), b1.begin());
+      std::copy(w2.b.begin(), w2.b.end(), b2.begin());
+      d.wfrag = reinterpret_cast<uint2*>(dev_upload(f1));
+      d.bias = dev_upload(b1);
+      d2.wfrag = reinterpret_cast<uint2*>(dev_upload(f2));
+      d2.bias = dev_upload(b2);
     } else if (o.kind == OP_CONV) {
       // sibling fusion: one weight matrix [Cout_a padded to 16 | Cout_b] x Cin x k x k, one bias vector
       HostLayerWeights fused;
@@ -325,6 +366,20 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
           const long total = static_cast<long>(nb) * o.y.H * o.y.W * o.y.Cp;
           L.fn = [p, total](cudaStream_t st) { conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(p); };
         }
+        break;
+      }
+      case OP_BNECK: {
+        const LayerRec &l = net.layers[o.layer], &l2 = net.layers[o.layer2];
+        BneckParams p{};
+        p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
+        p.w1 = r->dl[o.layer].wfrag; p.b1 = r->dl[o.layer].bias; p.w2 = r->dl[o.layer2].wfrag; p.b2 = r->dl[o.layer2].bias;
+        p.B = nb; p.H = o.x.H; p.W = o.x.W;
+        const int c1 = o.x.Cp, cm = round_up(l.cout, 8), c2 = o.y.Cp;
+        const bool res = o.has_res;
+        L.name = l.name.substr(0, l.name.size() - 4);          // "b2.m0"
+        L.flops = 2.0 * px_out * 9 * (static_cast<double>(l.cin) * l.cout + static_cast<double>(l2.cin) * l2.cout);
+        L.bytes = (px_in * l.cin + px_out * l2.cout + 9.0 * (l.cin * l.cout + l2.cin * l2.cout)) * 2;
+        L.fn = [p, c1, cm, c2, res](cudaStream_t st) { launch_bneck(c1, cm, c2, p, res, st); };
         break;
       }
       case OP_DW: {
@@ -799,7 +854,7 @@ xrseg_runner::~xrseg_runner() {
   for (cudaEvent_t e : ev_copy) cudaEventDestroy(e);
   cudaFree(scratch);
   for (DevLayer& d : dl) {
-    cudaFree(d.wpack); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
+    cudaFree(d.wpack); cudaFree(d.wfrag); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
   void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx, d_filt_list,
                   d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,
@@ -954,6 +1009,7 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     for (auto& e : r->ev) XR_CUDA(cudaEventCreate(&e));
     conv_umma_prepare_device();
     conv_tma_prepare_device();
+    bneck_prepare_device();
     XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     XR_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 65 * 8));
@@ -961,7 +1017,8 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     r->mb = c.micro_batch > 0 ? std::min(c.micro_batch, c.max_batch) : c.max_batch;
     const char* fuse_env = getenv("XRSEG_FUSE");
     const bool fuse = c.conv_impl == XRSEG_CONV_UMMA && !(fuse_env && fuse_env[0] == '0');
-    r->net.reset(new Net(c.model_scale, r->mb, 640, fuse));
+    const char* bneck_env = getenv("XRSEG_FUSE_BNECK");
+    r->net.reset(new Net(c.model_scale, r->mb, 640, fuse, !(bneck_env && bneck_env[0] == '0')));
     Net& net = *r->net;
     r->A = net.fh[0] * net.fw[0] + net.fh[1] * net.fw[1] + net.fh[2] * net.fw[2];
     std::vector<HostLayerWeights> hw;
@@ -1638,6 +1695,68 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
     XR_CUDA(cudaDeviceSynchronize());
     XR_CUDA(cudaMemcpy(y, d_y32, ny * sizeof(float), cudaMemcpyDeviceToHost));
     cudaFree(d_x32); cudaFree(d_y32); cudaFree(d_r32); cudaFree(d_x); cudaFree(d_y); cudaFree(d_r); cudaFree(d_w); cudaFree(d_b);
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+// The fused Bottleneck kernel on caller tensors (test hook): y = silu(conv3x3(silu(conv3x3(x, w1) + b1), w2) + b2) (+ x).
+// x [b,c1,h,w], w1 [cm,c1,3,3], w2 [c2,cm,3,3], y [b,c2,h,w], all fp32 NCHW on the host.
+int xrseg_debug_bottleneck(int device, const float* x, int b, int c1, int h, int w, const float* w1, const float* b1, int cm,
+                           const float* w2, const float* b2, int c2, int residual, float* y) {
+  if (!x || !w1 || !b1 || !w2 || !b2 || !y) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    XR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { g_create_error = "not an sm_100 device"; return XRSEG_ERR_NO_DEVICE; }
+    const int c1p = round_up(c1, 16), cmp = round_up(cm, 8), c2p = round_up(c2, 16);
+    if (!bneck_supported(c1p, cmp, c2p) || (residual && c1 != c2)) { g_create_error = "unsupported channel triple"; return XRSEG_ERR_INVALID; }
+    bneck_prepare_device();
+    const size_t nx = static_cast<size_t>(b) * c1 * h * w, ny = static_cast<size_t>(b) * c2 * h * w;
+    float* d_x32 = dev_alloc<float>(nx);
+    float* d_y32 = dev_alloc<float>(ny);
+    __half* d_x = dev_alloc<__half>(static_cast<size_t>(b) * h * w * c1p);
+    __half* d_y = dev_alloc<__half>(static_cast<size_t>(b) * h * w * c2p);
+    XR_CUDA(cudaMemcpy(d_x32, x, nx * sizeof(float), cudaMemcpyHostToDevice));
+    nchw_f32_to_nhwc_f16_kernel<<<grid_for(static_cast<long>(b) * h * w * c1p), 256>>>(d_x32, d_x, b, c1, h, w, c1p, c1p);
+    XR_CUDA(cudaMemset(d_y, 0, static_cast<size_t>(b) * h * w * c2p * sizeof(__half)));
+    std::vector<uint32_t> f1, f2;
+    pack_bneck_weights(w1, c1, cm, c1p, cmp, f1);
+    pack_bneck_weights(w2, cm, c2, cmp, c2p, f2);
+    std::vector<float> hb1(cmp, 0.f), hb2(c2p, 0.f);
+    std::copy(b1, b1 + cm, hb1.begin());
+    std::copy(b2, b2 + c2, hb2.begin());
+    uint32_t *d_f1 = dev_upload(f1), *d_f2 = dev_upload(f2);
+    float *d_b1 = dev_upload(hb1), *d_b2 = dev_upload(hb2);
+    BneckParams p{};
+    p.in = d_x; p.in_pitch = c1p; p.out = d_y; p.out_pitch = c2p;
+    p.w1 = reinterpret_cast<uint2*>(d_f1); p.w2 = reinterpret_cast<uint2*>(d_f2); p.b1 = d_b1; p.b2 = d_b2;
+    p.B = b; p.H = h; p.W = w;
+    const int reps = getenv("XRSEG_DBG_TIME") ? 5 : 1;
+    cudaEvent_t e0, e1;
+    XR_CUDA(cudaEventCreate(&e0));
+    XR_CUDA(cudaEventCreate(&e1));
+    for (int rep = 0; rep < reps; ++rep) {
+      if (rep == reps - 1) XR_CUDA(cudaEventRecord(e0, 0));
+      launch_bneck(c1p, cmp, c2p, p, residual != 0, 0);
+    }
+    XR_CUDA(cudaEventRecord(e1, 0));
+    XR_CUDA(cudaEventSynchronize(e1));
+    XR_CUDA(cudaGetLastError());
+    if (reps > 1) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      fprintf(stderr, "xrseg_debug_bottleneck: %d-%d-%d %dx%d batch %d: %.1f us\n", c1p, cmp, c2p, h, w, b, ms * 1e3f);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    nhwc_f16_to_nchw_f32_kernel<<<grid_for(static_cast<long>(ny)), 256>>>(d_y, d_y32, b, c2, h, w, c2p);
+    XR_CUDA(cudaDeviceSynchronize());
+    XR_CUDA(cudaMemcpy(y, d_y32, ny * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_x32); cudaFree(d_y32); cudaFree(d_x); cudaFree(d_y); cudaFree(d_f1); cudaFree(d_f2); cudaFree(d_b1); cudaFree(d_b2);
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_CUDA;

@@ -315,6 +315,18 @@ def debug_conv(x, w, b, k, stride, act, transposed=False, residual=None, impl=_l
     return y
 
 
+def debug_bottleneck(x, w1, b1, w2, b2, residual=True, device=0):
+    """The fused Bottleneck kernel (Conv3x3+SiLU -> Conv3x3+SiLU (+ x)) on caller tensors (parity tests)."""
+    lib = _lib.load_library()
+    x, w1, b1, w2, b2 = (np.ascontiguousarray(a, np.float32) for a in (x, w1, b1, w2, b2))
+    B, c1, h, wd = x.shape
+    cm, c2 = w1.shape[0], w2.shape[0]
+    y = np.zeros((B, c2, h, wd), np.float32)
+    _lib.check(lib.xrseg_debug_bottleneck(device, x.ctypes.data, B, c1, h, wd, w1.ctypes.data, b1.ctypes.data, cm,
+                                          w2.ctypes.data, b2.ctypes.data, c2, int(residual), y.ctypes.data))
+    return y
+
+
 # --------------------------------------------------------------------------------------------------
 # Inference Engine mirror
 # --------------------------------------------------------------------------------------------------

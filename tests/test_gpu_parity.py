@@ -98,6 +98,29 @@ def test_fused_bottleneck_vs_torch(lib, case):
     np.testing.assert_allclose(y, ref, atol=4e-3 * max(1.0, float(np.abs(ref).max())), rtol=4e-3)
 
 
+@pytest.mark.parametrize("case", [(2, 28, 42), (1, 37, 45), (1, 5, 7), (1, 160, 160)])
+def test_fused_c3k2_block_vs_torch(lib, case):
+    """cv1 (1x1) -> Bottleneck -> cv2 (1x1) of the b2 block in one launch against torch fp32 with every intermediate
+    rounded to fp16 like the kernel's shared-memory copies."""
+    B, h, wd = case
+    cin, c, cm, cout = 32, 16, 8, 64
+    rng = np.random.default_rng(abs(hash(case)) % 2**32)
+    x = rng.standard_normal((B, cin, h, wd), dtype=np.float32)
+    mk = lambda co, ci, k: rng.standard_normal((co, ci, k, k), dtype=np.float32) * np.float32(1.5 / np.sqrt(ci * k * k))
+    w_cv1, w_m1, w_m2, w_cv2 = mk(2 * c, cin, 1), mk(cm, c, 3), mk(c, cm, 3), mk(cout, 3 * c, 1)
+    b_cv1, b_m1, b_m2, b_cv2 = (rng.standard_normal(n, dtype=np.float32) for n in (2 * c, cm, c, cout))
+    h16 = lambda a: torch.from_numpy(a).half().float()
+    silu16 = lambda t: (t * torch.sigmoid(t)).half().float()
+    ab = silu16(F.conv2d(h16(x), h16(w_cv1), torch.from_numpy(b_cv1)))
+    bb = ab[:, c:]
+    t = silu16(F.conv2d(bb, h16(w_m1), torch.from_numpy(b_m1), padding=1))
+    m = (silu16(F.conv2d(t, h16(w_m2), torch.from_numpy(b_m2), padding=1)) + bb).half().float()
+    ref = F.conv2d(torch.cat([ab, m], 1), h16(w_cv2), torch.from_numpy(b_cv2))
+    ref = (ref * torch.sigmoid(ref)).numpy()
+    y = I.debug_c3k2(x, w_cv1[:, :, 0, 0], b_cv1, w_m1, b_m1, w_m2, b_m2, w_cv2[:, :, 0, 0], b_cv2)
+    np.testing.assert_allclose(y, ref, atol=6e-3 * max(1.0, float(np.abs(ref).max())), rtol=6e-3)
+
+
 # ---- whole path on the reference's frames ------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def runner(golden):

@@ -18,10 +18,13 @@ timeout 1200 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --secti
 full() {  # name regex skip count
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o gpurun_out/${T}_full_$1 python tools/ncu_step.py > gpurun_out/${T}_ncu_$1.log 2>&1; echo "ncu full $1 exit $?"
 }
+NC=$(grep -c conv_halo_tma gpurun_out/${T}_launches.csv)   # TMA conv launches per pass (launch order = op order)
+echo "conv_halo_tma launches per pass: $NC"
 full stem stem_mma 1 1
-full s2_b1 conv_halo_tma $((91 + 0)) 1         # b1 (3x3 stride 2, parity-plane TMA) of pass 2
-full flat_b2cv1 conv_halo_tma $((91 + 1)) 1    # b2.cv1 (1x1, flat TMA) of pass 2
-full halo_protocv2 conv_halo_tma $((91 + 89)) 1  # proto.cv2 (3x3 stride 1, halo TMA) of pass 2
+full s2_b1 conv_halo_tma $((NC + 0)) 1         # b1 (3x3 stride 2, parity-plane TMA) of pass 2
+full flat_b2cv1 conv_halo_tma $((NC + 1)) 1    # b2.cv1 (1x1, flat TMA) of pass 2
+full halo_protocv2 conv_halo_tma $((NC + NC - 2)) 1  # proto.cv2 (3x3 stride 1, halo TMA) of pass 2
+full bneck_b2m0 bottleneck_mma 3 1             # b2.m0 (fused Bottleneck) of pass 2
 full dw dwconv3x3 $((7 + 1)) 1                 # h3.cls.1dw of pass 2
 full decode decode_filter 1 1
 full maskprob mask_prob 1 1

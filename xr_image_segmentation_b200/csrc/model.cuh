@@ -28,7 +28,7 @@ struct LayerRec {
   int cin, cout, k, stride, groups, act, transposed, h_in, w_in;
 };
 
-enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN, OP_BNECK };
+enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN, OP_BNECK, OP_C3K2 };
 
 struct Op {
   OpKind kind;
@@ -45,10 +45,14 @@ struct Op {
   // (OP_BNECK: the second 3x3 convolution of the fused Bottleneck, whose output is y)
   int layer2 = -1;
   TV y2;
+  // OP_C3K2 (whole-block fusion): layer = X.cv1, layer2 = X.m0.cv1, layer3 = X.m0.cv2, layer4 = X.cv2
+  int layer3 = -1, layer4 = -1;
 };
 
 // Channel triples (input, middle, output; as laid out in shared memory) the fused Bottleneck kernel is built for
 // (bottleneck.cuh).  Anything else keeps its two tcgen05 launches.
+// (input, split width c, bottleneck middle, output) of the C3k2 blocks the whole-block kernel is built for
+static inline bool c3k2_supported(int cin, int c, int cm, int cout) { return cin == 32 && c == 16 && cm == 8 && cout == 64; }
 static inline bool bneck_supported(int c1, int cm, int c2) {
   return (c1 == 16 && cm == 8 && c2 == 16) || (c1 == 32 && cm == 16 && c2 == 32);
 }
@@ -86,12 +90,13 @@ class Net {
   int cur_branch = 0, pending_wait = 0;   // see Op::branch
   bool fuse_enabled = true;               // sibling fusion (fuse_siblings); off for the direct-convolution cross-check
   bool fuse_bneck = true;                 // Bottleneck fusion (fuse_bottlenecks)
+  bool fuse_c3k2 = false;                 // whole-block fusion (fuse_c3k2_blocks); measured slower, opt-in (XRSEG_FUSE_C3K2=1)
   TV input;                 // [B,640,640,4] fp16
   TV box[3], cls[3], coef[3], protos;
   int fh[3], fw[3];
 
-  Net(int scale, int batch, int in_hw = 640, bool fuse = true, bool bneck = true)
-      : B(batch), sp(make_spec(scale)), fuse_enabled(fuse), fuse_bneck(fuse && bneck) { build(in_hw); }
+  Net(int scale, int batch, int in_hw = 640, bool fuse = true, bool bneck = true, bool c3k2_blocks = false)
+      : B(batch), sp(make_spec(scale)), fuse_enabled(fuse), fuse_bneck(fuse && bneck), fuse_c3k2(c3k2_blocks) { build(in_hw); }
 
   TV alloc(int H, int W, int C, int pitch_override = 0) {
     TV t;
@@ -262,6 +267,30 @@ class Net {
     }
   }
 
+  // X.cv1 (1x1) -> fused Bottleneck -> X.cv2 (1x1) over the block's concat buffer become ONE launch when the channel
+  // counts are small enough for everything to stay in shared memory (b2 of the n scale): the concat buffer is never
+  // materialised.  Runs after fuse_bottlenecks().
+  void fuse_c3k2_blocks() {
+    if (!fuse_bneck || !fuse_c3k2) return;
+    for (size_t i = 0; i + 2 < ops.size(); ++i) {
+      Op& a = ops[i];
+      const Op m = ops[i + 1], z = ops[i + 2];
+      if (a.kind != OP_CONV || m.kind != OP_BNECK || z.kind != OP_CONV || a.layer2 >= 0 || z.layer2 >= 0) continue;
+      const int c = m.x.Cp;
+      const bool chain = a.k == 1 && z.k == 1 && a.stride == 1 && z.stride == 1 && a.act && z.act && !a.has_res && !z.has_res &&
+                         !a.transposed && !z.transposed && m.has_res && a.y.Cp == 2 * c && m.x.off == a.y.off + c &&
+                         m.y.off == a.y.off + 2 * c && z.x.off == a.y.off && z.x.Cp == 3 * c && z.x.pitch == a.y.pitch &&
+                         a.branch == m.branch && m.branch == z.branch && m.wait_tag == 0 && z.wait_tag == 0 &&
+                         a.signal_tag == 0 && m.signal_tag == 0 && layers[a.layer].cout == 2 * c && layers[z.layer].cin == 3 * c;
+      if (!chain || !c3k2_supported(a.x.Cp, c, round_up(layers[m.layer].cout, 8), z.y.Cp)) continue;
+      a.kind = OP_C3K2;
+      a.layer2 = m.layer; a.layer3 = m.layer2; a.layer4 = z.layer;
+      a.y = z.y;
+      a.signal_tag = z.signal_tag;
+      ops.erase(ops.begin() + i + 1, ops.begin() + i + 3);
+    }
+  }
+
   void build(int hw) {
     const int c1 = sp.ch[0], c2 = sp.ch[1], c5 = sp.ch[4];
     input = alloc(hw, hw, 3, 4);
@@ -349,6 +378,7 @@ class Net {
     named["p3"] = p3; named["p4"] = p4; named["p5"] = p5;
     fuse_siblings();
     fuse_bottlenecks();
+    fuse_c3k2_blocks();
     fh[0] = p3.H; fw[0] = p3.W; fh[1] = p4.H; fw[1] = p4.W; fh[2] = p5.H; fw[2] = p5.W;
   }
 };

@@ -58,6 +58,14 @@ void bneck_prepare_device() {
   bneck_prepare_t<16, 8, 16, 14>();
   bneck_prepare_t<32, 16, 32, 14>();
 }
+void c3k2_prepare_device() {
+  XR_CUDA(cudaFuncSetAttribute(c3k2_mma_kernel<32, 16, 8, 64, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3k2Cfg<32, 16, 8, 64, 14>::SMEM_BYTES));
+}
+void launch_c3k2(int cin, int c, int cm, int cout, const C3k2Params& p, cudaStream_t st) {
+  XR_CHECK(c3k2_supported(cin, c, cm, cout), "no fused C3k2 kernel for %d-%d-%d-%d channels", cin, c, cm, cout);
+  const dim3 grid(ceil_div(p.W, BNECK_TW), ceil_div(p.H, 14), p.B);
+  launch_k(c3k2_mma_kernel<32, 16, 8, 64, 14>, grid, 256, C3k2Cfg<32, 16, 8, 64, 14>::SMEM_BYTES, st, p);
+}
 void launch_bneck(int c1, int cm, int c2, const BneckParams& p, bool res, cudaStream_t st) {
   if (c1 == 16 && cm == 8 && c2 == 16) bneck_launch_t<16, 8, 16, 14>(p, res, st);
   else if (c1 == 32 && cm == 16 && c2 == 32) bneck_launch_t<32, 16, 32, 14>(p, res, st);
@@ -193,6 +201,21 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       }
       d.w32 = dev_upload(ws);
       d.bias = dev_upload(bs);
+    } else if (o.kind == OP_C3K2) {
+      const int ids[4] = {o.layer, o.layer2, o.layer3, o.layer4};
+      const int c = net.layers[o.layer].cout / 2, cm = round_up(net.layers[o.layer2].cout, 8);
+      const int kdim[4] = {o.x.Cp, c, cm, 3 * c}, ndim[4] = {2 * c, cm, c, o.y.Cp}, taps[4] = {1, 9, 9, 1};
+      std::vector<float> bias;
+      for (int j = 0; j < 4; ++j) {
+        const LayerRec& lj = net.layers[ids[j]];
+        std::vector<uint32_t> f;
+        pack_bneck_weights(hw[ids[j]].w.data(), lj.cin, lj.cout, kdim[j], ndim[j], f, taps[j]);
+        r->dl[ids[j]].wfrag = reinterpret_cast<uint2*>(dev_upload(f));
+        std::vector<float> bj(ndim[j], 0.f);
+        std::copy(hw[ids[j]].b.begin(), hw[ids[j]].b.end(), bj.begin());
+        bias.insert(bias.end(), bj.begin(), bj.end());
+      }
+      d.bias = dev_upload(bias);
     } else if (o.kind == OP_BNECK) {
       const LayerRec& l2 = net.layers[o.layer2];
       const HostLayerWeights& w2 = hw[o.layer2];
@@ -366,6 +389,21 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
           const long total = static_cast<long>(nb) * o.y.H * o.y.W * o.y.Cp;
           L.fn = [p, total](cudaStream_t st) { conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(p); };
         }
+        break;
+      }
+      case OP_C3K2: {
+        const LayerRec &l = net.layers[o.layer], &l2 = net.layers[o.layer2], &l3 = net.layers[o.layer3], &l4 = net.layers[o.layer4];
+        C3k2Params p{};
+        p.in = ptr_of(r, o.x); p.in_pitch = o.x.pitch; p.out = ptr_of(r, o.y); p.out_pitch = o.y.pitch;
+        p.w_cv1 = r->dl[o.layer].wfrag; p.w_m1 = r->dl[o.layer2].wfrag; p.w_m2 = r->dl[o.layer3].wfrag; p.w_cv2 = r->dl[o.layer4].wfrag;
+        p.bias = r->dl[o.layer].bias;
+        p.B = nb; p.H = o.x.H; p.W = o.x.W;
+        const int cin = o.x.Cp, c = l.cout / 2, cm = round_up(l2.cout, 8), cout = o.y.Cp;
+        const double macs = static_cast<double>(l.cin) * l.cout + 9.0 * (l2.cin * l2.cout + l3.cin * l3.cout) + static_cast<double>(l4.cin) * l4.cout;
+        L.name = l.name.substr(0, l.name.size() - 4);          // "b2"
+        L.flops = 2.0 * px_out * macs;
+        L.bytes = (px_in * l.cin + px_out * l4.cout + macs) * 2;
+        L.fn = [p, cin, c, cm, cout](cudaStream_t st) { launch_c3k2(cin, c, cm, cout, p, st); };
         break;
       }
       case OP_BNECK: {
@@ -1010,6 +1048,7 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     conv_umma_prepare_device();
     conv_tma_prepare_device();
     bneck_prepare_device();
+    c3k2_prepare_device();
     XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     XR_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 65 * 8));
@@ -1018,7 +1057,9 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     const char* fuse_env = getenv("XRSEG_FUSE");
     const bool fuse = c.conv_impl == XRSEG_CONV_UMMA && !(fuse_env && fuse_env[0] == '0');
     const char* bneck_env = getenv("XRSEG_FUSE_BNECK");
-    r->net.reset(new Net(c.model_scale, r->mb, 640, fuse, !(bneck_env && bneck_env[0] == '0')));
+    // whole-block C3k2 kernel: parity-tested but measured slower than cv1 + fused Bottleneck + cv2: opt-in
+    const char* c3k2_env = getenv("XRSEG_FUSE_C3K2");
+    r->net.reset(new Net(c.model_scale, r->mb, 640, fuse, !(bneck_env && bneck_env[0] == '0'), c3k2_env && c3k2_env[0] == '1'));
     Net& net = *r->net;
     r->A = net.fh[0] * net.fw[0] + net.fh[1] * net.fw[1] + net.fh[2] * net.fw[2];
     std::vector<HostLayerWeights> hw;
@@ -1757,6 +1798,74 @@ int xrseg_debug_bottleneck(int device, const float* x, int b, int c1, int h, int
     XR_CUDA(cudaDeviceSynchronize());
     XR_CUDA(cudaMemcpy(y, d_y32, ny * sizeof(float), cudaMemcpyDeviceToHost));
     cudaFree(d_x32); cudaFree(d_y32); cudaFree(d_x); cudaFree(d_y); cudaFree(d_f1); cudaFree(d_f2); cudaFree(d_b1); cudaFree(d_b2);
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+
+// The whole-block C3k2 kernel on caller tensors (test hook): ab = silu(cv1 x), m = b + silu(m2 silu(m1 b)), y = silu(cv2 [a|b|m]).
+// x [b,cin,h,w]; w_cv1 [2c,cin], w_m1 [cm,c,3,3], w_m2 [c,cm,3,3], w_cv2 [cout,3c]; y [b,cout,h,w]; fp32 NCHW on the host.
+int xrseg_debug_c3k2(int device, const float* x, int b, int cin, int h, int w, int c, int cm, int cout, const float* w_cv1,
+                     const float* b_cv1, const float* w_m1, const float* b_m1, const float* w_m2, const float* b_m2,
+                     const float* w_cv2, const float* b_cv2, float* y) {
+  if (!x || !w_cv1 || !b_cv1 || !w_m1 || !b_m1 || !w_m2 || !b_m2 || !w_cv2 || !b_cv2 || !y) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    XR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { g_create_error = "not an sm_100 device"; return XRSEG_ERR_NO_DEVICE; }
+    if (!c3k2_supported(cin, c, cm, cout)) { g_create_error = "unsupported channel counts"; return XRSEG_ERR_INVALID; }
+    c3k2_prepare_device();
+    const size_t nx = static_cast<size_t>(b) * cin * h * w, ny = static_cast<size_t>(b) * cout * h * w;
+    float* d_x32 = dev_alloc<float>(nx);
+    float* d_y32 = dev_alloc<float>(ny);
+    __half* d_x = dev_alloc<__half>(static_cast<size_t>(b) * h * w * cin);
+    __half* d_y = dev_alloc<__half>(static_cast<size_t>(b) * h * w * cout);
+    XR_CUDA(cudaMemcpy(d_x32, x, nx * sizeof(float), cudaMemcpyHostToDevice));
+    nchw_f32_to_nhwc_f16_kernel<<<grid_for(static_cast<long>(b) * h * w * cin), 256>>>(d_x32, d_x, b, cin, h, w, cin, cin);
+    XR_CUDA(cudaMemset(d_y, 0, static_cast<size_t>(b) * h * w * cout * sizeof(__half)));
+    const float* ws[4] = {w_cv1, w_m1, w_m2, w_cv2};
+    const float* bs[4] = {b_cv1, b_m1, b_m2, b_cv2};
+    const int kin[4] = {cin, c, cm, 3 * c}, nout[4] = {2 * c, cm, c, cout}, taps[4] = {1, 9, 9, 1};
+    uint32_t* d_f[4];
+    std::vector<float> bias;
+    for (int j = 0; j < 4; ++j) {
+      std::vector<uint32_t> f;
+      pack_bneck_weights(ws[j], kin[j], nout[j], kin[j], nout[j], f, taps[j]);
+      d_f[j] = dev_upload(f);
+      bias.insert(bias.end(), bs[j], bs[j] + nout[j]);
+    }
+    float* d_b = dev_upload(bias);
+    C3k2Params p{};
+    p.in = d_x; p.in_pitch = cin; p.out = d_y; p.out_pitch = cout;
+    p.w_cv1 = reinterpret_cast<uint2*>(d_f[0]); p.w_m1 = reinterpret_cast<uint2*>(d_f[1]);
+    p.w_m2 = reinterpret_cast<uint2*>(d_f[2]); p.w_cv2 = reinterpret_cast<uint2*>(d_f[3]);
+    p.bias = d_b; p.B = b; p.H = h; p.W = w;
+    const int reps = getenv("XRSEG_DBG_TIME") ? 5 : 1;
+    cudaEvent_t e0, e1;
+    XR_CUDA(cudaEventCreate(&e0));
+    XR_CUDA(cudaEventCreate(&e1));
+    for (int rep = 0; rep < reps; ++rep) {
+      if (rep == reps - 1) XR_CUDA(cudaEventRecord(e0, 0));
+      launch_c3k2(cin, c, cm, cout, p, 0);
+    }
+    XR_CUDA(cudaEventRecord(e1, 0));
+    XR_CUDA(cudaEventSynchronize(e1));
+    XR_CUDA(cudaGetLastError());
+    if (reps > 1) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      fprintf(stderr, "xrseg_debug_c3k2: %d-%d-%d-%d %dx%d batch %d: %.1f us\n", cin, c, cm, cout, h, w, b, ms * 1e3f);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    nhwc_f16_to_nchw_f32_kernel<<<grid_for(static_cast<long>(ny)), 256>>>(d_y, d_y32, b, cout, h, w, cout);
+    XR_CUDA(cudaDeviceSynchronize());
+    XR_CUDA(cudaMemcpy(y, d_y32, ny * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_x32); cudaFree(d_y32); cudaFree(d_x); cudaFree(d_y); cudaFree(d_b);
+    for (auto f : d_f) cudaFree(f);
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_CUDA;

@@ -157,8 +157,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-micro-batch", type=int, default=0, help="frames per network pass of the e2e leg (0 = whole batch)")
     ap.add_argument("--latency-iters", type=int, default=300, help="batch-1 latency samples (0 = skip)")
-    ap.add_argument("--e2e-depth", type=int, default=3, help="runners of the end-to-end leg (submissions in flight + 1)")
-    ap.add_argument("--value-streams", type=int, default=3, help="runners (streams) the device-resident leg alternates over")
+    ap.add_argument("--e2e-depth", type=int, default=4, help="runners of the end-to-end leg (submissions in flight + 1)")
+    ap.add_argument("--value-streams", type=int, default=4, help="runners (streams) the device-resident leg alternates over")
     ap.add_argument("--profile-ops", type=int, default=5, help="iterations for the per-launch timing pass (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

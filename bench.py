@@ -35,6 +35,7 @@ SEED_FRAMES, SEED_WEIGHTS = 0, 1
 CLS_BIAS = None   # frozen per-scale default of weights.random_weights
 METRIC = "YOLO11-seg 640x640 frames/s"
 WORKLOAD = "YOLO11n-seg 640x640, batch 64 synthetic uint8 frames per GPU, random-init weights (seed 1)"
+SCALE = "n"       # --scale s: BASELINE.json configs[2] shapes (YOLO11s-seg); not the default bench line
 
 
 def synthetic_frames(n, seed):
@@ -100,12 +101,12 @@ def cpu_oracle_fps(ws, frames, threads, budget_s=12.0, chunk=4, max_frames=64):
     from oracle import yolo11seg as Y
     torch.set_num_threads(threads)
     x = torch.from_numpy(np.concatenate([pre.to_tensor(f) for f in frames[:chunk]]))
-    Y.run_model(ws, x[:1], "n")                                       # warm-up
+    Y.run_model(ws, x[:1], SCALE)                                       # warm-up
     done, t0 = 0, time.perf_counter()
     while True:
         i = done % len(frames)
         x = torch.from_numpy(np.concatenate([pre.to_tensor(f) for f in frames[i:i + chunk]]))
-        Y.run_model(ws, x, "n")
+        Y.run_model(ws, x, SCALE)
         done += x.shape[0]
         dt = time.perf_counter() - t0
         if dt >= budget_s or done >= max_frames:
@@ -119,7 +120,7 @@ def run_reference(args, rank, world):
     import torch
 
     from xr_image_segmentation_b200 import weights as W
-    _, ws = W.random_weights("n", SEED_WEIGHTS, CLS_BIAS)
+    _, ws = W.random_weights(SCALE, SEED_WEIGHTS, CLS_BIAS)
     frames = synthetic_frames(8, SEED_FRAMES)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -128,11 +129,11 @@ def run_reference(args, rank, world):
     sample = 8
     x = torch.from_numpy(np.concatenate([pre.to_tensor(f) for f in frames]))
     for _ in range(max(1, min(args.warmup, 2))):
-        Y.run_model(ws, x[:2], "n")
+        Y.run_model(ws, x[:2], SCALE)
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        Y.run_model(ws, x, "n")
+        Y.run_model(ws, x, SCALE)
         times.append(time.perf_counter() - t0)
     t = float(np.sum(times))
     fps = sample * args.steps / t
@@ -155,12 +156,20 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scale", default="n", choices=["n", "s"], help="n = BASELINE configs[1] (default); s = configs[2] shapes")
     ap.add_argument("--e2e-micro-batch", type=int, default=0, help="frames per network pass of the e2e leg (0 = whole batch)")
     ap.add_argument("--latency-iters", type=int, default=300, help="batch-1 latency samples (0 = skip)")
     ap.add_argument("--e2e-depth", type=int, default=4, help="runners of the end-to-end leg (submissions in flight + 1)")
     ap.add_argument("--value-streams", type=int, default=4, help="runners (streams) the device-resident leg alternates over")
     ap.add_argument("--profile-ops", type=int, default=5, help="iterations for the per-launch timing pass (0 = skip)")
     args = ap.parse_args()
+    global SCALE, WORKLOAD, SEED_WEIGHTS
+    if args.scale == "s":
+        SCALE, SEED_WEIGHTS = "s", 3
+        WORKLOAD = (f"YOLO11s-seg 640x640, batch {args.batch} synthetic uint8 frames per GPU, random-init weights (seed 3); "
+                    "BASELINE.json configs[2] per-GPU share")
+    elif args.batch != BATCH:
+        WORKLOAD = WORKLOAD.replace("batch 64", f"batch {args.batch}")
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -191,8 +200,8 @@ def main():
         raise SystemExit("bench.py: no B200 visible and there is no CPU fallback (use --impl reference for the CPU oracle)")
 
     B = args.batch
-    layers, ws = W.random_weights("n", SEED_WEIGHTS, CLS_BIAS)
-    model = I.Model(W.write_pack("n", layers, ws), "n")
+    layers, ws = W.random_weights(SCALE, SEED_WEIGHTS, CLS_BIAS)
+    model = I.Model(W.write_pack(SCALE, layers, ws), SCALE)
     runner = I.Runner(model, device=local_rank, max_batch=B)
     # end-to-end leg: runners used round-robin (inference.PipelinedRunner): the host->device copies and the network passes
     # of the next steps overlap the readback of step i; every step still copies its frames from pinned host memory and
@@ -291,7 +300,7 @@ def main():
             ts.append(time.perf_counter() - t0)
         ts = np.array(ts[20:]) * 1e3
         lat = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "iters": int(len(ts)),
-               "config": "YOLO11n-seg batch 1, 1280x960 RGB host frame -> letterbox 640 -> boxes+labels+bit masks on the host"}
+               "config": f"YOLO11{SCALE}-seg batch 1, 1280x960 RGB host frame -> letterbox 640 -> boxes+labels+bit masks on the host"}
         lib.xrseg_host_free(hf)
         r1.close()
     clocks = sampler.stop() if sampler else None
@@ -331,7 +340,7 @@ def main():
             ridge = tf_sust * 1e12 / (hbm * 1e9)                      # FLOP/B above which a kernel is tensor-bound
             traffic_tab = {}
             tpath = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tpath):
+            if os.path.exists(tpath) and SCALE == "n" and B == BATCH:
                 traffic_tab = json.load(open(tpath)).get("launches", {})
 
             def roof(o):

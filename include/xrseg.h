@@ -225,6 +225,11 @@ int xrseg_debug_fetch(xrseg_runner* r, const char* name, float* dst, size_t cap_
  * box_logits [batch,A,64], cls_logits [batch,A,80], coefs [batch,A,32], protos [batch,32,160*160]. */
 int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
                      const float* protos, int batch);
+/* Same tensors through the PRODUCT kernels: rounded to fp16 on the device (prototypes re-laid out NHWC like the network's),
+ * then the streaming decode filter, NMS and the mma.sync mask assembly of the per-frame path (tools/bench_post.py:
+ * BASELINE.json configs[4], the post-processing stress shape). */
+int xrseg_debug_post_f16(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
+                         const float* protos, int batch);
 /* NMS alone on caller-provided corners [batch,A,4] + scores [batch,A]; results through xrseg_keep_indices. */
 int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, int batch, int num_anchors);
 /* Threshold + crop of caller-provided mask probabilities f32 [n,160,160] with caller boxes (C# convention

@@ -202,7 +202,8 @@ def plan_dump(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("batch,scale", [(1, "n"), (3, "n"), (64, "n"), (64, "s"), (5, "s")])
+@pytest.mark.parametrize("batch,scale", [(1, "n"), (3, "n"), (64, "n"), (64, "s"), (5, "s"), (72, "n"), (256, "n"), (512, "n"),
+                                         (96, "s"), (256, "s")])
 def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
     """Every convolution of the network gets a TMA plan (no thread-gather fallback at 640x640) that fits the SM:
     <= 227 KB shared memory, <= 512 TMEM columns, >= 2 pipeline stages, <= 4 sub-tiles, and covers all its work."""
@@ -219,3 +220,5 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
         assert 1 <= int(f["nsub"]) <= 4 and int(f["items"]) >= 1, l
         if mode != "flat_tma":
             assert int(f["R"]) >= 1, l
+        else:
+            assert int(f["nsub"]) in (1, 2, 4), l   # an item is whole TMA boxes of <= 256 rows (batch > 64 once picked 3)

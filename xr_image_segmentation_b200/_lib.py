@@ -89,6 +89,7 @@ SIGNATURES = {
     "xrseg_profile_ops": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_float), C.c_char_p, _P(C.c_double), _P(C.c_double), C.c_int]),
     "xrseg_debug_fetch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_size_t, _P(C.c_int64)]),
     "xrseg_debug_post": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "xrseg_debug_post_f16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "xrseg_debug_nms": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "xrseg_debug_mask_threshold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "xrseg_debug_conv": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -422,7 +422,8 @@ static inline bool plan_conv_flat_tma_impl(const ConvDesc& d, int num_sms, ConvP
   const int tiles128 = ceil_div(p.flat_rows, 128);
   int nsub = 256 / p.Ntile;
   if (nsub > 4) nsub = 4;
-  if (nsub < 1) nsub = 1;
+  if (nsub == 3) nsub = 2;                         // an item is one or two FULL boxes of <= 256 rows: power-of-two sub-tiles only
+  if (nsub < 1) nsub = 1;                          // (N = 80 at more than 64 frames picked 3: two 256-row boxes into 384 slots)
   while (nsub > 1 && ceil_div(tiles128, nsub) < 8 * num_sms) nsub >>= 1;    // keep >= 8 items per CTA for balance
   for (;; nsub >>= 1) {
     p.nsub = nsub;

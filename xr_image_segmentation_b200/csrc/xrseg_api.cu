@@ -135,6 +135,7 @@ struct xrseg_runner {
   int *o_labels = nullptr, *o_anchor = nullptr, *o_frame = nullptr;
   // debug staging for xrseg_debug_post / xrseg_debug_nms
   float *dbg_box = nullptr, *dbg_cls = nullptr, *dbg_coef = nullptr, *dbg_proto = nullptr, *dbg_corners = nullptr;
+  __half* dbg_h16 = nullptr;        // xrseg_debug_post_f16: [box | cls | coef | protos NHWC] rounded to fp16
   // host mirrors
   int *h_counts = nullptr, *h_offsets = nullptr;   // pinned
   int batch = 0;                   // batch of the scheduled / finished run
@@ -502,7 +503,8 @@ void net_scale_src(xrseg_runner* r, ScaleSrc<__half> (&s)[3]) {
   fill_scale_src<__half>(s, r->arena, r->arena, r->arena, net.fh, net.fw, bstr, pitch, off);
 }
 
-void dense_scale_src(xrseg_runner* r, ScaleSrc<float> (&s)[3], const float* box, const float* cls, const float* coef) {
+template <typename T>
+void dense_scale_src(xrseg_runner* r, ScaleSrc<T> (&s)[3], const T* box, const T* cls, const T* coef) {
   Net& net = *r->net;
   long bstr[3][3], off[3][3];
   int pitch[3][3];
@@ -516,7 +518,12 @@ void dense_scale_src(xrseg_runner* r, ScaleSrc<float> (&s)[3], const float* box,
     }
     a_off += net.fh[i] * net.fw[i];
   }
-  fill_scale_src<float>(s, box, cls, coef, net.fh, net.fw, bstr, pitch, off);
+  fill_scale_src<T>(s, box, cls, coef, net.fh, net.fw, bstr, pitch, off);
+}
+
+__global__ void f32_to_f16_kernel(const float* src, __half* dst, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2half_rn(src[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -588,7 +595,9 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     Launch L;
     L.name = "post.nms_reduce";
     L.fn = [rp, words, nb](cudaStream_t st) {
-      launch_k(nms_reduce_kernel, nb, 128, static_cast<size_t>(words) * 65 * sizeof(unsigned long long), st, rp);
+      const size_t smem = static_cast<size_t>(words) * 128 * sizeof(unsigned long long);
+      if (words <= 32) launch_k(nms_reduce_kernel<1>, nb, 128, smem, st, rp);
+      else launch_k(nms_reduce_kernel<5>, nb, 128, smem, st, rp);
     };
     out.push_back(std::move(L));
   }
@@ -704,6 +713,7 @@ int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st, int part = 
   // kernels keep only part of the SMs busy; this lets independent ones share the GPU.
   const bool fork = part == 2 && r->side[0] != nullptr && r->cfg.use_cuda_graph && !branches_disabled();
   bool used[5] = {};
+  static const bool dbg_sync = getenv("XRSEG_DBG_SYNC") != nullptr;
   for (size_t i = lo; i < hi; ++i) {
     Launch& L = (*ls)[i];
     cudaStream_t s = st;
@@ -720,6 +730,10 @@ int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st, int part = 
         }
     }
     L.fn(s);
+    if (dbg_sync && !r->cfg.use_cuda_graph) {            // XRSEG_DBG_SYNC=1 (no graph): name the launch that faults
+      const cudaError_t e = cudaStreamSynchronize(s);
+      XR_CHECK(e == cudaSuccess, "launch %zu '%s' (frames %d..%d): %s", i, L.name.c_str(), b0, b0 + nb - 1, cudaGetErrorString(e));
+    }
     if (fork && L.signal_tag) XR_CUDA(cudaEventRecord(r->ev_tag[L.signal_tag - 3], s));
   }
   XR_CUDA(cudaGetLastError());
@@ -896,7 +910,7 @@ xrseg_runner::~xrseg_runner() {
   }
   void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx, d_filt_list,
                   d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,
-                  o_probs, o_labels, o_anchor, o_frame, dbg_box, dbg_cls, dbg_coef, dbg_proto, dbg_corners};
+                  o_probs, o_labels, o_anchor, o_frame, dbg_box, dbg_cls, dbg_coef, dbg_proto, dbg_corners, dbg_h16};
   for (void* b : bufs) cudaFree(b);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_offsets) cudaFreeHost(h_offsets);
@@ -1051,7 +1065,8 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     c3k2_prepare_device();
     XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     XR_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 65 * 8));
+    XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 128 * 8));
+    XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 128 * 8));
 
     r->mb = c.micro_batch > 0 ? std::min(c.micro_batch, c.max_batch) : c.max_batch;
     const char* fuse_env = getenv("XRSEG_FUSE");
@@ -1505,8 +1520,8 @@ int xrseg_debug_fetch(xrseg_runner* r, const char* name, float* dst, size_t cap_
   return XRSEG_OK;
 }
 
-int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
-                     const float* protos, int batch) {
+static int debug_post_impl(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
+                           const float* protos, int batch, bool as_f16) {
   if (!r || !box_logits || !cls_logits || !coefs || !protos || batch < 1 || batch > r->cfg.max_batch)
     return XRSEG_ERR_INVALID;
   try {
@@ -1527,11 +1542,54 @@ int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_
     r->batch = batch;
     r->timed = false;
     reset_counters(r, batch, st);
-    ScaleSrc<float> src[3];
-    dense_scale_src(r, src, r->dbg_box, r->dbg_cls, r->dbg_coef);
     std::vector<Launch> ls;
-    add_post_launches<float, true>(r, 0, batch, src, r->dbg_proto, static_cast<long>(NM) * PROTO_PIX, 0, true, false, ls);
-    for (Launch& l : ls) l.fn(st);
+    if (as_f16) {
+      // the product kernels (fp16 head tensors, NHWC prototypes, mma.sync mask assembly) on the caller's tensors
+      const size_t nb_ = batch * A * 64, nc_ = batch * A * NC, nm_ = batch * A * NM, np_ = static_cast<size_t>(batch) * NM * PROTO_PIX;
+      if (!r->dbg_h16) r->dbg_h16 = dev_alloc<__half>(B * (A * (64 + NC + NM) + static_cast<size_t>(NM) * PROTO_PIX));
+      __half *hb = r->dbg_h16, *hc = hb + B * A * 64, *hm = hc + B * A * NC, *hp = hm + B * A * NM;
+      f32_to_f16_kernel<<<grid_for(static_cast<long>(nb_)), 256, 0, st>>>(r->dbg_box, hb, static_cast<long>(nb_));
+      f32_to_f16_kernel<<<grid_for(static_cast<long>(nc_)), 256, 0, st>>>(r->dbg_cls, hc, static_cast<long>(nc_));
+      f32_to_f16_kernel<<<grid_for(static_cast<long>(nm_)), 256, 0, st>>>(r->dbg_coef, hm, static_cast<long>(nm_));
+      nchw_f32_to_nhwc_f16_kernel<<<grid_for(static_cast<long>(np_)), 256, 0, st>>>(r->dbg_proto, hp, batch, NM, 160, 160, NM, NM);
+      ScaleSrc<__half> src[3];
+      dense_scale_src<__half>(r, src, hb, hc, hm);
+      add_post_launches<__half, false>(r, 0, batch, src, hp, static_cast<long>(NM) * PROTO_PIX, NM, true, false, ls);
+    } else {
+      ScaleSrc<float> src[3];
+      dense_scale_src<float>(r, src, r->dbg_box, r->dbg_cls, r->dbg_coef);
+      add_post_launches<float, true>(r, 0, batch, src, r->dbg_proto, static_cast<long>(NM) * PROTO_PIX, 0, true, false, ls);
+    }
+    if (getenv("XRSEG_DBG_TIME")) {
+      // per-launch CUDA-event timing of the post-processing stage on these tensors (tools/bench_post.py): one untimed pass,
+      // counters reset, then every launch between two events on the runner's stream
+      for (Launch& l : ls) l.fn(st);
+      std::vector<cudaEvent_t> ev(ls.size() + 1);
+      for (auto& e : ev) XR_CUDA(cudaEventCreate(&e));
+      reset_counters(r, batch, st);
+      for (size_t i = 0; i < ls.size(); ++i) {
+        XR_CUDA(cudaEventRecord(ev[i], st));
+        ls[i].fn(st);
+      }
+      XR_CUDA(cudaEventRecord(ev[ls.size()], st));
+      XR_CUDA(cudaStreamSynchronize(st));
+      int kept = 0;
+      std::vector<int> kn(batch);
+      XR_CUDA(cudaMemcpy(kn.data(), r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost));
+      for (int v : kn) kept += v;
+      for (size_t i = 0; i < ls.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        double bytes = ls[i].bytes;
+        if (ls[i].name == "post.mask_prob") bytes += static_cast<double>(kept) * PROTO_PIX * sizeof(float);
+        fprintf(stderr, "xrseg_debug_post: %-20s %8.1f us  %8.1f MB  %7.1f GB/s\n", ls[i].name.c_str(), ms * 1e3f, bytes / 1e6,
+                bytes > 0 ? bytes / (ms * 1e6) : 0.0);
+      }
+      fprintf(stderr, "xrseg_debug_post: batch %d, %d detections kept\n", batch, kept);
+      for (auto& e : ev) cudaEventDestroy(e);
+    } else {
+      for (Launch& l : ls) l.fn(st);
+    }
     launch_k(add_frame_base_kernel, batch, 64, 0, st, r->o_frame, r->d_offsets, 0, batch);
     XR_CUDA(cudaGetLastError());
     XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
@@ -1543,6 +1601,15 @@ int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
+}
+
+int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
+                     const float* protos, int batch) {
+  return debug_post_impl(r, box_logits, cls_logits, coefs, protos, batch, false);
+}
+int xrseg_debug_post_f16(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
+                         const float* protos, int batch) {
+  return debug_post_impl(r, box_logits, cls_logits, coefs, protos, batch, true);
 }
 
 int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, int batch, int num_anchors) {

@@ -233,17 +233,19 @@ class Runner:
     # ---- parity / debug ----
     def fetch(self, name: str) -> np.ndarray:
         shp = (C.c_int64 * 4)()
-        cap = 64 * 1024 * 1024
+        cap = max(64, self.max_batch) * 1024 * 1024      # the largest tensor fetched by the tests: protos, 0.82 M floats per frame
         buf = np.empty(cap, np.float32)
         self._ck(self.lib.xrseg_debug_fetch(self.h, name.encode(), buf.ctypes.data, cap, shp))
         shape = [int(s) for s in shp]
         return buf[:int(np.prod(shape))].reshape(shape).copy()
 
-    def debug_post(self, box_logits, cls_logits, coefs, protos):
+    def debug_post(self, box_logits, cls_logits, coefs, protos, f16=False):
+        """Post-processing alone on caller tensors: fp32 bit-exact kernels, or (f16) the product's fp16 kernels."""
         arrs = [np.ascontiguousarray(a, np.float32) for a in (box_logits, cls_logits, coefs, protos)]
         b = arrs[0].shape[0]
         self.batch = b
-        self._ck(self.lib.xrseg_debug_post(self.h, *(a.ctypes.data for a in arrs), b))
+        fn = self.lib.xrseg_debug_post_f16 if f16 else self.lib.xrseg_debug_post
+        self._ck(fn(self.h, *(a.ctypes.data for a in arrs), b))
 
     def debug_nms(self, corners, scores):
         c = np.ascontiguousarray(corners, np.float32)

@@ -395,18 +395,18 @@ struct ReduceParams {
 // (3) kept indices are written with a popcount prefix.  The next block's rows are copied with cp.async meanwhile.
 // (The first version re-read the removed word, the kept counter and the row from shared memory for every candidate:
 // ~480 cycles per candidate, 215 us for the 854 candidates of the post-processing stress configuration.)
-template <int NMS_RW>      // removed words per lane: 1 covers 2048 candidates (the default cap), 5 covers all 8400 anchors
+template <int NMS_RW, int NBUF>   // removed words per lane: 1 covers 2048 candidates (the default cap), 5 all 8400 anchors; NBUF-deep row ring
 __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
   XR_PDL_ENTRY();
-  extern __shared__ unsigned long long rsm[];  // two buffers of 64 rows x words
+  extern __shared__ unsigned long long rsm[];  // NBUF buffers of 64 rows x words
   const int b = blockIdx.x;
   const int n = p.n_cand[b];
   const int nw = (n + 63) / 64;
   const int lane = threadIdx.x & 31;
   const unsigned long long* gmask = p.mask + static_cast<long>(b) * p.max_cand * p.words;
-  auto stage = [&](int blk) {                   // rows [64 blk, 64 blk + 64) x words [blk, nw) -> buffer blk & 1
-    unsigned long long* dst = rsm + static_cast<size_t>(blk & 1) * 64 * p.words;
-    const int rows = min(64, n - 64 * blk), span = nw - blk;
+  auto stage = [&](int blk) {                   // rows [64 blk, 64 blk + 64) x words [blk, nw) -> buffer blk % NBUF
+    unsigned long long* dst = rsm + static_cast<size_t>(blk % NBUF) * 64 * p.words;
+    const int rows = blk < nw ? min(64, n - 64 * blk) : 0, span = nw - blk;   // past the end: an empty group keeps the count uniform
     for (int i = threadIdx.x; i < rows * span; i += blockDim.x) {
       const int r = i / span, w = blk + i - r * span;
       const unsigned long long* src = gmask + static_cast<long>(64 * blk + r) * p.words + w;
@@ -418,13 +418,13 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
 #pragma unroll
   for (int j = 0; j < NMS_RW; ++j) remv[j] = 0ull;
   int kept = 0;
-  if (nw > 0) stage(0);
+  for (int k = 0; k < NBUF - 1; ++k) stage(k);
   for (int blk = 0; blk < nw; ++blk) {
-    cp_async_wait<0>();
-    __syncthreads();                            // block blk is in shared memory; buffer (blk + 1) & 1 is free again
-    if (blk + 1 < nw) stage(blk + 1);
+    cp_async_wait<NBUF - 2>();                  // groups are committed in block order: block blk has landed
+    __syncthreads();                            // ... for every thread's copies; the buffer of block blk - 1 is free again
+    stage(blk + NBUF - 1);
     if (threadIdx.x < 32) {
-      const unsigned long long* chunk = rsm + static_cast<size_t>(blk & 1) * 64 * p.words;
+      const unsigned long long* chunk = rsm + static_cast<size_t>(blk % NBUF) * 64 * p.words;
       const int rows = min(64, n - 64 * blk);
       unsigned long long own = 0ull;            // removed word of this block
 #pragma unroll
@@ -436,13 +436,12 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
       const int id_lo = lane < rows ? sidx[lane] : 0, id_hi = lane + 32 < rows ? sidx[lane + 32] : 0;
       unsigned long long keepmask = 0ull;
       const unsigned long long* diag = chunk + blk;   // every lane reads the same word: one broadcast load per row, independent
-#pragma unroll 16                                   // of the loop-carried `cur`, so the loads run ahead of the decision chain
-      for (int r = 0; r < 64; ++r) {
+#pragma unroll                                      // of the loop-carried `cur`, so the loads run ahead of the decision chain
+      for (int r = 0; r < 64; ++r) {             // (fully unrolled: shifts by immediates)
         const unsigned long long d = diag[r * p.words];
-        if (r < rows && !((cur >> r) & 1ull)) {
-          keepmask |= 1ull << r;
-          cur |= d;
-        }
+        const bool take = r < rows && !((cur >> r) & 1ull);     // branch-free: a branch would sink the load under it and
+        keepmask |= take ? (1ull << r) : 0ull;                  // put a shared-memory round trip into every step of the chain
+        cur |= take ? d : 0ull;
       }
       // kept indices in selection order
 #pragma unroll
@@ -461,9 +460,11 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
         const int w = lane + 32 * j;
         if (w > blk && w < nw) {
           unsigned long long acc = 0ull;
-#pragma unroll 16
-          for (int r = 0; r < 64; ++r)
-            if ((keepmask >> r) & 1ull) acc |= chunk[r * p.words + w];
+#pragma unroll
+          for (int r = 0; r < 64; ++r) {
+            const unsigned long long row = chunk[r * p.words + w];   // rows past `rows` hold stale words: masked by keepmask
+            acc |= ((keepmask >> r) & 1ull) ? row : 0ull;
+          }
           remv[j] |= acc;
         }
       }

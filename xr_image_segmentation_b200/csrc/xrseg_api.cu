@@ -595,9 +595,9 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
     Launch L;
     L.name = "post.nms_reduce";
     L.fn = [rp, words, nb](cudaStream_t st) {
-      const size_t smem = static_cast<size_t>(words) * 128 * sizeof(unsigned long long);
-      if (words <= 32) launch_k(nms_reduce_kernel<1>, nb, 128, smem, st, rp);
-      else launch_k(nms_reduce_kernel<5>, nb, 128, smem, st, rp);
+      const size_t row_block = static_cast<size_t>(words) * 64 * sizeof(unsigned long long);
+      if (words <= 32) launch_k(nms_reduce_kernel<1, 4>, nb, 128, 4 * row_block, st, rp);
+      else launch_k(nms_reduce_kernel<5, 2>, nb, 128, 2 * row_block, st, rp);
     };
     out.push_back(std::move(L));
   }
@@ -1065,8 +1065,8 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     c3k2_prepare_device();
     XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     XR_CUDA(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 128 * 8));
-    XR_CUDA(cudaFuncSetAttribute(nms_reduce_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 128 * 8));
+    XR_CUDA(cudaFuncSetAttribute((nms_reduce_kernel<1, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32 * 64 * 8));
+    XR_CUDA(cudaFuncSetAttribute((nms_reduce_kernel<5, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 132 * 64 * 8));
 
     r->mb = c.micro_batch > 0 ? std::min(c.micro_batch, c.max_batch) : c.max_batch;
     const char* fuse_env = getenv("XRSEG_FUSE");

@@ -599,7 +599,7 @@ __global__ void __launch_bounds__(416) attention_kernel(const AttnParams p) {
 struct StemMmaParams {
   const uint8_t* src; int stride_bytes, bpp;   // [B,H,W,bpp] uint8, rows 4-byte aligned
   __half* out; int out_pitch;                  // [B,H/2,W/2,Cout]
-  const __half* w16;                           // [Cout][12 taps][4] fp16, zero padded
+  const __half* w16;                           // stem_mma_kernel: [Cout][12 taps][4] fp16, zero padded; stem_rows_kernel: [Cout][3][16]
   const float* bias;                           // [Cout]
   int B, H, W;
   float in_scale;                              // 1/255
@@ -740,6 +740,113 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
         if (ox0 + px + 8 < Wo)
           *reinterpret_cast<uint32_t*>(o1 + nt * 8) =
               silu_pack_h2(fmaf(c[nt][2], p.in_scale, bs[nt][0]), fmaf(c[nt][3], p.in_scale, bs[nt][1]));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem, second version for packed RGB frames (the normal case: 16-byte aligned rows, 3 W a multiple of 16).  The first
+// version expanded every RGB pixel of its patch into an RGBX word (~12 instructions per input pixel) and re-loaded its
+// weight fragments for 32 pixels per thread: two thirds of its issue slots went into staging (ncu: issue-bound at
+// 75 %, 145 us for 64 frames).  Here the K axis is (kernel row, 16 consecutive BYTES of the raw image row):
+//   k-step kh covers bytes [6 ox - 3, 6 ox + 13) of image row 2 oy + kh - 1 -- the nine bytes of the three taps
+//   (kw, c) = k, k < 9, followed by seven bytes that meet zero weights.
+// so the patch is staged as RAW bytes (one 16-byte load, four funnel shifts and one 16-byte shared store per 5.3 pixels;
+// the one-byte shift makes every tap window start at an even shared-memory offset) and an A-fragment register is one
+// 16-bit shared load + PRMT + HSUB2 ("0x6400 | byte" = fp16 1024 + byte).  Block = 16 output rows x 64 output columns,
+// a warp owns two rows = eight 16-pixel M-tiles against the same 12 weight-fragment registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int STEM2_ROWS = 16, STEM2_COLS = 64;
+constexpr int STEM2_PR = 2 * STEM2_ROWS + 1;            // patch rows
+constexpr int STEM2_CHUNKS = 26;                        // 16-byte chunks per patch row (13 + 387 bytes -> 416)
+constexpr int STEM2_PITCH = STEM2_CHUNKS * 16;          // shared bytes per patch row
+
+template <int NT>
+__global__ void __launch_bounds__(256) stem_rows_kernel(const StemMmaParams p) {
+  XR_PDL_ENTRY();
+  __shared__ __align__(16) uint8_t patch[STEM2_PR * STEM2_PITCH];
+  const int Ho = p.H >> 1, Wo = p.W >> 1;
+  const int ox0 = blockIdx.x * STEM2_COLS, oy0 = blockIdx.y * STEM2_ROWS, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const uint8_t* img = p.src + static_cast<size_t>(b) * p.H * p.stride_bytes;
+  const int row_bytes = p.W * 3;
+  const int a0 = ((6 * ox0 - 3) & ~15);                // global byte of shared byte 1 of every patch row (may be -16)
+  // weights + bias -> registers: b0 = W[2t, 2t+1][n], b1 = W[2t+8, 2t+9][n] of k-step kh, n = 8 nt + g
+  uint32_t wb[3][NT][2];
+  float bs[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const __half* w = p.w16 + ((nt * 8 + g) * 3 + kh) * 16 + 2 * t;
+      wb[kh][nt][0] = *reinterpret_cast<const uint32_t*>(w);
+      wb[kh][nt][1] = *reinterpret_cast<const uint32_t*>(w + 8);
+    }
+    bs[nt][0] = p.bias[nt * 8 + 2 * t];
+    bs[nt][1] = p.bias[nt * 8 + 2 * t + 1];
+  }
+  // stage the raw patch: shared byte s of row r = image byte a0 + s - 1 of row 2 oy0 - 1 + r (zero outside the image)
+  for (int u = tid; u < STEM2_PR * STEM2_CHUNKS; u += 256) {
+    const int r = u / STEM2_CHUNKS, j = u - r * STEM2_CHUNKS;
+    const int iy = 2 * oy0 - 1 + r;
+    const int off = a0 + 16 * j;                        // first image byte of the 16-byte load
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t prev = 0u;
+    if (iy >= 0 && iy < p.H) {
+      const uint8_t* rowp = img + static_cast<size_t>(iy) * p.stride_bytes;
+      if (off >= 0 && off < row_bytes) v = __ldg(reinterpret_cast<const uint4*>(rowp + off));
+      if (off >= 4 && off - 4 < row_bytes) prev = __ldg(reinterpret_cast<const uint32_t*>(rowp + off - 4));
+    }
+    uint4 o;
+    o.x = __funnelshift_l(prev, v.x, 8);                // shift the byte stream up by one byte
+    o.y = __funnelshift_l(v.x, v.y, 8);
+    o.z = __funnelshift_l(v.y, v.z, 8);
+    o.w = __funnelshift_l(v.z, v.w, 8);
+    *reinterpret_cast<uint4*>(patch + r * STEM2_PITCH + 16 * j) = o;
+  }
+  __syncthreads();
+  auto cvt = [](uint32_t pair) {                        // two bytes -> two fp16 values
+    uint32_t v = __byte_perm(pair, 0x64646464u, 0x4140u);
+    const uint32_t k1024 = 0x64006400u;
+    __half2 r = __hsub2(*reinterpret_cast<__half2*>(&v), *reinterpret_cast<const __half2*>(&k1024));
+    return *reinterpret_cast<uint32_t*>(&r);
+  };
+  // tap window of tile column c starts at shared byte 6 c + 14 (image byte 6 ox - 3, shifted by a0 and the extra byte)
+  const uint32_t lane_off = 6 * g + 14 + 2 * t;
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int orow = 2 * warp + rr, oy = oy0 + orow;
+    const uint8_t* prow = patch + (2 * orow) * STEM2_PITCH + lane_off;
+#pragma unroll
+    for (int mt = 0; mt < STEM2_COLS / 16; ++mt) {
+      float c[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const uint8_t* q = prow + kh * STEM2_PITCH + 96 * mt;   // 16 pixels x 6 bytes per M-tile
+        uint32_t a[4];
+        a[0] = cvt(*reinterpret_cast<const uint16_t*>(q));
+        a[1] = cvt(*reinterpret_cast<const uint16_t*>(q + 48));      // pixel g + 8
+        a[2] = cvt(*reinterpret_cast<const uint16_t*>(q + 8));       // k + 8
+        a[3] = cvt(*reinterpret_cast<const uint16_t*>(q + 56));
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) hmma_16816(c[nt], a, wb[kh][nt][0], wb[kh][nt][1]);
+      }
+      const int px = ox0 + mt * 16 + g;
+      if (oy < Ho) {
+        __half* o0 = p.out + ((static_cast<size_t>(b) * Ho + oy) * Wo + px) * p.out_pitch + 2 * t;
+        __half* o1 = o0 + static_cast<size_t>(8) * p.out_pitch;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {          // (trading halves between lanes for 8-byte stores measured slower: 102 -> 117 us)
+          if (px < Wo)
+            *reinterpret_cast<uint32_t*>(o0 + nt * 8) =
+                silu_pack_h2(fmaf(c[nt][0], p.in_scale, bs[nt][0]), fmaf(c[nt][1], p.in_scale, bs[nt][1]));
+          if (px + 8 < Wo)
+            *reinterpret_cast<uint32_t*>(o1 + nt * 8) =
+                silu_pack_h2(fmaf(c[nt][2], p.in_scale, bs[nt][0]), fmaf(c[nt][3], p.in_scale, bs[nt][1]));
+        }
       }
     }
   }

@@ -38,6 +38,7 @@ struct DevLayer {
   float* w32 = nullptr;
   float* w32_u8 = nullptr;         // stem weights / 255 for the fused uint8 path
   uint2* wfrag = nullptr;          // OP_BNECK: mma.sync B-fragment order (bottleneck.cuh)
+  __half* w16_rows = nullptr;      // stem_rows_kernel weights
 };
 
 // ---- fused Bottleneck (bottleneck.cuh): one instantiation per supported channel triple ---------------------------------
@@ -191,6 +192,12 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
         for (int ci = 0; ci < 3; ++ci)
           for (int t = 0; t < 9; ++t) wt[(static_cast<size_t>(n) * 12 + t) * 4 + ci] = __half(w.w[(static_cast<size_t>(n) * 3 + ci) * 9 + t]);
       d.w16 = dev_upload(wt);
+      std::vector<__half> wr(static_cast<size_t>(co) * 48, __half(0.f));     // [Cout][kh][16]: k = 3 kw + c < 9 for stem_rows_kernel
+      for (int n = 0; n < l.cout; ++n)
+        for (int ci = 0; ci < 3; ++ci)
+          for (int t = 0; t < 9; ++t)
+            wr[(static_cast<size_t>(n) * 3 + t / 3) * 16 + 3 * (t % 3) + ci] = __half(w.w[(static_cast<size_t>(n) * 3 + ci) * 9 + t]);
+      d.w16_rows = dev_upload(wr);
       for (float& v : ws) v = v / 255.0f;
       d.w32_u8 = dev_upload(ws);
     } else if (o.kind == OP_DW) {
@@ -336,9 +343,19 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         mq.out = q.out; mq.out_pitch = q.out_pitch; mq.w16 = r->dl[o.layer].w16; mq.bias = q.bias;
         mq.B = nb; mq.H = o.x.H; mq.W = o.x.W; mq.in_scale = 1.0f / 255.0f;
         const int nt = o.y.Cp / 8;
-        L.fn = [r, p, q, mq, nt, total, smem, smem_u8, nb](cudaStream_t st) {
+        const __half* w16_rows = r->dl[o.layer].w16_rows;
+        static const bool stem_rows_off = [] { const char* e = getenv("XRSEG_STEM_ROWS"); return e && e[0] == '0'; }();
+        L.fn = [r, p, q, mq, nt, total, smem, smem_u8, nb, w16_rows](cudaStream_t st) {
           const bool aligned = (reinterpret_cast<uintptr_t>(r->fused_src) % 4 == 0) && (r->fused_stride % 4 == 0);
-          if (r->fused_src && aligned && (nt == 2 || nt == 4) && r->cfg.conv_impl == XRSEG_CONV_UMMA) {
+          const bool wide = (reinterpret_cast<uintptr_t>(r->fused_src) % 16 == 0) && (r->fused_stride % 16 == 0) &&
+                            (mq.W * 3) % 16 == 0 && r->fused_bpp == 3;
+          if (r->fused_src && wide && !stem_rows_off && (nt == 2 || nt == 4) && r->cfg.conv_impl == XRSEG_CONV_UMMA) {
+            StemMmaParams u = mq;                        // packed RGB rows: raw-byte staging (stem_rows_kernel)
+            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = 3; u.w16 = w16_rows;
+            const dim3 grid(ceil_div(u.W / 2, STEM2_COLS), ceil_div(u.H / 2, STEM2_ROWS), nb);
+            if (nt == 2) launch_k(stem_rows_kernel<2>, grid, 256, 0, st, u);
+            else launch_k(stem_rows_kernel<4>, grid, 256, 0, st, u);
+          } else if (r->fused_src && aligned && (nt == 2 || nt == 4) && r->cfg.conv_impl == XRSEG_CONV_UMMA) {
             StemMmaParams u = mq;
             u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
             const dim3 grid(ceil_div(u.W / 2, 32), ceil_div(u.H / 2, 8), nb);
@@ -906,7 +923,7 @@ xrseg_runner::~xrseg_runner() {
   for (cudaEvent_t e : ev_copy) cudaEventDestroy(e);
   cudaFree(scratch);
   for (DevLayer& d : dl) {
-    cudaFree(d.wpack); cudaFree(d.wfrag); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
+    cudaFree(d.wpack); cudaFree(d.wfrag); cudaFree(d.w16_rows); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
   void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx, d_filt_list,
                   d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,

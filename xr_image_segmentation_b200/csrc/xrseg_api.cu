@@ -466,10 +466,10 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
       }
       case OP_UP: {
         UpParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, nb, o.x.H, o.x.W, o.x.Cp};
-        const long total = static_cast<long>(nb) * o.x.H * o.x.W * 4 * (o.x.Cp / 8);
+        const dim3 grid(ceil_div(o.x.W * (o.x.Cp / 8), 256), o.x.H, nb);
         L.name = "upsample2x";
         L.bytes = px_in * o.x.C * 5 * 2;
-        L.fn = [p, total](cudaStream_t st) { launch_k(upsample2x_kernel, grid_for(total), 256, 0, st, p); };
+        L.fn = [p, grid](cudaStream_t st) { launch_k(upsample2x_kernel, grid, 256, 0, st, p); };
         break;
       }
       case OP_ATTN: {

@@ -20,7 +20,7 @@ full() {  # name regex skip count
 }
 NC=$(grep -c conv_halo_tma gpurun_out/${T}_launches.csv)   # TMA conv launches per pass (launch order = op order)
 echo "conv_halo_tma launches per pass: $NC"
-full stem stem_mma 1 1
+full stem stem_ 1 1                             # stem_rows_kernel (packed RGB) or stem_mma_kernel
 full s2_b1 conv_halo_tma $((NC + 0)) 1         # b1 (3x3 stride 2, parity-plane TMA) of pass 2
 full flat_b2cv1 conv_halo_tma $((NC + 1)) 1    # b2.cv1 (1x1, flat TMA) of pass 2
 full halo_protocv2 conv_halo_tma $((NC + NC - 2)) 1  # proto.cv2 (3x3 stride 1, halo TMA) of pass 2

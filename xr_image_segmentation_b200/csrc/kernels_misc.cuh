@@ -766,7 +766,7 @@ constexpr int STEM2_CHUNKS = 26;                        // 16-byte chunks per pa
 constexpr int STEM2_PITCH = STEM2_CHUNKS * 16;          // shared bytes per patch row
 
 template <int NT>
-__global__ void __launch_bounds__(256) stem_rows_kernel(const StemMmaParams p) {
+__global__ void __launch_bounds__(256, NT == 2 ? 5 : 3) stem_rows_kernel(const StemMmaParams p) {
   XR_PDL_ENTRY();
   __shared__ __align__(16) uint8_t patch[STEM2_PR * STEM2_PITCH];
   const int Ho = p.H >> 1, Wo = p.W >> 1;
@@ -821,6 +821,9 @@ __global__ void __launch_bounds__(256) stem_rows_kernel(const StemMmaParams p) {
   for (int rr = 0; rr < 2; ++rr) {
     const int orow = 2 * warp + rr, oy = oy0 + orow;
     const uint8_t* prow = patch + (2 * orow) * STEM2_PITCH + lane_off;
+    const bool row_ok = oy < Ho;
+    // this lane's first output pixel of the row (pixel ox0 + g, channels 2t, 2t + 1)
+    __half* orow_out = p.out + ((static_cast<size_t>(b) * Ho + (row_ok ? oy : 0)) * Wo + ox0 + g) * p.out_pitch + 2 * t;
 #pragma unroll
     for (int mt = 0; mt < STEM2_COLS / 16; ++mt) {
       float c[NT][4];
@@ -837,19 +840,22 @@ __global__ void __launch_bounds__(256) stem_rows_kernel(const StemMmaParams p) {
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) hmma_16816(c[nt], a, wb[kh][nt][0], wb[kh][nt][1]);
       }
+      // values first, then plainly predicated stores (an if-block around the SiLU math costs a BSSY / BSYNC pair per store;
+      // trading halves between lanes for 8-byte stores measured slower: 102 -> 117 us)
       const int px = ox0 + mt * 16 + g;
-      if (oy < Ho) {
-        __half* o0 = p.out + ((static_cast<size_t>(b) * Ho + oy) * Wo + px) * p.out_pitch + 2 * t;
-        __half* o1 = o0 + static_cast<size_t>(8) * p.out_pitch;
+      uint32_t v0[NT], v1[NT];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {          // (trading halves between lanes for 8-byte stores measured slower: 102 -> 117 us)
-          if (px < Wo)
-            *reinterpret_cast<uint32_t*>(o0 + nt * 8) =
-                silu_pack_h2(fmaf(c[nt][0], p.in_scale, bs[nt][0]), fmaf(c[nt][1], p.in_scale, bs[nt][1]));
-          if (px + 8 < Wo)
-            *reinterpret_cast<uint32_t*>(o1 + nt * 8) =
-                silu_pack_h2(fmaf(c[nt][2], p.in_scale, bs[nt][0]), fmaf(c[nt][3], p.in_scale, bs[nt][1]));
-        }
+      for (int nt = 0; nt < NT; ++nt) {
+        v0[nt] = silu_pack_h2(fmaf(c[nt][0], p.in_scale, bs[nt][0]), fmaf(c[nt][1], p.in_scale, bs[nt][1]));
+        v1[nt] = silu_pack_h2(fmaf(c[nt][2], p.in_scale, bs[nt][0]), fmaf(c[nt][3], p.in_scale, bs[nt][1]));
+      }
+      uint32_t* o0 = reinterpret_cast<uint32_t*>(orow_out + static_cast<size_t>(mt * 16) * p.out_pitch);
+      uint32_t* o1 = reinterpret_cast<uint32_t*>(orow_out + static_cast<size_t>(mt * 16 + 8) * p.out_pitch);
+      const bool ok0 = row_ok && px < Wo, ok1 = row_ok && px + 8 < Wo;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (ok0) o0[nt * 4] = v0[nt];
+        if (ok1) o1[nt * 4] = v1[nt];
       }
     }
   }

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) bottleneck_mma_kernel(const BneckParams p
       const int y = ty0 - 2 + r, x = tx0 - 2 + col;
       v[k] = make_uint4(0u, 0u, 0u, 0u);
       if (i < TOTAL && y >= 0 && y < p.H && x >= 0 && x < p.W)
-        v[k] = __ldg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(y) * p.W + x) * p.in_pitch + c * 8));
+        v[k] = __ldcg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(y) * p.W + x) * p.in_pitch + c * 8));
     }
 #pragma unroll
     for (int k = 0; k < ITERS; ++k) {
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256) c3k2_mma_kernel(const C3k2Params p) {
       const int y = ty0 - 2 + r, x = tx0 - 2 + col;
       v[k] = make_uint4(0u, 0u, 0u, 0u);
       if (i < TOTAL && y >= 0 && y < p.H && x >= 0 && x < p.W)
-        v[k] = __ldg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(y) * p.W + x) * p.in_pitch + c * 8));
+        v[k] = __ldcg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(y) * p.W + x) * p.in_pitch + c * 8));
     }
 #pragma unroll
     for (int k = 0; k < ITERS; ++k) {

@@ -121,6 +121,28 @@ def test_fused_c3k2_block_vs_torch(lib, case):
     np.testing.assert_allclose(y, ref, atol=6e-3 * max(1.0, float(np.abs(ref).max())), rtol=6e-3)
 
 
+def test_whole_block_c3k2_inside_the_network(lib, monkeypatch):
+    """The opt-in whole-block kernel (XRSEG_FUSE_C3K2=1) inside the captured, PDL-launched pipeline against the default
+    three launches: same b2 output.  (With ld.global.nc window loads it read stale lines under programmatic dependent
+    launch while the stand-alone hook test passed.)"""
+    layers, ws = W.random_weights("n", seed=1)
+    model = I.Model(W.write_pack("n", layers, ws), "n")
+    fr = np.random.default_rng(0).integers(0, 256, (2, 640, 640, 3), dtype=np.uint8)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("XRSEG_FUSE_C3K2", flag)
+        r = I.Runner(model, max_batch=2)
+        for _ in range(2):                               # second pass replays the captured graph
+            r.schedule(fr)
+            r.wait()
+        out[flag] = (r.fetch("b2.cv2"), r.counts().copy(), r.launch_count())
+        r.close()
+    assert out["1"][2] == out["0"][2] - 2
+    ref = out["0"][0]
+    assert np.abs(out["1"][0] - ref).max() <= 4e-3 * max(1.0, float(np.abs(ref).max()))
+    assert out["1"][1].tolist() == out["0"][1].tolist()
+
+
 # ---- whole path on the reference's frames ------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def runner(golden):

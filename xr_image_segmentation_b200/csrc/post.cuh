@@ -177,6 +177,10 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams<T>
     // ---- class sigmoid + max / first argmax (chains 416, 464, 471): like the graph, the maximum is taken over the
     // fp32 PROBABILITIES (two different logits can round to the same probability; the first index then wins).
     const T* cl = s.cls + b * s.cls_bstride + static_cast<long>(al) * s.cls_pitch;
+    // the DFL logits are fetched together with the class logits (one memory round trip instead of two; 128 bytes per listed
+    // anchor are wasted when its exact score misses the threshold)
+    const T* bl = s.box + b * s.box_bstride + static_cast<long>(al) * s.box_pitch;
+    const float l0 = ldf(bl + lane), l1 = ldf(bl + lane + 32);
     float best = -1.f;
     int besti = 0;
     for (int c = lane; c < NC; c += 32) {
@@ -197,28 +201,34 @@ __global__ void __launch_bounds__(256) decode_exact_kernel(const DecodeParams<T>
     }
     if (!(best > p.score_thr)) continue;     // warp-uniform after the reduction
 
-    // ---- DFL (chains 401-406): softmax over 16 bins, expectation with weights 0..15; lane = side
-    float dv = 0.f;
-    if (lane < 4) {
-      const T* bl = s.box + b * s.box_bstride + static_cast<long>(al) * s.box_pitch;
-      float l[16];
-      load16(bl + lane * 16, l);
-      float mx = -3.0e38f;
+    // ---- DFL (chains 401-406): softmax over 16 bins, expectation with weights 0..15.  The 64 bins are spread over the
+    // warp (lane -> bins lane and lane + 32, i.e. sides lane / 16 and 2 + lane / 16, bin lane % 16): the exponentials and
+    // the IEEE divisions run in parallel, the two sums keep the oracle's sequential bin order (every lane of a 16-lane
+    // group replays the additions on shuffled operands).  Four lanes doing 16 expf + 16 divisions each took 2.5x longer.
+    float m0 = l0, m1 = l1;
 #pragma unroll
-      for (int k = 0; k < 16; ++k) mx = fmaxf(mx, l[k]);
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        l[k] = expf(__fsub_rn(l[k], mx));
-        sum = __fadd_rn(sum, l[k]);
-      }
-      float e = 0.f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) e = __fadd_rn(e, __fmul_rn(__fdiv_rn(l[k], sum), static_cast<float>(k)));
-      dv = e;
+    for (int o = 8; o >= 1; o >>= 1) {
+      m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+      m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
     }
-    const float d0 = __shfl_sync(0xffffffffu, dv, 0), d1 = __shfl_sync(0xffffffffu, dv, 1);
-    const float d2 = __shfl_sync(0xffffffffu, dv, 2), d3 = __shfl_sync(0xffffffffu, dv, 3);
+    const float e0 = expf(__fsub_rn(l0, m0)), e1 = expf(__fsub_rn(l1, m1));
+    const int grp = lane & 16;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      sum0 = __fadd_rn(sum0, __shfl_sync(0xffffffffu, e0, grp + k));
+      sum1 = __fadd_rn(sum1, __shfl_sync(0xffffffffu, e1, grp + k));
+    }
+    const float kf = static_cast<float>(lane & 15);
+    const float q0 = __fmul_rn(__fdiv_rn(e0, sum0), kf), q1 = __fmul_rn(__fdiv_rn(e1, sum1), kf);
+    float x0 = 0.f, x1e = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      x0 = __fadd_rn(x0, __shfl_sync(0xffffffffu, q0, grp + k));
+      x1e = __fadd_rn(x1e, __shfl_sync(0xffffffffu, q1, grp + k));
+    }
+    const float d0 = __shfl_sync(0xffffffffu, x0, 0), d1 = __shfl_sync(0xffffffffu, x0, 16);
+    const float d2 = __shfl_sync(0xffffffffu, x1e, 0), d3 = __shfl_sync(0xffffffffu, x1e, 16);
     if (lane != 0) continue;
     // chains 407-415
     const float x1 = __fsub_rn(ax, d0), y1 = __fsub_rn(ay, d1);

@@ -251,6 +251,8 @@ int xrseg_debug_bottleneck(int device, const float* x, int b, int c1, int h, int
 int xrseg_debug_c3k2(int device, const float* x, int b, int cin, int h, int w, int c, int cm, int cout,
                      const float* w_cv1, const float* b_cv1, const float* w_m1, const float* b_m1, const float* w_m2,
                      const float* b_m2, const float* w_cv2, const float* b_cv2, float* y);
+/* Host-only: weight packing of the fused Bottleneck / C3k2 kernels into mma.sync B-fragment order (CPU layout tests). */
+int xrseg_debug_pack_bneck(const float* w, int cin, int cout, int C, int N, int taps, uint32_t* out, size_t cap_words);
 /* Host-side emulation of the UMMA conv kernel's data movement (slot mapping, weight packing, tap shifts)
  * in fp32 -- used by CPU tests to validate index math without a GPU.  NOT a product path. */
 int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const float* wgt, const float* bias,

@@ -222,3 +222,34 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
             assert int(f["R"]) >= 1, l
         else:
             assert int(f["nsub"]) in (1, 2, 4), l   # an item is whole TMA boxes of <= 256 rows (batch > 64 once picked 3)
+
+
+# ---- fused Bottleneck kernel: weight fragment order (host-only) ------------------------------------------------------
+@pytest.mark.parametrize("cin,cout,C,N,taps", [(16, 8, 16, 8, 9), (8, 16, 8, 16, 9), (32, 16, 32, 16, 9), (16, 32, 16, 32, 9),
+                                               (32, 32, 32, 32, 1), (48, 64, 48, 64, 1), (12, 5, 16, 8, 9)])
+def test_bottleneck_weight_fragments(cin, cout, C, N, taps):
+    """pack_bneck_weights (bottleneck.cuh) against the mma.sync m16n8k16 B-fragment definition: word 0 of lane (g, t) of
+    (k-step s, n-tile nt) holds W[16 s + 2 t][8 nt + g] (low half) and W[16 s + 2 t + 1][..]; word 1 the rows + 8;
+    W[k][n] = w[n][c][tap] with k = tap * C + c, zero beyond the real channels and beyond K = taps * C."""
+    import ctypes as C_
+    from xr_image_segmentation_b200 import _lib
+    lib = _lib.load_library()
+    rng = np.random.default_rng(cin * 131 + cout)
+    w = rng.standard_normal((cout, cin, taps)).astype(np.float32)
+    K = taps * C
+    KS, NT = (K + 15) // 16, N // 8
+    out = np.zeros(KS * NT * 64, np.uint32)
+    n = lib.xrseg_debug_pack_bneck(w.ctypes.data, cin, cout, C, N, taps, out.ctypes.data, out.size)
+    assert n == out.size
+    Wm = np.zeros((KS * 16, N), np.float16)
+    for tap in range(taps):
+        Wm[tap * C:tap * C + cin, :cout] = w[:, :, tap].T.astype(np.float16)
+    halves = out.view(np.float16).reshape(KS, NT, 32, 2, 2)          # [s][nt][lane][word][low/high]
+    for lane in range(32):
+        g, t = lane >> 2, lane & 3
+        for word in range(2):
+            for h in range(2):
+                k = 2 * t + 8 * word + h
+                got = halves[:, :, lane, word, h]                     # [KS, NT]
+                exp = Wm.reshape(KS, 16, NT, 8)[:, k, :, g]
+                assert np.array_equal(got, exp), (lane, word, h)

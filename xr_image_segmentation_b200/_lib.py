@@ -97,6 +97,7 @@ SIGNATURES = {
     "xrseg_debug_bottleneck": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "xrseg_debug_c3k2": (C.c_int, [C.c_int, C.c_void_p] + [C.c_int] * 7 + [C.c_void_p] * 9),
+    "xrseg_debug_pack_bneck": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "xrseg_debug_emulate_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "xrseg_extract_points": (C.c_int, [C.c_void_p, _P(DepthParams), C.c_void_p, C.c_void_p, C.c_int, _P(C.c_int)]),

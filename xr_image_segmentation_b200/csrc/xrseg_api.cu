@@ -1957,6 +1957,17 @@ int xrseg_debug_c3k2(int device, const float* x, int b, int cin, int h, int w, i
   return XRSEG_OK;
 }
 
+// Host-only: the B-fragment weight packing of the fused Bottleneck / C3k2 kernels (bottleneck.cuh), for CPU tests of the
+// layout.  w [cout][cin][taps] fp32; out receives ceil(taps*C/16) * (N/8) * 64 words; returns the word count or < 0.
+int xrseg_debug_pack_bneck(const float* w, int cin, int cout, int C, int N, int taps, uint32_t* out, size_t cap_words) {
+  if (!w || !out || cin < 1 || cout < 1 || C < cin || C % 8 || N < cout || N % 8 || (taps != 1 && taps != 9)) return XRSEG_ERR_INVALID;
+  std::vector<uint32_t> f;
+  pack_bneck_weights(w, cin, cout, C, N, f, taps);
+  if (f.size() > cap_words) return XRSEG_ERR_INVALID;
+  memcpy(out, f.data(), f.size() * sizeof(uint32_t));
+  return static_cast<int>(f.size());
+}
+
 // Host emulation of the UMMA kernel's data movement (test infrastructure; fp32; no GPU involved).
 int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const float* wgt, const float* bias, int cout,
                              int k, int stride, int act, int transposed, const float* residual, float* y, int variant) {

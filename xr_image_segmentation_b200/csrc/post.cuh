@@ -395,6 +395,9 @@ struct ReduceParams {
   int* keep_idx;   // [B,max_det] anchor indices in selection order
   int* keep_n;     // [B]
   int* overflow;
+  // exclusive scan of keep_n over the frames [0, scan_upto) of the run -> offsets[scan_upto + 1], done by the block that
+  // finishes last (ticket counter `done`, left at zero again): replaces a separate one-thread launch
+  const int* keep_n_all; int* offsets; int* done; int scan_upto;
 };
 
 // One warp resolves a frame, 64 candidates (one bitmask row block) at a time; the other three warps only help to stage
@@ -480,19 +483,31 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
       }
     }
   }
-  if (threadIdx.x == 0) p.keep_n[b] = min(kept, p.max_det);
-}
-
-// exclusive scan of keep_n over frames -> offsets[B+1]
-__global__ void offsets_kernel(const int* keep_n, int B, int* offsets) {
-  XR_PDL_ENTRY();
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int acc = 0;
-    for (int b = 0; b < B; ++b) {
-      offsets[b] = acc;
-      acc += keep_n[b];
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    p.keep_n[b] = min(kept, p.max_det);
+    __threadfence();
+    const int ticket = atomicAdd(p.done, 1);
+    s_last = ticket == static_cast<int>(gridDim.x) - 1;
+    if (s_last) *p.done = 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < 32) {
+    __threadfence();
+    int base = 0;
+    for (int f0 = 0; f0 < p.scan_upto; f0 += 32) {
+      const int f = f0 + lane;
+      const int v = f < p.scan_upto ? __ldcg(p.keep_n_all + f) : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (f < p.scan_upto) p.offsets[f] = base + incl - v;
+      base += __shfl_sync(0xffffffffu, incl, 31);
     }
-    offsets[B] = acc;
+    if (lane == 0) p.offsets[p.scan_upto] = base;
   }
 }
 

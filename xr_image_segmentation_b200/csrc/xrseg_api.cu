@@ -131,7 +131,7 @@ struct xrseg_runner {
   int *d_cand_count = nullptr, *d_n_cand = nullptr, *d_sorted_idx = nullptr, *d_overflow = nullptr, *d_filt_list = nullptr;
   float4* d_sorted_corners = nullptr;
   unsigned long long* d_mask = nullptr;
-  int *d_keep_idx = nullptr, *d_keep_n = nullptr, *d_offsets = nullptr;
+  int *d_keep_idx = nullptr, *d_keep_n = nullptr, *d_offsets = nullptr, *d_done = nullptr;
   float *o_boxes = nullptr, *o_coefs = nullptr, *o_scores = nullptr, *o_probs = nullptr;
   int *o_labels = nullptr, *o_anchor = nullptr, *o_frame = nullptr;
   // debug staging for xrseg_debug_post / xrseg_debug_nms
@@ -595,6 +595,7 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
   rp.keep_idx = r->d_keep_idx + static_cast<long>(b0) * r->max_det;
   rp.keep_n = r->d_keep_n + b0;
   rp.overflow = r->d_overflow;
+  rp.keep_n_all = r->d_keep_n; rp.offsets = r->d_offsets; rp.done = r->d_done; rp.scan_upto = b0 + nb;
   const int words = r->words;
   {
     Launch L;
@@ -616,15 +617,6 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
       if (words <= 32) launch_k(nms_reduce_kernel<1, 4>, nb, 128, 4 * row_block, st, rp);
       else launch_k(nms_reduce_kernel<5, 2>, nb, 128, 2 * row_block, st, rp);
     };
-    out.push_back(std::move(L));
-  }
-  {
-    Launch L;
-    L.name = "post.offsets";
-    const int* keep_n = r->d_keep_n;
-    int* offsets = r->d_offsets;
-    const int upto = b0 + nb;
-    L.fn = [keep_n, offsets, upto](cudaStream_t st) { launch_k(offsets_kernel, 1, 32, 0, st, keep_n, upto, offsets); };
     out.push_back(std::move(L));
   }
   if (!src[0].coef) return;  // NMS-only debug path
@@ -777,6 +769,7 @@ void* ensure_scratch(xrseg_runner* r, size_t bytes) {
 void reset_counters(xrseg_runner* r, int batch, cudaStream_t st) {
   XR_CUDA(cudaMemsetAsync(r->d_cand_count, 0, sizeof(int) * 2 * r->cfg.max_batch, st));   // candidate + filter counters
   XR_CUDA(cudaMemsetAsync(r->d_overflow, 0, sizeof(int), st));
+  XR_CUDA(cudaMemsetAsync(r->d_done, 0, sizeof(int), st));                                // nms_reduce's ticket (self-resetting; belt and braces)
 }
 
 int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, int h, int stride_bytes, int fmt,
@@ -926,7 +919,7 @@ xrseg_runner::~xrseg_runner() {
     cudaFree(d.wpack); cudaFree(d.wfrag); cudaFree(d.w16_rows); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
   void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx, d_filt_list,
-                  d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, o_boxes, o_coefs, o_scores,
+                  d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, d_done, o_boxes, o_coefs, o_scores,
                   o_probs, o_labels, o_anchor, o_frame, dbg_box, dbg_cls, dbg_coef, dbg_proto, dbg_corners, dbg_h16};
   for (void* b : bufs) cudaFree(b);
   if (h_counts) cudaFreeHost(h_counts);
@@ -1145,6 +1138,8 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     r->d_keep_idx = dev_alloc<int>(static_cast<size_t>(B) * r->max_det);
     r->d_keep_n = dev_alloc<int>(B);
     r->d_offsets = dev_alloc<int>(B + 1);
+    r->d_done = dev_alloc<int>(1);
+    XR_CUDA(cudaMemset(r->d_done, 0, sizeof(int)));
     const size_t cap = static_cast<size_t>(B) * r->max_det;
     r->o_boxes = dev_alloc<float>(cap * 4);
     r->o_labels = dev_alloc<int>(cap);

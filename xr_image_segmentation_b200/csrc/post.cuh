@@ -525,27 +525,31 @@ struct GatherParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(128) gather_kernel(const GatherParams<T> p) {
+__global__ void __launch_bounds__(256) gather_kernel(const GatherParams<T> p) {
   XR_PDL_ENTRY();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // grid = (16, frames) x 8 warps: the 128 warps of a frame stride over its detections (a grid of frames x max_det warps launched
+  // thousands of blocks that found nothing to do at ~10 detections per frame)
   const int lane = threadIdx.x & 31;
-  const int b = warp / p.max_det;
-  const int i = warp - b * p.max_det;
-  if (b >= p.B || i >= p.keep_n[b]) return;
-  const int a = p.keep_idx[static_cast<long>(b) * p.max_det + i];
-  const int o = p.offsets[b] + i;
-  int si = 0;
-  if (a >= p.s[1].a_off) si = 1;
-  if (a >= p.s[2].a_off) si = 2;
-  const ScaleSrc<T>& s = p.s[si];
-  const float c = ldf(s.coef + b * s.coef_bstride + static_cast<long>(a - s.a_off) * s.coef_pitch + lane);
-  p.out_coefs[static_cast<long>(o) * NM + lane] = c;
-  if (lane < 4) p.out_boxes[static_cast<long>(o) * 4 + lane] = p.boxes[(static_cast<long>(b) * p.A + a) * 4 + lane];
-  if (lane == 0) {
-    p.out_labels[o] = p.labels[static_cast<long>(b) * p.A + a];
-    p.out_scores[o] = p.scores[static_cast<long>(b) * p.A + a];
-    p.out_anchor[o] = a;
-    p.out_frame[o] = b;
+  const int b = blockIdx.y;
+  const int n = p.keep_n[b];
+  const int base = p.offsets[b];
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+    const int a = p.keep_idx[static_cast<long>(b) * p.max_det + i];
+    const int o = base + i;
+    int si = 0;
+    if (a >= p.s[1].a_off) si = 1;
+    if (a >= p.s[2].a_off) si = 2;
+    const ScaleSrc<T>& s = p.s[si];
+    const float c = ldf(s.coef + b * s.coef_bstride + static_cast<long>(a - s.a_off) * s.coef_pitch + lane);
+    p.out_coefs[static_cast<long>(o) * NM + lane] = c;
+    if (lane < 4) p.out_boxes[static_cast<long>(o) * 4 + lane] = p.boxes[(static_cast<long>(b) * p.A + a) * 4 + lane];
+    if (lane == 0) {
+      p.out_labels[o] = p.labels[static_cast<long>(b) * p.A + a];
+      p.out_scores[o] = p.scores[static_cast<long>(b) * p.A + a];
+      p.out_anchor[o] = a;
+      p.out_frame[o] = b;
+    }
   }
 }
 

@@ -632,8 +632,7 @@ void add_post_launches(xrseg_runner* r, int b0, int nb, const ScaleSrc<T> (&src)
   {
     Launch L;
     L.name = "post.gather";
-    const int blocks = ceil_div(nb * r->max_det * 32, 128);
-    L.fn = [gp, blocks](cudaStream_t st) { launch_k(gather_kernel<T>, blocks, 128, 0, st, gp); };
+    L.fn = [gp, nb](cudaStream_t st) { launch_k(gather_kernel<T>, dim3(16, nb), 256, 0, st, gp); };
     out.push_back(std::move(L));
   }
   if (protos) {

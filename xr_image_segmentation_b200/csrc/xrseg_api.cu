@@ -333,7 +333,7 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         const size_t smem = (37 * o.y.Cp) * sizeof(float);
         L.name = l.name;
         L.flops = 2.0 * px_out * l.cout * 27;
-        L.bytes = px_in * 8 + px_out * l.cout * 2;
+        L.bytes = px_in * 3 + px_out * l.cout * 2;     // the fused stem reads the caller's uint8 RGB frame (3 B per pixel)
         StemU8Params q{};
         q.out = ptr_of(r, o.y); q.out_pitch = o.y.pitch; q.w = r->dl[o.layer].w32_u8; q.bias = r->dl[o.layer].bias;
         q.B = nb; q.H = o.x.H; q.W = o.x.W; q.Cout = o.y.Cp;

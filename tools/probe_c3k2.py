@@ -1,6 +1,11 @@
-import os, sys
+"""Developer probe: the opt-in whole-block C3k2 kernel (XRSEG_FUSE_C3K2=1) inside the network against the default path,
+and the debug hook on the network's own tensors."""
+import os
+import sys
+
 import numpy as np
-sys.path.insert(0, "/root/repo")
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from xr_image_segmentation_b200 import inference as I, weights as W
 layers, ws = W.random_weights("n", 1, None)
 model = I.Model(W.write_pack("n", layers, ws), "n")

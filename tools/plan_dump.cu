@@ -7,6 +7,17 @@ using namespace xrseg;
 int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 64;
   const int scale = argc > 2 ? argv[2][0] : 'n';
+  if (argc > 3 && argv[3][0] == 'o') {   // "ops": the fused launch list (one line per network launch) instead of the conv plans
+    Net fused(scale, B, 640, true, true, argc > 4 && argv[4][0] == '1');
+    const char* kind_name[] = {"stem", "conv", "dw", "sppf", "up", "attn", "bneck", "c3k2"};
+    for (const Op& o : fused.ops) {
+      std::string name = o.layer >= 0 ? fused.layers[o.layer].name : std::string("-");
+      if (o.kind == OP_CONV && o.layer2 >= 0) name += "+" + fused.layers[o.layer2].name;
+      printf("op %-6s %-28s in %3dx%-3d c%-3d out c%-3d res %d branch %d\n", kind_name[o.kind], name.c_str(), o.x.H, o.x.W, o.x.Cp,
+             o.y.Cp, o.has_res ? 1 : 0, o.branch);
+    }
+    return 0;
+  }
   Net net(scale, B, 640, true, false);   // Bottleneck fusion off: every convolution keeps its own plan
   const char* mode_name[] = {"gather", "halo", "halo_tma", "flat_tma", "s2_tma"};
   long total_smem_small = 0;

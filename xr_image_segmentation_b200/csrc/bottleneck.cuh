@@ -224,17 +224,10 @@ __global__ void __launch_bounds__(256) bottleneck_mma_kernel(const BneckParams p
               v[nt] = *reinterpret_cast<const uint32_t*>(&s2);
             }
           }
-          // lanes t and t^1 trade halves of an n-tile pair: even t keeps 4 channels of tile 2j, odd t of tile 2j+1 (8-byte stores)
-          __half* dst = row + ox * p.out_pitch;
+          uint32_t* dst = reinterpret_cast<uint32_t*>(row + ox * p.out_pitch + 2 * t);
 #pragma unroll
-          for (int j = 0; j < NT2 / 2; ++j) {
-            const uint32_t send = (t & 1) ? v[2 * j] : v[2 * j + 1];
-            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
-            if (ok) {
-              if (t & 1) *reinterpret_cast<uint2*>(dst + (2 * j + 1) * 8 + 2 * (t - 1)) = make_uint2(recv, v[2 * j + 1]);
-              else *reinterpret_cast<uint2*>(dst + (2 * j) * 8 + 2 * t) = make_uint2(v[2 * j], recv);
-            }
-          }
+          for (int nt = 0; nt < NT2; ++nt)
+            if (ok) dst[nt * 4] = v[nt];
         }
       }
     }

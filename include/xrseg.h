@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define XRSEG_ABI_VERSION 1
+#define XRSEG_ABI_VERSION 2
 
 typedef enum xrseg_status {
   XRSEG_OK = 0,
@@ -34,12 +34,20 @@ typedef enum xrseg_status {
   XRSEG_ERR_WEIGHTS = -4,      /* weight pack does not match the requested topology */
   XRSEG_ERR_STATE = -5,        /* call not valid in the current runner state (e.g. peek before schedule) */
   XRSEG_ERR_NO_DETECTIONS = -6,/* run finished with N == 0 (the reference's Error state, IEE:453-454) */
-  XRSEG_ERR_CAPACITY = -7      /* destination buffer too small */
+  XRSEG_ERR_CAPACITY = -7      /* destination buffer too small, or (from xrseg_poll / xrseg_wait / the first accessor of a
+                                  finished run) the run hit max_candidates / max_det: results are truncated, see
+                                  xrseg_overflow */
 } xrseg_status;
 
 typedef enum xrseg_pixel_format {
   XRSEG_FMT_RGB8 = 0,          /* 3 bytes per pixel, top row first */
-  XRSEG_FMT_RGBA8 = 1          /* 4 bytes per pixel, alpha ignored (Quest passthrough WebCamTexture) */
+  XRSEG_FMT_RGBA8 = 1,         /* 4 bytes per pixel, alpha ignored (Quest passthrough WebCamTexture) */
+  /* Row order.  By default the FIRST row in memory is the TOP row of the picture (what the Python mirror's ToTensor and
+   * every test feed).  OR this flag into `fmt` when the buffer is bottom-up, i.e. memory row 0 is the BOTTOM of the
+   * picture -- Unity's Texture2D.GetPixels32 / WebCamTexture.GetPixels32 / GetRawTextureData order (texture origin
+   * bottom-left), which TextureConverter.ToTensor (IEE:370) turns into a top-first tensor internally.  The stem and the
+   * resample kernel then read image row y from memory row h-1-y; nothing is copied. */
+  XRSEG_FMT_BOTTOM_UP = 0x100
 } xrseg_pixel_format;
 
 typedef enum xrseg_resize_mode {
@@ -67,9 +75,14 @@ typedef struct xrseg_config {
   const void* weights;         /* host memory: the sample's .sentis asset bytes (yolo11n-seg-sentis.sentis, loaded like
                                   ModelLoader.Load, IEE:382) or an XRSW weight pack (weights.py) */
   size_t weights_bytes;
-  float iou_threshold;         /* 0 -> 0.43 */
-  float score_threshold;       /* 0 -> 0.301 */
-  float mask_threshold;        /* 0 -> 0.5 */
+  float iou_threshold;         /* 0 -> 0.43 (or the value baked into a .sentis asset) */
+  float score_threshold;       /* 0 -> 0.301 (ditto) */
+  float mask_threshold;        /* 0 -> 0.5 (IEE:32 _confidenceThreshold); negative -> exactly 0 */
+  /* DEVIATION from the reference, which runs NonMaxSuppression unlimited (maxOutputBoxesPerClass = -1,
+   * IEModelEditorConverter.cs:76): device buffers are sized by these two caps.  A run that exceeds either is NOT silently
+   * truncated: xrseg_poll / xrseg_wait (or the first accessor) return XRSEG_ERR_CAPACITY once, xrseg_overflow() tells
+   * which cap was hit, and the truncated results stay readable.  max_candidates = 8400 and max_det = 8400 reproduce the
+   * unlimited behaviour exactly (at 8.9 MB of IoU bitmask and 860 MB of mask probabilities per frame of max_batch). */
   int32_t max_det;             /* per-frame cap on kept detections, 0 -> 300 */
   int32_t max_candidates;      /* per-frame cap on score-filtered candidates entering NMS, 0 -> 2048 */
   int32_t resize_mode;         /* xrseg_resize_mode */
@@ -116,6 +129,8 @@ typedef struct xrseg_mask_params {
   float screen_w, screen_h;    /* Screen.width/height used by ParseBoxes / DrawBoxes */
   int32_t image_w, image_h;    /* imageWidth/imageHeight argument of DrawMask / DrawSingleMask */
   int32_t first, count;        /* detection range over the compacted batch; count <= 0 -> all */
+  float threshold;             /* mask-probability threshold (IEM:104 _confidenceThreshold): 0 -> the runner's
+                                  mask_threshold; negative -> exactly 0 */
 } xrseg_mask_params;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -129,7 +144,9 @@ int xrseg_abi_version(void);
 /* ---- per-frame path ------------------------------------------------------------------------- */
 /* ↔ TextureConverter.ToTensor(tex,640,640,3) + Worker.ScheduleIterable(input) (IEE:370-371).
  * `frames` is HOST memory: batch images of h x w pixels, `stride_bytes` per row, image i at
- * frames + i*h*stride_bytes.  Asynchronous: returns after enqueueing copy + preprocess + forward + post. */
+ * frames + i*h*stride_bytes.  `fmt` = xrseg_pixel_format, optionally | XRSEG_FMT_BOTTOM_UP (row-order contract above:
+ * without the flag memory row 0 is the top of the picture).  Asynchronous: returns after enqueueing copy + preprocess +
+ * forward + post. */
 int xrseg_schedule(xrseg_runner* r, const uint8_t* frames, int w, int h, int stride_bytes, int fmt, int batch);
 /* Same with frames already resident in device memory (no host->device copy). */
 int xrseg_schedule_device(xrseg_runner* r, const uint8_t* d_frames, int w, int h, int stride_bytes, int fmt, int batch);
@@ -139,6 +156,9 @@ int xrseg_poll(xrseg_runner* r);
 int xrseg_wait(xrseg_runner* r);
 /* Per-frame detection counts of the finished run (n ints, n = scheduled batch). */
 int xrseg_counts(xrseg_runner* r, int32_t* counts, int cap);
+/* Capacity flags of the finished run: bit 0 = a frame had more score-filtered candidates than max_candidates,
+ * bit 1 = a frame kept more boxes than max_det (0 = the results are exactly the unlimited NMS of the reference). */
+int xrseg_overflow(xrseg_runner* r);
 /* ↔ Worker.PeekOutput(i) (IEE:426): idx 0 boxes f32 [N,4] cx,cy,w,h; 1 labels i32 [N]; 2 coefs f32 [N,32];
  * 3 mask probabilities f32 [N,160,160].  Rows in NMS (descending score) order per frame. */
 int xrseg_peek_output(xrseg_runner* r, int idx, xrseg_tensor_view* view);
@@ -217,47 +237,8 @@ int xrseg_sync(xrseg_runner* r);
  * its label, flops[i] / bytes[i] its algorithmic work.  Returns the number of launches. */
 int xrseg_profile_ops(xrseg_runner* r, int iters, float* ms, char* names, double* flops, double* bytes, int cap);
 
-/* ---- parity / debug entry points (used by tests only) --------------------------------------- */
-/* Copy a named intermediate activation of the last run to host as f32 NCHW [batch,C,H,W].
- * names: "p3","p4","p5","box_logits","cls_logits","coefs","protos","input" and every layer name. */
-int xrseg_debug_fetch(xrseg_runner* r, const char* name, float* dst, size_t cap_floats, int64_t* shape4);
-/* Run ONLY the post-processing stage on caller-provided fp32 head tensors (the oracle's own tensors):
- * box_logits [batch,A,64], cls_logits [batch,A,80], coefs [batch,A,32], protos [batch,32,160*160]. */
-int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
-                     const float* protos, int batch);
-/* Same tensors through the PRODUCT kernels: rounded to fp16 on the device (prototypes re-laid out NHWC like the network's),
- * then the streaming decode filter, NMS and the mma.sync mask assembly of the per-frame path (tools/bench_post.py:
- * BASELINE.json configs[4], the post-processing stress shape). */
-int xrseg_debug_post_f16(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
-                         const float* protos, int batch);
-/* NMS alone on caller-provided corners [batch,A,4] + scores [batch,A]; results through xrseg_keep_indices. */
-int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, int batch, int num_anchors);
-/* Threshold + crop of caller-provided mask probabilities f32 [n,160,160] with caller boxes (C# convention
- * boxes, 4 floats each) -- the bit-exact leg of IEMasker. */
-int xrseg_debug_mask_threshold(xrseg_runner* r, const float* probs, const float* boxes, int n, int image_w,
-                               int image_h, float thr, uint8_t* out);
-/* One convolution through the selected engine: x f32 NCHW [b,cin,h,w], w f32 [cout,cin/g,k,k] (or
- * [cin,cout,k,k] when transposed), optional residual f32 NCHW; y f32 NCHW out. */
-int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h, int w, const float* wgt,
-                     const float* bias, int cout, int k, int stride, int groups, int act, int transposed,
-                     const float* residual, float* y, int variant);
-/* The fused Bottleneck kernel (Conv3x3+SiLU -> Conv3x3+SiLU (+ x), graph chains X.m0.cv1 / X.m0.cv2 of the C3k2 blocks,
- * SURVEY.md Appendix A) on caller tensors: x f32 NCHW [b,c1,h,w], w1 [cm,c1,3,3], w2 [c2,cm,3,3]; y f32 NCHW out.
- * Channel triples: 16-8-16 and 32-16-32 (after padding). */
-int xrseg_debug_bottleneck(int device, const float* x, int b, int c1, int h, int w, const float* w1, const float* b1,
-                           int cm, const float* w2, const float* b2, int c2, int residual, float* y);
-/* The whole-block C3k2 kernel (graph chains X.cv1, X.m0.cv1, X.m0.cv2, X.cv2 in one launch; built for the n-scale b2
- * block: 32 -> [16|16] -> 8 -> 16 -> 64 channels) on caller tensors, fp32 NCHW on the host. */
-int xrseg_debug_c3k2(int device, const float* x, int b, int cin, int h, int w, int c, int cm, int cout,
-                     const float* w_cv1, const float* b_cv1, const float* w_m1, const float* b_m1, const float* w_m2,
-                     const float* b_m2, const float* w_cv2, const float* b_cv2, float* y);
-/* Host-only: weight packing of the fused Bottleneck / C3k2 kernels into mma.sync B-fragment order (CPU layout tests). */
-int xrseg_debug_pack_bneck(const float* w, int cin, int cout, int C, int N, int taps, uint32_t* out, size_t cap_words);
-/* Host-side emulation of the UMMA conv kernel's data movement (slot mapping, weight packing, tap shifts)
- * in fp32 -- used by CPU tests to validate index math without a GPU.  NOT a product path. */
-int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const float* wgt, const float* bias,
-                             int cout, int k, int stride, int act, int transposed, const float* residual,
-                             float* y, int variant);
+/* The parity / probe hooks used by tests/ and tools/ (xrseg_debug_*) are NOT part of this library: they are declared in
+ * xrseg_debug.h and exported only by libxrseg_debug.so, a second build of the same sources with -DXRSEG_DEBUG_API. */
 
 #ifdef __cplusplus
 }

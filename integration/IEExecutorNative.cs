@@ -29,7 +29,9 @@ public class IEExecutorNative : MonoBehaviour
     [StructLayout(LayoutKind.Sequential)]
     struct NativeBox { public float centerX, centerY, width, height; public int labelId, frame; }
     [StructLayout(LayoutKind.Sequential)]
-    struct MaskParams { public uint structSize; public int mode, boxConvention; public float screenW, screenH; public int imageW, imageH, first, count; }
+    struct MaskParams { public uint structSize; public int mode, boxConvention; public float screenW, screenH; public int imageW, imageH, first, count; public float threshold; }
+    const int FmtRgba8 = 1, FmtBottomUp = 0x100;   // xrseg_pixel_format
+    const int ErrCapacity = -7;
 
     [DllImport(Lib)] static extern int xrseg_create(ref Config cfg, out IntPtr runner);
     [DllImport(Lib)] static extern void xrseg_destroy(IntPtr runner);
@@ -87,11 +89,14 @@ public class IEExecutorNative : MonoBehaviour
             if (_pixels.IsCreated) _pixels.Dispose();
             _pixels = new NativeArray<Color32>(tex.width * tex.height, Allocator.Persistent);
         }
-        _pixels.CopyFrom(tex.GetPixels32());            // RGBA8, stretched to 640x640 on the GPU like ToTensor
+        // GetPixels32 returns rows BOTTOM-UP (texture origin bottom-left); XRSEG_FMT_BOTTOM_UP makes the library read image
+        // row y from memory row h-1-y, which is what TextureConverter.ToTensor does internally.  RGBA8, stretched to 640x640
+        // on the GPU like ToTensor.
+        _pixels.CopyFrom(tex.GetPixels32());
         _texW = tex.width; _texH = tex.height;
         unsafe
         {
-            int rc = xrseg_schedule(_runner, (IntPtr)_pixels.GetUnsafeReadOnlyPtr(), _texW, _texH, _texW * 4, /*RGBA8*/ 1, 1);
+            int rc = xrseg_schedule(_runner, (IntPtr)_pixels.GetUnsafeReadOnlyPtr(), _texW, _texH, _texW * 4, FmtRgba8 | FmtBottomUp, 1);
             _state = rc < 0 ? State.Error : State.Running;
         }
     }
@@ -102,7 +107,8 @@ public class IEExecutorNative : MonoBehaviour
         {
             int st = xrseg_poll(_runner);               // never blocks the frame loop
             if (st == 0) return;
-            _state = st < 0 ? State.Error : State.Success;
+            if (st == ErrCapacity) Debug.LogWarning("xrseg: " + Marshal.PtrToStringAnsi(xrseg_last_error(_runner)));   // truncated, still usable
+            _state = st < 0 && st != ErrCapacity ? State.Error : State.Success;
         }
         if (_state == State.Success) ProcessResult();
         if (_state == State.Error) _state = State.Idle; // retry on the next trigger, like CleanupResources
@@ -128,7 +134,7 @@ public class IEExecutorNative : MonoBehaviour
     // IEMasker.DrawSingleMask's pixel loop for detection `index`, computed on the GPU
     public unsafe bool FetchMask(int index)
     {
-        var mp = new MaskParams { structSize = (uint)Marshal.SizeOf<MaskParams>(), mode = 0, boxConvention = 0, screenW = Screen.width, screenH = Screen.height, imageW = _texW, imageH = _texH, first = index, count = 1 };
+        var mp = new MaskParams { structSize = (uint)Marshal.SizeOf<MaskParams>(), mode = 0, boxConvention = 0, screenW = Screen.width, screenH = Screen.height, imageW = _texW, imageH = _texH, first = index, count = 1, threshold = 0f /* the runner's _confidenceThreshold */ };
         fixed (byte* dst = TargetMask) return xrseg_masks(_runner, ref mp, (IntPtr)dst, (UIntPtr)TargetMask.Length) == 1;
     }
 

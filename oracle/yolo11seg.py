@@ -54,10 +54,11 @@ def silu(x):
 class _ConvFeed:
     """Hands out (w, b) pairs in canonical order and applies the convolution."""
 
-    def __init__(self, weights=None, record=None):
+    def __init__(self, weights=None, record=None, trace=None):
         self.weights = weights
         self.i = 0
         self.record = record  # list to append layer specs to (trace mode)
+        self.trace = trace    # dict: layer name -> output tensor of that convolution (+ activation), for per-layer parity sweeps
 
     def __call__(self, x, cout, k=1, s=1, act=True, groups=1, transposed=False, name=""):
         cin = x.shape[1]
@@ -79,7 +80,10 @@ class _ConvFeed:
         else:
             assert tuple(w.shape) == (cout, cin // groups, k, k), (name, tuple(w.shape), (cout, cin // groups, k, k))
             y = F.conv2d(x, w, b, stride=s, padding=k // 2, groups=groups)
-        return silu(y) if act else y
+        y = silu(y) if act else y
+        if self.trace is not None:
+            self.trace[name] = y
+        return y
 
 
 def _bottleneck(x, conv, c_mid, c_out, name):
@@ -267,9 +271,10 @@ def random_weights(scale: str, seed: int, cls_bias: float | None = None, gain: f
 # full pipeline
 # --------------------------------------------------------------------------------------
 @torch.no_grad()
-def run_raw(weights, images: torch.Tensor, scale: str = "n", taps=None):
+def run_raw(weights, images: torch.Tensor, scale: str = "n", taps=None, trace=None):
+    """trace: optional dict filled with every convolution's output by layer name."""
     sp = make_spec(scale)
-    feed = _ConvFeed(weights=weights)
+    feed = _ConvFeed(weights=weights, trace=trace)
     out = forward_raw(images.float(), feed, sp, taps)
     assert feed.i == len(weights), "unused weights"
     return out

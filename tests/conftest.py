@@ -17,10 +17,18 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def lib():
+    """libxrseg.so: the product library (include/xrseg.h only)."""
     from xr_image_segmentation_b200 import _lib
-    if not os.path.exists(_lib.library_path()):
+    if not os.path.exists(_lib.library_path()) or not os.path.exists(_lib.library_path(True)):
         _lib.build_library()
     return _lib.load_library()
+
+
+@pytest.fixture(scope="session")
+def dlib(lib):
+    """libxrseg_debug.so: the same sources + the parity hooks of include/xrseg_debug.h."""
+    from xr_image_segmentation_b200 import _lib
+    return _lib.load_library(True)
 
 
 @pytest.fixture(scope="session")

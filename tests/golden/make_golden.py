@@ -33,6 +33,9 @@ SENTIS = f"{REF}/Assets/Resources/Model/yolo11n-seg-sentis.sentis"
 IMAGES = {
     "coco139": f"{REF}/Assets/Resources/Images/000000000139.jpg",
     "coco632": f"{REF}/Assets/Resources/Images/000000000632.jpg",
+    "coco2006": f"{REF}/Assets/Resources/Images/000000002006.jpg",
+    "coco4495": f"{REF}/Assets/Resources/Images/000000004495.jpg",
+    "coco7108": f"{REF}/Assets/Resources/Images/000000007108.jpg",
     "bus": f"{REF}/bus.png",
 }
 SCREEN = (1920.0, 1080.0)   # a Screen.width/height for the C# box conventions

@@ -16,16 +16,24 @@ from xr_image_segmentation_b200 import _lib, inference as I, sharding as S, weig
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-def test_exports_every_declared_symbol(lib):
-    hdr = open(os.path.join(ROOT, "include", "xrseg.h")).read()
-    declared = set(re.findall(r"\b(xrseg_[a-z0-9_]+)\s*\(", hdr))
-    declared -= {"xrseg_class_name"}          # mentioned in a comment only
-    assert len(declared) >= 25
-    for name in sorted(declared):
-        assert hasattr(lib, name), f"{name} declared in include/xrseg.h but not exported"
-        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.xrseg_abi_version() == 1
-    assert C.sizeof(_lib.Config) == 96 or C.sizeof(_lib.Config) > 0
+def _declared(header):
+    hdr = open(os.path.join(ROOT, "include", header)).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)                  # declarations only, not names mentioned in comments
+    return set(re.findall(r"\b(xrseg_[a-z0-9_]+)\s*\(", hdr))
+
+
+def test_exports_every_declared_symbol(lib, dlib):
+    product, debug = _declared("xrseg.h"), _declared("xrseg_debug.h")
+    assert len(product) >= 28 and len(debug) >= 11 and not (product & debug)
+    assert product == set(_lib.PRODUCT_SIGNATURES) and debug == set(_lib.DEBUG_SIGNATURES)
+    for name in sorted(product):
+        assert hasattr(lib, name), f"{name} declared in include/xrseg.h but not exported by libxrseg.so"
+        assert hasattr(dlib, name), f"{name} missing from libxrseg_debug.so"
+    for name in sorted(debug):
+        assert hasattr(dlib, name), f"{name} declared in include/xrseg_debug.h but not exported by libxrseg_debug.so"
+        assert not hasattr(lib, name), f"the product library exports the debug hook {name}"
+    assert lib.xrseg_abi_version() == dlib.xrseg_abi_version() == _lib.ABI_VERSION == 2
+    assert C.sizeof(_lib.Config) == 104 and C.sizeof(_lib.MaskParams) == 40
 
 
 @pytest.mark.parametrize("scale", ["n", "s"])
@@ -84,7 +92,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES)
-def test_umma_conv_index_math_emulation(lib, case):
+def test_umma_conv_index_math_emulation(dlib, case):
     """Host emulation (fp32) of the tcgen05 kernel's packing / slot mapping / tap shifts / epilogue scatter."""
     B, cin, cout, h, wd, k, s, act, tr, useres, variant = case
     rng = np.random.default_rng(hash(case) % 2**32)
@@ -102,7 +110,7 @@ def test_umma_conv_index_math_emulation(lib, case):
         res = rng.standard_normal(tuple(ref.shape), dtype=np.float32)
         ref = ref + torch.from_numpy(res)
     y = np.zeros(tuple(ref.shape), np.float32)
-    rc = lib.xrseg_debug_emulate_conv(x.ctypes.data, B, cin, h, wd, w.ctypes.data, b.ctypes.data, cout, k, s, act, int(tr),
+    rc = dlib.xrseg_debug_emulate_conv(x.ctypes.data, B, cin, h, wd, w.ctypes.data, b.ctypes.data, cout, k, s, act, int(tr),
                                       res.ctypes.data if res is not None else None, y.ctypes.data, variant)
     assert rc == 0, lib.xrseg_last_error(None)
     np.testing.assert_allclose(y, ref.numpy(), atol=2e-5, rtol=1e-5)
@@ -255,7 +263,7 @@ def test_bottleneck_weight_fragments(cin, cout, C, N, taps):
     W[k][n] = w[n][c][tap] with k = tap * C + c, zero beyond the real channels and beyond K = taps * C."""
     import ctypes as C_
     from xr_image_segmentation_b200 import _lib
-    lib = _lib.load_library()
+    lib = _lib.load_library(True)
     rng = np.random.default_rng(cin * 131 + cout)
     w = rng.standard_normal((cout, cin, taps)).astype(np.float32)
     K = taps * C

@@ -12,7 +12,7 @@ from oracle import preprocess as pre
 from oracle import yolo11seg as Y
 
 REF_SENTIS = "/root/reference/Assets/Resources/Model/yolo11n-seg-sentis.sentis"
-NAMES = ["coco139", "coco632", "bus"]
+NAMES = ["coco139", "coco632", "coco2006", "coco4495", "coco7108", "bus"]   # all six sample frames of the reference
 
 
 @pytest.fixture(scope="module")

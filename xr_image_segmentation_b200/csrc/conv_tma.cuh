@@ -644,6 +644,10 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
 }
 
 // ---- the kernel --------------------------------------------------------------------------------------------------
+// PROBE = true (libxrseg_debug.so only, tools/probe_tma.py): per-role clock64() counters (p.dbg_clk) and the p.dbg_skip
+// switches (1 = no MMAs, 2 = no stores, 4 = no TMA loads, 8 = software-pipelined epilogue).  The product instantiation
+// contains none of it.
+template <bool PROBE>
 __global__ void __launch_bounds__(TMA_THREADS, 2)
 conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ TmapSet tmaps) {
   const CUtensorMap& tmap = tmaps.m[0];
@@ -714,7 +718,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const uint32_t b_stride = p.sw ? static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023) : static_cast<uint32_t>(p.b_stage_bytes);
       pdl_wait();   // the weights above are constants; the activations below are the previous kernels' output
       int it = 0;
-      long long t_wait = 0, t0;
+      long long t_wait = 0, t0 = 0;
       const bool flat = p.mode == MODE_FLAT_TMA;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int tile = p.n_tiles == 1 ? w : (w >> 1);
@@ -723,10 +727,12 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         const int y0 = (tile - b * p.tpi) * p.R;
         for (int ks = 0; ks < p.nks; ++ks, ++it) {
           const int slot = it % p.S;
-          t0 = clock64();
+          if (PROBE) t0 = clock64();
           if (it >= p.S) mbar_wait(&empty[slot], static_cast<uint32_t>((it / p.S) - 1) & 1u);
-          t_wait += clock64() - t0;
-          if (p.dbg_skip & 4) { mbar_arrive(&full[slot]); continue; }
+          if (PROBE) {
+            t_wait += clock64() - t0;
+            if (p.dbg_skip & 4) { mbar_arrive(&full[slot]); continue; }
+          }
           mbar_arrive_expect_tx(&full[slot], a_tx + (p.b_resident ? 0u : static_cast<uint32_t>(p.b_stage_bytes)));
           const uint32_t a_dst = a_u32 + slot * p.a_stage_bytes;
           if (p.mode == MODE_S2_TMA) {
@@ -758,7 +764,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           }
         }
       }
-      if (p.dbg_clk) p.dbg_clk[blockIdx.x * 12 + 0] = t_wait;
+      if (PROBE && p.dbg_clk) p.dbg_clk[blockIdx.x * 12 + 0] = t_wait;
     }
   } else if (warp < TMA_FIRST_EPI_WARP) {
     // ======================================= MMA issuers =========================================
@@ -782,27 +788,27 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const uint32_t b_stride_sw = static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023);
       const uint32_t layout = p.sw == 3 ? 2u : (p.sw == 2 ? 4u : 6u);
       const uint64_t hi_sw = static_cast<uint64_t>(((8u * rb) >> 4) | (1u << 14) | (layout << 29)) << 32;
-      const bool mma_on = !(p.dbg_skip & 1);
-      long long t_start = clock64(), t_bres, t_tempty = 0, t_full = 0, t_issue = 0, t_fence = 0, t_commit = 0, t0;
+      const bool mma_on = !PROBE || !(p.dbg_skip & 1);
+      long long t_start = 0, t_bres = 0, t_tempty = 0, t_full = 0, t_issue = 0, t_fence = 0, t_commit = 0, t0 = 0;
+      if (PROBE) t_start = clock64();
       if (p.b_resident) mbar_wait(bres, 0);
-      t_bres = clock64() - t_start;
+      if (PROBE) t_bres = clock64() - t_start;
       int it = 0, tcount = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
         const int buf = tcount % nbuf;
         const int use = tcount / nbuf;
-        t0 = clock64();
+        if (PROBE) t0 = clock64();
         if (use >= 1) mbar_wait(&tempty[buf], static_cast<uint32_t>(use - 1) & 1u);
-        t_tempty += clock64() - t0;
+        if (PROBE) t_tempty += clock64() - t0;
         tc_fence_after();
         const uint32_t d_base = tmem_base + static_cast<uint32_t>(buf * p.nsub * p.Ntile);
         for (int ks = 0; ks < p.nks; ++ks, ++it) {
           const int slot = it % p.S;
-          t0 = clock64();
+          if (PROBE) t0 = clock64();
           mbar_wait(&full[slot], static_cast<uint32_t>(it / p.S) & 1u);
-          t_full += clock64() - t0;
-          t0 = clock64();
+          if (PROBE) { t_full += clock64() - t0; t0 = clock64(); }
           tc_fence_after();
-          t_fence += clock64() - t0;
+          if (PROBE) { t_fence += clock64() - t0; t0 = clock64(); }
           const uint32_t a_base = a_u32 + slot * p.a_stage_bytes;
           if (p.sw) {
             // swizzled operands: row = K-block of cb channels (rb bytes); tap = row shift; k16 step = +32 bytes.
@@ -837,7 +843,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
               umma_commit(&empty[slot]);
             }
             __syncwarp();
-            t_issue += clock64() - t0;
+            if (PROBE) t_issue += clock64() - t0;
             continue;
           }
           const uint32_t b_base = b_u32 + (p.b_resident ? ks : slot) * p.b_stage_bytes;
@@ -867,7 +873,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         }
         if (elect_one()) umma_commit(&tfull[buf]);
       }
-      if (p.dbg_clk && lane == 0 && warp == 1) {
+      if (PROBE && p.dbg_clk && lane == 0 && warp == 1) {
         p.dbg_clk[blockIdx.x * 12 + 1] = t_bres;
         p.dbg_clk[blockIdx.x * 12 + 2] = t_tempty;
         p.dbg_clk[blockIdx.x * 12 + 3] = t_full;
@@ -883,7 +889,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
     const int half = ew >> 2;
     int tcount = 0;
-    long long e_wait = 0, e_work = 0, t0;
+    long long e_wait = 0, e_work = 0, t0 = 0;
     pdl_wait();   // before the first residual read / output store
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
       const int tile = p.n_tiles == 1 ? w : (w >> 1);
@@ -892,10 +898,9 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const int y0 = (tile - b * p.tpi) * p.R;
       const int buf = tcount % nbuf;
       const int use = tcount / nbuf;
-      t0 = clock64();
+      if (PROBE) t0 = clock64();
       mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
-      e_wait += clock64() - t0;
-      t0 = clock64();
+      if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
       tc_fence_after();
       // Work units of this item: (sub-tile u, 16-column chunk c), unit index k = u * nch + c.  The two warp halves take
       // alternating units (so thin layers with a single chunk per sub-tile still use all eight warps), and the TMEM load
@@ -927,13 +932,13 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
           pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
         }
-        if (valid && !(p.dbg_skip & 2)) {
+        if (valid && !(PROBE && (p.dbg_skip & 2))) {
           const int n = n_tile * p.Ntile + c * 16;
           __half* dst = (p.split_n && n >= p.split_n) ? p.out2 + pix * p.out2_pitch + (n - p.split_n) : p.out + pix * p.out_pitch + n;
           epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr, dst);
         }
       };
-      if (!(p.dbg_skip & 8) || p.transposed) {
+      if (!PROBE || !(p.dbg_skip & 8) || p.transposed) {
         // default: per sub-tile the two warp halves take alternating 16-column chunks; with an odd chunk count the
         // starting chunk alternates with the sub-tile, so single-chunk layers (N = 16) still use all eight warps
         for (int u = 0; u < p.nsub; ++u) {
@@ -951,7 +956,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
             pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
           }
-          valid = valid && !(p.dbg_skip & 2);
+          valid = valid && !(PROBE && (p.dbg_skip & 2));
           int tb = 0, th = 0, tw = 0;
           if (p.transposed) {                      // 2x2 stride-2 ConvTranspose: input pixel (image, h, w) of this row
             const int m = static_cast<int>(pix);
@@ -1001,9 +1006,9 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
-      e_work += clock64() - t0;
+      if (PROBE) e_work += clock64() - t0;
     }
-    if (p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
+    if (PROBE && p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
       p.dbg_clk[blockIdx.x * 12 + 6] = e_wait;
       p.dbg_clk[blockIdx.x * 12 + 7] = e_work;
     }
@@ -1018,11 +1023,20 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
 }
 
 static inline void conv_tma_prepare_device() {
-  XR_CUDA(cudaFuncSetAttribute(conv_halo_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
+  XR_CUDA(cudaFuncSetAttribute(conv_halo_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
+#ifdef XRSEG_DEBUG_API
+  XR_CUDA(cudaFuncSetAttribute(conv_halo_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
+#endif
 }
 
 static inline void launch_conv_halo_tma(const ConvParams& p, const TmapSet& maps, cudaStream_t stream) {
-  launch_k(conv_halo_tma_kernel, p.grid, TMA_THREADS, p.smem_bytes, stream, p, maps);
+#ifdef XRSEG_DEBUG_API
+  if (p.dbg_skip || p.dbg_clk) {   // probe instantiation: only reachable through xrseg_debug_conv
+    launch_k(conv_halo_tma_kernel<true>, p.grid, TMA_THREADS, p.smem_bytes, stream, p, maps);
+    return;
+  }
+#endif
+  launch_k(conv_halo_tma_kernel<false>, p.grid, TMA_THREADS, p.smem_bytes, stream, p, maps);
 }
 static inline void launch_conv_halo_tma(const ConvParams& p, const CUtensorMap& map, cudaStream_t stream) {
   TmapSet t{};

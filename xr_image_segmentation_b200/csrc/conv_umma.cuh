@@ -59,6 +59,13 @@ __host__ __device__ __forceinline__ int fd_div(const FastDiv& f, int n) {
 #endif
 }
 
+// profiling switches of the probe builds (libxrseg_debug.so); constant false in the product library
+#ifdef XRSEG_DEBUG_API
+#define XR_DBG_SKIP(p, bit) (((p).dbg_skip & (bit)) != 0)
+#else
+#define XR_DBG_SKIP(p, bit) false
+#endif
+
 struct ConvParams {
   const __half* in;
   __half* out;
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
 
         if (p.mode == MODE_GATHER) {
           const int kelem = (ks * 8 + gc) * 8;
-          if (kelem < p.K_total && !(p.dbg_skip & 4)) {
+          if (kelem < p.K_total && !XR_DBG_SKIP(p, 4)) {
             if (fast1x1) {
               // A is the activation matrix itself: row m, channels kelem..kelem+7
 #pragma unroll
@@ -543,7 +550,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
             if (kj > 4) kj = 4;
             uint32_t a_lo = a_lo0, b_lo = b_lo0;
             for (int j = 0; j < kj; ++j) {
-              if (elect_one() && !(p.dbg_skip & 1)) umma_f16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | a_lo, (static_cast<uint64_t>(desc_hi) << 32) | b_lo,
+              if (elect_one() && !XR_DBG_SKIP(p, 1)) umma_f16(d_tmem, (static_cast<uint64_t>(desc_hi) << 32) | a_lo, (static_cast<uint64_t>(desc_hi) << 32) | b_lo,
                        p.idesc, acc);
               acc = 1;
               a_lo += 2 * lbo_a16;
@@ -620,7 +627,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
           co = n - pos * p.Cout;
           pix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
         }
-        if (valid && !(p.dbg_skip & 2))
+        if (valid && !XR_DBG_SKIP(p, 2))
           epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + co : nullptr,
                            p.out + pix * p.out_pitch + co);
       }

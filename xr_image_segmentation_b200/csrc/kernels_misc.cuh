@@ -27,6 +27,7 @@ struct PreParams {
   int mode;         // 0 stretch, 1 letterbox
   float scale_x, scale_y;
   int left, top, nw, nh;   // letterbox placement
+  int flip;                // 1: the frame's rows are stored bottom-up (Unity GetPixels32 / texture origin bottom-left)
 };
 
 __global__ void preprocess_kernel(const PreParams p) {
@@ -53,8 +54,8 @@ __global__ void preprocess_kernel(const PreParams p) {
     int x1 = x0 + 1, y1 = y0 + 1;
     x0 = min(max(x0, 0), p.sw - 1); x1 = min(max(x1, 0), p.sw - 1);
     y0 = min(max(y0, 0), p.sh - 1); y1 = min(max(y1, 0), p.sh - 1);
-    const uint8_t* r0 = img + static_cast<size_t>(y0) * p.stride_bytes;
-    const uint8_t* r1 = img + static_cast<size_t>(y1) * p.stride_bytes;
+    const uint8_t* r0 = img + static_cast<size_t>(p.flip ? p.sh - 1 - y0 : y0) * p.stride_bytes;
+    const uint8_t* r1 = img + static_cast<size_t>(p.flip ? p.sh - 1 - y1 : y1) * p.stride_bytes;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       const float a = static_cast<float>(r0[x0 * p.bpp + c]), bq = static_cast<float>(r0[x1 * p.bpp + c]);
@@ -150,6 +151,7 @@ struct StemU8Params {
   const float* w;      // [9][4][Cout], already divided by 255
   const float* bias;
   int B, H, W, Cout;
+  int flip;            // rows stored bottom-up
 };
 
 __global__ void __launch_bounds__(256) stem_u8_kernel(const StemU8Params p) {
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(256) stem_u8_kernel(const StemU8Params p) {
     const int iy = iy0 + py, ix = ix0 + px;
     uint32_t v = 0;
     if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {
-      const uint8_t* s = img + static_cast<size_t>(iy) * p.stride_bytes + ix * p.bpp;
+      const uint8_t* s = img + static_cast<size_t>(p.flip ? p.H - 1 - iy : iy) * p.stride_bytes + ix * p.bpp;
       v = s[0] | (s[1] << 8) | (s[2] << 16);
     }
     reinterpret_cast<uint32_t*>(patch)[i] = v;
@@ -606,6 +608,7 @@ struct StemMmaParams {
   const float* bias;                           // [Cout]
   int B, H, W;
   float in_scale;                              // 1/255
+  int flip;                                    // rows stored bottom-up (image row y lives at memory row H-1-y)
 };
 
 constexpr int STEM_PW = 65, STEM_PH = 17, STEM_RAW_WORDS = 56, STEM_RAW_CHUNKS = 14;
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
       const int iy = iy0 + r, ix = ix0 + c;
       uint32_t v = 0;
       if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-        v = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(iy) * p.stride_bytes + ix * 4) & 0x00FFFFFFu;
+        v = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(p.flip ? p.H - 1 - iy : iy) * p.stride_bytes + ix * 4) & 0x00FFFFFFu;
       patch[i] = v;
     }
   } else {
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
         const int off = a0 + 16 * j;
         if (iy >= 0 && iy < p.H && off < p.W * 3 && off < (c_hi + 1) * 3)
           *reinterpret_cast<uint4*>(&raw[r][4 * j]) =
-              *reinterpret_cast<const uint4*>(img + static_cast<size_t>(iy) * p.stride_bytes + off);
+              *reinterpret_cast<const uint4*>(img + static_cast<size_t>(p.flip ? p.H - 1 - iy : iy) * p.stride_bytes + off);
       }
     } else {
       const int nwords = ((c_hi + 1) * 3 - a0 + 3) >> 2;
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(256) stem_mma_kernel(const StemMmaParams p) {
         const int r = i / STEM_RAW_WORDS, j = i - r * STEM_RAW_WORDS;
         const int iy = iy0 + r;
         if (j < nwords && iy >= 0 && iy < p.H)
-          raw[r][j] = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(iy) * p.stride_bytes + a0 + 4 * j);
+          raw[r][j] = *reinterpret_cast<const uint32_t*>(img + static_cast<size_t>(p.flip ? p.H - 1 - iy : iy) * p.stride_bytes + a0 + 4 * j);
       }
     }
     __syncthreads();
@@ -797,7 +800,7 @@ __global__ void __launch_bounds__(256, NT == 2 ? 5 : 3) stem_rows_kernel(const S
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     uint32_t prev = 0u;
     if (iy >= 0 && iy < p.H) {
-      const uint8_t* rowp = img + static_cast<size_t>(iy) * p.stride_bytes;
+      const uint8_t* rowp = img + static_cast<size_t>(p.flip ? p.H - 1 - iy : iy) * p.stride_bytes;
       if (off >= 0 && off < row_bytes) v = __ldg(reinterpret_cast<const uint4*>(rowp + off));
       if (off >= 4 && off - 4 < row_bytes) prev = __ldg(reinterpret_cast<const uint32_t*>(rowp + off - 4));
     }

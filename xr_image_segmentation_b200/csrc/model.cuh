@@ -427,7 +427,7 @@ static inline void xrsw_load(const void* data, size_t bytes, const std::vector<L
     XR_CHECK(static_cast<int>(r.cout) == l.cout && static_cast<int>(r.cin_g) == cin_g && static_cast<int>(r.k) == l.k &&
                  static_cast<int>(r.stride) == l.stride && static_cast<int>(r.groups) == l.groups &&
                  static_cast<int>(r.transposed) == l.transposed && static_cast<int>(r.act) == l.act,
-             "layer %u (%s) does not match topology layer %s", i, r.name, l.name.c_str());
+             "layer %u (%.32s) does not match topology layer %s", i, r.name, l.name.c_str());
     const size_t nw = static_cast<size_t>(l.cout) * cin_g * l.k * l.k;
     const size_t nb = l.cout;
     const size_t esz = r.dtype == 0 ? 4 : 1;

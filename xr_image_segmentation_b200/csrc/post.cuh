@@ -276,7 +276,7 @@ struct SortParams {
   int* sorted_idx;                 // [B,max_cand]
   float4* sorted_corners;          // [B,max_cand]
   int* n_cand;                     // [B] = min(count, max_cand)
-  int* overflow;                   // [1] set when count > max_cand
+  int* overflow;                   // [1] bit 0 set when count > max_cand (bit 1: nms_reduce, kept > max_det)
 };
 
 __global__ void __launch_bounds__(1024) nms_sort_kernel(const SortParams p) {
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(1024) nms_sort_kernel(const SortParams p) {
   const int n = min(cnt, p.max_cand);
   if (threadIdx.x == 0) {
     p.n_cand[b] = n;
-    if (cnt > p.max_cand) atomicExch(p.overflow, 1);
+    if (cnt > p.max_cand) atomicOr(p.overflow, 1);
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int a = static_cast<int>(skeys[i] & 0xFFFFFFFFull);
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(128) nms_reduce_kernel(const ReduceParams p) {
         if ((keepmask >> r) & 1ull) {
           const int k = kept + __popcll(keepmask & ((1ull << r) - 1ull));
           if (k < p.max_det) p.keep_idx[static_cast<long>(b) * p.max_det + k] = half ? id_hi : id_lo;
-          else if (k == p.max_det) atomicExch(p.overflow, 2);
+          else if (k == p.max_det) atomicOr(p.overflow, 2);
         }
       }
       kept += __popcll(keepmask);
@@ -723,23 +723,28 @@ struct BoxOut {
   int label, frame;
 };
 
-// per-frame cap (50 / 200 / none) applied like the C# loops; writes rows compacted again over the batch
-__global__ void boxes_to_screen_kernel(const float* boxes, const int* labels, const int* keep_n, const int* offsets,
-                                       int B, int conv, float sw, float sh, int cap, BoxOut* out, int* out_n) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int w = 0;
-  for (int b = 0; b < B; ++b) {
-    const int n = cap > 0 ? min(keep_n[b], cap) : keep_n[b];
-    for (int i = 0; i < n; ++i) {
-      const int o = offsets[b] + i;
-      const float4 r = box_convention(reinterpret_cast<const float4*>(boxes)[o], conv, sw, sh);
-      out[w].cx = r.x; out[w].cy = r.y; out[w].w = r.z; out[w].h = r.w;
-      out[w].label = labels[o];
-      out[w].frame = b;
-      ++w;
-    }
+// per-frame cap (50 / 200 / none) applied like the C# loops; writes rows compacted again over the batch.
+// One block (one warp) per frame: its output base is the capped count of the frames before it (warp-reduced), then the
+// lanes convert the frame's boxes in parallel.
+__global__ void __launch_bounds__(32) boxes_to_screen_kernel(const float* boxes, const int* labels, const int* keep_n,
+                                                             const int* offsets, int B, int conv, float sw, float sh, int cap,
+                                                             BoxOut* out, int* out_n) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  int base = 0;
+  for (int f = lane; f < b; f += 32) base += cap > 0 ? min(keep_n[f], cap) : keep_n[f];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) base += __shfl_xor_sync(0xffffffffu, base, o);
+  const int n = cap > 0 ? min(keep_n[b], cap) : keep_n[b];
+  const int first = offsets[b];
+  for (int i = lane; i < n; i += 32) {
+    const float4 r = box_convention(reinterpret_cast<const float4*>(boxes)[first + i], conv, sw, sh);
+    BoxOut v;
+    v.cx = r.x; v.cy = r.y; v.w = r.z; v.h = r.w;
+    v.label = labels[first + i];
+    v.frame = b;
+    out[base + i] = v;
   }
-  *out_n = w;
+  if (b == B - 1 && lane == 0) *out_n = base + n;
 }
 
 // IEMasker.PixelInBoundingBox (IEM:232-247) on a C#-convention box
@@ -932,6 +937,7 @@ struct Mask640Params {
   const float* coefs; const float* boxes; const int* frames;
   int first;
   uint8_t* out;   // [n,640,640]
+  float logit_thr;  // logit of the probability threshold (0 for 0.5)
 };
 
 __global__ void __launch_bounds__(256) mask640_kernel(const Mask640Params p) {
@@ -991,7 +997,7 @@ __global__ void __launch_bounds__(256) mask640_kernel(const Mask640Params p) {
     const float bot = __fadd_rn(__fmul_rn(c, __fsub_rn(1.f, wx)), __fmul_rn(dq, wx));
     const float val = __fadd_rn(__fmul_rn(top, __fsub_rn(1.f, wy)), __fmul_rn(bot, wy));
     const float xf = static_cast<float>(X), yf = static_cast<float>(Y);
-    const bool on = (val > 0.f) && xf >= x1 && xf < x2 && yf >= y1 && yf < y2;
+    const bool on = (val > p.logit_thr) && xf >= x1 && xf < x2 && yf >= y1 && yf < y2;
     packed[i >> 2] |= (on ? 1u : 0u) << ((i & 3) * 8);
   }
   uint4 v = make_uint4(packed[0], packed[1], packed[2], packed[3]);

@@ -91,10 +91,20 @@ struct SentisTensor {
   std::vector<int32_t> shape;
   bool is_const = false;
   int64_t offset = 0;
+  // element count; throws on a negative dimension or a product past 2^31 (the bytes come from a caller)
   size_t count() const {
     size_t n = 1;
-    for (int32_t d : shape) n *= static_cast<size_t>(d);
+    for (int32_t d : shape) {
+      XR_CHECK(d >= 0, "sentis: negative tensor dimension %d", d);
+      n *= static_cast<size_t>(d);
+      XR_CHECK(n <= (static_cast<size_t>(1) << 31), "sentis: tensor too large");
+    }
     return n;
+  }
+  // true when [offset, offset + bytes) lies inside a blob of `blob_size` bytes (offset is a sign-extended i32: reject < 0;
+  // written without additions that could wrap)
+  bool inside(size_t bytes, size_t blob_size) const {
+    return offset >= 0 && static_cast<size_t>(offset) <= blob_size && bytes <= blob_size - static_cast<size_t>(offset);
   }
 };
 
@@ -180,8 +190,7 @@ static inline SentisWeights sentis_load(const void* data, size_t bytes) {
     if (id < 0) return false;
     const Val& v = value(id);
     if (v.kind == 3) { *dst = v.f; return true; }
-    if (v.kind == 6 && v.t.is_const && v.t.dtype == 0 && v.t.count() == 1 &&
-        static_cast<size_t>(v.t.offset) + 4 <= blob.size()) {
+    if (v.kind == 6 && v.t.is_const && v.t.dtype == 0 && v.t.count() == 1 && v.t.inside(4, blob.size())) {
       memcpy(dst, blob.data() + v.t.offset, 4);
       return true;
     }
@@ -206,7 +215,7 @@ static inline SentisWeights sentis_load(const void* data, size_t bytes) {
       const Val& q = value(ins[0]);
       XR_CHECK(q.kind == 6 && q.t.is_const && q.t.dtype == 3, "sentis: DequantizeUint8 input is not a constant u8 tensor");
       const size_t n = q.t.count();
-      XR_CHECK(static_cast<size_t>(q.t.offset) + n <= blob.size(), "sentis: tensor data outside the weight blob");
+      XR_CHECK(q.t.inside(n, blob.size()), "sentis: tensor data outside the weight blob");
       const float scale = scalar_f(args[0]);
       const float zp = scalar_f(args[1]);
       Deq d;

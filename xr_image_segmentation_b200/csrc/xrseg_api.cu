@@ -2,11 +2,15 @@
 // (copy -> preprocess -> network -> decode -> NMS -> gather -> masks) on one CUDA stream, CUDA-graph replay, and the
 // parity / debug entry points.  One runner per GPU; no CPU fallback anywhere on this path.
 #include "../../include/xrseg.h"
+#ifdef XRSEG_DEBUG_API
+#include "../../include/xrseg_debug.h"
+#endif
 
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <memory>
 #include <type_traits>
@@ -157,7 +161,8 @@ struct xrseg_runner {
   bool timed = false;
   // fused preprocess + stem: set by do_schedule when the frames are 640x640 (no resample), consumed by OP_STEM
   const uint8_t* fused_src = nullptr;
-  int fused_stride = 0, fused_bpp = 0;
+  int fused_stride = 0, fused_bpp = 0, fused_flip = 0;
+  int* h_overflow = nullptr;          // pinned: bit 0 = more candidates than max_candidates, bit 1 = more kept boxes than max_det
 
   ~xrseg_runner();
 };
@@ -274,7 +279,9 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       } else {
         d.cp = plan_conv(cd, r->num_sms, 0);
       }
+#ifdef XRSEG_DEBUG_API
       if (const char* e = getenv("XRSEG_EPI")) d.cp.dbg_skip |= (e[0] == '1') ? 8 : 0;   // A/B of the TMA kernel's epilogue
+#endif
       if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
         std::vector<__half> wp;
         std::vector<float> bp;
@@ -351,19 +358,19 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
                             (mq.W * 3) % 16 == 0 && r->fused_bpp == 3;
           if (r->fused_src && wide && !stem_rows_off && (nt == 2 || nt == 4) && r->cfg.conv_impl == XRSEG_CONV_UMMA) {
             StemMmaParams u = mq;                        // packed RGB rows: raw-byte staging (stem_rows_kernel)
-            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = 3; u.w16 = w16_rows;
+            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = 3; u.w16 = w16_rows; u.flip = r->fused_flip;
             const dim3 grid(ceil_div(u.W / 2, STEM2_COLS), ceil_div(u.H / 2, STEM2_ROWS), nb);
             if (nt == 2) launch_k(stem_rows_kernel<2>, grid, 256, 0, st, u);
             else launch_k(stem_rows_kernel<4>, grid, 256, 0, st, u);
           } else if (r->fused_src && aligned && (nt == 2 || nt == 4) && r->cfg.conv_impl == XRSEG_CONV_UMMA) {
             StemMmaParams u = mq;
-            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
+            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp; u.flip = r->fused_flip;
             const dim3 grid(ceil_div(u.W / 2, 32), ceil_div(u.H / 2, 8), nb);
             if (nt == 2) launch_k(stem_mma_kernel<2>, grid, 256, 0, st, u);
             else launch_k(stem_mma_kernel<4>, grid, 256, 0, st, u);
           } else if (r->fused_src) {
             StemU8Params u = q;
-            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp;
+            u.src = r->fused_src; u.stride_bytes = r->fused_stride; u.bpp = r->fused_bpp; u.flip = r->fused_flip;
             launch_k(stem_u8_kernel, dim3(ceil_div(u.W / 2, 16), ceil_div(u.H / 2, 16), nb), 256, smem_u8, st, u);
           } else {
             launch_k(stem_conv_kernel, grid_for(total), 256, smem, st, p);
@@ -538,10 +545,16 @@ void dense_scale_src(xrseg_runner* r, ScaleSrc<T> (&s)[3], const T* box, const T
   fill_scale_src<T>(s, box, cls, coef, net.fh, net.fw, bstr, pitch, off);
 }
 
+#ifdef XRSEG_DEBUG_API
+__global__ void f16_to_f32_kernel(const __half* src, float* dst, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
+    dst[i] = __half2float(src[i]);
+}
 __global__ void f32_to_f16_kernel(const float* src, __half* dst, long n) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x)
     dst[i] = __float2half_rn(src[i]);
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // post-processing of frames [b0, b0 + nb): decode -> sort -> bitmask -> reduce -> offsets -> gather -> masks
@@ -666,16 +679,17 @@ __global__ void add_frame_base_kernel(int* frames, const int* offsets, int b0, i
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) frames[i] = b0 + b;
 }
 
-void preprocess(xrseg_runner* r, const uint8_t* d_src, int w, int h, int stride_bytes, int fmt, int nb, cudaStream_t st) {
+void preprocess(xrseg_runner* r, const uint8_t* d_src, int w, int h, int stride_bytes, int fmt, int flip, int nb, cudaStream_t st) {
   PreParams p{};
   p.src = d_src;
   p.dst = ptr_of(r, r->net->input);
   p.B = nb; p.sw = w; p.sh = h; p.stride_bytes = stride_bytes; p.bpp = fmt == XRSEG_FMT_RGBA8 ? 4 : 3;
   p.mode = r->cfg.resize_mode;
+  p.flip = flip;
   if (p.mode == XRSEG_RESIZE_LETTERBOX) {
     const double rr = std::min(640.0 / h, 640.0 / w);
-    p.nh = static_cast<int>(std::lround(h * rr));
-    p.nw = static_cast<int>(std::lround(w * rr));
+    p.nh = static_cast<int>(std::nearbyint(h * rr));   // round half to even, like Python's round() in oracle/preprocess.letterbox
+    p.nw = static_cast<int>(std::nearbyint(w * rr));
     p.top = (640 - p.nh) / 2;
     p.left = (640 - p.nw) / 2;
     p.scale_x = static_cast<float>(w) / static_cast<float>(p.nw);
@@ -771,9 +785,11 @@ void reset_counters(xrseg_runner* r, int batch, cudaStream_t st) {
   XR_CUDA(cudaMemsetAsync(r->d_done, 0, sizeof(int), st));                                // nms_reduce's ticket (self-resetting; belt and braces)
 }
 
-int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, int h, int stride_bytes, int fmt,
+int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, int h, int stride_bytes, int fmt_flags,
                 int batch) {
   if (!r) return XRSEG_ERR_INVALID;
+  const int flip = (fmt_flags & XRSEG_FMT_BOTTOM_UP) ? 1 : 0;
+  const int fmt = fmt_flags & ~XRSEG_FMT_BOTTOM_UP;
   try {
     if (!src || batch < 1 || batch > r->cfg.max_batch || w < 1 || h < 1 ||
         stride_bytes < w * (fmt == XRSEG_FMT_RGBA8 ? 4 : 3) || (fmt != XRSEG_FMT_RGB8 && fmt != XRSEG_FMT_RGBA8)) {
@@ -815,13 +831,14 @@ int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, 
     const bool fused = (w == 640 && h == 640);     // no resample needed: the stem reads the uint8 frames directly
     r->fused_stride = stride_bytes;
     r->fused_bpp = fmt == XRSEG_FMT_RGBA8 ? 4 : 3;
+    r->fused_flip = flip;
     int launches = 0;
     for (int k = 0; k < n_chunks; ++k) {
       const int b0 = k * r->mb, nb = std::min(r->mb, batch - b0);
       const uint8_t* chunk_src = d_src + static_cast<size_t>(b0) * frame_bytes;
       if (!src_on_device) XR_CUDA(cudaStreamWaitEvent(st, r->ev_copy[k], 0));   // chunk k+1 copies while chunk k computes
       r->fused_src = fused ? chunk_src : nullptr;
-      if (!fused) preprocess(r, chunk_src, w, h, stride_bytes, fmt, nb, st);
+      if (!fused) preprocess(r, chunk_src, w, h, stride_bytes, fmt, flip, nb, st);
       if (r->timed && k == 0) XR_CUDA(cudaEventRecord(r->ev[1], st));
       launches += fused ? 0 : 1;
       if (r->cfg.use_cuda_graph) {
@@ -855,11 +872,18 @@ int do_schedule(xrseg_runner* r, const uint8_t* src, bool src_on_device, int w, 
     if (r->timed) XR_CUDA(cudaEventRecord(r->ev[2], st));
     XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_overflow, r->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaEventRecord(r->ev_done, st));
     r->state = 1;
     return XRSEG_OK;
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
 }
@@ -876,6 +900,17 @@ int finish(xrseg_runner* r) {
       cudaGetLastError();  // an unrecorded event is not an error of the run
     }
     r->state = 2;
+    // The reference's NonMaxSuppression is unlimited (maxOutputBoxesPerClass = -1, IEModelEditorConverter.cs:76); this build
+    // works inside max_candidates / max_det.  A run that hit either cap is reported ONCE, here: the (truncated) results stay
+    // readable, later calls on the finished run return normally, xrseg_overflow() keeps the bits.
+    if (*r->h_overflow) {
+      char b[200];
+      snprintf(b, sizeof(b), "NMS capacity exceeded:%s%s -- results are truncated; recreate the runner with larger caps",
+               (*r->h_overflow & 1) ? " more score-filtered candidates than max_candidates" : "",
+               (*r->h_overflow & 2) ? " more kept boxes than max_det" : "");
+      r->err = b;
+      return XRSEG_ERR_CAPACITY;
+    }
   }
   return 1;
 }
@@ -923,6 +958,7 @@ xrseg_runner::~xrseg_runner() {
   for (void* b : bufs) cudaFree(b);
   if (h_counts) cudaFreeHost(h_counts);
   if (h_offsets) cudaFreeHost(h_offsets);
+  if (h_overflow) cudaFreeHost(h_overflow);
   if (ev_done) cudaEventDestroy(ev_done);
   for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : user_ev) if (e) cudaEventDestroy(e);
@@ -971,6 +1007,12 @@ int xrseg_layer_count(int model_scale) {
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_INVALID;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_INVALID;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return XRSEG_ERR_INVALID;
   }
 }
 
@@ -988,6 +1030,12 @@ int xrseg_layer_info_get(int model_scale, int index, xrseg_layer_info* info) {
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_INVALID;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_INVALID;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return XRSEG_ERR_INVALID;
   }
 }
 
@@ -1002,6 +1050,12 @@ int xrseg_sentis_info(const void* data, size_t bytes, int32_t* n_convs, float* i
     return XRSEG_OK;
   } catch (const CudaError& e) {
     g_create_error = e.msg;
+    return XRSEG_ERR_WEIGHTS;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_WEIGHTS;
+  } catch (...) {
+    g_create_error = "unknown exception";
     return XRSEG_ERR_WEIGHTS;
   }
 }
@@ -1023,6 +1077,12 @@ int xrseg_sentis_layer(const void* data, size_t bytes, int index, float* w, size
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_WEIGHTS;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_WEIGHTS;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return XRSEG_ERR_WEIGHTS;
   }
 }
 
@@ -1038,6 +1098,7 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
   if (c.iou_threshold == 0.f) c.iou_threshold = 0.43f;
   if (c.score_threshold == 0.f) c.score_threshold = 0.301f;
   if (c.mask_threshold == 0.f) c.mask_threshold = 0.5f;
+  if (c.mask_threshold < 0.f) c.mask_threshold = 0.f;   // negative = "exactly 0" (0 itself means default)
   if (c.max_det <= 0) c.max_det = 300;
   if (c.max_candidates <= 0) c.max_candidates = 2048;
   if (c.max_candidates > NUM_ANCHORS_MAX) c.max_candidates = NUM_ANCHORS_MAX;
@@ -1114,6 +1175,12 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     } catch (const CudaError& e) {
       g_create_error = e.msg;
       return XRSEG_ERR_WEIGHTS;
+    } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+      g_create_error = std::string("unexpected exception: ") + e.what();
+      return XRSEG_ERR_WEIGHTS;
+    } catch (...) {
+      g_create_error = "unknown exception";
+      return XRSEG_ERR_WEIGHTS;
     }
     r->arena = dev_alloc<__half>(net.arena_elems);
     XR_CUDA(cudaMemset(r->arena, 0, net.arena_elems * sizeof(__half)));
@@ -1151,11 +1218,19 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     XR_CUDA(cudaHostAlloc(&r->h_offsets, sizeof(int) * (B + 1), cudaHostAllocDefault));
     memset(r->h_counts, 0, sizeof(int) * B);
     memset(r->h_offsets, 0, sizeof(int) * (B + 1));
+    XR_CUDA(cudaHostAlloc(&r->h_overflow, sizeof(int), cudaHostAllocDefault));
+    *r->h_overflow = 0;
     XR_CUDA(cudaMemset(r->d_keep_n, 0, sizeof(int) * B));
     XR_CUDA(cudaMemset(r->d_offsets, 0, sizeof(int) * (B + 1)));
     XR_CUDA(cudaDeviceSynchronize());
   } catch (const CudaError& e) {
     g_create_error = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    g_create_error = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   *out = r.release();
@@ -1195,6 +1270,12 @@ int xrseg_counts(xrseg_runner* r, int32_t* counts, int cap) {
   return r->batch;
 }
 
+int xrseg_overflow(xrseg_runner* r) {
+  if (!r) return XRSEG_ERR_INVALID;
+  if (r->state != 2) { r->err = "no finished run"; return XRSEG_ERR_STATE; }
+  return *r->h_overflow;
+}
+
 int xrseg_peek_output(xrseg_runner* r, int idx, xrseg_tensor_view* v) {
   if (!r || !v || idx < 0 || idx > 3) return XRSEG_ERR_INVALID;
   int rc = finish(r);
@@ -1228,6 +1309,12 @@ int xrseg_readback(xrseg_runner* r, int idx, void* dst, size_t cap_bytes, int64_
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
+    return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
 }
@@ -1245,6 +1332,12 @@ int xrseg_keep_indices(xrseg_runner* r, int32_t* idx, float* scores, int cap) {
     XR_CUDA(cudaStreamSynchronize(r->stream));
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return n;
@@ -1265,12 +1358,18 @@ int xrseg_decode(xrseg_runner* r, float screen_w, float screen_h, int convention
     XR_CUDA(cudaSetDevice(r->device));
     BoxOut* d_out = static_cast<BoxOut*>(ensure_scratch(r, sizeof(BoxOut) * total + 16));
     int* d_n = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(d_out) + sizeof(BoxOut) * total);
-    boxes_to_screen_kernel<<<1, 32, 0, r->stream>>>(r->o_boxes, r->o_labels, r->d_keep_n, r->d_offsets, r->batch,
+    boxes_to_screen_kernel<<<r->batch, 32, 0, r->stream>>>(r->o_boxes, r->o_labels, r->d_keep_n, r->d_offsets, r->batch,
                                                     convention, screen_w, screen_h, per_frame_cap, d_out, d_n);
     XR_CUDA(cudaMemcpyAsync(out, d_out, sizeof(BoxOut) * total, cudaMemcpyDeviceToHost, r->stream));
     XR_CUDA(cudaStreamSynchronize(r->stream));
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
@@ -1294,34 +1393,55 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
     default: return XRSEG_ERR_INVALID;
   }
   if (cap_bytes < per * count) { r->err = "mask buffer too small"; return XRSEG_ERR_CAPACITY; }
+  if (mp->mode == XRSEG_MASK_REFERENCE_160 &&
+      (mp->image_w < 1 || mp->image_h < 1 || !(mp->screen_w > 0.f) || !(mp->screen_h > 0.f) ||
+       mp->box_convention < 0 || mp->box_convention > 2)) {
+    r->err = "xrseg_masks: REFERENCE_160 needs image_w/image_h >= 1, screen_w/screen_h > 0 and a box convention";
+    return XRSEG_ERR_INVALID;
+  }
+  // threshold: 0 -> the runner's mask_threshold (IEE:32 _confidenceThreshold); a negative value asks for exactly 0
+  const float thr = mp->threshold == 0.f ? r->cfg.mask_threshold : (mp->threshold < 0.f ? 0.f : mp->threshold);
   try {
     XR_CUDA(cudaSetDevice(r->device));
     uint8_t* d_out = static_cast<uint8_t*>(ensure_scratch(r, per * count));
-    if (mp->mode == XRSEG_MASK_UPSAMPLE_640) {
-      const TV& pr = r->net->protos;
-      Mask640Params p{ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch, pr.pitch, r->o_coefs, r->o_boxes,
-                      r->o_frame, first, d_out};
-      if (r->batch > r->mb) {
-        r->err = "640-px masks need the prototypes of every frame resident: use micro_batch >= batch";
-        return XRSEG_ERR_STATE;
+    if (mp->mode == XRSEG_MASK_UPSAMPLE_640 && r->batch > r->mb) {
+      r->err = "640-px masks need the prototypes of every frame resident: use micro_batch >= batch";
+      return XRSEG_ERR_STATE;
+    }
+    // gridDim.y / .z hold the detection index: at most 65535 per launch (batch 512 x 300 detections = 153600)
+    for (int s0 = 0; s0 < count; s0 += 65535) {
+      const int n = std::min(65535, count - s0);
+      uint8_t* slice_out = d_out + per * s0;
+      if (mp->mode == XRSEG_MASK_UPSAMPLE_640) {
+        const TV& pr = r->net->protos;
+        Mask640Params p{ptr_of(r, pr), static_cast<long>(pr.H) * pr.W * pr.pitch, pr.pitch, r->o_coefs, r->o_boxes,
+                        r->o_frame, first + s0, slice_out,
+                        thr <= 0.f ? -3.0e38f : (thr >= 1.f ? 3.0e38f : logf(thr / (1.f - thr)))};
+        if (thr == 0.5f) p.logit_thr = 0.f;
+        mask640_kernel<<<dim3(10, 10, n), 256, 0, r->stream>>>(p);
+      } else {
+        MaskThrParams p{};
+        p.probs = r->o_probs; p.boxes = r->o_boxes; p.n = n; p.first = first + s0;
+        p.mode = mp->mode == XRSEG_MASK_REFERENCE_160 ? 0 : 1;
+        p.conv = mp->box_convention; p.sw = mp->screen_w; p.sh = mp->screen_h;
+        p.image_w = mp->image_w; p.image_h = mp->image_h; p.thr = thr; p.out = slice_out;
+        if (mp->mode == XRSEG_MASK_BITS_160)
+          mask_bits_kernel<<<dim3(PROTO_HW, n), PROTO_HW, 0, r->stream>>>(p);
+        else
+          mask_threshold_kernel<<<dim3(PROTO_PIX / 256, n), 256, 0, r->stream>>>(p);
       }
-      mask640_kernel<<<dim3(10, 10, count), 256, 0, r->stream>>>(p);
-    } else {
-      MaskThrParams p{};
-      p.probs = r->o_probs; p.boxes = r->o_boxes; p.n = count; p.first = first;
-      p.mode = mp->mode == XRSEG_MASK_REFERENCE_160 ? 0 : 1;
-      p.conv = mp->box_convention; p.sw = mp->screen_w; p.sh = mp->screen_h;
-      p.image_w = mp->image_w; p.image_h = mp->image_h; p.thr = r->cfg.mask_threshold; p.out = d_out;
-      if (mp->mode == XRSEG_MASK_BITS_160)
-        mask_bits_kernel<<<dim3(PROTO_HW, count), PROTO_HW, 0, r->stream>>>(p);
-      else
-        mask_threshold_kernel<<<dim3(PROTO_PIX / 256, count), 256, 0, r->stream>>>(p);
     }
     XR_CUDA(cudaGetLastError());
     XR_CUDA(cudaMemcpyAsync(out, d_out, per * count, cudaMemcpyDeviceToHost, r->stream));
     XR_CUDA(cudaStreamSynchronize(r->stream));
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return count;
@@ -1369,6 +1489,12 @@ int xrseg_extract_points(xrseg_runner* r, const xrseg_depth_params* dp, const ui
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
+    return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
 }
@@ -1397,6 +1523,12 @@ int xrseg_associate(xrseg_runner* r, int frame, float lx, float ly, int llabel, 
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
+    return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
 }
@@ -1420,6 +1552,12 @@ int xrseg_event_record(xrseg_runner* r, int slot) {
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
+    return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
 }
@@ -1431,6 +1569,12 @@ int xrseg_event_elapsed_ms(xrseg_runner* r, int a, int b, float* ms) {
     XR_CUDA(cudaEventElapsedTime(ms, r->user_ev[a], r->user_ev[b]));
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
@@ -1489,10 +1633,17 @@ int xrseg_profile_ops(xrseg_runner* r, int iters, float* ms, char* names, double
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
+    return XRSEG_ERR_CUDA;
   }
 }
 
-// ---- debug / parity --------------------------------------------------------------------------------------------
+// ---- debug / parity: exported by libxrseg_debug.so only (include/xrseg_debug.h) -----------------------------------------
+#ifdef XRSEG_DEBUG_API
 int xrseg_debug_fetch(xrseg_runner* r, const char* name, float* dst, size_t cap_floats, int64_t* shape4) {
   if (!r || !name || !dst) return XRSEG_ERR_INVALID;
   int rc = finish(r);
@@ -1526,6 +1677,12 @@ int xrseg_debug_fetch(xrseg_runner* r, const char* name, float* dst, size_t cap_
     cudaFree(d);
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
@@ -1605,10 +1762,17 @@ static int debug_post_impl(xrseg_runner* r, const float* box_logits, const float
     XR_CUDA(cudaGetLastError());
     XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_overflow, r->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaEventRecord(r->ev_done, st));
     r->state = 1;
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
@@ -1647,6 +1811,7 @@ int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, 
     // anchors / scores of the kept boxes, compacted (no coefficient gather on this path)
     XR_CUDA(cudaMemcpyAsync(r->h_offsets, r->d_offsets, sizeof(int) * (batch + 1), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaMemcpyAsync(r->h_counts, r->d_keep_n, sizeof(int) * batch, cudaMemcpyDeviceToHost, st));
+    XR_CUDA(cudaMemcpyAsync(r->h_overflow, r->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     XR_CUDA(cudaStreamSynchronize(st));
     std::vector<int> keep(static_cast<size_t>(batch) * r->max_det);
     XR_CUDA(cudaMemcpy(keep.data(), r->d_keep_idx, sizeof(int) * keep.size(), cudaMemcpyDeviceToHost));
@@ -1666,6 +1831,12 @@ int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, 
     r->state = 1;
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
@@ -1691,6 +1862,12 @@ int xrseg_debug_mask_threshold(xrseg_runner* r, const float* probs, const float*
     cudaFree(d_p); cudaFree(d_b); cudaFree(d_o);
   } catch (const CudaError& e) {
     r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    r->err = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
@@ -1817,6 +1994,12 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
 }
@@ -1878,6 +2061,12 @@ int xrseg_debug_bottleneck(int device, const float* x, int b, int c1, int h, int
     cudaFree(d_x32); cudaFree(d_y32); cudaFree(d_x); cudaFree(d_y); cudaFree(d_f1); cudaFree(d_f2); cudaFree(d_b1); cudaFree(d_b2);
   } catch (const CudaError& e) {
     g_create_error = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    g_create_error = "unknown exception";
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
@@ -1947,6 +2136,12 @@ int xrseg_debug_c3k2(int device, const float* x, int b, int cin, int h, int w, i
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
 }
@@ -2005,8 +2200,54 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_INVALID;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_INVALID;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return XRSEG_ERR_INVALID;
   }
   return XRSEG_OK;
 }
+
+// The C2PSA attention kernel alone (graph chains 160-168) on caller tensors: qkv f32 [b, n, heads*(32+32+64)] per token
+// and head (query | key | value), out f32 [b, n, heads*64].
+int xrseg_debug_attention(int device, const float* qkv, int b, int n, int heads, float* out) {
+  if (!qkv || !out || b < 1 || heads < 1 || n < 16 || n % 16 || n % ATT_CHUNK || n / 16 > 26) return XRSEG_ERR_INVALID;
+  try {
+    XR_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    XR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) { g_create_error = "not an sm_100 device"; return XRSEG_ERR_NO_DEVICE; }
+    XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    const int cq = heads * (2 * ATT_KD + ATT_HD), co = heads * ATT_HD;
+    const size_t nq = static_cast<size_t>(b) * n * cq, no = static_cast<size_t>(b) * n * co;
+    float* d_q32 = dev_alloc<float>(nq);
+    float* d_o32 = dev_alloc<float>(no);
+    __half* d_q = dev_alloc<__half>(nq);
+    __half* d_o = dev_alloc<__half>(no);
+    XR_CUDA(cudaMemcpy(d_q32, qkv, nq * sizeof(float), cudaMemcpyHostToDevice));
+    f32_to_f16_kernel<<<grid_for(static_cast<long>(nq)), 256>>>(d_q32, d_q, static_cast<long>(nq));
+    AttnParams p{d_q, cq, d_o, co, b, n, heads, 1.0f / sqrtf(static_cast<float>(ATT_KD))};
+    const size_t smem = static_cast<size_t>(n) * (ATT_KSTRIDE + ATT_VSTRIDE) * sizeof(__half);
+    launch_k(attention_kernel, dim3(b * heads, ceil_div(n / 16, 13)), 13 * 32, smem, 0, p);
+    XR_CUDA(cudaGetLastError());
+    f16_to_f32_kernel<<<grid_for(static_cast<long>(no)), 256>>>(d_o, d_o32, static_cast<long>(no));
+    XR_CUDA(cudaDeviceSynchronize());
+    XR_CUDA(cudaMemcpy(out, d_o32, no * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_q32); cudaFree(d_o32); cudaFree(d_q); cudaFree(d_o);
+  } catch (const CudaError& e) {
+    g_create_error = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (const std::exception& e) {   // nothing may unwind across the C boundary
+    g_create_error = std::string("unexpected exception: ") + e.what();
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    g_create_error = "unknown exception";
+    return XRSEG_ERR_CUDA;
+  }
+  return XRSEG_OK;
+}
+#endif  // XRSEG_DEBUG_API
 
 }  // extern "C"

@@ -60,11 +60,16 @@ class IEMasker:
     def __init__(self, confidenceThreshold: float = 0.5):
         self._confidenceThreshold = confidenceThreshold   # ↔ IEMasker.Initialize(display, 0.5) (IEE:262)
 
+    def _thr(self) -> float:
+        """The threshold of `mask[i,y,x] > _confidenceThreshold` (IEM:104,176) in the C ABI's encoding (0 = the runner's
+        default, negative = exactly 0)."""
+        return -1.0 if self._confidenceThreshold == 0 else float(self._confidenceThreshold)
+
     def DrawMask(self, executor: "IEExecutor", imageWidth: int, imageHeight: int) -> np.ndarray:
         """↔ IEMasker.DrawMask(boundBoxes, mask, imageWidth, imageHeight) (IEM:82-119) with the DrawBoxes boxes:
         uint8 [n,160,160] in texture order, 1 where the C# writes the mask colour."""
         return executor._runner.masks(_lib.MASK_REFERENCE_160, _lib.BOX_DRAWBOXES, float(imageWidth), float(imageHeight),
-                                      int(imageWidth), int(imageHeight))
+                                      int(imageWidth), int(imageHeight), threshold=self._thr())
 
     def DrawSingleMask(self, executor: "IEExecutor", targetIndex: int, screenW: float, screenH: float, imageWidth: int,
                        imageHeight: int) -> np.ndarray | None:
@@ -73,7 +78,7 @@ class IEMasker:
         if targetIndex < 0:
             return None
         m = executor._runner.masks(_lib.MASK_REFERENCE_160, _lib.BOX_PARSEBOXES, float(screenW), float(screenH),
-                                   int(imageWidth), int(imageHeight), first=targetIndex, count=1)
+                                   int(imageWidth), int(imageHeight), first=targetIndex, count=1, threshold=self._thr())
         return m[0]
 
 
@@ -115,6 +120,8 @@ class IEExecutor:
     # ↔ LoadModel (IEE:380-387): load, create the worker, warm-up run on a blank frame
     def _LoadModel(self, sentisModel, device, runner_kw):
         model = ModelLoader.Load(sentisModel)
+        # _confidenceThreshold (IEE:32) is also the runner's mask threshold (depth extraction IEE:102, bit-packed masks)
+        runner_kw.setdefault("mask_thr", -1.0 if self._confidenceThreshold == 0 else float(self._confidenceThreshold))
         self._inferenceEngineWorker = Worker(model, self._backend, device=device, **runner_kw)
         self._runner = self._inferenceEngineWorker._runner
         blank = TextureConverter.ToTensor(np.zeros((self._inputSize[1], self._inputSize[0], 3), np.uint8), 640, 640, 3)

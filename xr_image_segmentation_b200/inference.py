@@ -59,8 +59,11 @@ class Runner:
 
     def __init__(self, model: Model, device: int = 0, max_batch: int = 1, iou=0.0, score=0.0, mask_thr=0.0,
                  max_det=0, max_candidates=0, resize_mode=_lib.RESIZE_STRETCH, conv_impl=_lib.CONV_UMMA,
-                 use_cuda_graph=True, micro_batch=0):
-        self.lib = _lib.load_library()
+                 use_cuda_graph=True, micro_batch=0, debug=False):
+        # debug=True: the runner lives in libxrseg_debug.so (same sources + the parity hooks of include/xrseg_debug.h:
+        # fetch / debug_post / debug_nms / debug_mask_threshold); the product library exports none of them
+        self.debug = debug
+        self.lib = _lib.load_library(debug)
         self._pack = C.create_string_buffer(model.pack, len(model.pack))
         cfg = _lib.Config()
         cfg.struct_size = C.sizeof(_lib.Config)
@@ -75,7 +78,7 @@ class Runner:
         cfg.use_cuda_graph = 1 if use_cuda_graph else 0
         cfg.micro_batch = micro_batch
         self.h = C.c_void_p()
-        _lib.check(self.lib.xrseg_create(C.byref(cfg), C.byref(self.h)))
+        _lib.check(self.lib.xrseg_create(C.byref(cfg), C.byref(self.h)), None, self.lib)
         self.max_batch = max_batch
         self.batch = 0
 
@@ -91,14 +94,21 @@ class Runner:
             pass
 
     def _ck(self, rc):
-        return _lib.check(rc, self.h)
+        return _lib.check(rc, self.h, self.lib)
+
+    def _need_debug(self):
+        if not self.debug:
+            raise XrsegError(_lib.ERR_STATE, "parity hook: create the Runner with debug=True (libxrseg_debug.so)")
 
     # ---- per-frame path ----
-    def schedule(self, frames: np.ndarray, fmt=None):
-        """frames uint8 [B,H,W,3|4] (host).  Asynchronous."""
+    def schedule(self, frames: np.ndarray, fmt=None, bottom_up=False):
+        """frames uint8 [B,H,W,3|4] (host).  Asynchronous.  bottom_up: memory row 0 is the BOTTOM of the picture (Unity's
+        GetPixels32 order, XRSEG_FMT_BOTTOM_UP)."""
         assert frames.dtype == np.uint8 and frames.ndim == 4 and frames.flags.c_contiguous
         b, h, w, c = frames.shape
         fmt = (_lib.FMT_RGBA8 if c == 4 else _lib.FMT_RGB8) if fmt is None else fmt
+        if bottom_up:
+            fmt |= _lib.FMT_BOTTOM_UP
         self._keep = frames
         self.batch = b
         self._ck(self.lib.xrseg_schedule(self.h, frames.ctypes.data, w, h, w * c, fmt, b))
@@ -114,8 +124,18 @@ class Runner:
     def poll(self) -> int:
         return self._ck(self.lib.xrseg_poll(self.h))
 
-    def wait(self):
-        self._ck(self.lib.xrseg_wait(self.h))
+    def wait(self, strict=True):
+        """Blocks until the run is complete.  A run that hit max_candidates / max_det raises XrsegError(ERR_CAPACITY) once
+        (strict=False: returns the overflow bits instead; the truncated results stay readable either way)."""
+        rc = self.lib.xrseg_wait(self.h)
+        if rc == _lib.ERR_CAPACITY and not strict:
+            return self.overflow()
+        self._ck(rc)
+        return 0
+
+    def overflow(self) -> int:
+        """Capacity flags of the finished run (bit 0: candidates > max_candidates, bit 1: kept > max_det)."""
+        return self._ck(self.lib.xrseg_overflow(self.h))
 
     def counts(self) -> np.ndarray:
         out = np.zeros(self.max_batch, np.int32)
@@ -161,7 +181,7 @@ class Runner:
         return out, lab, frm
 
     def masks(self, mode: int, box_convention=_lib.BOX_DRAWBOXES, screen_w=640.0, screen_h=640.0, image_w=640,
-              image_h=640, first=0, count=0) -> np.ndarray:
+              image_h=640, first=0, count=0, threshold=0.0) -> np.ndarray:
         total = int(self.peek(0).shape[0])
         n = count if count > 0 else total - first
         shape = {_lib.MASK_REFERENCE_160: (n, 160, 160), _lib.MASK_CROP_160: (n, 160, 160),
@@ -169,7 +189,8 @@ class Runner:
         out = np.zeros(shape, np.uint8)
         if n == 0:
             return out
-        p = _lib.MaskParams(C.sizeof(_lib.MaskParams), mode, box_convention, screen_w, screen_h, image_w, image_h, first, n)
+        p = _lib.MaskParams(C.sizeof(_lib.MaskParams), mode, box_convention, screen_w, screen_h, image_w, image_h, first, n,
+                            threshold)
         self._ck(self.lib.xrseg_masks(self.h, C.byref(p), out.ctypes.data, out.nbytes))
         return out.view(np.uint32).reshape(n, 160, 5) if mode == _lib.MASK_BITS_160 else out
 
@@ -232,6 +253,7 @@ class Runner:
 
     # ---- parity / debug ----
     def fetch(self, name: str) -> np.ndarray:
+        self._need_debug()
         shp = (C.c_int64 * 4)()
         cap = max(64, self.max_batch) * 1024 * 1024      # the largest tensor fetched by the tests: protos, 0.82 M floats per frame
         buf = np.empty(cap, np.float32)
@@ -241,6 +263,7 @@ class Runner:
 
     def debug_post(self, box_logits, cls_logits, coefs, protos, f16=False):
         """Post-processing alone on caller tensors: fp32 bit-exact kernels, or (f16) the product's fp16 kernels."""
+        self._need_debug()
         arrs = [np.ascontiguousarray(a, np.float32) for a in (box_logits, cls_logits, coefs, protos)]
         b = arrs[0].shape[0]
         self.batch = b
@@ -248,12 +271,14 @@ class Runner:
         self._ck(fn(self.h, *(a.ctypes.data for a in arrs), b))
 
     def debug_nms(self, corners, scores):
+        self._need_debug()
         c = np.ascontiguousarray(corners, np.float32)
         s = np.ascontiguousarray(scores, np.float32)
         self.batch = c.shape[0]
         self._ck(self.lib.xrseg_debug_nms(self.h, c.ctypes.data, s.ctypes.data, c.shape[0], c.shape[1]))
 
     def debug_mask_threshold(self, probs, boxes, image_w, image_h, thr=0.5):
+        self._need_debug()
         p = np.ascontiguousarray(probs, np.float32)
         bx = np.ascontiguousarray(boxes, np.float32)
         out = np.zeros(p.shape, np.uint8)
@@ -300,8 +325,8 @@ class PipelinedRunner:
 
 
 def debug_conv(x, w, b, k, stride, act, transposed=False, residual=None, impl=_lib.CONV_UMMA, variant=0, device=0):
-    """One convolution through the CUDA library (parity tests)."""
-    lib = _lib.load_library()
+    """One convolution through the CUDA library (parity tests; libxrseg_debug.so)."""
+    lib = _lib.load_library(True)
     x = np.ascontiguousarray(x, np.float32)
     w = np.ascontiguousarray(w, np.float32)
     B, cin, h, wd = x.shape
@@ -313,31 +338,41 @@ def debug_conv(x, w, b, k, stride, act, transposed=False, residual=None, impl=_l
     rr = None if residual is None else np.ascontiguousarray(residual, np.float32)
     _lib.check(lib.xrseg_debug_conv(device, impl, x.ctypes.data, B, cin, h, wd, w.ctypes.data,
                                     bb.ctypes.data if bb is not None else None, cout, k, stride, 1, int(act),
-                                    int(transposed), rr.ctypes.data if rr is not None else None, y.ctypes.data, variant))
+                                    int(transposed), rr.ctypes.data if rr is not None else None, y.ctypes.data, variant), None, lib)
     return y
 
 
 def debug_bottleneck(x, w1, b1, w2, b2, residual=True, device=0):
     """The fused Bottleneck kernel (Conv3x3+SiLU -> Conv3x3+SiLU (+ x)) on caller tensors (parity tests)."""
-    lib = _lib.load_library()
+    lib = _lib.load_library(True)
     x, w1, b1, w2, b2 = (np.ascontiguousarray(a, np.float32) for a in (x, w1, b1, w2, b2))
     B, c1, h, wd = x.shape
     cm, c2 = w1.shape[0], w2.shape[0]
     y = np.zeros((B, c2, h, wd), np.float32)
     _lib.check(lib.xrseg_debug_bottleneck(device, x.ctypes.data, B, c1, h, wd, w1.ctypes.data, b1.ctypes.data, cm,
-                                          w2.ctypes.data, b2.ctypes.data, c2, int(residual), y.ctypes.data))
+                                          w2.ctypes.data, b2.ctypes.data, c2, int(residual), y.ctypes.data), None, lib)
     return y
 
 
 def debug_c3k2(x, w_cv1, b_cv1, w_m1, b_m1, w_m2, b_m2, w_cv2, b_cv2, device=0):
     """The whole-block C3k2 kernel (cv1 -> Bottleneck -> cv2 in one launch) on caller tensors (parity tests)."""
-    lib = _lib.load_library()
+    lib = _lib.load_library(True)
     arrs = [np.ascontiguousarray(a, np.float32) for a in (x, w_cv1, b_cv1, w_m1, b_m1, w_m2, b_m2, w_cv2, b_cv2)]
     B, cin, h, wd = arrs[0].shape
     c, cm, cout = arrs[1].shape[0] // 2, arrs[3].shape[0], arrs[7].shape[0]
     y = np.zeros((B, cout, h, wd), np.float32)
     _lib.check(lib.xrseg_debug_c3k2(device, arrs[0].ctypes.data, B, cin, h, wd, c, cm, cout,
-                                    *[a.ctypes.data for a in arrs[1:]], y.ctypes.data))
+                                    *[a.ctypes.data for a in arrs[1:]], y.ctypes.data), None, lib)
+    return y
+
+
+def debug_attention(qkv, heads, device=0):
+    """The C2PSA attention kernel alone: qkv f32 [B,N,heads*128] (per head 32 q | 32 k | 64 v) -> [B,N,heads*64]."""
+    lib = _lib.load_library(True)
+    q = np.ascontiguousarray(qkv, np.float32)
+    B, N, _ = q.shape
+    y = np.zeros((B, N, heads * 64), np.float32)
+    _lib.check(lib.xrseg_debug_attention(device, q.ctypes.data, B, N, heads, y.ctypes.data), None, lib)
     return y
 
 

@@ -166,7 +166,8 @@ int xrseg_peek_output(xrseg_runner* r, int idx, xrseg_tensor_view* view);
 int xrseg_readback(xrseg_runner* r, int idx, void* dst, size_t cap_bytes, int64_t* shape, int* rank);
 /* ↔ IEExecutor.ParseBoxes (IEE:529-559) / IEBoxer.DrawBoxes (IEB:37-81).  Per frame the C# caps apply. */
 int xrseg_decode(xrseg_runner* r, float screen_w, float screen_h, int convention, xrseg_box* out, int cap, int* n);
-/* ↔ IEMasker.DrawMask / DrawSingleMask + PixelInBoundingBox (IEM:82-119,124-196,232-247). */
+/* ↔ IEMasker.DrawMask / DrawSingleMask + PixelInBoundingBox (IEM:82-119,124-196,232-247).  Returns the number of masks
+ * written.  out == NULL: the masks are computed into the runner's device scratch only (no device->host copy). */
 int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* p, uint8_t* out, size_t cap_bytes);
 /* Kept anchor indices (0..8399) and scores of the finished run, compacted like output_0. */
 int xrseg_keep_indices(xrseg_runner* r, int32_t* idx, float* scores, int cap);

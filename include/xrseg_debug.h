@@ -26,6 +26,9 @@ int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_
  * BASELINE.json configs[4], the post-processing stress shape). */
 int xrseg_debug_post_f16(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,
                          const float* protos, int batch);
+/* Per-launch CUDA-event times of the last xrseg_debug_post* call made with XRSEG_DBG_TIME=1 in the environment
+ * (bench.py --config 4): ms[i], algorithmic bytes[i], names[i*32].  Returns the number of launches. */
+int xrseg_debug_post_timings(xrseg_runner* r, float* ms, double* bytes, char* names, int cap);
 /* NMS alone on caller-provided corners [batch,A,4] + scores [batch,A]; results through xrseg_keep_indices. */
 int xrseg_debug_nms(xrseg_runner* r, const float* corners, const float* scores, int batch, int num_anchors);
 /* Threshold + crop of caller-provided mask probabilities f32 [n,160,160] with caller boxes (C# convention

@@ -117,13 +117,16 @@ DEBUG_SIGNATURES = {
     "xrseg_debug_pack_bneck": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "xrseg_debug_emulate_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "xrseg_debug_post_timings": (C.c_int, [C.c_void_p, _P(C.c_float), _P(C.c_double), C.c_char_p, C.c_int]),
     "xrseg_debug_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 SIGNATURES = {**PRODUCT_SIGNATURES, **DEBUG_SIGNATURES}   # what libxrseg_debug.so exports
 
 
 def library_path(debug: bool = False) -> str:
-    return os.path.join(_HERE, "libxrseg_debug.so" if debug else "libxrseg.so")
+    variant = os.environ.get("XRSEG_LIB_VARIANT", "")          # A/B builds of `make variants` (e.g. silu32); default: none
+    name = ("libxrseg_debug" if debug else "libxrseg") + (f"_{variant}" if variant else "")
+    return os.path.join(_HERE, name + ".so")
 
 
 def build_library(verbose: bool = False) -> str:

@@ -59,6 +59,16 @@ __device__ __forceinline__ float silu_f(float y) { return __fdividef(y, 1.0f + _
 // half2 ops per PAIR of outputs, against two MUFUs and five fp32 ops per output for y / (1 + exp(-y)).  The epilogues
 // are issue-bound at N <= 128, so this is what lets them keep up with the tensor pipe.  The result is fp16 anyway.
 __device__ __forceinline__ uint32_t silu_pack_h2(float a, float b) {
+#ifdef XRSEG_SILU_F32
+  // A/B build (make variants): the same identity evaluated in fp32 -- one tanh.approx.f32 (MUFU) and one FFMA per output,
+  // a single rounding to fp16 at the end instead of three
+  const float ha = 0.5f * a, hb = 0.5f * b;
+  float ta, tb;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(ta) : "f"(ha));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(tb) : "f"(hb));
+  __half2 r32 = __floats2half2_rn(fmaf(ha, ta, ha), fmaf(hb, tb, hb));
+  return *reinterpret_cast<uint32_t*>(&r32);
+#endif
   __half2 h = __floats2half2_rn(0.5f * a, 0.5f * b);
   uint32_t hu = *reinterpret_cast<uint32_t*>(&h), tu;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(hu));

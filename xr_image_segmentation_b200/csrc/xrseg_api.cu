@@ -158,6 +158,7 @@ struct xrseg_runner {
   size_t scratch_cap = 0;
   int launches = 0, chunk_launches = 0;
   float timings[5] = {};
+  std::vector<std::pair<std::string, std::pair<float, double>>> post_times;   // xrseg_debug_post under XRSEG_DBG_TIME: name, ms, bytes
   bool timed = false;
   // fused preprocess + stem: set by do_schedule when the frames are 640x640 (no resample), consumed by OP_STEM
   const uint8_t* fused_src = nullptr;
@@ -1376,7 +1377,7 @@ int xrseg_decode(xrseg_runner* r, float screen_w, float screen_h, int convention
 }
 
 int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size_t cap_bytes) {
-  if (!r || !mp || !out || mp->struct_size != sizeof(xrseg_mask_params)) return XRSEG_ERR_INVALID;
+  if (!r || !mp || mp->struct_size != sizeof(xrseg_mask_params)) return XRSEG_ERR_INVALID;
   int rc = finish(r);
   if (rc < 0) return rc;
   const int total = r->h_offsets[r->batch];
@@ -1392,7 +1393,7 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
     case XRSEG_MASK_BITS_160: per = PROTO_HW * 5 * 4; break;
     default: return XRSEG_ERR_INVALID;
   }
-  if (cap_bytes < per * count) { r->err = "mask buffer too small"; return XRSEG_ERR_CAPACITY; }
+  if (out && cap_bytes < per * count) { r->err = "mask buffer too small"; return XRSEG_ERR_CAPACITY; }
   if (mp->mode == XRSEG_MASK_REFERENCE_160 &&
       (mp->image_w < 1 || mp->image_h < 1 || !(mp->screen_w > 0.f) || !(mp->screen_h > 0.f) ||
        mp->box_convention < 0 || mp->box_convention > 2)) {
@@ -1432,8 +1433,10 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
       }
     }
     XR_CUDA(cudaGetLastError());
-    XR_CUDA(cudaMemcpyAsync(out, d_out, per * count, cudaMemcpyDeviceToHost, r->stream));
-    XR_CUDA(cudaStreamSynchronize(r->stream));
+    if (out) {   // out == NULL: the masks stay in the runner's device scratch (kernel timing, device-side consumers)
+      XR_CUDA(cudaMemcpyAsync(out, d_out, per * count, cudaMemcpyDeviceToHost, r->stream));
+      XR_CUDA(cudaStreamSynchronize(r->stream));
+    }
   } catch (const CudaError& e) {
     r->err = e.msg;
     return XRSEG_ERR_CUDA;
@@ -1752,6 +1755,8 @@ static int debug_post_impl(xrseg_runner* r, const float* box_logits, const float
         if (ls[i].name == "post.mask_prob") bytes += static_cast<double>(kept) * PROTO_PIX * sizeof(float);
         fprintf(stderr, "xrseg_debug_post: %-20s %8.1f us  %8.1f MB  %7.1f GB/s\n", ls[i].name.c_str(), ms * 1e3f, bytes / 1e6,
                 bytes > 0 ? bytes / (ms * 1e6) : 0.0);
+        if (i == 0) r->post_times.clear();
+        r->post_times.push_back({ls[i].name, {ms, bytes}});
       }
       fprintf(stderr, "xrseg_debug_post: batch %d, %d detections kept\n", batch, kept);
       for (auto& e : ev) cudaEventDestroy(e);
@@ -1776,6 +1781,21 @@ static int debug_post_impl(xrseg_runner* r, const float* box_logits, const float
     return XRSEG_ERR_CUDA;
   }
   return XRSEG_OK;
+}
+
+// Per-launch CUDA-event times of the last xrseg_debug_post* call made with XRSEG_DBG_TIME set: ms[i], bytes[i]
+// (algorithmic), names[i*32].  Returns the number of launches.
+int xrseg_debug_post_timings(xrseg_runner* r, float* ms, double* bytes, char* names, int cap) {
+  if (!r || !ms || !bytes || !names) return XRSEG_ERR_INVALID;
+  const int n = static_cast<int>(r->post_times.size());
+  if (n > cap) return XRSEG_ERR_CAPACITY;
+  for (int i = 0; i < n; ++i) {
+    ms[i] = r->post_times[i].second.first;
+    bytes[i] = r->post_times[i].second.second;
+    memset(names + i * 32, 0, 32);
+    strncpy(names + i * 32, r->post_times[i].first.c_str(), 31);
+  }
+  return n;
 }
 
 int xrseg_debug_post(xrseg_runner* r, const float* box_logits, const float* cls_logits, const float* coefs,

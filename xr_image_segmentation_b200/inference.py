@@ -181,16 +181,19 @@ class Runner:
         return out, lab, frm
 
     def masks(self, mode: int, box_convention=_lib.BOX_DRAWBOXES, screen_w=640.0, screen_h=640.0, image_w=640,
-              image_h=640, first=0, count=0, threshold=0.0) -> np.ndarray:
+              image_h=640, first=0, count=0, threshold=0.0, to_host=True) -> np.ndarray:
         total = int(self.peek(0).shape[0])
         n = count if count > 0 else total - first
         shape = {_lib.MASK_REFERENCE_160: (n, 160, 160), _lib.MASK_CROP_160: (n, 160, 160),
                  _lib.MASK_UPSAMPLE_640: (n, 640, 640), _lib.MASK_BITS_160: (n, 160, 20)}[mode]
-        out = np.zeros(shape, np.uint8)
+        out = np.zeros(shape, np.uint8) if to_host else None
         if n == 0:
             return out
         p = _lib.MaskParams(C.sizeof(_lib.MaskParams), mode, box_convention, screen_w, screen_h, image_w, image_h, first, n,
                             threshold)
+        if not to_host:                                   # masks stay in the runner's device scratch (kernel timing)
+            self._ck(self.lib.xrseg_masks(self.h, C.byref(p), None, 0))
+            return None
         self._ck(self.lib.xrseg_masks(self.h, C.byref(p), out.ctypes.data, out.nbytes))
         return out.view(np.uint32).reshape(n, 160, 5) if mode == _lib.MASK_BITS_160 else out
 
@@ -270,6 +273,14 @@ class Runner:
         fn = self.lib.xrseg_debug_post_f16 if f16 else self.lib.xrseg_debug_post
         self._ck(fn(self.h, *(a.ctypes.data for a in arrs), b))
 
+    def debug_post_timings(self):
+        """(name, ms, algorithmic bytes) per launch of the last debug_post call made with XRSEG_DBG_TIME=1."""
+        self._need_debug()
+        cap = 64
+        ms, by, names = (C.c_float * cap)(), (C.c_double * cap)(), C.create_string_buffer(cap * 32)
+        n = self._ck(self.lib.xrseg_debug_post_timings(self.h, ms, by, names, cap))
+        return [(names.raw[i * 32:(i + 1) * 32].split(b"\0")[0].decode(), ms[i], by[i]) for i in range(n)]
+
     def debug_nms(self, corners, scores):
         self._need_debug()
         c = np.ascontiguousarray(corners, np.float32)
@@ -311,12 +322,16 @@ class PipelinedRunner:
         self._inflight.append(self._head)
         self._head = (self._head + 1) % len(self.runners)
 
-    def collect(self, mask_mode=_lib.MASK_BITS_160):
-        """Results of the oldest submission: (counts, boxes [N,4], labels [N], masks)."""
+    def collect(self, mask_mode=_lib.MASK_BITS_160, contract=False):
+        """Results of the oldest submission: (counts, boxes [N,4], labels [N], masks).  contract=True: the reference's own
+        readback instead -- all four graph outputs as ReadbackAndClone would return them (IEE:446-449): (counts, output_0
+        f32 [N,4], output_1 i32 [N], output_2 f32 [N,32], output_3 f32 [N,160,160])."""
         if not self._inflight:
             raise XrsegError(_lib.ERR_STATE, "nothing in flight")
         r = self.runners[self._inflight.pop(0)]
         r.wait()
+        if contract:
+            return (r.counts(),) + tuple(r.readback(i) for i in range(4))
         return r.counts(), r.readback(0), r.readback(1), r.masks(mask_mode)
 
     def close(self):

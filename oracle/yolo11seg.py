@@ -83,6 +83,7 @@ class _ConvFeed:
         y = silu(y) if act else y
         if self.trace is not None:
             self.trace[name] = y
+            self.trace["in:" + name] = x
         return y
 
 

@@ -185,7 +185,10 @@ def test_reference_frames_end_to_end(golden, golden_weights, runner, name):
     cf = np.concatenate([runner.fetch(f"coefs.{i}").reshape(32, -1) for i in range(3)], axis=1).T
     for got, ref in ((bl, raw["box_logits"][0].numpy()), (cl, raw["cls_logits"][0].numpy()), (cf, raw["coefs"][0].numpy())):
         d = np.abs(got - ref)
-        assert d.max() <= 0.25 and d.mean() <= 0.02      # fp16 storage + packed-fp16 SiLU in the conv epilogues
+        assert d.max() <= 0.2 and d.mean() <= 0.01, (float(d.max()), float(d.mean()))   # fp16 storage, fp32 accumulate + SiLU
+    # class PROBABILITY within 2e-2 of the oracle's
+    sig = lambda z: 1.0 / (1.0 + np.exp(-z.astype(np.float64)))
+    assert np.abs(sig(cl) - sig(raw["cls_logits"][0].numpy())).max() <= 2e-2
     pr = runner.fetch("protos").reshape(32, -1)
     assert np.abs(pr - res[0]["protos"]).max() <= 5e-2
 

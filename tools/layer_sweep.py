@@ -3,7 +3,7 @@
 libxrseg_debug.so) against the oracle's fp32 tensor of the same layer, on the committed golden frames.
 
   python tools/layer_sweep.py [--out gpurun_out/layer_sweep.md] [--frames coco139,coco632,bus]
-  XRSEG_LIB_VARIANT=silu32 python tools/layer_sweep.py ...        (the fp32-SiLU A/B build of `make variants`)
+  XRSEG_LIB_VARIANT=silu16 python tools/layer_sweep.py ...        (the packed-fp16-SiLU A/B build of `make variants`)
 
 Per layer: relative L2 error ||gpu - ref|| / ||ref|| and max abs error over the sampled frames, plus the error of the
 layer's INPUT (so one can see whether a layer adds error or only passes it on).  Layers whose tensor does not exist in the
@@ -24,6 +24,9 @@ from oracle import yolo11seg as Y  # noqa: E402
 from xr_image_segmentation_b200 import inference as I, weights as W  # noqa: E402
 
 IN_PLACE = {"b10.attn.proj", "b10.ffn.1"}       # written into the C2PSA `b` slice, which later layers update again
+# second convolution of every Bottleneck: its launch adds the Bottleneck input (fused residual)
+RESIDUAL = {f"{b}.m0.cv2" for b in ("b2", "b4", "n13", "n16", "n19")} | \
+           {f"{b}.m0.{m}.cv2" for b in ("b6", "b8", "n22") for m in ("m0", "m1")}
 FUSED_AWAY = {"b2.m0.cv1", "b4.m0.cv1", "n16.m0.cv1"}   # intermediate of the fused Bottleneck lives in shared memory only
 
 
@@ -50,10 +53,14 @@ def main():
         for n in names:
             if n in FUSED_AWAY:
                 continue
-            got = r.fetch(n)[0]
-            ref = trace[n][0].numpy()
             if n == "b10.attn.pe":
                 continue                                   # the kernel writes pe + attention output (fused residual)
+            got = r.fetch(n)[0]
+            ref = trace[n][0].numpy()
+            if n in RESIDUAL:
+                ref = ref + trace["in:" + n[:-1] + "1"][0].numpy()      # Bottleneck: the launch writes x + cv2(cv1(x))
+            elif n == "b10.cv1":
+                got, ref = got[:got.shape[0] // 2], ref[:ref.shape[0] // 2]   # the second half is the in-place residual target
             d = got - ref
             a = acc[n]
             a[0] += float((d.astype(np.float64) ** 2).sum())
@@ -73,7 +80,7 @@ def main():
         h[0] += float((d.astype(np.float64) ** 2).sum()); h[1] += float((ref.astype(np.float64) ** 2).sum())
         h[2] = max(h[2], float(np.abs(d).max()))
     r.close()
-    variant = os.environ.get("XRSEG_LIB_VARIANT", "") or "product (packed-fp16 tanh SiLU)"
+    variant = os.environ.get("XRSEG_LIB_VARIANT", "") or "product build"
     lines = [f"# Per-layer error of the GPU network vs the fp32 oracle ({variant}; frames: {args.frames})", "",
              "relative L2 = ||gpu - oracle|| / ||oracle|| over the whole tensor, fp16 storage on the GPU side.", "",
              "| layer | rel L2 | max abs | note |", "|---|---|---|---|"]

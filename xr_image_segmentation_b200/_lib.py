@@ -124,7 +124,7 @@ SIGNATURES = {**PRODUCT_SIGNATURES, **DEBUG_SIGNATURES}   # what libxrseg_debug.
 
 
 def library_path(debug: bool = False) -> str:
-    variant = os.environ.get("XRSEG_LIB_VARIANT", "")          # A/B builds of `make variants` (e.g. silu32); default: none
+    variant = os.environ.get("XRSEG_LIB_VARIANT", "")          # A/B builds of `make variants` (e.g. silu16: the packed-fp16 SiLU); default: none
     name = ("libxrseg_debug" if debug else "libxrseg") + (f"_{variant}" if variant else "")
     return os.path.join(_HERE, name + ".so")
 

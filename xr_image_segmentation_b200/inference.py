@@ -158,6 +158,13 @@ class Runner:
         self._ck(self.lib.xrseg_readback(self.h, idx, out.ctypes.data, out.nbytes, shp, C.byref(rank)))
         return out
 
+    def readback_into(self, idx: int, host_ptr: int, cap_bytes: int):
+        """↔ ReadbackAndClone into caller memory (e.g. pinned memory of xrseg_host_alloc): returns the tensor's shape."""
+        shp = (C.c_int64 * 4)()
+        rank = C.c_int()
+        self._ck(self.lib.xrseg_readback(self.h, idx, host_ptr, cap_bytes, shp, C.byref(rank)))
+        return tuple(int(shp[i]) for i in range(rank.value))
+
     def keep_indices(self):
         n = int(self.peek(0).shape[0])
         idx = np.zeros(max(n, 1), np.int32)
@@ -322,7 +329,7 @@ class PipelinedRunner:
         self._inflight.append(self._head)
         self._head = (self._head + 1) % len(self.runners)
 
-    def collect(self, mask_mode=_lib.MASK_BITS_160, contract=False):
+    def collect(self, mask_mode=_lib.MASK_BITS_160, contract=False, pinned=None):
         """Results of the oldest submission: (counts, boxes [N,4], labels [N], masks).  contract=True: the reference's own
         readback instead -- all four graph outputs as ReadbackAndClone would return them (IEE:446-449): (counts, output_0
         f32 [N,4], output_1 i32 [N], output_2 f32 [N,32], output_3 f32 [N,160,160])."""
@@ -330,6 +337,8 @@ class PipelinedRunner:
             raise XrsegError(_lib.ERR_STATE, "nothing in flight")
         r = self.runners[self._inflight.pop(0)]
         r.wait()
+        if contract and pinned is not None:           # pinned = [(host_ptr, cap_bytes)] * 4: returns the four shapes
+            return (r.counts(),) + tuple(r.readback_into(i, *pinned[i]) for i in range(4))
         if contract:
             return (r.counts(),) + tuple(r.readback(i) for i in range(4))
         return r.counts(), r.readback(0), r.readback(1), r.masks(mask_mode)

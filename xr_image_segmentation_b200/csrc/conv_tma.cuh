@@ -32,8 +32,18 @@ struct TmapSet {
   CUtensorMap m[4];
 };
 // warp 0: TMA producer; warps 1-4: MMA issuers (one per 128-row sub-tile: a single thread cannot issue tcgen05.mma faster
-// than one per ~50-65 cycles, which bounded every thin layer); warps 5-12: epilogue
-enum { TMA_THREADS = 416, TMA_TAIL_PAD = 4096, TMA_FIRST_EPI_WARP = 5 };
+// than one per ~50-65 cycles, which bounded every thin layer); warps 5 .. 5 + TMA_EPI_WARPS - 1: epilogue.  The epilogue
+// warps form TMA_EPI_WARPS / 4 groups of four (one warp per TMEM lane quadrant); the 16-column units of an item are dealt
+// round-robin to the groups.  16 epilogue warps (four per scheduler) is the measured optimum: the epilogue is bound by
+// dependency stalls, not by issue slots or the MUFU (tools/probe_mufu.cu: 15.4 SiLU / clk / SM with eight warps), so more
+// warps per scheduler hide more of them -- 8 / 12 / 16 / 20 / 24 warps: 31.7k / 32.6k / 33.4k / 32.2k / 29.5k frames/s
+// (past 16 the register cap of a 1-CTA-per-SM launch, 65536 / threads, forces spills).
+#ifndef XRSEG_EPI_WARPS
+#define XRSEG_EPI_WARPS 16
+#endif
+enum { TMA_EPI_WARPS = XRSEG_EPI_WARPS, TMA_EPI_GROUPS = XRSEG_EPI_WARPS / 4, TMA_THREADS = 32 * (5 + XRSEG_EPI_WARPS),
+       TMA_TAIL_PAD = 4096, TMA_FIRST_EPI_WARP = 5 };
+static_assert(XRSEG_EPI_WARPS % 4 == 0 && XRSEG_EPI_WARPS >= 8 && XRSEG_EPI_WARPS <= 24, "whole groups of four epilogue warps");
 
 struct TmaPlanExtra {
   int R, nsub, tpi, hbox, slots_box;
@@ -172,10 +182,16 @@ static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvP
       int S = (XR_TMA_BUDGET - fixed) / (a_stage + (res ? 0 : round_up(b_stage, 1024)));
       if (S > CONV_MAX_STAGES) S = CONV_MAX_STAGES;
       if (S > 2 * (d.Cin / cb) + 2) S = 2 * (d.Cin / cb) + 2;
-      if (S >= 3 || (S == 2 && best_S < 2)) {
+      // The TMA unit delivers one box ROW per ~1.5 cycles whatever its width (tools/probe_tma_rate.cu: 21 / 42 / 85 B/clk per SM
+      // for 32 / 64 / 128-byte rows), so a layer that splits its channels into narrow K-blocks pays the row cost Cin / cb
+      // times.  XRSEG_HALO_MIN_S=2 takes the WIDEST K-block that still leaves a two-stage ring; measured on the network
+      // (proto.cv2 148 -> 154 us, h4.box.0 33 -> 35 us, n13/n19.m0.cv1 equal) the deeper three-stage ring with narrower
+      // blocks is still the better trade, so 3 stays the default.
+      static const int min_S = [] { const char* e = getenv("XRSEG_HALO_MIN_S"); return e ? atoi(e) : 3; }();
+      if (S >= min_S || (S == 2 && best_S < 2)) {
         best_cb = cb;
         best_S = S;
-        if (S >= 3) break;
+        if (S >= min_S) break;
       }
     }
     if (best_S < 2) return false;
@@ -324,10 +340,18 @@ static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvPar
       if (S > 2 * (d.Cin / cb) + 2) S = 2 * (d.Cin / cb) + 2;
       if (S < 2) continue;
       const int nks = d.Cin / cb, nsub = ceil_div(R * p.Wp, 128);
-      const double mma_each = p.Ntile / 2.0 > 50.0 ? p.Ntile / 2.0 : 50.0;
-      const double t_mma = nks * 600.0 + 9.0 * (d.Cin / 16) * nsub * mma_each;
+      // operand fetch.  XRSEG_S2_ROWCOST=1 models it as ~1.5 cycles per TMA box row whatever its width
+      // (tools/probe_tma_rate.cu), four plane boxes per K-block, and the MMA issue as parallel over the sub-tile warps;
+      // measured on the network: n17 33 -> 28 us but b3 65 -> 70 us, so the old bytes / 40 B/clk estimate stays the default
+      static const bool rowcost = [] { const char* e = getenv("XRSEG_S2_ROWCOST"); return e && e[0] == '1'; }();
+      // one issuing warp per sub-tile: the issue cost (~50 cycles per MMA, ~600 per stage hand-over) is paid in parallel,
+      // the tensor pipe (128 x N x 16 MACs per MMA at 4096 MACs / cycle) is shared
+      const double t_issue = nks * 600.0 + 9.0 * (d.Cin / 16) * 50.0;
+      const double t_pipe = 9.0 * (d.Cin / 16) * nsub * (p.Ntile / 2.0 > 16.0 ? p.Ntile / 2.0 : 16.0);
+      const double t_mma = rowcost ? (t_issue > t_pipe ? t_issue : t_pipe)
+                                   : nks * 600.0 + 9.0 * (d.Cin / 16) * nsub * (p.Ntile / 2.0 > 50.0 ? p.Ntile / 2.0 : 50.0);
       const double t_epi = nsub * ceil_div(p.Ntile, 32) * 650.0;
-      const double t_mem = 4.0 * (R + 1) * p.Wp * d.Cin * 2 / 40.0;          // smem fill at ~40 B/clk from L2
+      const double t_mem = rowcost ? 1.5 * 4.0 * (R + 1) * p.Wp * nks : 4.0 * (R + 1) * p.Wp * d.Cin * 2 / 40.0;
       double t = t_mma > t_epi ? t_mma : t_epi;
       if (t_mem > t) t = t_mem;
       t = (t + 800.0) * (S >= 3 ? 1.0 : 1.15);
@@ -390,7 +414,7 @@ static inline TmapSet make_s2_tensor_maps(const __half* base, int B, int H, int 
 // its time in its own arrive/wait traffic there (tools/probe_umma.py).  Channels beyond Cin inside the last K-block are
 // out of bounds for the tensor map and arrive as zeros, so Cin only has to be a multiple of 16 (e.g. the 48-channel
 // C3k2 concat).
-static inline bool plan_conv_flat_tma_impl(const ConvDesc& d, int num_sms, ConvParams& p) {
+static inline bool plan_conv_flat_tma_impl(const ConvDesc& d, int num_sms, ConvParams& p, bool chain = false) {
   // also the 2x2 stride-2 ConvTranspose: the same GEMM with N = 4 positions x Cout, scattered by the epilogue
   const bool convt = d.transposed && d.k == 2 && d.stride == 2 && d.res_pitch == 0;
   if (!((d.k == 1 && d.stride == 1 && !d.transposed) || convt)) return false;
@@ -424,7 +448,11 @@ static inline bool plan_conv_flat_tma_impl(const ConvDesc& d, int num_sms, ConvP
   if (nsub > 4) nsub = 4;
   if (nsub == 3) nsub = 2;                         // an item is one or two FULL boxes of <= 256 rows: power-of-two sub-tiles only
   if (nsub < 1) nsub = 1;                          // (N = 80 at more than 64 frames picked 3: two 256-row boxes into 384 slots)
-  while (nsub > 1 && ceil_div(tiles128, nsub) < 8 * num_sms) nsub >>= 1;    // keep >= 8 items per CTA for balance
+  if (chain) {                                     // one CTA walks the whole frame: as many sub-tiles per item as it has rows for
+    while (nsub > 1 && 128 * (nsub >> 1) >= p.flat_rows) nsub >>= 1;
+  } else {
+    while (nsub > 1 && ceil_div(tiles128, nsub) < 8 * num_sms) nsub >>= 1;  // keep >= 8 items per CTA for balance
+  }
   for (;; nsub >>= 1) {
     p.nsub = nsub;
     p.slots = 128 * nsub;
@@ -648,7 +676,7 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
 // switches (1 = no MMAs, 2 = no stores, 4 = no TMA loads, 8 = software-pipelined epilogue).  The product instantiation
 // contains none of it.
 template <bool PROBE>
-__global__ void __launch_bounds__(TMA_THREADS, 2)
+__global__ void __launch_bounds__(TMA_THREADS, 1)
 conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ TmapSet tmaps) {
   const CUtensorMap& tmap = tmaps.m[0];
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -676,7 +704,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], n_issuers);       // ... and the accumulators it has finished
-      mbar_init(&tempty[i], 8);              // one arrival per epilogue warp
+      mbar_init(&tempty[i], TMA_EPI_WARPS);  // one arrival per epilogue warp
     }
     mbar_init(bres, 1);
     mbar_fence_init();
@@ -699,7 +727,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     tmem_alloc(tmem_slot, static_cast<uint32_t>(p.tmem_cols));
     tmem_relinquish();
   }
-  for (int i = tid; i < p.n_tiles * p.Ntile; i += TMA_THREADS) bias_s[i] = p.bias[i];
+  // bias for the epilogue; activated layers keep 0.5 * bias (epilogue_chunk16_hb: h = 0.5 acc + 0.5 bias in one FFMA)
+  for (int i = tid; i < p.n_tiles * p.Ntile; i += TMA_THREADS) bias_s[i] = p.act ? 0.5f * p.bias[i] : p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -887,121 +916,108 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     // ======================================= epilogue ============================================
     const int ew = warp - TMA_FIRST_EPI_WARP;
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;
+    const int grp = ew >> 2;             // unit k of an item (sub-tile u, 16-column chunk c; k = u * nch + c) goes to group k % G
+    constexpr int G = TMA_EPI_GROUPS;
+    // loop invariants out of constant memory, once.  (Pinning them into per-thread registers -- the compiler otherwise
+    // re-reads some kernel parameters through LDCU inside the unit loop -- was measured SLOWER: 2.79 -> 2.92 ms summed over
+    // the launches of a pass; the uniform datapath is not what holds the epilogue back.)
+    const int nsub = p.nsub, Ntile = p.Ntile, nch = Ntile >> 4;
+    const bool flat = p.mode == MODE_FLAT_TMA, tr = p.transposed != 0, act = p.act != 0;
+    const int Wp = p.Wp, Rr = p.R, Hh = p.H, Ww = p.W, slots = p.slots, flat_rows = p.flat_rows, tpi = p.tpi;
+    const int Ho = p.Ho, Wo = p.Wo, Cout = p.Cout, n_tiles = p.n_tiles;
+    const int out_pitch = p.out_pitch, out2_pitch = p.out2_pitch, res_pitch = p.res_pitch, split_n = p.split_n;
+    __half* const outp = p.out;
+    __half* const out2p = p.out2;
+    const __half* const resp = p.res;
+    const FastDiv fd_wp = p.fd_wp, fd_tpi = p.fd_hp1, fd_hw = p.fd_hw, fd_wo = p.fd_wo, fd_cout = p.fd_cout;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool no_store = PROBE && (p.dbg_skip & 2);
+    const bool pipelined = !(PROBE && (p.dbg_skip & 8));   // probe switch 8: wait for every TMEM load right after issuing it
+    const int probe_epi = PROBE ? (p.dbg_skip >> 4) & 3 : 0;  // probe switches 16 (no store) / 32 (no math)
+    int gu0 = 0, gc0 = grp;              // first unit of this group
+    while (gc0 >= nch) { gc0 -= nch; ++gu0; }
     int tcount = 0;
     long long e_wait = 0, e_work = 0, t0 = 0;
     pdl_wait();   // before the first residual read / output store
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
-      const int tile = p.n_tiles == 1 ? w : (w >> 1);
-      const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
-      const int b = fd_div(p.fd_hp1, tile);
-      const int y0 = (tile - b * p.tpi) * p.R;
+      const int tile = n_tiles == 1 ? w : (w >> 1);
+      const int n_tile = n_tiles == 1 ? 0 : (w & 1);
+      const int b = fd_div(fd_tpi, tile);
+      const int y0 = (tile - b * tpi) * Rr;
       const int buf = tcount % nbuf;
       const int use = tcount / nbuf;
+      // this lane's output pixel in each sub-tile (-1: padding column / row past the image / row past the matrix);
+      // ConvTranspose: the top-left pixel of the 2x2 output block of input pixel (image, h, w)
+      int pix[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pix[u] = -1;
+        if (u < nsub) {
+          const int j = 128 * u + q * 32 + lane;
+          if (flat) {
+            const int m = tile * slots + j;
+            if (m < flat_rows) pix[u] = m;
+          } else {
+            const int yy = fd_div(fd_wp, j);
+            const int cc = j - yy * Wp;
+            const int y = y0 + yy;
+            if (yy < Rr && y < Hh && cc >= 1 && cc <= Ww) pix[u] = (b * Hh + y) * Ww + (cc - 1);
+          }
+          if (tr && pix[u] >= 0) {
+            const int m = pix[u];
+            const int tb = fd_div(fd_hw, m);
+            const int rem = m - tb * fd_hw.d;
+            const int th = fd_div(fd_wo, rem);
+            const int tw = rem - th * fd_wo.d;
+            pix[u] = (tb * Ho + 2 * th) * Wo + 2 * tw;
+          }
+          if (no_store) pix[u] = -1;
+        }
+      }
       if (PROBE) t0 = clock64();
       mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
       if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
       tc_fence_after();
-      // Work units of this item: (sub-tile u, 16-column chunk c), unit index k = u * nch + c.  The two warp halves take
-      // alternating units (so thin layers with a single chunk per sub-tile still use all eight warps), and the TMEM load
-      // of the next unit is in flight while the current one is converted and stored.
-      const int nch = p.Ntile >> 4;
-      auto first_c = [&](int u) { return (half + u * nch) & 1; };
-      auto advance = [&](int& u, int& c) {     // next unit of this half after (u, c); u == nsub when exhausted
-        c += 2;
-        while (c >= nch) {
-          if (++u >= p.nsub) return;
-          c = first_c(u);
-        }
-      };
-      auto t_addr = [&](int u, int c) {
-        return tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>((buf * p.nsub + u) * p.Ntile + c * 16);
-      };
+      const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * Ntile);
       auto finish_unit = [&](const uint32_t (&v)[16], int u, int c) {
-        const int j = 128 * u + q * 32 + lane;
-        bool valid;
-        size_t pix;
-        if (p.mode == MODE_FLAT_TMA) {
-          const int m = tile * p.slots + j;
-          valid = m < p.flat_rows;
-          pix = static_cast<size_t>(m);
+        const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
+        if (px < 0) return;
+        const int n = n_tile * Ntile + c * 16;
+        __half* dst;
+        if (tr) {                                    // column chunk -> output position (pos >> 1, pos & 1) and channel
+          const int pos = fd_div(fd_cout, n);
+          const int co = n - pos * Cout;
+          dst = outp + static_cast<size_t>(px + (pos >> 1) * Wo + (pos & 1)) * out_pitch + co;
+        } else if (split_n && n >= split_n) {
+          dst = out2p + static_cast<size_t>(px) * out2_pitch + (n - split_n);
         } else {
-          const int yy = fd_div(p.fd_wp, j);
-          const int cc = j - yy * p.Wp;
-          const int y = y0 + yy;
-          valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
-          pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
+          dst = outp + static_cast<size_t>(px) * out_pitch + n;
         }
-        if (valid && !(PROBE && (p.dbg_skip & 2))) {
-          const int n = n_tile * p.Ntile + c * 16;
-          __half* dst = (p.split_n && n >= p.split_n) ? p.out2 + pix * p.out2_pitch + (n - p.split_n) : p.out + pix * p.out_pitch + n;
-          epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr, dst);
-        }
+        epilogue_chunk16_hb(v, bias_s + n, act, resp ? resp + static_cast<size_t>(px) * res_pitch + n : nullptr, dst, probe_epi);
       };
-      if (!PROBE || !(p.dbg_skip & 8) || p.transposed) {
-        // default: per sub-tile the two warp halves take alternating 16-column chunks; with an odd chunk count the
-        // starting chunk alternates with the sub-tile, so single-chunk layers (N = 16) still use all eight warps
-        for (int u = 0; u < p.nsub; ++u) {
-          const int j = 128 * u + q * 32 + lane;
-          bool valid;
-          size_t pix;
-          if (p.mode == MODE_FLAT_TMA) {
-            const int m = tile * p.slots + j;
-            valid = m < p.flat_rows;
-            pix = static_cast<size_t>(m);
-          } else {
-            const int yy = fd_div(p.fd_wp, j);
-            const int cc = j - yy * p.Wp;
-            const int y = y0 + yy;
-            valid = yy < p.R && y < p.H && cc >= 1 && cc <= p.W;
-            pix = (static_cast<size_t>(b) * p.H + y) * p.W + (cc - 1);
-          }
-          valid = valid && !(PROBE && (p.dbg_skip & 2));
-          int tb = 0, th = 0, tw = 0;
-          if (p.transposed) {                      // 2x2 stride-2 ConvTranspose: input pixel (image, h, w) of this row
-            const int m = static_cast<int>(pix);
-            tb = fd_div(p.fd_hw, m);
-            const int rem = m - tb * p.fd_hw.d;
-            th = fd_div(p.fd_wo, rem);
-            tw = rem - th * p.fd_wo.d;
-          }
-          for (int c = first_c(u); c < nch; c += 2) {
-            uint32_t v[16];
-            tmem_ld16(t_addr(u, c), v);
-            tmem_ld_wait();
-            if (valid) {
-              const int n = n_tile * p.Ntile + c * 16;
-              if (p.transposed) {                  // column chunk -> output position (pos >> 1, pos & 1) and channel
-                const int pos = fd_div(p.fd_cout, n);
-                const int co = n - pos * p.Cout;
-                const size_t opix = (static_cast<size_t>(tb) * p.Ho + (2 * th + (pos >> 1))) * p.Wo + (2 * tw + (pos & 1));
-                epilogue_chunk16(v, bias_s + n, p.act, nullptr, p.out + opix * p.out_pitch + co);
-              } else {
-                __half* dst = (p.split_n && n >= p.split_n) ? p.out2 + pix * p.out2_pitch + (n - p.split_n)
-                                                             : p.out + pix * p.out_pitch + n;
-                epilogue_chunk16(v, bias_s + n, p.act, p.res ? p.res + pix * p.res_pitch + n : nullptr, dst);
-              }
-            }
-          }
-        }
-      } else {   // XRSEG_EPI=1: software-pipelined variant (TMEM load of the next unit in flight), kept for A/B runs
-        int u = 0, c = first_c(0) - 2;
+      auto advance = [&](int& u, int& c) {           // next unit of this group (u == nsub: none left)
+        c += G;
+        while (c >= nch) { c -= nch; ++u; }
+      };
+      // software pipeline over this group's units: the TMEM load of the next unit is in flight while the current one is
+      // converted and stored (tcgen05.wait::ld covers only the load issued one step earlier)
+      int u = gu0, c = gc0;
+      uint32_t va[16], vb[16];
+      if (u < nsub) tmem_ld16(acc + static_cast<uint32_t>(u * Ntile + c * 16), va);
+      while (u < nsub) {
+        int u2 = u, c2 = c;
+        advance(u2, c2);
+        tmem_ld_wait();
+        if (u2 < nsub) tmem_ld16(acc + static_cast<uint32_t>(u2 * Ntile + c2 * 16), vb);
+        if (!pipelined) tmem_ld_wait();
+        finish_unit(va, u, c);
+        if (u2 >= nsub) break;
+        u = u2; c = c2;
         advance(u, c);
-        uint32_t va[16], vb[16];
-        if (u < p.nsub) tmem_ld16(t_addr(u, c), va);
-        while (u < p.nsub) {
-          tmem_ld_wait();
-          int u2 = u, c2 = c;
-          advance(u2, c2);
-          if (u2 < p.nsub) tmem_ld16(t_addr(u2, c2), vb);
-          finish_unit(va, u, c);
-          if (u2 >= p.nsub) break;
-          tmem_ld_wait();
-          u = u2; c = c2;
-          advance(u, c);
-          if (u < p.nsub) tmem_ld16(t_addr(u, c), va);
-          finish_unit(vb, u2, c2);
-        }
+        tmem_ld_wait();
+        if (u < nsub) tmem_ld16(acc + static_cast<uint32_t>(u * Ntile + c * 16), va);
+        if (!pipelined) tmem_ld_wait();
+        finish_unit(vb, u2, c2);
       }
       tc_fence_before();
       __syncwarp();

@@ -97,6 +97,9 @@ struct ConvParams {
   // output columns >= split_n go to out2 (pixel pitch out2_pitch), relative to split_n.  split_n == 0: single output.
   __half* out2;
   int split_n, out2_pitch;
+  // Chain kernel (conv_chain.cuh), flat mode: rows of ONE frame (H * W); a work item is `slots` rows of one frame and
+  // tpi = ceil(frame_rows / slots) items make a frame.  0 outside chains.
+  int frame_rows;
 };
 
 struct ConvDesc {

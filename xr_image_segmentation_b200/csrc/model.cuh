@@ -9,6 +9,7 @@
 
 #include <string.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -28,7 +29,7 @@ struct LayerRec {
   int cin, cout, k, stride, groups, act, transposed, h_in, w_in;
 };
 
-enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN, OP_BNECK, OP_C3K2 };
+enum OpKind { OP_STEM, OP_CONV, OP_DW, OP_SPPF, OP_UP, OP_ATTN, OP_BNECK, OP_C3K2, OP_CHAIN };
 
 struct Op {
   OpKind kind;
@@ -47,6 +48,9 @@ struct Op {
   TV y2;
   // OP_C3K2 (whole-block fusion): layer = X.cv1, layer2 = X.m0.cv1, layer3 = X.m0.cv2, layer4 = X.cv2
   int layer3 = -1, layer4 = -1;
+  // OP_CHAIN (conv_chain.cuh): consecutive convolutions of the 20x20 / 40x40 stages run by one launch, a CTA per frame;
+  // `chain` holds the OP_CONV ops in order (x / y of the chain op itself are those of its first / last convolution)
+  std::vector<Op> chain;
 };
 
 // Channel triples (input, middle, output; as laid out in shared memory) the fused Bottleneck kernel is built for
@@ -289,6 +293,39 @@ class Net {
       a.signal_tag = z.signal_tag;
       ops.erase(ops.begin() + i + 1, ops.begin() + i + 3);
     }
+  }
+
+  // Consecutive OP_CONV ops on small maps (input <= 40x40) of the same branch become one OP_CHAIN launch: a CTA walks the
+  // whole chain for one frame (frames are independent, so no grid-wide dependency exists inside these stages).  `can_chain`
+  // says whether the chain kernel has a plan for a convolution.  A chain starts at an op that waits for an event (or at any
+  // eligible op) and ends at an op that signals one, so the branch / event structure of the graph is unchanged.
+  void fuse_chains(const std::function<bool(const Op&)>& can_chain, int max_pixels = 1600) {
+    std::vector<Op> out;
+    for (size_t i = 0; i < ops.size();) {
+      auto eligible = [&](const Op& o) {
+        return o.kind == OP_CONV && !o.transposed && o.x.H * o.x.W <= max_pixels && can_chain(o);
+      };
+      if (!eligible(ops[i])) { out.push_back(ops[i++]); continue; }
+      size_t j = i + 1;
+      if (ops[i].signal_tag == 0)
+        while (j < ops.size() && eligible(ops[j]) && ops[j].branch == ops[i].branch && ops[j].wait_tag == 0) {
+          ++j;
+          if (ops[j - 1].signal_tag != 0) break;     // a signalling op ends its chain
+        }
+      if (j - i < 2) { out.push_back(ops[i++]); continue; }
+      Op c;
+      c.kind = OP_CHAIN;
+      c.layer = ops[i].layer;
+      c.x = ops[i].x;
+      c.y = ops[j - 1].y;
+      c.branch = ops[i].branch;
+      c.wait_tag = ops[i].wait_tag;
+      c.signal_tag = ops[j - 1].signal_tag;
+      c.chain.assign(ops.begin() + i, ops.begin() + j);
+      out.push_back(c);
+      i = j;
+    }
+    ops.swap(out);
   }
 
   void build(int hw) {

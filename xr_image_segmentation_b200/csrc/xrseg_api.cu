@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "conv_tma.cuh"
+#include "conv_chain.cuh"
 #include "conv_umma.cuh"
 #include "kernels_misc.cuh"
 #include "model.cuh"
@@ -44,6 +45,19 @@ struct DevLayer {
   uint2* wfrag = nullptr;          // OP_BNECK: mma.sync B-fragment order (bottleneck.cuh)
   __half* w16_rows = nullptr;      // stem_rows_kernel weights
 };
+
+// one OP_CHAIN launch (conv_chain.cuh): the per-layer plans + tensor maps in device memory
+struct ChainDev {
+  ChainLayer* d_layers = nullptr;
+  int n = 0, smem = 0;
+};
+
+// XRSEG_CHAIN=1: the convolutions of the 20x20 / 40x40 stages as per-frame chain launches (conv_chain.cuh).  Parity-tested,
+// but measured no faster than one launch per layer (dead ends): off unless asked for.
+bool chains_disabled() {
+  const char* e = getenv("XRSEG_CHAIN");
+  return !(e && e[0] == '1');
+}
 
 // ---- fused Bottleneck (bottleneck.cuh): one instantiation per supported channel triple ---------------------------------
 template <int C1, int CM, int C2, int TH>
@@ -125,6 +139,7 @@ struct xrseg_runner {
   int mb = 1;                      // frames per network pass
   int A = 8400;
   std::vector<DevLayer> dl;
+  std::vector<ChainDev> chains;    // indexed like net->ops (empty entries for everything but OP_CHAIN)
   __half* arena = nullptr;
   uint8_t* d_frames = nullptr;
   size_t d_frames_cap = 0;
@@ -175,10 +190,83 @@ inline __half* ptr_of(xrseg_runner* r, const TV& t) { return r->arena + t.off; }
 // ------------------------------------------------------------------------------------------------
 // weights -> device, per layer kind
 // ------------------------------------------------------------------------------------------------
+ConvDesc conv_desc_of(const Op& o, int batch) {
+  ConvDesc cd{};
+  cd.B = batch; cd.H = o.x.H; cd.W = o.x.W; cd.Cin = o.x.Cp; cd.in_pitch = o.x.pitch;
+  cd.Cout = o.y.Cp + (o.layer2 >= 0 ? o.y2.Cp : 0); cd.out_pitch = o.y.pitch;
+  cd.k = o.k; cd.stride = o.stride; cd.act = o.act; cd.transposed = o.transposed;
+  cd.res_pitch = o.has_res ? o.res.pitch : 0;
+  return cd;
+}
+
+// weights of a convolution op (with its fused sibling, if any) as one [Cout_a padded | Cout_b] x Cin x k x k matrix
+const HostLayerWeights& conv_weights_of(const Net& net, const Op& o, const std::vector<HostLayerWeights>& hw, HostLayerWeights& fused,
+                                        int* cout_real) {
+  const LayerRec& l = net.layers[o.layer];
+  *cout_real = l.cout;
+  if (o.layer2 < 0) return hw[o.layer];
+  const LayerRec& l2 = net.layers[o.layer2];
+  const HostLayerWeights &w = hw[o.layer], &w2 = hw[o.layer2];
+  const size_t per = static_cast<size_t>(l.cin) * l.k * l.k;
+  fused.w.assign((static_cast<size_t>(o.y.Cp) + l2.cout) * per, 0.f);
+  fused.b.assign(static_cast<size_t>(o.y.Cp) + l2.cout, 0.f);
+  std::copy(w.w.begin(), w.w.end(), fused.w.begin());
+  std::copy(w.b.begin(), w.b.end(), fused.b.begin());
+  std::copy(w2.w.begin(), w2.w.end(), fused.w.begin() + static_cast<size_t>(o.y.Cp) * per);
+  std::copy(w2.b.begin(), w2.b.end(), fused.b.begin() + o.y.Cp);
+  *cout_real = o.y.Cp + l2.cout;
+  return fused;
+}
+
+// OP_CHAIN: plan every convolution of the chain for the chain kernel, pack its weights, build its tensor maps, and put the
+// resulting ChainLayer array into device memory
+void upload_chain(xrseg_runner* r, size_t op_index, const Op& o, const std::vector<HostLayerWeights>& hw) {
+  Net& net = *r->net;
+  std::vector<ChainLayer> host;
+  int smem = 0;
+  for (const Op& s : o.chain) {
+    const LayerRec& l = net.layers[s.layer];
+    DevLayer& d = r->dl[s.layer];
+    XR_CHECK(plan_chain_layer(conv_desc_of(s, r->mb), d.cp), "no chain plan for %s", l.name.c_str());
+    d.use_tma = true;
+    if (d.cp.mode == MODE_HALO_TMA)
+      d.tmaps.m[0] = make_halo_tensor_map(ptr_of(r, s.x), r->mb, s.x.H, s.x.W, s.x.Cp, s.x.pitch, d.cp.Wp, d.cp.hbox, d.cp.cb, d.cp.sw);
+    else if (d.cp.mode == MODE_FLAT_TMA)
+      d.tmaps.m[0] = make_flat_tensor_map(ptr_of(r, s.x), static_cast<long>(r->mb) * s.x.H * s.x.W, s.x.Cp, s.x.pitch, d.cp);
+    else
+      d.tmaps = make_s2_tensor_maps(ptr_of(r, s.x), r->mb, s.x.H, s.x.W, s.x.Cp, s.x.pitch, d.cp);
+    HostLayerWeights fused;
+    int cout_real = 0;
+    const HostLayerWeights& wsrc = conv_weights_of(net, s, hw, fused, &cout_real);
+    std::vector<__half> wp;
+    std::vector<float> bp;
+    pack_conv_weights_sw<__half>(d.cp, wsrc.w.data(), wsrc.b.data(), l.cin, cout_real, wp, bp);
+    d.wpack = dev_upload(wp);
+    d.bias = dev_upload(bp);
+    ChainLayer cl{};
+    cl.tmaps = d.tmaps;
+    cl.p = d.cp;
+    cl.p.in = ptr_of(r, s.x); cl.p.out = ptr_of(r, s.y);
+    if (s.layer2 >= 0) { cl.p.out2 = ptr_of(r, s.y2); cl.p.split_n = s.y.Cp; cl.p.out2_pitch = s.y2.pitch; }
+    cl.p.res = s.has_res ? ptr_of(r, s.res) : nullptr;
+    cl.p.wpack = d.wpack; cl.p.bias = d.bias;
+    host.push_back(cl);
+    smem = std::max(smem, d.cp.smem_bytes);
+  }
+  ChainDev& c = r->chains[op_index];
+  c.n = static_cast<int>(host.size());
+  c.smem = smem;
+  XR_CUDA(cudaMalloc(&c.d_layers, host.size() * sizeof(ChainLayer)));
+  XR_CUDA(cudaMemcpy(c.d_layers, host.data(), host.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
+}
+
 void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
   Net& net = *r->net;
   r->dl.resize(net.layers.size());
-  for (const Op& o : net.ops) {
+  r->chains.assign(net.ops.size(), ChainDev{});
+  for (size_t oi = 0; oi < net.ops.size(); ++oi) {
+    const Op& o = net.ops[oi];
+    if (o.kind == OP_CHAIN) { upload_chain(r, oi, o, hw); continue; }
     if (o.layer < 0) continue;
     const LayerRec& l = net.layers[o.layer];
     const HostLayerWeights& w = hw[o.layer];
@@ -329,7 +417,8 @@ struct Launch {
 
 void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
   Net& net = *r->net;
-  for (const Op& o : net.ops) {
+  for (size_t oi = 0; oi < net.ops.size(); ++oi) {
+    const Op& o = net.ops[oi];
     Launch L;
     const double px_in = static_cast<double>(nb) * o.x.H * o.x.W, px_out = static_cast<double>(nb) * o.y.H * o.y.W;
     switch (o.kind) {
@@ -415,6 +504,49 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
           const long total = static_cast<long>(nb) * o.y.H * o.y.W * o.y.Cp;
           L.fn = [p, total](cudaStream_t st) { conv_direct_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, st>>>(p); };
         }
+        break;
+      }
+      case OP_CHAIN: {
+        const ChainDev c = r->chains[oi];
+        const int num_sms = r->num_sms;
+        L.name = "chain:" + net.layers[o.chain.front().layer].name + ".." + net.layers[o.chain.back().layer].name;
+        if (L.name.size() > 31) L.name.resize(31);
+        for (const Op& s : o.chain) {               // algorithmic work: the sum over the chain's convolutions
+          const LayerRec& l = net.layers[s.layer];
+          const double pin = static_cast<double>(nb) * s.x.H * s.x.W, pout = static_cast<double>(nb) * s.y.H * s.y.W;
+          const int cout_alg = l.cout + (s.layer2 >= 0 ? net.layers[s.layer2].cout : 0);
+          L.flops += 2.0 * pout * cout_alg * l.cin * s.k * s.k;
+          L.bytes += (pin * l.cin + pout * cout_alg * (s.has_res ? 2 : 1) + static_cast<double>(cout_alg) * l.cin * s.k * s.k) * 2;
+        }
+#ifdef XRSEG_DEBUG_API
+        if (getenv("XRSEG_CHAIN_PROBE")) {
+          // per-layer phase clocks of CTA 0 (printed after a synchronous launch; timing experiments only)
+          std::vector<std::string> names;
+          for (const Op& s : o.chain) names.push_back(net.layers[s.layer].name);
+          L.fn = [c, nb, num_sms, names](cudaStream_t st) {
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(st, &cs);
+            if (cs != cudaStreamCaptureStatusNone) { launch_conv_chain(c.d_layers, c.n, nb, c.smem, num_sms, st); return; }
+            long long* d = nullptr;
+            cudaMalloc(&d, sizeof(long long) * 8 * c.n);
+            cudaMemset(d, 0, sizeof(long long) * 8 * c.n);
+            launch_conv_chain(c.d_layers, c.n, nb, c.smem, num_sms, st, d);
+            cudaStreamSynchronize(st);
+            std::vector<long long> h(8 * c.n);
+            cudaMemcpy(h.data(), d, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+            cudaFree(d);
+            for (int l = 0; l < c.n; ++l) {
+              const long long* t = &h[8 * l];
+              const long long next = l + 1 < c.n ? h[8 * (l + 1)] : t[4];
+              // all relative to the moment MMA warp 1 has its weights (same SM sub-partition clock as the epilogue thread)
+              (void)next;
+              fprintf(stderr, "chain probe %-18s data +%5lld  mma-done +%5lld  prefetch-issued +%5lld  first-ld +%5lld  epi-done +%5lld  fenced +%5lld cycles\n",
+                      names[l].c_str(), t[1] - t[5], t[2] - t[1], t[6] - t[2], t[7] - t[6], t[3] - t[7], t[4] - t[3]);
+            }
+          };
+        } else
+#endif
+        L.fn = [c, nb, num_sms](cudaStream_t st) { launch_conv_chain(c.d_layers, c.n, nb, c.smem, num_sms, st); };
         break;
       }
       case OP_C3K2: {
@@ -752,6 +884,19 @@ int pipeline_chunk(xrseg_runner* r, int b0, int nb, cudaStream_t st, int part = 
           used[b] = false;
         }
     }
+#ifdef XRSEG_DEBUG_API
+    // XRSEG_SKIP=prefix1,prefix2,...: leave out every launch whose name starts with one of the prefixes (timing experiments
+    // only: the results are garbage) -- how much of a step a group of launches costs INSIDE the captured graph
+    static const std::string skip_env = getenv("XRSEG_SKIP") ? getenv("XRSEG_SKIP") : "";
+    bool skipped = false;
+    for (size_t a0 = 0; a0 < skip_env.size();) {
+      size_t a1 = skip_env.find(',', a0);
+      if (a1 == std::string::npos) a1 = skip_env.size();
+      if (a1 > a0 && L.name.compare(0, a1 - a0, skip_env, a0, a1 - a0) == 0) skipped = true;
+      a0 = a1 + 1;
+    }
+    if (!skipped)
+#endif
     L.fn(s);
     if (dbg_sync && !r->cfg.use_cuda_graph) {            // XRSEG_DBG_SYNC=1 (no graph): name the launch that faults
       const cudaError_t e = cudaStreamSynchronize(s);
@@ -950,6 +1095,7 @@ xrseg_runner::~xrseg_runner() {
   for (cudaEvent_t e : ev_join) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ev_copy) cudaEventDestroy(e);
   cudaFree(scratch);
+  for (ChainDev& c : chains) cudaFree(c.d_layers);
   for (DevLayer& d : dl) {
     cudaFree(d.wpack); cudaFree(d.wfrag); cudaFree(d.w16_rows); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
@@ -1132,6 +1278,7 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     for (auto& e : r->ev) XR_CUDA(cudaEventCreate(&e));
     conv_umma_prepare_device();
     conv_tma_prepare_device();
+    conv_chain_prepare_device();
     bneck_prepare_device();
     c3k2_prepare_device();
     XR_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1147,6 +1294,13 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     const char* c3k2_env = getenv("XRSEG_FUSE_C3K2");
     r->net.reset(new Net(c.model_scale, r->mb, 640, fuse, !(bneck_env && bneck_env[0] == '0'), c3k2_env && c3k2_env[0] == '1'));
     Net& net = *r->net;
+    if (c.conv_impl == XRSEG_CONV_UMMA && !chains_disabled()) {
+      const int mb = r->mb;
+      net.fuse_chains([mb](const Op& o) {
+        ConvParams tmp;
+        return plan_chain_layer(conv_desc_of(o, mb), tmp);
+      });
+    }
     r->A = net.fh[0] * net.fw[0] + net.fh[1] * net.fw[1] + net.fh[2] * net.fw[2];
     std::vector<HostLayerWeights> hw;
     try {

@@ -592,7 +592,14 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1)) * 2;
         const bool narrow = !dw_wide();             // 8 channels per thread (default) or 4 (XRSEG_DW_NARROW=1)
         const dim3 grid(ceil_div(p.W * (p.C / (narrow ? 4 : 8)), 128), ceil_div(p.H, p.rows), nb);
-        if (narrow) L.fn = [p, grid](cudaStream_t st) { launch_k(dwconv3x3_kernel<2>, grid, 128, 0, st, p); };
+        static const bool dw_smem = [] { const char* e = getenv("XRSEG_DW_SMEM"); return e && e[0] == '1'; }();   // opt-in: measured slower
+        const DwSmemGeom geo = dw_smem_geom(p.W, p.C);
+        if (dw_smem && p.C % 8 == 0 && geo.threads <= 192 && geo.smem_bytes <= 48 * 1024) {
+          const dim3 sgrid((p.C / 8) / geo.CG, ceil_div(p.H, geo.TR), nb);
+          L.fn = [p, sgrid, geo](cudaStream_t st) {
+            launch_k(dwconv3x3_smem_kernel, sgrid, geo.threads, static_cast<size_t>(geo.smem_bytes), st, p, geo.TR, geo.CG);
+          };
+        } else if (narrow) L.fn = [p, grid](cudaStream_t st) { launch_k(dwconv3x3_kernel<2>, grid, 128, 0, st, p); };
         else L.fn = [p, grid](cudaStream_t st) { launch_k(dwconv3x3_kernel<4>, grid, 128, 0, st, p); };
         break;
       }

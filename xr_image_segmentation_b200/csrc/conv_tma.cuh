@@ -671,6 +671,199 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
   }
 }
 
+// ---- epilogue ---------------------------------------------------------------------------------------------------
+// One 16-channel unit of one pixel, specialised at compile time: accumulator -> (+ bias, SiLU) -> (+ residual) -> fp16 -> one
+// 256-bit store.  hb16 (shared memory) holds 0.5 * bias when ACT (h = 0.5 acc + 0.5 bias is ONE FFMA).
+template <bool ACT, bool RES, bool BREG>
+__device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const float* hb16, const float (&hbr)[16],
+                                                  const __half* res, __half* out, int probe) {
+  uint32_t o[8];
+  if (probe & 2) {                         // PROBE builds only: store the raw accumulators
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __half2 h = __floats2half2_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      o[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    st_global_256(out, o);
+    return;
+  }
+  uint32_t rr[8];
+  if (RES) ld_global_256(res, rr);         // issued first: in flight under the math
+  if (ACT) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = BREG ? make_float4(hbr[4 * i], hbr[4 * i + 1], hbr[4 * i + 2], hbr[4 * i + 3])
+                             : reinterpret_cast<const float4*>(hb16)[i];
+      o[2 * i] = silu_pack_from_half_arg(fmaf(__uint_as_float(v[4 * i]), 0.5f, b4.x), fmaf(__uint_as_float(v[4 * i + 1]), 0.5f, b4.y));
+      o[2 * i + 1] = silu_pack_from_half_arg(fmaf(__uint_as_float(v[4 * i + 2]), 0.5f, b4.z), fmaf(__uint_as_float(v[4 * i + 3]), 0.5f, b4.w));
+    }
+    if (RES) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        __half2 s2 = __hadd2(*reinterpret_cast<__half2*>(&o[i]), *reinterpret_cast<const __half2*>(&rr[i]));
+        o[i] = *reinterpret_cast<uint32_t*>(&s2);
+      }
+    }
+  } else {
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = BREG ? make_float4(hbr[4 * i], hbr[4 * i + 1], hbr[4 * i + 2], hbr[4 * i + 3])
+                             : reinterpret_cast<const float4*>(hb16)[i];
+      y[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
+      y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
+      y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
+      y[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b4.w;
+    }
+    if (RES) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&rr[i]));
+        y[2 * i] += f.x;
+        y[2 * i + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __half2 h = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+      o[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  if (probe & 1) {                         // PROBE builds only: keep the math alive without the store
+    if ((o[0] ^ o[1] ^ o[2] ^ o[3] ^ o[4] ^ o[5] ^ o[6] ^ o[7]) == 0x12345678u) st_global_256(out, o);
+    return;
+  }
+  st_global_256(out, o);
+}
+
+// The epilogue warps' whole item loop, specialised on the destination kind (0: one tensor, 1: two tensors split at
+// split_n -- fused siblings, 2: ConvTranspose scatter), the activation and the residual.  The per-unit code of the generic
+// version was a long serial chain on the uniform datapath (kernel parameters re-read through LDCU, uniform compares and
+// branches on act / res / transposed / split_n per 16-channel unit): the epilogue, not the tensor pipe or HBM, bounded every
+// large layer at ~5 outputs per clock and SM.  Here everything that does not depend on the unit is resolved at compile time or
+// hoisted out of the unit loop: a unit is one TMEM load, the math, one address and one store.
+template <bool PROBE, int KIND, bool ACT, bool RES, bool BREG>
+__device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
+                                                  const float* bias_s, int nbuf, int warp, int lane, int total_work) {
+  constexpr int G = TMA_EPI_GROUPS;
+  const int ew = warp - TMA_FIRST_EPI_WARP;
+  const int q = warp & 3;              // TMEM lane quadrant this warp may access
+  const int grp = ew >> 2;             // unit k of an item (sub-tile u, 16-column chunk c; k = u * nch + c) goes to group k % G
+  const int nsub = p.nsub, Ntile = p.Ntile, nch = Ntile >> 4, n_units = nsub * nch;
+  const bool flat = p.mode == MODE_FLAT_TMA;
+  const int Wp = p.Wp, Rr = p.R, Hh = p.H, Ww = p.W, slots = p.slots, flat_rows = p.flat_rows, tpi = p.tpi;
+  const int Wo = p.Wo, Cout = p.Cout, n_tiles = p.n_tiles;
+  const int out_pitch = p.out_pitch, out2_pitch = p.out2_pitch, res_pitch = p.res_pitch, split_n = p.split_n;
+  __half* const outp = p.out;
+  __half* const out2p = p.out2;
+  const __half* const resp = p.res;
+  const FastDiv fd_wp = p.fd_wp, fd_tpi = p.fd_hp1, fd_hw = p.fd_hw, fd_wo = p.fd_wo, fd_cout = p.fd_cout;
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const bool no_store = PROBE && (p.dbg_skip & 2);
+  const bool pipelined = !(PROBE && (p.dbg_skip & 8));   // probe switch 8: wait for every TMEM load right after issuing it
+  const int probe_epi = PROBE ? (p.dbg_skip >> 4) & 3 : 0;  // probe switches 16 (no store) / 32 (no math)
+  int gu0 = 0, gc0 = grp;              // first unit of this group
+  while (gc0 >= nch) { gc0 -= nch; ++gu0; }
+  // BREG: the number of chunks divides the number of groups, so this group only ever sees chunk grp % nch -- its 16 bias
+  // values live in registers for the whole launch.  (Under load the tensor core's operand reads keep the shared-memory pipe
+  // busy: the four LDS.128 of a unit were the longest single stall of the epilogue.)
+  float hbr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hbr[i] = BREG ? bias_s[gc0 * 16 + i] : 0.f;
+  int tcount = 0;
+  long long e_wait = 0, e_work = 0, t0 = 0;
+  pdl_wait();   // before the first residual read / output store
+  for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+    const int tile = n_tiles == 1 ? w : (w >> 1);
+    const int n_tile = n_tiles == 1 ? 0 : (w & 1);
+    const int b = fd_div(fd_tpi, tile);
+    const int y0 = (tile - b * tpi) * Rr;
+    const int buf = tcount % nbuf;
+    const int use = tcount / nbuf;
+    // this lane's output pixel in each sub-tile (-1: padding column / row past the image / row past the matrix);
+    // ConvTranspose: the top-left pixel of the 2x2 output block of input pixel (image, h, w)
+    int pix[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pix[u] = -1;
+      if (u < nsub) {
+        const int j = 128 * u + q * 32 + lane;
+        if (flat) {
+          const int m = tile * slots + j;
+          if (m < flat_rows) pix[u] = m;
+        } else {
+          const int yy = fd_div(fd_wp, j);
+          const int cc = j - yy * Wp;
+          const int y = y0 + yy;
+          if (yy < Rr && y < Hh && cc >= 1 && cc <= Ww) pix[u] = (b * Hh + y) * Ww + (cc - 1);
+        }
+        if (KIND == 2 && pix[u] >= 0) {
+          const int m = pix[u];
+          const int tb = fd_div(fd_hw, m);
+          const int rem = m - tb * fd_hw.d;
+          const int th = fd_div(fd_wo, rem);
+          const int tw = rem - th * fd_wo.d;
+          pix[u] = (tb * p.Ho + 2 * th) * Wo + 2 * tw;
+        }
+        if (no_store) pix[u] = -1;
+      }
+    }
+    const int n_base = n_tile * Ntile;
+    if (PROBE) t0 = clock64();
+    mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
+    if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
+    tc_fence_after();
+    const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * Ntile);
+    auto finish_unit = [&](const uint32_t (&v)[16], int u, int c) {
+      const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
+      if (px < 0) return;
+      const int n = n_base + c * 16;
+      __half* dst;
+      if (KIND == 2) {                               // column chunk -> output position (pos >> 1, pos & 1) and channel
+        const int pos = fd_div(fd_cout, n);
+        const int co = n - pos * Cout;
+        dst = outp + static_cast<size_t>(px + (pos >> 1) * Wo + (pos & 1)) * out_pitch + co;
+      } else if (KIND == 1 && n >= split_n) {
+        dst = out2p + static_cast<size_t>(px) * out2_pitch + (n - split_n);
+      } else {
+        dst = outp + static_cast<size_t>(px) * out_pitch + n;
+      }
+      tma_epilogue_unit<ACT, RES, BREG>(v, bias_s + n, hbr, RES ? resp + static_cast<size_t>(px) * res_pitch + n : nullptr, dst,
+                                        probe_epi);
+    };
+    // software pipeline over this group's units (unit k = u * nch + c lives at accumulator column 16 k): the TMEM load of
+    // the next unit is in flight while the current one is converted and stored
+    int u = gu0, c = gc0, k = grp;
+    uint32_t va[16], vb[16];
+    if (k < n_units) tmem_ld16(acc + static_cast<uint32_t>(16 * k), va);
+    while (k < n_units) {
+      tmem_ld_wait();
+      if (k + G < n_units) tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), vb);
+      if (!pipelined) tmem_ld_wait();
+      finish_unit(va, u, c);
+      k += G;
+      if (k >= n_units) break;
+      c += G;
+      while (c >= nch) { c -= nch; ++u; }
+      tmem_ld_wait();
+      if (k + G < n_units) tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), va);
+      if (!pipelined) tmem_ld_wait();
+      finish_unit(vb, u, c);
+      k += G;
+      c += G;
+      while (c >= nch) { c -= nch; ++u; }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[buf]);
+    if (PROBE) e_work += clock64() - t0;
+  }
+  if (PROBE && p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
+    p.dbg_clk[blockIdx.x * 12 + 6] = e_wait;
+    p.dbg_clk[blockIdx.x * 12 + 7] = e_work;
+  }
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------------
 // PROBE = true (libxrseg_debug.so only, tools/probe_tma.py): per-role clock64() counters (p.dbg_clk) and the p.dbg_skip
 // switches (1 = no MMAs, 2 = no stores, 4 = no TMA loads, 8 = software-pipelined epilogue).  The product instantiation
@@ -914,120 +1107,23 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     }
   } else {
     // ======================================= epilogue ============================================
-    const int ew = warp - TMA_FIRST_EPI_WARP;
-    const int q = warp & 3;              // TMEM lane quadrant this warp may access
-    const int grp = ew >> 2;             // unit k of an item (sub-tile u, 16-column chunk c; k = u * nch + c) goes to group k % G
-    constexpr int G = TMA_EPI_GROUPS;
-    // loop invariants out of constant memory, once.  (Pinning them into per-thread registers -- the compiler otherwise
-    // re-reads some kernel parameters through LDCU inside the unit loop -- was measured SLOWER: 2.79 -> 2.92 ms summed over
-    // the launches of a pass; the uniform datapath is not what holds the epilogue back.)
-    const int nsub = p.nsub, Ntile = p.Ntile, nch = Ntile >> 4;
-    const bool flat = p.mode == MODE_FLAT_TMA, tr = p.transposed != 0, act = p.act != 0;
-    const int Wp = p.Wp, Rr = p.R, Hh = p.H, Ww = p.W, slots = p.slots, flat_rows = p.flat_rows, tpi = p.tpi;
-    const int Ho = p.Ho, Wo = p.Wo, Cout = p.Cout, n_tiles = p.n_tiles;
-    const int out_pitch = p.out_pitch, out2_pitch = p.out2_pitch, res_pitch = p.res_pitch, split_n = p.split_n;
-    __half* const outp = p.out;
-    __half* const out2p = p.out2;
-    const __half* const resp = p.res;
-    const FastDiv fd_wp = p.fd_wp, fd_tpi = p.fd_hp1, fd_hw = p.fd_hw, fd_wo = p.fd_wo, fd_cout = p.fd_cout;
-    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const bool no_store = PROBE && (p.dbg_skip & 2);
-    const bool pipelined = !(PROBE && (p.dbg_skip & 8));   // probe switch 8: wait for every TMEM load right after issuing it
-    const int probe_epi = PROBE ? (p.dbg_skip >> 4) & 3 : 0;  // probe switches 16 (no store) / 32 (no math)
-    int gu0 = 0, gc0 = grp;              // first unit of this group
-    while (gc0 >= nch) { gc0 -= nch; ++gu0; }
-    int tcount = 0;
-    long long e_wait = 0, e_work = 0, t0 = 0;
-    pdl_wait();   // before the first residual read / output store
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
-      const int tile = n_tiles == 1 ? w : (w >> 1);
-      const int n_tile = n_tiles == 1 ? 0 : (w & 1);
-      const int b = fd_div(fd_tpi, tile);
-      const int y0 = (tile - b * tpi) * Rr;
-      const int buf = tcount % nbuf;
-      const int use = tcount / nbuf;
-      // this lane's output pixel in each sub-tile (-1: padding column / row past the image / row past the matrix);
-      // ConvTranspose: the top-left pixel of the 2x2 output block of input pixel (image, h, w)
-      int pix[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        pix[u] = -1;
-        if (u < nsub) {
-          const int j = 128 * u + q * 32 + lane;
-          if (flat) {
-            const int m = tile * slots + j;
-            if (m < flat_rows) pix[u] = m;
-          } else {
-            const int yy = fd_div(fd_wp, j);
-            const int cc = j - yy * Wp;
-            const int y = y0 + yy;
-            if (yy < Rr && y < Hh && cc >= 1 && cc <= Ww) pix[u] = (b * Hh + y) * Ww + (cc - 1);
-          }
-          if (tr && pix[u] >= 0) {
-            const int m = pix[u];
-            const int tb = fd_div(fd_hw, m);
-            const int rem = m - tb * fd_hw.d;
-            const int th = fd_div(fd_wo, rem);
-            const int tw = rem - th * fd_wo.d;
-            pix[u] = (tb * Ho + 2 * th) * Wo + 2 * tw;
-          }
-          if (no_store) pix[u] = -1;
-        }
-      }
-      if (PROBE) t0 = clock64();
-      mbar_wait(&tfull[buf], static_cast<uint32_t>(use) & 1u);
-      if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
-      tc_fence_after();
-      const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * Ntile);
-      auto finish_unit = [&](const uint32_t (&v)[16], int u, int c) {
-        const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
-        if (px < 0) return;
-        const int n = n_tile * Ntile + c * 16;
-        __half* dst;
-        if (tr) {                                    // column chunk -> output position (pos >> 1, pos & 1) and channel
-          const int pos = fd_div(fd_cout, n);
-          const int co = n - pos * Cout;
-          dst = outp + static_cast<size_t>(px + (pos >> 1) * Wo + (pos & 1)) * out_pitch + co;
-        } else if (split_n && n >= split_n) {
-          dst = out2p + static_cast<size_t>(px) * out2_pitch + (n - split_n);
-        } else {
-          dst = outp + static_cast<size_t>(px) * out_pitch + n;
-        }
-        epilogue_chunk16_hb(v, bias_s + n, act, resp ? resp + static_cast<size_t>(px) * res_pitch + n : nullptr, dst, probe_epi);
-      };
-      auto advance = [&](int& u, int& c) {           // next unit of this group (u == nsub: none left)
-        c += G;
-        while (c >= nch) { c -= nch; ++u; }
-      };
-      // software pipeline over this group's units: the TMEM load of the next unit is in flight while the current one is
-      // converted and stored (tcgen05.wait::ld covers only the load issued one step earlier)
-      int u = gu0, c = gc0;
-      uint32_t va[16], vb[16];
-      if (u < nsub) tmem_ld16(acc + static_cast<uint32_t>(u * Ntile + c * 16), va);
-      while (u < nsub) {
-        int u2 = u, c2 = c;
-        advance(u2, c2);
-        tmem_ld_wait();
-        if (u2 < nsub) tmem_ld16(acc + static_cast<uint32_t>(u2 * Ntile + c2 * 16), vb);
-        if (!pipelined) tmem_ld_wait();
-        finish_unit(va, u, c);
-        if (u2 >= nsub) break;
-        u = u2; c = c2;
-        advance(u, c);
-        tmem_ld_wait();
-        if (u < nsub) tmem_ld16(acc + static_cast<uint32_t>(u * Ntile + c * 16), va);
-        if (!pipelined) tmem_ld_wait();
-        finish_unit(vb, u2, c2);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
-      if (PROBE) e_work += clock64() - t0;
+    // one specialised instantiation per (destination kind, activation, residual): see tma_epilogue_loop
+    const int kind = p.transposed ? 2 : (p.split_n ? 1 : 0);
+    const int nch_ = p.Ntile >> 4;
+    const bool breg = p.n_tiles == 1 && nch_ <= TMA_EPI_GROUPS && TMA_EPI_GROUPS % nch_ == 0;
+    const int sel = (breg ? 16 : 0) + kind * 4 + (p.act ? 2 : 0) + (p.res ? 1 : 0);
+#define XR_EPI_CASE(id, K, A, R, B) \
+  case id: tma_epilogue_loop<PROBE, K, A, R, B>(p, tmem_base, tfull, tempty, bias_s, nbuf, warp, lane, total_work); break;
+    switch (sel) {
+      XR_EPI_CASE(0, 0, false, false, false) XR_EPI_CASE(1, 0, false, true, false) XR_EPI_CASE(2, 0, true, false, false)
+      XR_EPI_CASE(3, 0, true, true, false) XR_EPI_CASE(4, 1, false, false, false) XR_EPI_CASE(6, 1, true, false, false)
+      XR_EPI_CASE(8, 2, false, false, false) XR_EPI_CASE(10, 2, true, false, false)
+      XR_EPI_CASE(16, 0, false, false, true) XR_EPI_CASE(17, 0, false, true, true) XR_EPI_CASE(18, 0, true, false, true)
+      XR_EPI_CASE(19, 0, true, true, true) XR_EPI_CASE(20, 1, false, false, true) XR_EPI_CASE(22, 1, true, false, true)
+      XR_EPI_CASE(24, 2, false, false, true) XR_EPI_CASE(26, 2, true, false, true)
+      default: asm volatile("trap;"); break;       // split / transposed launches never carry a residual (checked at plan time)
     }
-    if (PROBE && p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
-      p.dbg_clk[blockIdx.x * 12 + 6] = e_wait;
-      p.dbg_clk[blockIdx.x * 12 + 7] = e_work;
-    }
+#undef XR_EPI_CASE
   }
 
   tc_fence_before();

@@ -484,6 +484,13 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         if (r->cfg.conv_impl == XRSEG_CONV_UMMA) {
           ConvParams p = d.cp;
           if (nb != p.B) p = replan_for_batch(d.cp, nb, r->num_sms);   // partial last chunk: same layout, fewer frames
+          {
+            // Experiment switch: launches with at most XRSEG_TINY_WORK items (default two per SM) use at most XRSEG_TINY_GRID
+            // CTAs, so that the latency-bound small-map kernels of two runners can sit side by side on disjoint SMs.
+            static const int tiny_grid = [] { const char* e = getenv("XRSEG_TINY_GRID"); return e ? atoi(e) : 0; }();
+            static const int tiny_work = [] { const char* e = getenv("XRSEG_TINY_WORK"); return e ? atoi(e) : 296; }();
+            if (tiny_grid > 0 && d.use_tma && p.m_tiles * p.n_tiles <= tiny_work && p.grid > tiny_grid) p.grid = tiny_grid;
+          }
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
           if (o.layer2 >= 0) { p.out2 = ptr_of(r, o.y2); p.split_n = o.y.Cp; p.out2_pitch = o.y2.pitch; }
           p.res = o.has_res ? ptr_of(r, o.res) : nullptr;

@@ -562,10 +562,11 @@ SCORE_THR, IOU_THR = 0.301, 0.43
 def match_detections(got, ref, frame="", explain_unpaired=True):
     """Detection-level parity of one frame (BASELINE.json north_star: post-NMS detections match at IoU >= 0.99 with mask
     pixel disagreement <= 0.1 %).  got / ref: dicts keep [n] (anchor ids), boxes [n,4] cxcywh, labels [n], scores [n],
-    masks bool [n,160,160] (+ probs f32 [n,160,160] on the oracle side).  Detections are paired by anchor id; every pair must
-    agree on label, IoU >= 0.99, box <= 1 px and the pair's mask bits; a differing mask pixel is accepted only when the
-    oracle's probability sits within 0.04 of the 0.5 threshold (a mask-logit error of 0.16: the fp16 network's relative L2
-    error of ~1e-2 on prototype / coefficient tensors of magnitude ~10; measured worst case 0.030 on the random-init nets).  An unpaired detection is accepted only when the fp16-vs-fp32 noise can explain it: its score
+    masks bool [n,160,160] (+ probs f32 [n,160,160]).  Detections are paired by anchor id; every pair must agree on label,
+    IoU >= 0.99, box <= 1 px, and -- when both sides carry mask probabilities -- on EVERY mask pixel's probability within
+    0.1 (a mask-logit error of 0.4 on sums of 32 fp16 products of magnitude ~10; measured worst case 0.057 (n) / 0.081 (s) on the
+    random-init networks), so a mask bit can only differ where the oracle's probability sits at the threshold.
+    An unpaired detection is accepted only when the fp16-vs-fp32 noise can explain it: its score
     sits within 0.02 of the score threshold, or its best overlap with a kept box of the other side sits within 0.03 of the
     IoU threshold (a suppression decided the other way).  Returns (pairs, unpaired, differing mask pixels, mask pixels)."""
     gi = {int(a): i for i, a in enumerate(got["keep"])}
@@ -581,8 +582,8 @@ def match_detections(got, ref, frame="", explain_unpaired=True):
         assert np.abs(got["boxes"][i] - ref["boxes"][j]).max() <= tol, (frame, a, got["boxes"][i], ref["boxes"][j])
         assert iou_cxcywh(got["boxes"][i:i + 1], ref["boxes"][j:j + 1])[0] >= 0.99, (frame, a)
         diff = got["masks"][i] != ref["masks"][j]
-        if "probs" in ref and diff.any():
-            assert np.abs(ref["probs"][j][diff] - np.float32(0.5)).max() <= 0.04, (frame, a)
+        if "probs" in ref and "probs" in got:
+            assert np.abs(ref["probs"][j] - got["probs"][i]).max() <= 0.1, (frame, a)
         bad_px += int(np.count_nonzero(diff))
         n_px += got["masks"][i].size
     unpaired = 0
@@ -609,7 +610,8 @@ def gpu_frames(r, n_frames):
     for f in range(n_frames):
         n = int(counts[f])
         sl = slice(off, off + n)
-        out.append(dict(keep=keep[sl], scores=scores[sl], boxes=boxes[sl], labels=labels[sl], masks=probs[sl] > np.float32(0.5)))
+        out.append(dict(keep=keep[sl], scores=scores[sl], boxes=boxes[sl], labels=labels[sl], masks=probs[sl] > np.float32(0.5),
+                        probs=probs[sl]))
         off += n
     return out
 
@@ -813,8 +815,8 @@ def test_config1_batch64_detection_parity(lib):
     # candidates right AT the threshold: many detections are borderline by construction.  Every unpaired one must be
     # explained by a score within 0.02 of the threshold or a suppression within 0.03 of the IoU threshold
     # (match_detections asserts that); every pair must meet IoU >= 0.99.  Mask pixels: the random-init prototypes give mask
-    # logits concentrated around 0, so more pixels than on the trained network sit at the threshold: every differing pixel
-    # must have an oracle probability within 0.04 of 0.5 (asserted per pixel) and at most 0.2 % may differ (0.1 % -- the
+    # logits concentrated around 0, so more pixels than on the trained network sit at the threshold: every pixel's
+    # probability must agree within 0.1 (asserted per pixel) and at most 0.2 % of the mask bits may differ (0.1 % -- the
     # north_star figure -- is what the trained reference network meets on all six sample frames).
     pairs, unpaired = assert_batch_parity([got[i] for i in sample], oracle_frames(res), min_pairs=20, max_unpaired=0.3,
                                           max_mask_diff=2e-3)
@@ -863,7 +865,8 @@ def test_config2_yolo11s_detection_parity(lib):
     got = gpu_frames(r, 4)
     x = torch.from_numpy(np.concatenate([pre.to_tensor(f) for f in frames]))
     res, _ = Y.run_model(ws, x, "s")
-    pairs, unpaired = assert_batch_parity(got, oracle_frames(res), min_pairs=20, explain_unpaired=False, max_unpaired=0.1)
+    pairs, unpaired = assert_batch_parity(got, oracle_frames(res), min_pairs=20, explain_unpaired=False, max_unpaired=0.1,
+                                          max_mask_diff=2e-3)
     print(f"config2 s-scale: {n} detections, {pairs} paired with the fp32 oracle on 4 frames, {unpaired} unpaired")
     r.close()
 

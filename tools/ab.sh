@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 i=0
 for cfg in "$@"; do
   [ "$cfg" = "-" ] && cfg=""
-  env $cfg timeout 600 python bench.py --steps ${STEPS:-60} --latency-iters ${LAT:-200} --no-cpu-baseline > gpurun_out/${T}_bench_$i.log 2>&1; rc=$?
+  env $cfg timeout 600 python bench.py --steps ${STEPS:-60} --latency-iters ${LAT:-200} --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/${T}_bench_$i.log 2>&1; rc=$?
   cp gpurun_out/ops_profile.json gpurun_out/${T}_ops_$i.json 2>/dev/null
   python - <<PY
 import json

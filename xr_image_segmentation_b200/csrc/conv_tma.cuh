@@ -41,6 +41,9 @@ struct TmapSet {
 #ifndef XRSEG_EPI_WARPS
 #define XRSEG_EPI_WARPS 16
 #endif
+#ifndef XRSEG_BIAS_PREFETCH
+#define XRSEG_BIAS_PREFETCH 0   // 1: fetch the bias of non-fixed chunks one unit ahead (needs 16 more registers: spills at the 80-register cap of a 21-warp CTA, measured slower)
+#endif
 enum { TMA_EPI_WARPS = XRSEG_EPI_WARPS, TMA_EPI_GROUPS = XRSEG_EPI_WARPS / 4, TMA_THREADS = 32 * (5 + XRSEG_EPI_WARPS),
        TMA_TAIL_PAD = 4096, TMA_FIRST_EPI_WARP = 5 };
 static_assert(XRSEG_EPI_WARPS % 4 == 0 && XRSEG_EPI_WARPS >= 8 && XRSEG_EPI_WARPS <= 24, "whole groups of four epilogue warps");
@@ -674,9 +677,9 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
 // ---- epilogue ---------------------------------------------------------------------------------------------------
 // One 16-channel unit of one pixel, specialised at compile time: accumulator -> (+ bias, SiLU) -> (+ residual) -> fp16 -> one
 // 256-bit store.  hb16 (shared memory) holds 0.5 * bias when ACT (h = 0.5 acc + 0.5 bias is ONE FFMA).
-template <bool ACT, bool RES, bool BREG>
-__device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const float* hb16, const float (&hbr)[16],
-                                                  const __half* res, __half* out, int probe) {
+template <bool ACT, bool RES>
+__device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const float (&hbr)[16], const __half* res, __half* out,
+                                                  int probe) {
   uint32_t o[8];
   if (probe & 2) {                         // PROBE builds only: store the raw accumulators
 #pragma unroll
@@ -692,8 +695,7 @@ __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const
   if (ACT) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = BREG ? make_float4(hbr[4 * i], hbr[4 * i + 1], hbr[4 * i + 2], hbr[4 * i + 3])
-                             : reinterpret_cast<const float4*>(hb16)[i];
+      const float4 b4 = make_float4(hbr[4 * i], hbr[4 * i + 1], hbr[4 * i + 2], hbr[4 * i + 3]);
       o[2 * i] = silu_pack_from_half_arg(fmaf(__uint_as_float(v[4 * i]), 0.5f, b4.x), fmaf(__uint_as_float(v[4 * i + 1]), 0.5f, b4.y));
       o[2 * i + 1] = silu_pack_from_half_arg(fmaf(__uint_as_float(v[4 * i + 2]), 0.5f, b4.z), fmaf(__uint_as_float(v[4 * i + 3]), 0.5f, b4.w));
     }
@@ -708,8 +710,7 @@ __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const
     float y[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = BREG ? make_float4(hbr[4 * i], hbr[4 * i + 1], hbr[4 * i + 2], hbr[4 * i + 3])
-                             : reinterpret_cast<const float4*>(hb16)[i];
+      const float4 b4 = make_float4(hbr[4 * i], hbr[4 * i + 1], hbr[4 * i + 2], hbr[4 * i + 3]);
       y[4 * i] = __uint_as_float(v[4 * i]) + b4.x;
       y[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b4.y;
       y[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b4.z;
@@ -814,10 +815,25 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
     if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
     tc_fence_after();
     const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * Ntile);
-    auto finish_unit = [&](const uint32_t (&v)[16], int u, int c) {
+    auto finish_unit = [&](const uint32_t (&v)[16], const float (&hb_in)[16], int u, int c) {
       const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
       if (px < 0) return;
       const int n = n_base + c * 16;
+#if XRSEG_BIAS_PREFETCH
+      const float (&hb)[16] = hb_in;
+#else
+      float hb[16];                                  // A/B build: bias fetched at the point of use
+      if (!BREG) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b4 = reinterpret_cast<const float4*>(bias_s + n)[i];
+          hb[4 * i] = b4.x; hb[4 * i + 1] = b4.y; hb[4 * i + 2] = b4.z; hb[4 * i + 3] = b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hb[i] = hb_in[i];
+      }
+#endif
       __half* dst;
       if (KIND == 2) {                               // column chunk -> output position (pos >> 1, pos & 1) and channel
         const int pos = fd_div(fd_cout, n);
@@ -828,30 +844,51 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
       } else {
         dst = outp + static_cast<size_t>(px) * out_pitch + n;
       }
-      tma_epilogue_unit<ACT, RES, BREG>(v, bias_s + n, hbr, RES ? resp + static_cast<size_t>(px) * res_pitch + n : nullptr, dst,
-                                        probe_epi);
+      tma_epilogue_unit<ACT, RES>(v, hb, RES ? resp + static_cast<size_t>(px) * res_pitch + n : nullptr, dst, probe_epi);
+    };
+    // bias of a unit: fixed per group (BREG, loaded once above) or fetched from shared memory ONE UNIT AHEAD, together with the
+    // unit's TMEM load, so that the LDS latency (long while the tensor core streams operands) hides under the previous unit
+    auto load_bias = [&](float (&h)[16], int cc) {
+      if (BREG || !XRSEG_BIAS_PREFETCH) return;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b4 = reinterpret_cast<const float4*>(bias_s + n_base + cc * 16)[i];
+        h[4 * i] = b4.x; h[4 * i + 1] = b4.y; h[4 * i + 2] = b4.z; h[4 * i + 3] = b4.w;
+      }
     };
     // software pipeline over this group's units (unit k = u * nch + c lives at accumulator column 16 k): the TMEM load of
     // the next unit is in flight while the current one is converted and stored
     int u = gu0, c = gc0, k = grp;
     uint32_t va[16], vb[16];
-    if (k < n_units) tmem_ld16(acc + static_cast<uint32_t>(16 * k), va);
+    float ha[16], hb[16];
+    if (k < n_units) {
+      tmem_ld16(acc + static_cast<uint32_t>(16 * k), va);
+      load_bias(ha, c);
+    }
     while (k < n_units) {
+      int u2 = u, c2 = c + G;
+      while (c2 >= nch) { c2 -= nch; ++u2; }
       tmem_ld_wait();
-      if (k + G < n_units) tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), vb);
+      if (k + G < n_units) {
+        tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), vb);
+        load_bias(hb, c2);
+      }
       if (!pipelined) tmem_ld_wait();
-      finish_unit(va, u, c);
+      finish_unit(va, BREG ? hbr : ha, u, c);
       k += G;
       if (k >= n_units) break;
-      c += G;
-      while (c >= nch) { c -= nch; ++u; }
+      u = u2; c = c2;
+      c2 = c + G;
+      while (c2 >= nch) { c2 -= nch; ++u2; }
       tmem_ld_wait();
-      if (k + G < n_units) tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), va);
+      if (k + G < n_units) {
+        tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), va);
+        load_bias(ha, c2);
+      }
       if (!pipelined) tmem_ld_wait();
-      finish_unit(vb, u, c);
+      finish_unit(vb, BREG ? hbr : hb, u, c);
       k += G;
-      c += G;
-      while (c >= nch) { c -= nch; ++u; }
+      u = u2; c = c2;
     }
     tc_fence_before();
     __syncwarp();

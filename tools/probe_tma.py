@@ -14,7 +14,7 @@ for name, cin, cout, h, w, k, s in cases:
     x = rng.standard_normal((B, cin, h, w), dtype=np.float32)
     wt = rng.standard_normal((cout, cin, k, k), dtype=np.float32) * np.float32(1 / np.sqrt(cin * k * k))
     b = rng.standard_normal(cout, dtype=np.float32)
-    for skip in (0, 2, 16, 32, 1):
+    for skip in [int(x) for x in os.environ.get("SKIPS", "0,2,16,32,1").split(",")]:
         os.environ["XRSEG_DBG_SKIP"] = str(skip)
         print("case", name, (B, cin, cout, h, w, k, s), "skip", skip, file=sys.stderr, flush=True)
         I.debug_conv(x, wt, b, k, s, 1, variant=0)

@@ -679,7 +679,7 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
 // 256-bit store.  hb16 (shared memory) holds 0.5 * bias when ACT (h = 0.5 acc + 0.5 bias is ONE FFMA).
 template <bool ACT, bool RES>
 __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const float (&hbr)[16], const __half* res, __half* out,
-                                                  int probe) {
+                                                  int probe, bool valid = true) {
   uint32_t o[8];
   if (probe & 2) {                         // PROBE builds only: store the raw accumulators
 #pragma unroll
@@ -692,7 +692,14 @@ __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const
   }
   uint32_t rr[8];
   if (RES) ld_global_256(res, rr);         // issued first: in flight under the math
-  if (ACT) {
+  if (ACT && (probe & 4)) {                // PROBE builds only: the same FP32-pipe work without the MUFU
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float ha = fmaf(__uint_as_float(v[2 * i]), 0.5f, hbr[2 * i]), hb = fmaf(__uint_as_float(v[2 * i + 1]), 0.5f, hbr[2 * i + 1]);
+      __half2 h = __floats2half2_rn(fmaf(ha, ha, ha), fmaf(hb, hb, hb));
+      o[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+  } else if (ACT) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 b4 = make_float4(hbr[4 * i], hbr[4 * i + 1], hbr[4 * i + 2], hbr[4 * i + 3]);
@@ -734,7 +741,7 @@ __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const
     if ((o[0] ^ o[1] ^ o[2] ^ o[3] ^ o[4] ^ o[5] ^ o[6] ^ o[7]) == 0x12345678u) st_global_256(out, o);
     return;
   }
-  st_global_256(out, o);
+  if (valid) st_global_256(out, o);
 }
 
 // The epilogue warps' whole item loop, specialised on the destination kind (0: one tensor, 1: two tensors split at
@@ -762,7 +769,8 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
   const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
   const bool no_store = PROBE && (p.dbg_skip & 2);
   const bool pipelined = !(PROBE && (p.dbg_skip & 8));   // probe switch 8: wait for every TMEM load right after issuing it
-  const int probe_epi = PROBE ? (p.dbg_skip >> 4) & 3 : 0;  // probe switches 16 (no store) / 32 (no math)
+  const int probe_epi = PROBE ? (p.dbg_skip >> 4) & 15 : 0;  // probe switches 16 (no store) / 32 (no math) / 64 (no MUFU) / 128 (no TMEM loads)
+  const bool ld_on = !(PROBE && (p.dbg_skip & 128));
   int gu0 = 0, gc0 = grp;              // first unit of this group
   while (gc0 >= nch) { gc0 -= nch; ++gu0; }
   // BREG: the number of chunks divides the number of groups, so this group only ever sees chunk grp % nch -- its 16 bias
@@ -815,6 +823,51 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
     if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
     tc_fence_after();
     const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * Ntile);
+    if constexpr (BREG) {
+      // Fixed chunk per group (nch divides G): this group's units are chunk gc0 of sub-tiles gu0, gu0 + G / nch, ...  The
+      // destination (tensor, channel offset, ConvTranspose position) is the same for all of them: one base pointer per
+      // launch, one pixel offset per sub-tile, no per-unit control flow; lanes without a pixel run the math and skip the store.
+      const int ustep = G / nch;
+      const int n = gc0 * 16;                                            // n_tiles == 1
+      __half* gbase;
+      int gpitch;
+      if (KIND == 2) {
+        const int pos = fd_div(fd_cout, n);
+        gbase = outp + static_cast<size_t>((pos >> 1) * Wo + (pos & 1)) * out_pitch + (n - pos * Cout);
+        gpitch = out_pitch;
+      } else if (KIND == 1 && n >= split_n) {
+        gbase = out2p + (n - split_n);
+        gpitch = out2_pitch;
+      } else {
+        gbase = outp + n;
+        gpitch = out_pitch;
+      }
+      const uint32_t acc_g = acc + static_cast<uint32_t>(gc0 * 16);
+      uint32_t va[16], vb[16];
+      if (!ld_on) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) va[i] = vb[i] = 0x3f000000u + i + lane;
+      }
+      if (gu0 < nsub && ld_on) tmem_ld16(acc_g + static_cast<uint32_t>(gu0 * Ntile), va);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int u = gu0 + j * ustep;
+        if (u >= nsub) break;
+        if (ld_on) tmem_ld_wait();
+        const int un = u + ustep;
+        if (un < nsub && ld_on) tmem_ld16(acc_g + static_cast<uint32_t>(un * Ntile), (j & 1) ? va : vb);
+        if (!pipelined) tmem_ld_wait();
+        const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
+        const size_t pxs = static_cast<size_t>(px < 0 ? 0 : px);
+        tma_epilogue_unit<ACT, RES>((j & 1) ? vb : va, hbr, RES ? resp + pxs * res_pitch + n : nullptr, gbase + pxs * gpitch, probe_epi,
+                                    px >= 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (PROBE) e_work += clock64() - t0;
+      continue;
+    }
     auto finish_unit = [&](const uint32_t (&v)[16], const float (&hb_in)[16], int u, int c) {
       const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
       if (px < 0) return;
@@ -861,16 +914,20 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
     int u = gu0, c = gc0, k = grp;
     uint32_t va[16], vb[16];
     float ha[16], hb[16];
+    if (!ld_on) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) va[i] = vb[i] = 0x3f000000u + i + lane;
+    }
     if (k < n_units) {
-      tmem_ld16(acc + static_cast<uint32_t>(16 * k), va);
+      if (ld_on) tmem_ld16(acc + static_cast<uint32_t>(16 * k), va);
       load_bias(ha, c);
     }
     while (k < n_units) {
       int u2 = u, c2 = c + G;
       while (c2 >= nch) { c2 -= nch; ++u2; }
-      tmem_ld_wait();
+      if (ld_on) tmem_ld_wait();
       if (k + G < n_units) {
-        tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), vb);
+        if (ld_on) tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), vb);
         load_bias(hb, c2);
       }
       if (!pipelined) tmem_ld_wait();
@@ -880,9 +937,9 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
       u = u2; c = c2;
       c2 = c + G;
       while (c2 >= nch) { c2 -= nch; ++u2; }
-      tmem_ld_wait();
+      if (ld_on) tmem_ld_wait();
       if (k + G < n_units) {
-        tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), va);
+        if (ld_on) tmem_ld16(acc + static_cast<uint32_t>(16 * (k + G)), va);
         load_bias(ha, c2);
       }
       if (!pipelined) tmem_ld_wait();
@@ -1049,7 +1106,11 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const uint64_t hi_sw = static_cast<uint64_t>(((8u * rb) >> 4) | (1u << 14) | (layout << 29)) << 32;
       const bool mma_on = !PROBE || !(p.dbg_skip & 1);
       long long t_start = 0, t_bres = 0, t_tempty = 0, t_full = 0, t_issue = 0, t_fence = 0, t_commit = 0, t0 = 0;
-      if (PROBE) t_start = clock64();
+      long long g_start = 0;
+      if (PROBE) {
+        t_start = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+      }
       if (p.b_resident) mbar_wait(bres, 0);
       if (PROBE) t_bres = clock64() - t_start;
       int it = 0, tcount = 0;
@@ -1140,6 +1201,9 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         p.dbg_clk[blockIdx.x * 12 + 5] = clock64() - t_start;
         p.dbg_clk[blockIdx.x * 12 + 8] = t_fence;
         p.dbg_clk[blockIdx.x * 12 + 9] = t_commit;
+        long long g_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+        p.dbg_clk[blockIdx.x * 12 + 10] = g_end - g_start;       // the MMA warp's lifetime in ns (mma_total is the same span in cycles)
       }
     }
   } else {

@@ -2149,8 +2149,8 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
           std::vector<long long> h(static_cast<size_t>(p.grid) * 12);
           XR_CUDA(cudaMemcpy(h.data(), d_clk, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
           const char* nm[12] = {"prod_wait_empty", "mma_wait_bres", "mma_wait_tempty", "mma_wait_full", "mma_issue", "mma_total",
-                                "epi_wait_tfull", "epi_work", "mma_fence", "mma_commit", "-", "-"};
-          for (int k = 0; k < 10; ++k) {
+                                "epi_wait_tfull", "epi_work", "mma_fence", "mma_commit", "mma_total_ns", "-"};
+          for (int k = 0; k < 11; ++k) {
             double sum = 0;
             for (int c = 0; c < p.grid; ++c) sum += static_cast<double>(h[c * 12 + k]);
             fprintf(stderr, "   %-16s avg %.0f cycles per CTA (last of %d launches)\n", nm[k], sum / p.grid, reps);

@@ -28,8 +28,9 @@ namespace xrseg {
 enum { MODE_HALO_TMA = 2, MODE_FLAT_TMA = 3, MODE_S2_TMA = 4 };
 
 // Up to four tensor maps per launch (MODE_S2_TMA reads four parity planes of the input; the other modes use m[0]).
+// m[4] / m[5]: output tensor maps of the TMA-store epilogue (out / out2), unused otherwise.
 struct TmapSet {
-  CUtensorMap m[4];
+  CUtensorMap m[6];
 };
 // warp 0: TMA producer; warps 1-4: MMA issuers (one per 128-row sub-tile: a single thread cannot issue tcgen05.mma faster
 // than one per ~50-65 cycles, which bounded every thin layer); warps 5 .. 5 + TMA_EPI_WARPS - 1: epilogue.  The epilogue
@@ -507,9 +508,12 @@ static inline bool plan_conv_flat_tma_impl(const ConvDesc& d, int num_sms, ConvP
 static inline bool same_tiling(const ConvParams& a, const ConvParams& b) {
   return a.cb == b.cb && a.R == b.R && a.nsub == b.nsub && a.kps == b.kps && a.b_resident == b.b_resident && a.S >= 2;
 }
-static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true) {
+static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true, int max_budget = CONV_SMEM_MAX) {
+  tma_budget_ref() = max_budget;
+  const bool ok = plan_conv_halo_tma_impl(d, num_sms, p, swizzled);
   tma_budget_ref() = CONV_SMEM_MAX;
-  if (!plan_conv_halo_tma_impl(d, num_sms, p, swizzled)) return false;
+  if (!ok) return false;
+  if (max_budget != CONV_SMEM_MAX) return true;
   if (tma_preferred_budget() < CONV_SMEM_MAX) {
     ConvParams q;
     tma_budget_ref() = tma_preferred_budget();
@@ -518,9 +522,12 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
   }
   return true;
 }
-static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& p, int max_budget = CONV_SMEM_MAX) {
+  tma_budget_ref() = max_budget;
+  const bool ok = plan_conv_s2_tma_impl(d, num_sms, p);
   tma_budget_ref() = CONV_SMEM_MAX;
-  if (!plan_conv_s2_tma_impl(d, num_sms, p)) return false;
+  if (!ok) return false;
+  if (max_budget != CONV_SMEM_MAX) return true;
   if (tma_preferred_budget() < CONV_SMEM_MAX) {
     ConvParams q;
     tma_budget_ref() = tma_preferred_budget();
@@ -529,9 +536,12 @@ static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& 
   }
   return true;
 }
-static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams& p) {
+static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams& p, int max_budget = CONV_SMEM_MAX) {
+  tma_budget_ref() = max_budget;
+  const bool ok = plan_conv_flat_tma_impl(d, num_sms, p);
   tma_budget_ref() = CONV_SMEM_MAX;
-  if (!plan_conv_flat_tma_impl(d, num_sms, p)) return false;
+  if (!ok) return false;
+  if (max_budget != CONV_SMEM_MAX) return true;
   if (tma_preferred_budget() < CONV_SMEM_MAX) {
     ConvParams q;
     tma_budget_ref() = tma_preferred_budget();
@@ -539,6 +549,73 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
     tma_budget_ref() = CONV_SMEM_MAX;
   }
   return true;
+}
+
+// ---- TMA-store epilogue -------------------------------------------------------------------------------------------
+// Direct epilogue stores are one 32-byte sector per lane at the pixel pitch: a warp instruction touches 32 different
+// 128-byte lines and every line is visited once per 16-channel chunk -- the L1 tag stage, not HBM, bounded the wide thin
+// layers (tools/probe_tma.py: b2.cv2 84 us with stores, 73 us without).  With st_tma the epilogue warps write their
+// 16-channel units into a shared-memory image of the item's output tile (conflict-free 16-byte stores in the hardware
+// swizzle) and ONE thread hands the tile to the TMA unit, which writes whole lines.  The destination is always seen as the
+// flat matrix [pixels, channels]: flat mode stores boxes of <= 256 rows; the halo / stride-2 modes store one box per IMAGE
+// ROW (W pixels, starting one tile row after the padding column), because a TMA store that starts at a negative coordinate
+// faults (tools/probe_tma_store.cu: "illegal instruction"; boxes that run past the upper bound are clipped as expected).
+// A store's shared-memory source must be 128-byte aligned: tiles with 64-byte rows are written one row down (st_shift) so
+// that every image row starts on an even tile row (needs an even W + 2, halo mode only).
+// Applies when every epilogue group owns one fixed chunk (Ntile 16 / 32 / 64), one N tile, no ConvTranspose scatter, and the
+// tile fits next to the operand ring without changing the tiling (fewer stages are accepted down to 2).
+// MEASURED (B200, batch 64, profiles/r2_experiments.md): correct on every parity test, but SLOWER than the direct stores in
+// this form -- b2.cv1 42 -> 60 us, b4.cv1 26 -> 35 us, 35.6k -> 34.1k frames/s: one tile per CTA means the epilogue of item
+// i + 1 waits for the TMA unit to have read item i, plus two 512-thread barriers per item, which costs more than the L1 tag
+// cycles it saves.  Opt-in (XRSEG_ST_TMA=1) until the tile is double-buffered.
+static inline bool tma_store_enabled() {
+  static const bool on = [] { const char* e = getenv("XRSEG_ST_TMA"); return e && e[0] == '1'; }();
+  return on;
+}
+static inline int tma_store_tile_bytes(const ConvParams& p) { return 128 * p.nsub * p.Ntile * 2 + 1024; }
+static inline int tma_store_cw(const ConvParams& p, int split_n) {
+  int cw = p.Ntile < 64 ? p.Ntile : 64;                       // channels per column block (row = 32 / 64 / 128 bytes)
+  if (split_n) while (split_n % cw || (p.Ntile - split_n) % cw) cw >>= 1;
+  return cw;
+}
+static inline bool tma_store_shape_ok(const ConvParams& p, int split_n) {
+  if (!(p.mode == MODE_HALO_TMA || p.mode == MODE_FLAT_TMA || p.mode == MODE_S2_TMA) || !p.sw || p.transposed) return false;
+  const int nch = p.Ntile >> 4;
+  if (p.n_tiles != 1 || !(nch == 1 || nch == 2 || nch == 4)) return false;
+  if (split_n && (split_n % 16 || split_n >= p.Ntile)) return false;
+  if (p.mode != MODE_FLAT_TMA) {
+    const int rbw = tma_store_cw(p, split_n) * 2;
+    if (p.W > 256) return false;
+    if (!(rbw == 128 || (rbw == 64 && p.mode == MODE_HALO_TMA && p.Wp % 2 == 0))) return false;
+  }
+  return true;
+}
+// Adds the output tile to a finished plan (call after plan_conv_*_tma and before packing weights; `replan` re-runs the same
+// planner under a smaller budget).  Returns true when the launch will use the TMA-store epilogue.
+template <typename Replan>
+static inline bool plan_tma_store(ConvParams& p, int split_n, Replan replan) {
+  p.st_tma = 0;
+  if (!tma_store_enabled() || !tma_store_shape_ok(p, split_n)) return false;
+  const int tile = tma_store_tile_bytes(p);
+  if (round_up(p.smem_bytes, 1024) + tile > CONV_SMEM_MAX) {
+    ConvParams q;
+    if (!replan(q, CONV_SMEM_MAX - tile - 1024) || !same_tiling(q, p) || q.Ntile != p.Ntile || q.mode != p.mode) return false;
+    p = q;
+  }
+  p.st_tma = 1;
+  p.st_cw = tma_store_cw(p, split_n);
+  p.st_nblk = p.Ntile / p.st_cw;
+  p.st_shift = (p.mode != MODE_FLAT_TMA && p.st_cw == 32) ? 1 : 0;
+  p.smem_off_o = round_up(p.smem_bytes, 1024);
+  p.smem_bytes = p.smem_off_o + tile;
+  return true;
+}
+// Output tensor map of the TMA-store epilogue for destination `base` (an NHWC slice of C channels, pixel pitch `pitch`,
+// B frames): the flat matrix (C, B*H*W); box = st_cw channels x (<= 256 rows | one image row of W pixels).
+static inline CUtensorMap make_store_tensor_map(const __half* base, const ConvParams& p, int B, int C, int pitch) {
+  const int sw = p.st_cw == 64 ? 3 : (p.st_cw == 32 ? 2 : 1);
+  const int rows_box = p.mode == MODE_FLAT_TMA ? (p.slots < 256 ? p.slots : 256) : p.W;   // s2: p.H / p.W are output geometry
+  return make_halo_tensor_map(base, 1, 1, B * p.H * p.W, C, pitch, rows_box, 1, p.st_cw, sw);
 }
 
 // Tensor map of the flat mode: the activation matrix [rows, C] (pixel pitch `pitch`) as (C, rows, 1, 1).
@@ -633,6 +710,20 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TMA_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // MMAs of one pipeline stage for ONE 128-row sub-tile, issued by one thread.  MODE: 0 halo (3x3 s1), 1 parity planes
 // (3x3 s2), 2 flat (1x1 / ConvT, kps K-blocks of one tap).  KJ = k16 steps per K-block.  a_sub / b_lo: low descriptor
 // words (start address >> 4 | LBO field) of the sub-tile's first row and of the stage's first weight tile.
@@ -679,7 +770,7 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
 // 256-bit store.  hb16 (shared memory) holds 0.5 * bias when ACT (h = 0.5 acc + 0.5 bias is ONE FFMA).
 template <bool ACT, bool RES>
 __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const float (&hbr)[16], const __half* res, __half* out,
-                                                  int probe, bool valid = true) {
+                                                  int probe, bool valid = true, uint32_t smem0 = 0, uint32_t smem1 = 0) {
   uint32_t o[8];
   if (probe & 2) {                         // PROBE builds only: store the raw accumulators
 #pragma unroll
@@ -741,6 +832,11 @@ __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const
     if ((o[0] ^ o[1] ^ o[2] ^ o[3] ^ o[4] ^ o[5] ^ o[6] ^ o[7]) == 0x12345678u) st_global_256(out, o);
     return;
   }
+  if (smem0) {                             // TMA-store epilogue: the unit's two 16-byte chunks of the shared-memory tile
+    st_shared_v4(smem0, o[0], o[1], o[2], o[3]);
+    st_shared_v4(smem1, o[4], o[5], o[6], o[7]);
+    return;
+  }
   if (valid) st_global_256(out, o);
 }
 
@@ -752,7 +848,8 @@ __device__ __forceinline__ void tma_epilogue_unit(const uint32_t (&v)[16], const
 // hoisted out of the unit loop: a unit is one TMEM load, the math, one address and one store.
 template <bool PROBE, int KIND, bool ACT, bool RES, bool BREG>
 __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
-                                                  const float* bias_s, int nbuf, int warp, int lane, int total_work) {
+                                                  const float* bias_s, int nbuf, int warp, int lane, int total_work,
+                                                  uint32_t tile_u32, const CUtensorMap* tmap_out, const CUtensorMap* tmap_out2) {
   constexpr int G = TMA_EPI_GROUPS;
   const int ew = warp - TMA_FIRST_EPI_WARP;
   const int q = warp & 3;              // TMEM lane quadrant this warp may access
@@ -843,6 +940,12 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
         gpitch = out_pitch;
       }
       const uint32_t acc_g = acc + static_cast<uint32_t>(gc0 * 16);
+      const bool st_tma = KIND != 2 && p.st_tma != 0;
+      if (st_tma) {
+        // the previous item's tile must have left shared memory before anyone overwrites it
+        if (ew == 0 && lane == 0) bulk_wait_group_read0();
+        epi_bar_sync();
+      }
       uint32_t va[16], vb[16];
       if (!ld_on) {
 #pragma unroll
@@ -859,12 +962,44 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
         if (!pipelined) tmem_ld_wait();
         const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
         const size_t pxs = static_cast<size_t>(px < 0 ? 0 : px);
+        uint32_t s0 = 0, s1 = 0;
+        if (st_tma) {                                  // row 128 u + 32 q + lane of column block n / st_cw, swizzled
+          const uint32_t rbw = static_cast<uint32_t>(p.st_cw) * 2u;
+          const uint32_t blk = static_cast<uint32_t>(n) / static_cast<uint32_t>(p.st_cw);
+          const uint32_t off = static_cast<uint32_t>(128 * u + q * 32 + lane + p.st_shift) * rbw + (static_cast<uint32_t>(n) * 2u) % rbw;
+          const uint32_t mask = rbw == 128u ? 7u : (rbw == 64u ? 3u : 1u);
+          const uint32_t base = tile_u32 + blk * static_cast<uint32_t>(128 * nsub) * rbw;   // (the shifted last row spills into the pad)
+          s0 = base + (off ^ (((off >> 7) & mask) << 4));
+          s1 = base + ((off + 16u) ^ ((((off + 16u) >> 7) & mask) << 4));
+        }
         tma_epilogue_unit<ACT, RES>((j & 1) ? vb : va, hbr, RES ? resp + pxs * res_pitch + n : nullptr, gbase + pxs * gpitch, probe_epi,
-                                    px >= 0);
+                                    px >= 0, s0, s1);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (st_tma) {
+        fence_proxy_async_smem();                      // generic-proxy writes of the tile -> visible to the TMA unit
+        epi_bar_sync();
+        if (ew == 0 && lane == 0 && !no_store) {
+          for (int blk = 0; blk < p.st_nblk; ++blk) {
+            const int n0 = blk * p.st_cw;
+            const bool second = KIND == 1 && n0 >= split_n;
+            const CUtensorMap* map = second ? tmap_out2 : tmap_out;
+            const int c0 = second ? n0 - split_n : n0;
+            const uint32_t rbw = static_cast<uint32_t>(p.st_cw) * 2u;
+            const uint32_t src = tile_u32 + static_cast<uint32_t>(blk) * static_cast<uint32_t>(128 * nsub) * rbw;
+            if (flat) {
+              for (int r0 = 0; r0 < slots; r0 += 256)
+                tma_store_4d(map, src + static_cast<uint32_t>(r0) * rbw, c0, tile * slots + r0, 0, 0);
+            } else {                                   // one box per image row: W pixels from tile row yy * Wp + 1 (+ shift)
+              for (int yy = 0; yy < Rr && y0 + yy < Hh; ++yy)
+                tma_store_4d(map, src + static_cast<uint32_t>(yy * Wp + 1 + p.st_shift) * rbw, c0, (b * Hh + y0 + yy) * Ww, 0, 0);
+            }
+          }
+          bulk_commit_group();
+        }
+      }
       if (PROBE) e_work += clock64() - t0;
       continue;
     }
@@ -952,6 +1087,7 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
     if (lane == 0) mbar_arrive(&tempty[buf]);
     if (PROBE) e_work += clock64() - t0;
   }
+  if (BREG && KIND != 2 && p.st_tma && ew == 0 && lane == 0) bulk_wait_group0();   // the last tile is in global memory before the CTA exits
   if (PROBE && p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
     p.dbg_clk[blockIdx.x * 12 + 6] = e_wait;
     p.dbg_clk[blockIdx.x * 12 + 7] = e_work;
@@ -998,6 +1134,10 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     prefetch_tensormap(&tmap);
     if (p.mode == MODE_S2_TMA)
       for (int i = 1; i < 4; ++i) prefetch_tensormap(&tmaps.m[i]);
+    if (p.st_tma) {
+      prefetch_tensormap(&tmaps.m[4]);
+      if (p.split_n) prefetch_tensormap(&tmaps.m[5]);
+    }
     if (p.b_resident) {
       // resident weights: fetched first thing (they are constants: no dependence on the previous kernel), so the copy
       // runs while warp 1 allocates TMEM -- which may have to wait for a co-resident CTA of the previous kernel
@@ -1214,7 +1354,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     const bool breg = p.n_tiles == 1 && nch_ <= TMA_EPI_GROUPS && TMA_EPI_GROUPS % nch_ == 0;
     const int sel = (breg ? 16 : 0) + kind * 4 + (p.act ? 2 : 0) + (p.res ? 1 : 0);
 #define XR_EPI_CASE(id, K, A, R, B) \
-  case id: tma_epilogue_loop<PROBE, K, A, R, B>(p, tmem_base, tfull, tempty, bias_s, nbuf, warp, lane, total_work); break;
+  case id: tma_epilogue_loop<PROBE, K, A, R, B>(p, tmem_base, tfull, tempty, bias_s, nbuf, warp, lane, total_work, \
+                                                smem_u32(smem + p.smem_off_o), &tmaps.m[4], &tmaps.m[5]); break;
     switch (sel) {
       XR_EPI_CASE(0, 0, false, false, false) XR_EPI_CASE(1, 0, false, true, false) XR_EPI_CASE(2, 0, true, false, false)
       XR_EPI_CASE(3, 0, true, true, false) XR_EPI_CASE(4, 1, false, false, false) XR_EPI_CASE(6, 1, true, false, false)

@@ -97,6 +97,10 @@ struct ConvParams {
   // output columns >= split_n go to out2 (pixel pitch out2_pitch), relative to split_n.  split_n == 0: single output.
   __half* out2;
   int split_n, out2_pitch;
+  // TMA-store epilogue (conv_tma.cuh: plan_tma_store): the epilogue writes the item's fp16 output tile into shared memory
+  // ([st_nblk column blocks][128 * nsub rows][st_cw channels], hardware swizzle of the row width) and one thread stores it
+  // with cp.async.bulk.tensor (tensor maps TmapSet::m[4] / m[5]); 0 = direct 32-byte stores from registers.
+  int st_tma, st_cw, st_nblk, smem_off_o, st_shift;   // st_shift: tile rows are written one row down (128-byte aligned image rows)
   // Chain kernel (conv_chain.cuh), flat mode: rows of ONE frame (H * W); a work item is `slots` rows of one frame and
   // tpi = ceil(frame_rows / slots) items make a frame.  0 outside chains.
   int frame_rows;

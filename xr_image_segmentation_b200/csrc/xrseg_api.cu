@@ -368,6 +368,19 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       } else {
         d.cp = plan_conv(cd, r->num_sms, 0);
       }
+      if (d.use_tma) {
+        // TMA-store epilogue where the shape allows it (conv_tma.cuh: plan_tma_store); output maps m[4] (out) / m[5] (out2)
+        const int split_n = o.layer2 >= 0 ? o.y.Cp : 0;
+        const int mode = d.cp.mode;
+        const int nsm = r->num_sms;
+        if (plan_tma_store(d.cp, split_n, [&](ConvParams& q, int budget) {
+              return mode == MODE_HALO_TMA ? plan_conv_halo_tma(cd, nsm, q, true, budget)
+                     : mode == MODE_FLAT_TMA ? plan_conv_flat_tma(cd, nsm, q, budget) : plan_conv_s2_tma(cd, nsm, q, budget);
+            })) {
+          d.tmaps.m[4] = make_store_tensor_map(ptr_of(r, o.y), d.cp, r->mb, o.y.Cp, o.y.pitch);
+          if (o.layer2 >= 0) d.tmaps.m[5] = make_store_tensor_map(ptr_of(r, o.y2), d.cp, r->mb, o.y2.Cp, o.y2.pitch);
+        }
+      }
 #ifdef XRSEG_DEBUG_API
       if (const char* e = getenv("XRSEG_EPI")) d.cp.dbg_skip |= (e[0] == '1') ? 8 : 0;   // A/B of the TMA kernel's epilogue
 #endif
@@ -2106,6 +2119,14 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
       const bool s2 = !tma && !flat && variant == 0 && plan_conv_s2_tma(cd, prop.multiProcessorCount, p);
       tma = tma || flat || s2;
       if (!tma) p = plan_conv(cd, prop.multiProcessorCount, variant & 1);
+      bool st_tma = false;
+      if (tma && variant == 0) {
+        const int mode = p.mode, nsm = prop.multiProcessorCount;
+        st_tma = plan_tma_store(p, 0, [&](ConvParams& q, int budget) {
+          return mode == MODE_HALO_TMA ? plan_conv_halo_tma(cd, nsm, q, true, budget)
+                 : mode == MODE_FLAT_TMA ? plan_conv_flat_tma(cd, nsm, q, budget) : plan_conv_s2_tma(cd, nsm, q, budget);
+        });
+      }
       std::vector<__half> wp;
       std::vector<float> bp;
       if (tma && p.sw) pack_conv_weights_sw<__half>(p, wgt, hb, cin, cout, wp, bp);
@@ -2133,6 +2154,7 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
           if (s2) maps = make_s2_tensor_maps(d_x, b, h, w, cin_p, cin_p, p);
           else maps.m[0] = flat ? make_flat_tensor_map(d_x, static_cast<long>(b) * h * w, cin_p, cin_p, p)
                                 : make_halo_tensor_map(d_x, b, h, w, cin_p, cin_p, p.Wp, p.hbox, p.sw ? p.cb : 8, p.sw);
+          if (st_tma) maps.m[4] = make_store_tensor_map(d_y, p, b, cout_p, cout_p);
           launch_conv_halo_tma(p, maps, 0);
         } else {
           launch_conv_umma(p, 0);
@@ -2143,8 +2165,8 @@ int xrseg_debug_conv(int device, int impl, const float* x, int b, int cin, int h
       if (reps > 1) {
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        fprintf(stderr, "xrseg_debug_conv: mode %d sw %d cb %d S %d nks %d nsub %d R %d grid %d smem %d tiles %d skip %d: %.1f us\n", p.mode, p.sw, p.cb,
-                p.S, p.nks, p.nsub, p.R, p.grid, p.smem_bytes, p.m_tiles * p.n_tiles, p.dbg_skip, ms * 1e3f);
+        fprintf(stderr, "xrseg_debug_conv: mode %d sw %d cb %d S %d nks %d nsub %d R %d grid %d smem %d tiles %d st_tma %d skip %d: %.1f us\n", p.mode, p.sw, p.cb,
+                p.S, p.nks, p.nsub, p.R, p.grid, p.smem_bytes, p.m_tiles * p.n_tiles, p.st_tma, p.dbg_skip, ms * 1e3f);
         if (d_clk) {
           std::vector<long long> h(static_cast<size_t>(p.grid) * 12);
           XR_CUDA(cudaMemcpy(h.data(), d_clk, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));

@@ -60,7 +60,8 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
 
 /* The C2PSA attention kernel alone (graph chains 160-168: Q^T K * 0.17678, softmax over keys, V A^T) on caller tensors:
  * qkv f32 [b, n, heads*128] (per token and head: 32 query | 32 key | 64 value channels), out f32 [b, n, heads*64]. */
-int xrseg_debug_attention(int device, const float* qkv, int b, int n, int heads, float* out);
+int xrseg_debug_attention(int device, const float* qkv, int b, int n, int heads, float* out, const float* pe_w, const float* pe_b,
+                          int map_w);   /* pe_w [heads*64][3][3] + pe_b [heads*64]: fused positional encoding (NULL: attention only) */
 
 #ifdef __cplusplus
 }

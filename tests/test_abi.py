@@ -233,13 +233,13 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
 
 
 @pytest.mark.parametrize("scale,whole_block,expect", [
-    ("n", "0", {"stem": 1, "conv": 80, "dw": 7, "sppf": 1, "up": 2, "attn": 1, "bneck": 3}),
-    ("n", "1", {"stem": 1, "conv": 78, "dw": 7, "sppf": 1, "up": 2, "attn": 1, "bneck": 2, "c3k2": 1}),
-    ("s", "0", {"stem": 1, "conv": 84, "dw": 7, "sppf": 1, "up": 2, "attn": 1, "bneck": 1}),
+    ("n", "0", {"stem": 1, "conv": 80, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 3}),
+    ("n", "1", {"stem": 1, "conv": 78, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 2, "c3k2": 1}),
+    ("s", "0", {"stem": 1, "conv": 84, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 1}),
 ])
 def test_fusion_passes_produce_the_expected_launch_list(plan_dump, scale, whole_block, expect):
-    """model.cuh: fuse_siblings / fuse_bottlenecks / fuse_c3k2_blocks.  n scale: 100 layers -> 95 network launches (six
-    sibling pairs, the Bottlenecks of b2 / b4 / n16); the opt-in whole-block kernel takes b2; the s scale has one supported
+    """model.cuh: fuse_siblings / fuse_bottlenecks / fuse_c3k2_blocks / fuse_attention_pe.  n scale: 100 layers -> 94 network
+    launches (six sibling pairs, the Bottlenecks of b2 / b4 / n16, the C2PSA positional encoding inside the attention kernel); the opt-in whole-block kernel takes b2; the s scale has one supported
     Bottleneck (b2: 32-16-32).  Every fused Bottleneck keeps its residual and stays on the main stream."""
     import subprocess
     out = subprocess.run([plan_dump, "64", scale, "ops", whole_block], capture_output=True, text=True, check=True).stdout
@@ -252,6 +252,8 @@ def test_fusion_passes_produce_the_expected_launch_list(plan_dump, scale, whole_
         if r[1] == "bneck":
             assert r[2].endswith(".m0.cv1") and r[r.index("res") + 1] == "1" and r[r.index("branch") + 1] == "0", r
     assert sum(1 for r in rows if r[1] == "conv" and "+" in r[2]) == 6
+    attn = [r for r in rows if r[1] == "attn"][0]
+    assert attn[2] == "b10.attn.pe"                         # the attention launch carries the depthwise layer's weights
 
 
 # ---- fused Bottleneck kernel: weight fragment order (host-only) ------------------------------------------------------

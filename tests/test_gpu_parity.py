@@ -754,6 +754,15 @@ def test_attention_kernel_vs_torch(dlib, heads, batch):
     ref = torch.einsum("bhqk,bkhd->bqhd", torch.softmax(att, dim=-1), v).reshape(batch, N, heads * 64).numpy()
     # P is rounded to fp16 before P V (relative 2^-11 per term), the output to fp16
     np.testing.assert_allclose(got, ref, atol=3e-3 * max(1.0, float(np.abs(ref).max())), rtol=3e-3)
+    # the same kernel with the block's positional encoding fused in (chains 169-170): + depthwise 3x3 (pad 1) + bias on V
+    C = heads * 64
+    pw = (rng.standard_normal((C, 3, 3)) * 0.3).astype(np.float32)
+    pb = rng.standard_normal(C).astype(np.float32)
+    got_pe = I.debug_attention(qkv, heads, pe_w=pw, pe_b=pb, map_w=20)
+    vmap = v.reshape(batch, 20, 20, C).permute(0, 3, 1, 2)
+    pe = F.conv2d(vmap, torch.from_numpy(pw)[:, None], torch.from_numpy(pb), padding=1, groups=C).permute(0, 2, 3, 1).reshape(batch, N, C)
+    ref_pe = ref + pe.numpy()
+    np.testing.assert_allclose(got_pe, ref_pe, atol=3e-3 * max(1.0, float(np.abs(ref_pe).max())), rtol=3e-3)
 
 
 def test_capacity_overflow_is_reported_not_silent(golden, lib):

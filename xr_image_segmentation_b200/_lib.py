@@ -118,7 +118,7 @@ DEBUG_SIGNATURES = {
     "xrseg_debug_emulate_conv": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "xrseg_debug_post_timings": (C.c_int, [C.c_void_p, _P(C.c_float), _P(C.c_double), C.c_char_p, C.c_int]),
-    "xrseg_debug_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "xrseg_debug_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
 }
 SIGNATURES = {**PRODUCT_SIGNATURES, **DEBUG_SIGNATURES}   # what libxrseg_debug.so exports
 

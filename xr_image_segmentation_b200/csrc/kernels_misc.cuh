@@ -570,6 +570,9 @@ struct AttnParams {
   __half* out; int out_pitch;    // [B,N,heads*hd]
   int B, N, heads;
   float scale;
+  // fused positional encoding (graph chains 169-170: x = attention(v) + pe(v), pe = depthwise 3x3 + bias on the V map):
+  // pe_w [9][heads*hd] fp32 (tap-major, as DwParams::w), pe_b [heads*hd], map width W (N = H * W).  nullptr: attention only.
+  const float* pe_w; const float* pe_b; int W;
 };
 
 constexpr int ATT_KD = 32, ATT_HD = 64;
@@ -596,15 +599,28 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // O = P V run on the tensor cores (mma.sync m16n8k16, fp32 accumulate) with a register-level online softmax: the
 // accumulator fragment of S is re-used directly as the A fragment of P V.  The whole working set of a head is 77 KB
 // of shared memory and 0.06 GFLOP per frame -- too small for a TMEM/tcgen05 pipeline to pay off.
+// With pe_w set, the block's positional encoding rides in the epilogue: the head's V map is already in shared memory, so
+// pe(v) = depthwise 3x3 (zero padding) + bias is nine shared-memory reads per output next to the normalised attention
+// output -- the separate depthwise launch (15 us for 0.06 GFLOP) and the round trip of the attention output are gone.
 __global__ void __launch_bounds__(416) attention_kernel(const AttnParams p) {
   XR_PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t att_smem[];
+  __shared__ float pe_ws[9][ATT_HD];
+  __shared__ float pe_bs[ATT_HD];
   __half* ks = reinterpret_cast<__half*>(att_smem);                       // [N][ATT_KSTRIDE]
   __half* vs = ks + static_cast<size_t>(p.N) * ATT_KSTRIDE;               // [N][ATT_VSTRIDE]
   const int bh = blockIdx.x;
   const int h = bh % p.heads;
   const int b = bh / p.heads;
   const int per_head = 2 * ATT_KD + ATT_HD;
+  if (p.pe_w) {                                                           // weights are constants: before the PDL wait would do too
+    const int C = p.heads * ATT_HD;
+    for (int i = threadIdx.x; i < 10 * ATT_HD; i += blockDim.x) {
+      const int t = i / ATT_HD, c = i - t * ATT_HD;
+      if (t < 9) pe_ws[t][c] = p.pe_w[t * C + h * ATT_HD + c];
+      else pe_bs[c] = p.pe_b[h * ATT_HD + c];
+    }
+  }
   const __half* base = p.qkv + static_cast<size_t>(b) * p.N * p.qkv_pitch + h * per_head;
   for (int i = threadIdx.x; i < p.N * 12; i += blockDim.x) {
     const int tok = i / 12, part = i - tok * 12;
@@ -708,12 +724,49 @@ __global__ void __launch_bounds__(416) attention_kernel(const AttnParams p) {
   sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
   const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    o[n][0] *= inv0; o[n][1] *= inv0;
+    o[n][2] *= inv1; o[n][3] *= inv1;
+  }
+  if (p.pe_w) {
+    // + pe(v): rows q0 + g and q0 + g + 8 of the map, channels n * 8 + 2t, + 1; fp32 accumulation in tap order
+    const int H = p.N / p.W;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int tok = q0 + g + 8 * rr;
+      const int y = tok / p.W, x = tok - y * p.W;
+      float acc[8][2];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        acc[n][0] = pe_bs[n * 8 + 2 * t];
+        acc[n][1] = pe_bs[n * 8 + 2 * t + 1];
+      }
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= p.W) continue;
+        const __half* vr = vs + (yy * p.W + xx) * ATT_VSTRIDE + 2 * t;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          const float2 v2 = __half22float2(*reinterpret_cast<const __half2*>(vr + n * 8));
+          acc[n][0] = fmaf(pe_ws[tap][n * 8 + 2 * t], v2.x, acc[n][0]);
+          acc[n][1] = fmaf(pe_ws[tap][n * 8 + 2 * t + 1], v2.y, acc[n][1]);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        o[n][2 * rr] += acc[n][0];
+        o[n][2 * rr + 1] += acc[n][1];
+      }
+    }
+  }
   __half* o0 = p.out + (static_cast<size_t>(b) * p.N + q0 + g) * p.out_pitch + h * ATT_HD + 2 * t;
   __half* o1 = o0 + static_cast<size_t>(8) * p.out_pitch;
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
-    *reinterpret_cast<uint32_t*>(o0 + n * 8) = pack_h2(o[n][0] * inv0, o[n][1] * inv0);
-    *reinterpret_cast<uint32_t*>(o1 + n * 8) = pack_h2(o[n][2] * inv1, o[n][3] * inv1);
+    *reinterpret_cast<uint32_t*>(o0 + n * 8) = pack_h2(o[n][0], o[n][1]);
+    *reinterpret_cast<uint32_t*>(o1 + n * 8) = pack_h2(o[n][2], o[n][3]);
   }
 }
 

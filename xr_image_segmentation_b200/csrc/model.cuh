@@ -94,6 +94,7 @@ class Net {
   int cur_branch = 0, pending_wait = 0;   // see Op::branch
   bool fuse_enabled = true;               // sibling fusion (fuse_siblings); off for the direct-convolution cross-check
   bool fuse_bneck = true;                 // Bottleneck fusion (fuse_bottlenecks)
+  bool fuse_pe = true;                    // C2PSA positional encoding inside the attention kernel (fuse_attention_pe)
   bool fuse_c3k2 = false;                 // whole-block fusion (fuse_c3k2_blocks); measured slower, opt-in (XRSEG_FUSE_C3K2=1)
   TV input;                 // [B,640,640,4] fp16
   TV box[3], cls[3], coef[3], protos;
@@ -241,6 +242,26 @@ class Net {
         ++tag;
       }
       ops.erase(ops.begin() + ib);
+    }
+  }
+
+  // C2PSA: x = attention(q, k, v) + pe(v).  The depthwise 3x3 `attn.pe` reads V in place from the qkv tensor and adds the
+  // attention output as its residual; the attention kernel already holds the head's V map in shared memory, so the pair
+  // becomes one OP_ATTN launch: layer = the pe layer (its weights), y = the pe op's destination.
+  void fuse_attention_pe() {
+    static const bool env_on = [] { const char* e = getenv("XRSEG_FUSE_PE"); return !(e && e[0] == '0'); }();
+    if (!fuse_pe || !env_on) return;
+    for (size_t i = 0; i + 1 < ops.size(); ++i) {
+      Op& a = ops[i];
+      const Op b = ops[i + 1];
+      if (a.kind != OP_ATTN || b.kind != OP_DW || a.layer >= 0) continue;
+      const bool ok = b.in_grp > 0 && b.x.off == a.x.off && b.has_res && b.res.off == a.y.off && !b.act && a.branch == b.branch &&
+                      b.wait_tag == 0 && a.signal_tag == 0;
+      if (!ok) continue;
+      a.layer = b.layer;
+      a.y = b.y;
+      a.signal_tag = b.signal_tag;
+      ops.erase(ops.begin() + i + 1);
     }
   }
 
@@ -416,6 +437,7 @@ class Net {
     fuse_siblings();
     fuse_bottlenecks();
     fuse_c3k2_blocks();
+    fuse_attention_pe();
     fh[0] = p3.H; fw[0] = p3.W; fh[1] = p4.H; fw[1] = p4.W; fh[2] = p5.H; fw[2] = p5.W;
   }
 };

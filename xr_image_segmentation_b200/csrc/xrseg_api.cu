@@ -294,7 +294,7 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
       d.w16_rows = dev_upload(wr);
       for (float& v : ws) v = v / 255.0f;
       d.w32_u8 = dev_upload(ws);
-    } else if (o.kind == OP_DW) {
+    } else if (o.kind == OP_DW || o.kind == OP_ATTN) {   // OP_ATTN with a layer: the fused positional encoding's depthwise weights
       const int c = o.y.Cp;
       std::vector<float> ws(9 * c, 0.f), bs(c, 0.f);
       for (int n = 0; n < l.cout; ++n) {
@@ -612,6 +612,10 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
         p.B = nb; p.H = o.x.H; p.W = o.x.W; p.C = o.y.Cp; p.act = o.act;
         p.in_grp = o.in_grp; p.in_grp_stride = o.in_grp_stride; p.in_grp_off = o.in_grp_off;
         p.rows = o.x.H >= 40 ? 16 : 10;
+        {
+          static const int dw_rows = [] { const char* e = getenv("XRSEG_DW_ROWS"); return e ? atoi(e) : 0; }();
+          if (dw_rows > 0) p.rows = dw_rows;
+        }
         L.name = l.name;
         L.flops = 2.0 * px_out * l.cout * 9;
         L.bytes = (px_in * l.cin + px_out * l.cout * (o.has_res ? 2 : 1)) * 2;
@@ -646,13 +650,15 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
       }
       case OP_ATTN: {
         AttnParams p{ptr_of(r, o.x), o.x.pitch, ptr_of(r, o.y), o.y.pitch, nb, o.x.H * o.x.W, o.heads,
-                     1.0f / sqrtf(static_cast<float>(ATT_KD))};
+                     1.0f / sqrtf(static_cast<float>(ATT_KD)), nullptr, nullptr, o.x.W};
+        if (o.layer >= 0) { p.pe_w = r->dl[o.layer].w32; p.pe_b = r->dl[o.layer].bias; }   // fused positional encoding
         const size_t smem = static_cast<size_t>(p.N) * (ATT_KSTRIDE + ATT_VSTRIDE) * sizeof(__half);
         XR_CHECK(p.N % 16 == 0 && p.N % ATT_CHUNK == 0 && p.N / 16 <= 26, "attention kernel needs N %% 80 == 0 and N <= 416 (N = %d)", p.N);
         const int threads = 13 * 32;
         dim3 g(nb * o.heads, ceil_div(p.N / 16, 13));
-        L.name = "c2psa.attention";
-        L.flops = 2.0 * nb * o.heads * static_cast<double>(p.N) * p.N * (ATT_KD + ATT_HD);
+        L.name = o.layer >= 0 ? "c2psa.attention+pe" : "c2psa.attention";
+        L.flops = 2.0 * nb * o.heads * static_cast<double>(p.N) * p.N * (ATT_KD + ATT_HD) +
+                  (o.layer >= 0 ? 2.0 * px_out * o.y.C * 9 : 0.0);
         L.bytes = px_in * (o.x.C + o.y.C) * 2;
         L.fn = [p, g, smem, threads](cudaStream_t st) { launch_k(attention_kernel, g, threads, smem, st, p); };
         break;
@@ -2427,8 +2433,10 @@ int xrseg_debug_emulate_conv(const float* x, int b, int cin, int h, int w, const
 
 // The C2PSA attention kernel alone (graph chains 160-168) on caller tensors: qkv f32 [b, n, heads*(32+32+64)] per token
 // and head (query | key | value), out f32 [b, n, heads*64].
-int xrseg_debug_attention(int device, const float* qkv, int b, int n, int heads, float* out) {
+int xrseg_debug_attention(int device, const float* qkv, int b, int n, int heads, float* out, const float* pe_w, const float* pe_b,
+                          int map_w) {
   if (!qkv || !out || b < 1 || heads < 1 || n < 16 || n % 16 || n % ATT_CHUNK || n / 16 > 26) return XRSEG_ERR_INVALID;
+  if (pe_w && (!pe_b || map_w < 1 || n % map_w)) return XRSEG_ERR_INVALID;
   try {
     XR_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop{};
@@ -2443,14 +2451,23 @@ int xrseg_debug_attention(int device, const float* qkv, int b, int n, int heads,
     __half* d_o = dev_alloc<__half>(no);
     XR_CUDA(cudaMemcpy(d_q32, qkv, nq * sizeof(float), cudaMemcpyHostToDevice));
     f32_to_f16_kernel<<<grid_for(static_cast<long>(nq)), 256>>>(d_q32, d_q, static_cast<long>(nq));
-    AttnParams p{d_q, cq, d_o, co, b, n, heads, 1.0f / sqrtf(static_cast<float>(ATT_KD))};
+    AttnParams p{d_q, cq, d_o, co, b, n, heads, 1.0f / sqrtf(static_cast<float>(ATT_KD)), nullptr, nullptr, map_w > 0 ? map_w : n};
+    float *d_pw = nullptr, *d_pb = nullptr;
+    if (pe_w) {                                  // pe_w: [heads*64][3][3] (the depthwise layer's own layout) -> tap-major [9][C]
+      std::vector<float> wt(static_cast<size_t>(9) * co), bt(pe_b, pe_b + co);
+      for (int c = 0; c < co; ++c)
+        for (int t = 0; t < 9; ++t) wt[static_cast<size_t>(t) * co + c] = pe_w[static_cast<size_t>(c) * 9 + t];
+      d_pw = dev_upload(wt);
+      d_pb = dev_upload(bt);
+      p.pe_w = d_pw; p.pe_b = d_pb;
+    }
     const size_t smem = static_cast<size_t>(n) * (ATT_KSTRIDE + ATT_VSTRIDE) * sizeof(__half);
     launch_k(attention_kernel, dim3(b * heads, ceil_div(n / 16, 13)), 13 * 32, smem, 0, p);
     XR_CUDA(cudaGetLastError());
     f16_to_f32_kernel<<<grid_for(static_cast<long>(no)), 256>>>(d_o, d_o32, static_cast<long>(no));
     XR_CUDA(cudaDeviceSynchronize());
     XR_CUDA(cudaMemcpy(out, d_o32, no * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(d_q32); cudaFree(d_o32); cudaFree(d_q); cudaFree(d_o);
+    cudaFree(d_q32); cudaFree(d_o32); cudaFree(d_q); cudaFree(d_o); cudaFree(d_pw); cudaFree(d_pb);
   } catch (const CudaError& e) {
     g_create_error = e.msg;
     return XRSEG_ERR_CUDA;

@@ -390,13 +390,17 @@ def debug_c3k2(x, w_cv1, b_cv1, w_m1, b_m1, w_m2, b_m2, w_cv2, b_cv2, device=0):
     return y
 
 
-def debug_attention(qkv, heads, device=0):
-    """The C2PSA attention kernel alone: qkv f32 [B,N,heads*128] (per head 32 q | 32 k | 64 v) -> [B,N,heads*64]."""
+def debug_attention(qkv, heads, device=0, pe_w=None, pe_b=None, map_w=0):
+    """The C2PSA attention kernel alone: qkv f32 [B,N,heads*128] (per head 32 q | 32 k | 64 v) -> [B,N,heads*64].
+    pe_w [heads*64,3,3] / pe_b [heads*64] / map_w: the fused positional encoding (depthwise 3x3 on the V map) is added."""
     lib = _lib.load_library(True)
     q = np.ascontiguousarray(qkv, np.float32)
     B, N, _ = q.shape
     y = np.zeros((B, N, heads * 64), np.float32)
-    _lib.check(lib.xrseg_debug_attention(device, q.ctypes.data, B, N, heads, y.ctypes.data), None, lib)
+    w = np.ascontiguousarray(pe_w, np.float32) if pe_w is not None else None
+    bb = np.ascontiguousarray(pe_b, np.float32) if pe_b is not None else None
+    _lib.check(lib.xrseg_debug_attention(device, q.ctypes.data, B, N, heads, y.ctypes.data, w.ctypes.data if w is not None else None,
+                                         bb.ctypes.data if bb is not None else None, map_w), None, lib)
     return y
 
 

@@ -498,16 +498,19 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
           ConvParams p = d.cp;
           if (nb != p.B) p = replan_for_batch(d.cp, nb, r->num_sms);   // partial last chunk: same layout, fewer frames
           {
-            // Small launches (at most XRSEG_TINY_WORK = 800 work items: every 20x20 layer, the 40x40 layers, the stride-2 convs in
-            // front of them) use at most HALF the SMs (XRSEG_TINY_GRID, 0 = off).  These kernels are latency-bound -- one or two
-            // items per CTA, most of their ~10 us is fill and drain -- and a throughput caller keeps several runners in flight:
-            // with half-width grids the small kernels of two steps sit side by side on disjoint SMs instead of taking turns on
-            // all of them.  Measured (B200, batch 64, four runners): 34.5k -> 36.7k frames/s, e2e 32.4k -> 34.0k; one runner
-            // alone 30.2k -> 29.9k; batch-1 latency unchanged (its grids are smaller than the cap anyway).
+            // Small launches use at most HALF the SMs (XRSEG_TINY_GRID, 0 = off): 3x3 layers with at most two work items per SM
+            // (XRSEG_TINY_WORK = 296: every 20x20 layer, the 3x3 convs of the 40x40 stage) and 1x1 layers with at most
+            // XRSEG_TINY_FLAT_WORK = 800 items (the 40x40 stage).  These kernels are latency-bound -- most of their ~10 us is fill
+            // and drain -- and a throughput caller keeps several runners in flight: with half-width grids the small kernels of
+            // two steps sit side by side on disjoint SMs instead of taking turns on all of them.  Measured (B200, batch 64, four
+            // runners, profiles/r2_experiments.md): 34.5k -> 36.7k frames/s, e2e 32.4k -> 34.0k; one runner alone 30.2k -> 29.9k;
+            // batch-1 latency unchanged (its grids are smaller than the cap anyway).
             static const int tiny_grid = [] { const char* e = getenv("XRSEG_TINY_GRID"); return e ? atoi(e) : -1; }();
-            static const int tiny_work = [] { const char* e = getenv("XRSEG_TINY_WORK"); return e ? atoi(e) : 800; }();
+            static const int tiny_work = [] { const char* e = getenv("XRSEG_TINY_WORK"); return e ? atoi(e) : 296; }();
+            static const int tiny_flat = [] { const char* e = getenv("XRSEG_TINY_FLAT_WORK"); return e ? atoi(e) : 800; }();
             const int cap = tiny_grid < 0 ? r->num_sms / 2 : tiny_grid;
-            if (cap > 0 && d.use_tma && p.m_tiles * p.n_tiles <= tiny_work && p.grid > cap) p.grid = cap;
+            const int work = p.m_tiles * p.n_tiles;
+            if (cap > 0 && d.use_tma && p.grid > cap && work <= (p.mode == MODE_FLAT_TMA ? tiny_flat : tiny_work)) p.grid = cap;
           }
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
           if (o.layer2 >= 0) { p.out2 = ptr_of(r, o.y2); p.split_n = o.y.Cp; p.out2_pitch = o.y2.pitch; }

@@ -506,6 +506,14 @@ def main():
                                "frac_of_hbm_peak": sum(o[3] for o in conv) / (conv_ms * 1e-3) / 1e9 / hbm, "ms": conv_ms},
                 "post": {o[0]: {"ms": o[1], "gbs": o[3] / (o[1] * 1e-3) / 1e9, "frac_of_hbm_peak": o[3] / (o[1] * 1e-3) / 1e9 / hbm} for o in post},
                 "sum_launch_ms": tot,
+                # the whole step against the same peaks: all algorithmic FLOPs / bytes of one pass over the TIMED step (`value`:
+                # four runners overlapped, sustained clocks) -- the per-launch figures above time every launch ALONE with its
+                # product grid, and the small launches deliberately use half the SMs (DESIGN.md 4 "Scheduling")
+                "whole_step": {"tflops": sum(o[2] for o in ops) / (out["ms_per_step"] * 1e-3) / 1e12,
+                               "frac_of_sustained_tensor_peak": sum(o[2] for o in ops) / (out["ms_per_step"] * 1e-3) / 1e12 / tf_sust,
+                               "gbs": sum(o[3] for o in ops) / (out["ms_per_step"] * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": sum(o[3] for o in ops) / (out["ms_per_step"] * 1e-3) / 1e9 / hbm,
+                               "ms": out["ms_per_step"]},
             })
             os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
             with open(os.path.join(ROOT, "gpurun_out", "ops_profile.json"), "w") as f:

@@ -496,6 +496,11 @@ def main():
             conv_ms, conv_fl = sum(o[1] for o in conv), sum(o[2] for o in conv)
             post = [o for o in ops if o[0] in ("post.decode", "post.decode_exact", "post.mask_prob")]
             out["roofline"] = roof(top)
+            if "+cv3" in top[0]:
+                out["roofline"]["note"] = ("proto.cv2 (3x3, 64->64) and proto.cv3 (1x1, 64->32) run as ONE launch: the 1x1 is a second set of "
+                                           "tcgen05.mma (A operand from tensor memory) on the epilogue's packed fp16 tile; FLOPs and bytes are those of "
+                                           "both layers without the 64-channel intermediate.  As two launches (XRSEG_FUSE_TAIL=0) the pair takes "
+                                           "133 + 58 us (proto.cv2 alone: 0.55-0.58 of the burst peak, the pair 0.40)")
             out["roofline"].update({
                 "peak_source": how + (" (burst bf16 cuBLAS: the launch is timed alone)" if out["roofline"]["bound"] == "tensor" else " (copy bandwidth)"),
                 "algorithmic": "flops = 2*M*Cout*Cin*k*k, bytes = (in + out (+res) + weights) * 2 B, real channel counts (DESIGN.md 4)",

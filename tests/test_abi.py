@@ -218,7 +218,8 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
     import subprocess
     out = subprocess.run([plan_dump, str(batch), scale], capture_output=True, text=True, check=True).stdout
     rows = [l for l in out.splitlines() if " smem " in l]
-    assert len(rows) == 86                       # 100 layers - stem - 7 depthwise - 6 fused siblings
+    # 100 layers - stem - 7 depthwise - 6 fused siblings (- proto.cv3 on the n scale: it runs inside proto.cv2's launch)
+    assert len(rows) == (85 if scale == "n" else 86)
     for l in rows:
         tok = l.split()
         f = {tok[i]: tok[i + 1] for i in range(len(tok) - 1)}
@@ -233,13 +234,14 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
 
 
 @pytest.mark.parametrize("scale,whole_block,expect", [
-    ("n", "0", {"stem": 1, "conv": 80, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 3}),
-    ("n", "1", {"stem": 1, "conv": 78, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 2, "c3k2": 1}),
+    ("n", "0", {"stem": 1, "conv": 79, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 3}),
+    ("n", "1", {"stem": 1, "conv": 77, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 2, "c3k2": 1}),
     ("s", "0", {"stem": 1, "conv": 84, "dw": 6, "sppf": 1, "up": 2, "attn": 1, "bneck": 1}),
 ])
 def test_fusion_passes_produce_the_expected_launch_list(plan_dump, scale, whole_block, expect):
-    """model.cuh: fuse_siblings / fuse_bottlenecks / fuse_c3k2_blocks / fuse_attention_pe.  n scale: 100 layers -> 94 network
-    launches (six sibling pairs, the Bottlenecks of b2 / b4 / n16, the C2PSA positional encoding inside the attention kernel); the opt-in whole-block kernel takes b2; the s scale has one supported
+    """model.cuh: fuse_siblings / fuse_bottlenecks / fuse_c3k2_blocks / fuse_attention_pe / fuse_tail_1x1.  n scale: 100 layers ->
+    93 network launches (six sibling pairs, the Bottlenecks of b2 / b4 / n16, the C2PSA positional encoding inside the attention
+    kernel, proto.cv3 inside proto.cv2's launch); the opt-in whole-block kernel takes b2; the s scale has one supported
     Bottleneck (b2: 32-16-32).  Every fused Bottleneck keeps its residual and stays on the main stream."""
     import subprocess
     out = subprocess.run([plan_dump, "64", scale, "ops", whole_block], capture_output=True, text=True, check=True).stdout

@@ -1094,6 +1094,112 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
   }
 }
 
+// Epilogue of a launch with a fused trailing 1x1 convolution (ConvParams::tail_n = 32 on a halo-mode layer with Ntile = 64:
+// proto.cv2 -> proto.cv3).  Each group owns chunk g of every sub-tile's 64 accumulator columns [64u, 64u + 64):
+//   pass 1: columns 16g .. 16g+15 -> + bias, SiLU -> 16 fp16 values = 8 packed columns, written BACK into tensor memory at
+//           column 64u + {0, 24, 32, 56}[g] (inside the group's own, already consumed, 16-column range) -> tready;
+//   the sub-tile's MMA warp then runs D2 = A[TMEM] x W2^T as two N = 16 halves into the freed column runs [8, 24) and [40, 56);
+//   pass 2 (after t2full): 16 tail channels per unit -> + bias2, SiLU -> one 32-byte store -> tempty.
+// The 64-channel intermediate never reaches shared or global memory.
+template <bool PROBE>
+__device__ __forceinline__ void tma_epilogue_loop_tail(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
+                                                       uint64_t* tready, uint64_t* t2full, const float* bias_s, int warp, int lane,
+                                                       int total_work) {
+  const int ew = warp - TMA_FIRST_EPI_WARP;
+  const int q = warp & 3;
+  const int g = ew >> 2;                      // group = chunk of pass 1 (TMA_EPI_GROUPS == 4 == Ntile / 16)
+  const int nsub = p.nsub;
+  const int Wp = p.Wp, Rr = p.R, Hh = p.H, Ww = p.W, tpi = p.tpi;
+  const int out_pitch = p.out_pitch;
+  __half* const outp = p.out;
+  const FastDiv fd_wp = p.fd_wp, fd_tpi = p.fd_hp1;
+  const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  const uint32_t pk_col = g == 0 ? 0u : (g == 1 ? 24u : (g == 2 ? 32u : 56u));
+  const int h2 = g & 1;                       // pass 2: tail channels [16 h2, 16 h2 + 16) of sub-tiles g >> 1 and (g >> 1) + 2
+  const uint32_t d2_col = h2 ? 40u : 8u;
+  float hbr[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) hbr[i] = bias_s[g * 16 + i];
+  int tcount = 0;
+  long long e_wait = 0, e_work = 0, t0 = 0;
+  pdl_wait();
+  for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+    const int tile = w;
+    const int b = fd_div(fd_tpi, tile);
+    const int y0 = (tile - b * tpi) * Rr;
+    const int buf = tcount & 1;
+    const uint32_t use = static_cast<uint32_t>(tcount >> 1);
+    int pix[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pix[u] = -1;
+      if (u < nsub) {
+        const int j = 128 * u + q * 32 + lane;
+        const int yy = fd_div(fd_wp, j);
+        const int cc = j - yy * Wp;
+        const int y = y0 + yy;
+        if (yy < Rr && y < Hh && cc >= 1 && cc <= Ww) pix[u] = (b * Hh + y) * Ww + (cc - 1);
+      }
+    }
+    if (PROBE) t0 = clock64();
+    mbar_wait(&tfull[buf], use & 1u);
+    if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
+    tc_fence_after();
+    const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * 64);
+    // ---- pass 1: 64 -> packed fp16 in tensor memory
+    {
+      uint32_t va[16], vb[16];
+      tmem_ld16(acc + static_cast<uint32_t>(16 * g), va);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u >= nsub) break;
+        tmem_ld_wait();
+        if (u + 1 < nsub) tmem_ld16(acc + static_cast<uint32_t>((u + 1) * 64 + 16 * g), (u & 1) ? va : vb);
+        const uint32_t (&v)[16] = (u & 1) ? vb : va;
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          o[i] = silu_pack_from_half_arg(fmaf(__uint_as_float(v[2 * i]), 0.5f, hbr[2 * i]), fmaf(__uint_as_float(v[2 * i + 1]), 0.5f, hbr[2 * i + 1]));
+        tmem_st8(acc + static_cast<uint32_t>(u * 64) + pk_col, o);
+      }
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tready[buf]);
+    // ---- pass 2: the tail's 32 channels
+    float hb2[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b4 = reinterpret_cast<const float4*>(bias_s + 256 + 16 * h2)[i];
+      hb2[4 * i] = b4.x; hb2[4 * i + 1] = b4.y; hb2[4 * i + 2] = b4.z; hb2[4 * i + 3] = b4.w;
+    }
+    mbar_wait(&t2full[buf], use & 1u);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int u = (g >> 1) + 2 * k;
+      if (u >= nsub) break;
+      uint32_t v[16];
+      tmem_ld16(acc + static_cast<uint32_t>(u * 64) + d2_col, v);
+      tmem_ld_wait();
+      const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
+      const size_t pxs = static_cast<size_t>(px < 0 ? 0 : px);
+      __half* dst = outp + pxs * out_pitch + 16 * h2;
+      if (p.tail_act) tma_epilogue_unit<true, false>(v, hb2, nullptr, dst, 0, px >= 0);
+      else tma_epilogue_unit<false, false>(v, hb2, nullptr, dst, 0, px >= 0);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[buf]);
+    if (PROBE) e_work += clock64() - t0;
+  }
+  if (PROBE && p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
+    p.dbg_clk[blockIdx.x * 12 + 6] = e_wait;
+    p.dbg_clk[blockIdx.x * 12 + 7] = e_work;
+  }
+}
+
 // ---- the kernel --------------------------------------------------------------------------------------------------
 // PROBE = true (libxrseg_debug.so only, tools/probe_tma.py): per-role clock64() counters (p.dbg_clk) and the p.dbg_skip
 // switches (1 = no MMAs, 2 = no stores, 4 = no TMA loads, 8 = software-pipelined epilogue).  The product instantiation
@@ -1109,7 +1215,9 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   uint64_t* tempty = tfull + 4;                             // [4]
   uint64_t* bres = tempty + 4;                              // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
-  float* bias_s = reinterpret_cast<float*>(smem + 256);     // [<=512]
+  uint64_t* tready = reinterpret_cast<uint64_t*>(smem + 208);   // [2] tail: packed intermediate of an item is in tensor memory
+  uint64_t* t2full = tready + 2;                                // [2] tail: the 1x1 layer's accumulators are complete
+  float* bias_s = reinterpret_cast<float*>(smem + 256);     // [<=512]; the tail's bias lives at [256, 256 + tail_n)
   uint8_t* smem_b = smem + p.smem_off_b;
   uint8_t* smem_a = smem + p.smem_off_a;
 
@@ -1130,6 +1238,12 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       mbar_init(&tempty[i], TMA_EPI_WARPS);  // one arrival per epilogue warp
     }
     mbar_init(bres, 1);
+    if (p.tail_n) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tready[i], TMA_EPI_WARPS);
+        mbar_init(&t2full[i], n_issuers);
+      }
+    }
     mbar_fence_init();
     prefetch_tensormap(&tmap);
     if (p.mode == MODE_S2_TMA)
@@ -1142,12 +1256,14 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       // resident weights: fetched first thing (they are constants: no dependence on the previous kernel), so the copy
       // runs while warp 1 allocates TMEM -- which may have to wait for a co-resident CTA of the previous kernel
       const uint32_t bytes = static_cast<uint32_t>(p.nks) * p.b_stage_bytes;
+      const uint32_t tail_bytes = p.tail_n ? static_cast<uint32_t>(p.tail_n) * 128u : 0u;   // W2: tail_n rows of 64 channels
       const uint32_t b_dst = smem_u32(smem_b);
-      mbar_arrive_expect_tx(bres, bytes);
+      mbar_arrive_expect_tx(bres, bytes + tail_bytes);
       for (uint32_t off = 0; off < bytes; off += 32768u) {
         const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
         bulk_copy_g2s(b_dst + off, reinterpret_cast<const uint8_t*>(p.wpack) + off, n, bres);
       }
+      if (tail_bytes) bulk_copy_g2s(smem_u32(smem + p.smem_off_w2), p.tail_w, tail_bytes, bres);
     }
   }
   if (warp == 1) {
@@ -1156,6 +1272,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   }
   // bias for the epilogue; activated layers keep 0.5 * bias (epilogue_chunk16_hb: h = 0.5 acc + 0.5 bias in one FFMA)
   for (int i = tid; i < p.n_tiles * p.Ntile; i += TMA_THREADS) bias_s[i] = p.act ? 0.5f * p.bias[i] : p.bias[i];
+  for (int i = tid; i < p.tail_n; i += TMA_THREADS) bias_s[256 + i] = p.tail_act ? 0.5f * p.tail_bias[i] : p.tail_bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1253,6 +1370,39 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       }
       if (p.b_resident) mbar_wait(bres, 0);
       if (PROBE) t_bres = clock64() - t_start;
+      // Fused trailing 1x1 (tail): item j's packed intermediate sits in this sub-tile's accumulator columns 64 u + {0, 24, 32, 56}
+      // (8 columns = one K step of 16 channels each); D2 = A[TMEM] x W2^T as two N = 16 halves into the freed column runs
+      // [8, 24) and [40, 56).  W2: [32 rows][128 bytes], 128-byte swizzle; a half starts 16 rows = 2048 bytes further.
+      // blocking = false: only if the epilogue has already delivered item j (polled between the K stages of the next item, so
+      // that the 1x1's accumulators are read out and the buffer is free again BEFORE the next item's MMAs finish -- otherwise
+      // the tensor pipe idles through the whole second epilogue pass of every item)
+      auto issue_tail = [&](int j, bool blocking) -> bool {
+        const int jb = j & 1;
+        const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
+        if (blocking) mbar_wait(&tready[jb], ph);
+        else if (!__any_sync(0xffffffffu, mbar_try_wait(&tready[jb], ph))) return false;
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t accj = tmem_base + static_cast<uint32_t>(jb * p.nsub * 64 + my_u * 64);
+          const uint32_t w2 = smem_u32(smem + p.smem_off_w2);
+          const uint64_t hi128 = static_cast<uint64_t>(((8u * 128u) >> 4) | (1u << 14) | (2u << 29)) << 32;
+          const uint32_t idesc16 = umma_idesc_f16(16, 0);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint32_t b_lo2 = (((w2 + static_cast<uint32_t>(hh) * 2048u) >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t d2 = accj + (hh ? 40u : 8u);
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) {
+              const uint32_t a_col = j2 == 0 ? 0u : (j2 == 1 ? 24u : (j2 == 2 ? 32u : 56u));
+              umma_f16_ts(d2, accj + a_col, hi128 | (b_lo2 + 2u * j2), idesc16, j2 > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&t2full[jb]);
+        }
+        __syncwarp();
+        return true;
+      };
+      int tail_pending = -1;                      // item whose 1x1 has not been issued yet
       int it = 0, tcount = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
         const int buf = tcount % nbuf;
@@ -1303,6 +1453,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
               umma_commit(&empty[slot]);
             }
             __syncwarp();
+            if (tail_pending >= 0 && issue_tail(tail_pending, false)) tail_pending = -1;
             if (PROBE) t_issue += clock64() - t0;
             continue;
           }
@@ -1332,7 +1483,10 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           if (elect_one()) umma_commit(&empty[slot]);
         }
         if (elect_one()) umma_commit(&tfull[buf]);
+        if (tail_pending >= 0) issue_tail(tail_pending, true);   // not delivered during this item's stages: queued behind its MMAs
+        tail_pending = p.tail_n ? tcount : -1;
       }
+      if (tail_pending >= 0) issue_tail(tail_pending, true);     // the last item's
       if (PROBE && p.dbg_clk && lane == 0 && warp == 1) {
         p.dbg_clk[blockIdx.x * 12 + 1] = t_bres;
         p.dbg_clk[blockIdx.x * 12 + 2] = t_tempty;
@@ -1349,6 +1503,9 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   } else {
     // ======================================= epilogue ============================================
     // one specialised instantiation per (destination kind, activation, residual): see tma_epilogue_loop
+    if (p.tail_n) {
+      tma_epilogue_loop_tail<PROBE>(p, tmem_base, tfull, tempty, tready, t2full, bias_s, warp, lane, total_work);
+    } else {
     const int kind = p.transposed ? 2 : (p.split_n ? 1 : 0);
     const int nch_ = p.Ntile >> 4;
     const bool breg = p.n_tiles == 1 && nch_ <= TMA_EPI_GROUPS && TMA_EPI_GROUPS % nch_ == 0;
@@ -1366,6 +1523,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       default: asm volatile("trap;"); break;       // split / transposed launches never carry a residual (checked at plan time)
     }
 #undef XR_EPI_CASE
+    }
   }
 
   tc_fence_before();

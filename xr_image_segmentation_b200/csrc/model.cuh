@@ -46,6 +46,10 @@ struct Op {
   // (OP_BNECK: the second 3x3 convolution of the fused Bottleneck, whose output is y)
   int layer2 = -1;
   TV y2;
+  // fused trailing 1x1 convolution (conv_tma.cuh "tail"): the 1x1 layer `tail_layer` consumes this op's 64-channel output inside
+  // the kernel; ytail is its destination (y stays the never-materialised intermediate)
+  int tail_layer = -1, tail_act = 0;
+  TV ytail;
   // OP_C3K2 (whole-block fusion): layer = X.cv1, layer2 = X.m0.cv1, layer3 = X.m0.cv2, layer4 = X.cv2
   int layer3 = -1, layer4 = -1;
   // OP_CHAIN (conv_chain.cuh): consecutive convolutions of the 20x20 / 40x40 stages run by one launch, a CTA per frame;
@@ -95,13 +99,14 @@ class Net {
   bool fuse_enabled = true;               // sibling fusion (fuse_siblings); off for the direct-convolution cross-check
   bool fuse_bneck = true;                 // Bottleneck fusion (fuse_bottlenecks)
   bool fuse_pe = true;                    // C2PSA positional encoding inside the attention kernel (fuse_attention_pe)
+  bool fuse_tail = true;                  // proto.cv3 (1x1, 64 -> 32) inside proto.cv2's launch (fuse_tail_1x1)
   bool fuse_c3k2 = false;                 // whole-block fusion (fuse_c3k2_blocks); measured slower, opt-in (XRSEG_FUSE_C3K2=1)
   TV input;                 // [B,640,640,4] fp16
   TV box[3], cls[3], coef[3], protos;
   int fh[3], fw[3];
 
   Net(int scale, int batch, int in_hw = 640, bool fuse = true, bool bneck = true, bool c3k2_blocks = false)
-      : B(batch), sp(make_spec(scale)), fuse_enabled(fuse), fuse_bneck(fuse && bneck), fuse_c3k2(c3k2_blocks) { build(in_hw); }
+      : B(batch), sp(make_spec(scale)), fuse_enabled(fuse), fuse_bneck(fuse && bneck), fuse_tail(fuse), fuse_c3k2(c3k2_blocks) { build(in_hw); }
 
   TV alloc(int H, int W, int C, int pitch_override = 0) {
     TV t;
@@ -242,6 +247,30 @@ class Net {
         ++tag;
       }
       ops.erase(ops.begin() + ib);
+    }
+  }
+
+  // Proto: cv2 (3x3, 64 -> 64, SiLU) -> cv3 (1x1, 64 -> 32, SiLU).  cv3 is the only consumer of cv2's output and rows are
+  // independent for a 1x1, so cv3 runs inside cv2's launch as a second set of MMAs on the epilogue's fp16 tile kept in tensor
+  // memory (ConvParams::tail_n): the 64-channel 160x160 tensor (3.3 MB per frame, written and read back) never exists in HBM.
+  // The kernel side is built for exactly this shape (Ntile 64 -> 32); anything else keeps its two launches.
+  void fuse_tail_1x1() {
+    static const bool env_on = [] { const char* e = getenv("XRSEG_FUSE_TAIL"); return !(e && e[0] == '0'); }();
+    if (!fuse_tail || !env_on) return;
+    for (size_t i = 0; i + 1 < ops.size(); ++i) {
+      Op& a = ops[i];
+      const Op b = ops[i + 1];
+      if (a.kind != OP_CONV || b.kind != OP_CONV || a.layer2 >= 0 || b.layer2 >= 0 || a.tail_layer >= 0) continue;
+      if (layers[a.layer].name != "proto.cv2" || layers[b.layer].name != "proto.cv3") continue;
+      const bool ok = a.k == 3 && a.stride == 1 && !a.transposed && a.act && !a.has_res && b.k == 1 && b.stride == 1 && !b.transposed &&
+                      !b.has_res && b.x.off == a.y.off && b.x.pitch == a.y.pitch && a.y.Cp == 64 && b.x.Cp == 64 && b.y.Cp == 32 &&
+                      a.branch == b.branch && b.wait_tag == 0 && a.signal_tag == 0 && a.x.W + 2 <= 256;
+      if (!ok) continue;
+      a.tail_layer = b.layer;
+      a.tail_act = b.act;
+      a.ytail = b.y;
+      a.signal_tag = b.signal_tag;
+      ops.erase(ops.begin() + i + 1);
     }
   }
 
@@ -438,6 +467,7 @@ class Net {
     fuse_bottlenecks();
     fuse_c3k2_blocks();
     fuse_attention_pe();
+    fuse_tail_1x1();
     fh[0] = p3.H; fw[0] = p3.W; fh[1] = p4.H; fw[1] = p4.W; fh[2] = p5.H; fw[2] = p5.W;
   }
 };

@@ -43,6 +43,8 @@ struct DevLayer {
   float* w32 = nullptr;
   float* w32_u8 = nullptr;         // stem weights / 255 for the fused uint8 path
   uint2* wfrag = nullptr;          // OP_BNECK: mma.sync B-fragment order (bottleneck.cuh)
+  __half* tail_w = nullptr;        // fused trailing 1x1 (Op::tail_layer): its [32][64] weights, 128-byte swizzle; bias in tail_bias
+  float* tail_bias = nullptr;
   __half* w16_rows = nullptr;      // stem_rows_kernel weights
 };
 
@@ -381,6 +383,26 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
           if (o.layer2 >= 0) d.tmaps.m[5] = make_store_tensor_map(ptr_of(r, o.y2), d.cp, r->mb, o.y2.Cp, o.y2.pitch);
         }
       }
+      if (o.tail_layer >= 0) {
+        // fused trailing 1x1 (model.cuh: fuse_tail_1x1): W2 as the 128-byte-swizzled image of a 1x1 layer with Ntile = 32, cb = 64
+        const LayerRec& lt = net.layers[o.tail_layer];
+        const HostLayerWeights& wt = hw[o.tail_layer];
+        XR_CHECK(d.use_tma && d.cp.mode == MODE_HALO_TMA && d.cp.sw && d.cp.Ntile == 64 && d.cp.n_tiles == 1 && d.cp.b_resident &&
+                     (d.cp.nbuf == 0 || d.cp.nbuf == 2) && !d.cp.st_tma && o.ytail.Cp == 32 && lt.cin <= 64,
+                 "fused trailing 1x1 needs the halo plan with Ntile 64, resident weights and two accumulator sets (%s)", l.name.c_str());
+        ConvParams t{};
+        t.Ntile = 32; t.n_tiles = 1; t.cb = 64; t.sw = 3; t.taps = 1; t.nks = 1; t.kps = 1; t.b_stage_bytes = 32 * 128; t.Cout = 32;
+        std::vector<__half> wp2;
+        std::vector<float> bp2;
+        pack_conv_weights_sw<__half>(t, wt.w.data(), wt.b.data(), lt.cin, lt.cout, wp2, bp2);
+        r->dl[o.tail_layer].tail_w = dev_upload(wp2);
+        r->dl[o.tail_layer].tail_bias = dev_upload(bp2);
+        d.cp.tail_n = 32;
+        d.cp.tail_act = o.tail_act;
+        d.cp.smem_off_w2 = round_up(d.cp.smem_bytes, 1024);
+        d.cp.smem_bytes = d.cp.smem_off_w2 + 32 * 128;
+        XR_CHECK(d.cp.smem_bytes <= CONV_SMEM_MAX, "no room for the tail's weights (%s)", l.name.c_str());
+      }
 #ifdef XRSEG_DEBUG_API
       if (const char* e = getenv("XRSEG_EPI")) d.cp.dbg_skip |= (e[0] == '1') ? 8 : 0;   // A/B of the TMA kernel's epilogue
 #endif
@@ -516,6 +538,14 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
           if (o.layer2 >= 0) { p.out2 = ptr_of(r, o.y2); p.split_n = o.y.Cp; p.out2_pitch = o.y2.pitch; }
           p.res = o.has_res ? ptr_of(r, o.res) : nullptr;
           p.wpack = d.wpack; p.bias = d.bias;
+          if (o.tail_layer >= 0) {                    // the launch's destination is the fused 1x1's
+            const LayerRec& lt = net.layers[o.tail_layer];
+            p.out = ptr_of(r, o.ytail); p.out_pitch = o.ytail.pitch;
+            p.tail_w = r->dl[o.tail_layer].tail_w; p.tail_bias = r->dl[o.tail_layer].tail_bias;
+            L.name = l.name + "+" + lt.name.substr(lt.name.find('.') + 1);
+            L.flops += 2.0 * px_out * lt.cout * lt.cin;
+            L.bytes = (px_in * l.cin + px_out * lt.cout + static_cast<double>(cout_alg) * l.cin * o.k * o.k + static_cast<double>(lt.cout) * lt.cin) * 2;
+          }
           if (d.use_tma) {
             const TmapSet maps = d.tmaps;
             L.fn = [p, maps](cudaStream_t st) { launch_conv_halo_tma(p, maps, st); };
@@ -1138,7 +1168,7 @@ xrseg_runner::~xrseg_runner() {
   cudaFree(scratch);
   for (ChainDev& c : chains) cudaFree(c.d_layers);
   for (DevLayer& d : dl) {
-    cudaFree(d.wpack); cudaFree(d.wfrag); cudaFree(d.w16_rows); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
+    cudaFree(d.wpack); cudaFree(d.wfrag); cudaFree(d.tail_w); cudaFree(d.tail_bias); cudaFree(d.w16_rows); cudaFree(d.bias); cudaFree(d.w16); cudaFree(d.w32); cudaFree(d.w32_u8);
   }
   void* bufs[] = {arena, d_frames, d_boxes, d_scores, d_labels, d_keys, d_cand_count, d_n_cand, d_sorted_idx, d_filt_list,
                   d_overflow, d_sorted_corners, d_mask, d_keep_idx, d_keep_n, d_offsets, d_done, o_boxes, o_coefs, o_scores,

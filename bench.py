@@ -287,11 +287,15 @@ def main():
     B = args.batch
     layers, ws = W.random_weights(SCALE, SEED_WEIGHTS, CLS_BIAS)
     model = I.Model(W.write_pack(SCALE, layers, ws), SCALE)
-    runner = I.Runner(model, device=local_rank, max_batch=B)
+    # the random-init YOLO11s-seg network produces ~150 overlapping detections per frame: run it with the reference's
+    # unlimited NMS (caps at the anchor count) instead of the 2048-candidate / 300-detection defaults, which would
+    # (correctly) report XRSEG_ERR_CAPACITY
+    caps = dict(max_candidates=8400, max_det=1000) if SCALE == "s" else {}
+    runner = I.Runner(model, device=local_rank, max_batch=B, **caps)
     # end-to-end leg: runners used round-robin (inference.PipelinedRunner): the host->device copies and the network passes
     # of the next steps overlap the readback of step i; every step still copies its frames from pinned host memory and
     # reads its detections back
-    pipe = I.PipelinedRunner(model, device=local_rank, max_batch=B, depth=args.e2e_depth, micro_batch=args.e2e_micro_batch)
+    pipe = I.PipelinedRunner(model, device=local_rank, max_batch=B, depth=args.e2e_depth, micro_batch=args.e2e_micro_batch, **caps)
     runner_e2e = pipe.runners[0]
     # 4 distinct frame sets (4 x 78.6 MB > 126 MB L2) so no step finds its input in L2; every rank has its own frames
     NSETS = 4
@@ -410,7 +414,7 @@ def main():
     # ---------------- batch-1 streaming latency (BASELINE.json configs[3]): 1280x960 -> letterbox -> detections on the host
     lat = None
     if rank == 0 and args.latency_iters > 0:
-        r1 = I.Runner(model, device=local_rank, max_batch=1, resize_mode=_lib.RESIZE_LETTERBOX)
+        r1 = I.Runner(model, device=local_rank, max_batch=1, resize_mode=_lib.RESIZE_LETTERBOX, **caps)
         fb = 960 * 1280 * 3
         hf = lib.xrseg_host_alloc(fb)
         C.memmove(hf, np.random.default_rng(4).integers(0, 256, fb, dtype=np.uint8).ctypes.data, fb)

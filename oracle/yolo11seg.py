@@ -253,8 +253,8 @@ CLS_FINAL = ("h3.cls.2", "h4.cls.2", "h5.cls.2")
 def random_weights(scale: str, seed: int, cls_bias: float | None = None, gain: float = 1.5, bias_std: float = 0.2):
     """Random-init weights for BASELINE.json configs 2/3 -- the same frozen recipe as the product-side generator
     (xr_image_segmentation_b200/weights.py, checked equal by tests/test_abi.py): w ~ N(0, (1.5/sqrt(fan_in))^2),
-    b ~ N(0, 0.2^2), final class-conv biases N(cls_bias, 0.05^2) with cls_bias -5.15 (n) / -4.87 (s)."""
-    cls_bias = {"n": -5.15, "s": -4.87}[scale] if cls_bias is None else cls_bias
+    b ~ N(0, 0.2^2), final class-conv biases N(cls_bias, 0.05^2) with cls_bias -5.15 (n) / -12.4 (s; see weights.INIT_CLS_BIAS)."""
+    cls_bias = {"n": -5.15, "s": -12.4}[scale] if cls_bias is None else cls_bias
     rng = np.random.default_rng(seed)
     out = []
     for l in layer_table(scale):

@@ -946,6 +946,21 @@ __global__ void __launch_bounds__(256) mask640_kernel(const Mask640Params p) {
   const int d = blockIdx.z;
   const int o = p.first + d;
   const int tx = blockIdx.x, ty = blockIdx.y;  // 10 x 10 tiles of 64
+  const float4 raw = reinterpret_cast<const float4*>(p.boxes)[o];
+  const float x1 = __fsub_rn(raw.x, __fmul_rn(raw.z, 0.5f)), x2 = __fadd_rn(raw.x, __fmul_rn(raw.z, 0.5f));
+  const float y1 = __fsub_rn(raw.y, __fmul_rn(raw.w, 0.5f)), y2 = __fadd_rn(raw.y, __fmul_rn(raw.w, 0.5f));
+  {
+    // A tile the box does not touch is all zeros whatever the logits are (the crop test below is xf >= x1 && xf < x2, same for
+    // y): write it without computing the patch.  Most of a 640x640 mask lies outside its box -- the kernel was bound by the ~40
+    // strictly ordered fp32 operations per output pixel, not by the 7.9 GB it writes at 300 detections x 64 frames.
+    const float tx0 = static_cast<float>(tx * 64), tx1 = static_cast<float>(tx * 64 + 63);
+    const float ty0 = static_cast<float>(ty * 64), ty1 = static_cast<float>(ty * 64 + 63);
+    if (!(tx1 >= x1 && tx0 < x2 && ty1 >= y1 && ty0 < y2)) {
+      const int ry = threadIdx.x >> 2, seg = threadIdx.x & 3;
+      __stcs(reinterpret_cast<uint4*>(p.out + (static_cast<long>(d) * 640 + ty * 64 + ry) * 640 + tx * 64 + seg * 16), make_uint4(0, 0, 0, 0));
+      return;
+    }
+  }
   if (threadIdx.x < NM) sc[threadIdx.x] = p.coefs[static_cast<long>(o) * NM + threadIdx.x];
   const int b = p.frames[o];
   __syncthreads();
@@ -971,9 +986,6 @@ __global__ void __launch_bounds__(256) mask640_kernel(const Mask640Params p) {
     patch[py][px] = acc;
   }
   __syncthreads();
-  const float4 raw = reinterpret_cast<const float4*>(p.boxes)[o];
-  const float x1 = __fsub_rn(raw.x, __fmul_rn(raw.z, 0.5f)), x2 = __fadd_rn(raw.x, __fmul_rn(raw.z, 0.5f));
-  const float y1 = __fsub_rn(raw.y, __fmul_rn(raw.w, 0.5f)), y2 = __fadd_rn(raw.y, __fmul_rn(raw.w, 0.5f));
   // each thread: 16 consecutive output pixels of one row (64 rows x 4 segments)
   const int ry = threadIdx.x >> 2, seg = threadIdx.x & 3;
   const int Y = ty * 64 + ry;

@@ -1094,32 +1094,40 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
   }
 }
 
-// Epilogue of a launch with a fused trailing 1x1 convolution (ConvParams::tail_n = 32 on a halo-mode layer with Ntile = 64:
-// proto.cv2 -> proto.cv3).  Each group owns chunk g of every sub-tile's 64 accumulator columns [64u, 64u + 64):
-//   pass 1: columns 16g .. 16g+15 -> + bias, SiLU -> 16 fp16 values = 8 packed columns, written BACK into tensor memory at
-//           column 64u + {0, 24, 32, 56}[g] (inside the group's own, already consumed, 16-column range) -> tready;
-//   the sub-tile's MMA warp then runs D2 = A[TMEM] x W2^T as two N = 16 halves into the freed column runs [8, 24) and [40, 56);
-//   pass 2 (after t2full): 16 tail channels per unit -> + bias2, SiLU -> one 32-byte store -> tempty.
-// The 64-channel intermediate never reaches shared or global memory.
+// Epilogue of a launch with a fused trailing 1x1 convolution (ConvParams::tail_n; main layer 3x3 stride 1 or 2 with Ntile = N1 in
+// {32, 64}, the 1x1 with N2 = tail_n in {32, 64}).  Group g owns chunk g % (N1/16) of the sub-tiles g / (N1/16), + 4/(N1/16), ...:
+//   pass 1: 16 accumulator columns -> + bias, SiLU -> 16 fp16 values = 8 packed columns, written BACK into tensor memory inside
+//           the group's own, already consumed, 16-column range -> tready;
+//   the sub-tile's MMA warp then runs D2 = A[TMEM] x W2^T (issue_tail in the kernel);
+//   pass 2 (after t2full): 16 channels of the 1x1 per unit -> + bias2, (SiLU) -> one 32-byte store -> tempty.
+// In-place form (proto.cv2 -> cv3, N1 = 64, N2 = 32, TMEM full): packed columns 64u + {0, 24, 32, 56}, D2 as two N = 16 halves
+// in the freed runs [8, 24) and [40, 56) of the same 64 columns.  Separate form (b1 -> b2.cv1, b3 -> b4.cv1): packed columns
+// N1 u + 16 c, D2 in its own region behind the main accumulators.  The intermediate never reaches shared or global memory.
+__device__ __forceinline__ uint32_t tail_pack_col(int inplace, int c) {
+  return inplace ? (c == 0 ? 0u : (c == 1 ? 24u : (c == 2 ? 32u : 56u))) : static_cast<uint32_t>(16 * c);
+}
 template <bool PROBE>
 __device__ __forceinline__ void tma_epilogue_loop_tail(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull, uint64_t* tempty,
                                                        uint64_t* tready, uint64_t* t2full, const float* bias_s, int warp, int lane,
                                                        int total_work) {
+  constexpr int G = TMA_EPI_GROUPS;
   const int ew = warp - TMA_FIRST_EPI_WARP;
   const int q = warp & 3;
-  const int g = ew >> 2;                      // group = chunk of pass 1 (TMA_EPI_GROUPS == 4 == Ntile / 16)
-  const int nsub = p.nsub;
+  const int g = ew >> 2;
+  const int nsub = p.nsub, N1 = p.Ntile, N2 = p.tail_n, inplace = p.tail_inplace;
+  const int nch1 = N1 >> 4, nch2 = N2 >> 4;
+  const int c1 = g % nch1, u1 = g / nch1, step1 = G / nch1;     // pass 1: chunk c1 of sub-tiles u1, u1 + step1, ...
+  const int c2 = g % nch2, u2 = g / nch2, step2 = G / nch2;     // pass 2: chunk c2 of the 1x1's channels, sub-tiles u2, ...
   const int Wp = p.Wp, Rr = p.R, Hh = p.H, Ww = p.W, tpi = p.tpi;
   const int out_pitch = p.out_pitch;
   __half* const outp = p.out;
   const FastDiv fd_wp = p.fd_wp, fd_tpi = p.fd_hp1;
   const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-  const uint32_t pk_col = g == 0 ? 0u : (g == 1 ? 24u : (g == 2 ? 32u : 56u));
-  const int h2 = g & 1;                       // pass 2: tail channels [16 h2, 16 h2 + 16) of sub-tiles g >> 1 and (g >> 1) + 2
-  const uint32_t d2_col = h2 ? 40u : 8u;
+  const uint32_t pk_col = tail_pack_col(inplace, c1);
+  const uint32_t d2_region = static_cast<uint32_t>(2 * nsub * N1);          // separate form: behind the two main accumulator sets
   float hbr[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) hbr[i] = bias_s[g * 16 + i];
+  for (int i = 0; i < 16; ++i) hbr[i] = bias_s[c1 * 16 + i];
   int tcount = 0;
   long long e_wait = 0, e_work = 0, t0 = 0;
   pdl_wait();
@@ -1145,47 +1153,50 @@ __device__ __forceinline__ void tma_epilogue_loop_tail(const ConvParams& p, uint
     mbar_wait(&tfull[buf], use & 1u);
     if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
     tc_fence_after();
-    const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * 64);
-    // ---- pass 1: 64 -> packed fp16 in tensor memory
+    const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * N1);
+    // ---- pass 1: accumulators -> packed fp16 in tensor memory
     {
       uint32_t va[16], vb[16];
-      tmem_ld16(acc + static_cast<uint32_t>(16 * g), va);
+      if (u1 < nsub) tmem_ld16(acc + static_cast<uint32_t>(u1 * N1 + 16 * c1), va);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int k = 0; k < 4; ++k) {
+        const int u = u1 + k * step1;
         if (u >= nsub) break;
         tmem_ld_wait();
-        if (u + 1 < nsub) tmem_ld16(acc + static_cast<uint32_t>((u + 1) * 64 + 16 * g), (u & 1) ? va : vb);
-        const uint32_t (&v)[16] = (u & 1) ? vb : va;
+        if (u + step1 < nsub) tmem_ld16(acc + static_cast<uint32_t>((u + step1) * N1 + 16 * c1), (k & 1) ? va : vb);
+        const uint32_t (&v)[16] = (k & 1) ? vb : va;
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           o[i] = silu_pack_from_half_arg(fmaf(__uint_as_float(v[2 * i]), 0.5f, hbr[2 * i]), fmaf(__uint_as_float(v[2 * i + 1]), 0.5f, hbr[2 * i + 1]));
-        tmem_st8(acc + static_cast<uint32_t>(u * 64) + pk_col, o);
+        tmem_st8(acc + static_cast<uint32_t>(u * N1) + pk_col, o);
       }
       tmem_st_wait();
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tready[buf]);
-    // ---- pass 2: the tail's 32 channels
+    // ---- pass 2: the 1x1's channels
     float hb2[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float4 b4 = reinterpret_cast<const float4*>(bias_s + 256 + 16 * h2)[i];
+      const float4 b4 = reinterpret_cast<const float4*>(bias_s + 256 + 16 * c2)[i];
       hb2[4 * i] = b4.x; hb2[4 * i + 1] = b4.y; hb2[4 * i + 2] = b4.z; hb2[4 * i + 3] = b4.w;
     }
     mbar_wait(&t2full[buf], use & 1u);
     tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int u = (g >> 1) + 2 * k;
+    for (int k = 0; k < 4; ++k) {
+      const int u = u2 + k * step2;
       if (u >= nsub) break;
+      const uint32_t d2 = inplace ? acc + static_cast<uint32_t>(u * N1) + (c2 ? 40u : 8u)
+                                  : lane_taddr + d2_region + static_cast<uint32_t>((buf * nsub + u) * N2 + 16 * c2);
       uint32_t v[16];
-      tmem_ld16(acc + static_cast<uint32_t>(u * 64) + d2_col, v);
+      tmem_ld16(d2, v);
       tmem_ld_wait();
       const int px = u == 0 ? pix[0] : (u == 1 ? pix[1] : (u == 2 ? pix[2] : pix[3]));
       const size_t pxs = static_cast<size_t>(px < 0 ? 0 : px);
-      __half* dst = outp + pxs * out_pitch + 16 * h2;
+      __half* dst = outp + pxs * out_pitch + 16 * c2;
       if (p.tail_act) tma_epilogue_unit<true, false>(v, hb2, nullptr, dst, 0, px >= 0);
       else tma_epilogue_unit<false, false>(v, hb2, nullptr, dst, 0, px >= 0);
     }
@@ -1256,7 +1267,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       // resident weights: fetched first thing (they are constants: no dependence on the previous kernel), so the copy
       // runs while warp 1 allocates TMEM -- which may have to wait for a co-resident CTA of the previous kernel
       const uint32_t bytes = static_cast<uint32_t>(p.nks) * p.b_stage_bytes;
-      const uint32_t tail_bytes = p.tail_n ? static_cast<uint32_t>(p.tail_n) * 128u : 0u;   // W2: tail_n rows of 64 channels
+      const uint32_t tail_bytes = p.tail_n ? static_cast<uint32_t>(p.tail_n) * static_cast<uint32_t>(p.Ntile) * 2u : 0u;   // W2: tail_n rows of Ntile channels
       const uint32_t b_dst = smem_u32(smem_b);
       mbar_arrive_expect_tx(bres, bytes + tail_bytes);
       for (uint32_t off = 0; off < bytes; off += 32768u) {
@@ -1383,19 +1394,28 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         else if (!__any_sync(0xffffffffu, mbar_try_wait(&tready[jb], ph))) return false;
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t accj = tmem_base + static_cast<uint32_t>(jb * p.nsub * 64 + my_u * 64);
+          const int N1 = p.Ntile, N2 = p.tail_n, nch1 = N1 >> 4;
+          const uint32_t accj = tmem_base + static_cast<uint32_t>((jb * p.nsub + my_u) * N1);
           const uint32_t w2 = smem_u32(smem + p.smem_off_w2);
-          const uint64_t hi128 = static_cast<uint64_t>(((8u * 128u) >> 4) | (1u << 14) | (2u << 29)) << 32;
-          const uint32_t idesc16 = umma_idesc_f16(16, 0);
+          // W2: [N2 rows][N1 channels] fp16, K-major, rows of N1 * 2 bytes in the hardware swizzle of that width
+          const uint32_t rb2 = static_cast<uint32_t>(N1) * 2u;
+          const uint64_t hi2 = static_cast<uint64_t>(((8u * rb2) >> 4) | (1u << 14) | ((rb2 == 128u ? 2u : 4u) << 29)) << 32;
+          if (p.tail_inplace) {
+            const uint32_t idesc16 = umma_idesc_f16(16, 0);
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const uint32_t b_lo2 = (((w2 + static_cast<uint32_t>(hh) * 2048u) >> 4) & 0x3FFFu) | (1u << 16);
-            const uint32_t d2 = accj + (hh ? 40u : 8u);
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t b_lo2 = (((w2 + static_cast<uint32_t>(hh) * 16u * rb2) >> 4) & 0x3FFFu) | (1u << 16);
+              const uint32_t d2 = accj + (hh ? 40u : 8u);
 #pragma unroll
-            for (int j2 = 0; j2 < 4; ++j2) {
-              const uint32_t a_col = j2 == 0 ? 0u : (j2 == 1 ? 24u : (j2 == 2 ? 32u : 56u));
-              umma_f16_ts(d2, accj + a_col, hi128 | (b_lo2 + 2u * j2), idesc16, j2 > 0 ? 1u : 0u);
+              for (int j2 = 0; j2 < 4; ++j2)
+                umma_f16_ts(d2, accj + tail_pack_col(1, j2), hi2 | (b_lo2 + 2u * j2), idesc16, j2 > 0 ? 1u : 0u);
             }
+          } else {
+            const uint32_t idesc2 = umma_idesc_f16(N2, 0);
+            const uint32_t b_lo2 = ((w2 >> 4) & 0x3FFFu) | (1u << 16);
+            const uint32_t d2 = tmem_base + static_cast<uint32_t>(2 * p.nsub * N1 + (jb * p.nsub + my_u) * N2);
+            for (int j2 = 0; j2 < nch1; ++j2)
+              umma_f16_ts(d2, accj + static_cast<uint32_t>(16 * j2), hi2 | (b_lo2 + 2u * j2), idesc2, j2 > 0 ? 1u : 0u);
           }
           umma_commit(&t2full[jb]);
         }

@@ -106,6 +106,8 @@ struct ConvParams {
   // tail_n = 32 output channels of the 1x1 layer in the freed accumulator columns, a second epilogue pass stores those.
   // `out` / `out_pitch` are then the TAIL's destination.  tail_n == 0: off.
   int tail_n, tail_act, smem_off_w2;
+  int tail_inplace;                 // 1: Ntile 64 -> 32 inside the sub-tile's own 64 columns (TMEM full); 0: the 1x1's accumulators live in
+                                    // their own TMEM region behind the main ones (column nbuf * nsub * Ntile + (buf * nsub + u) * tail_n)
   const __half* tail_w;             // [32][64] fp16, K-major 128-byte swizzle (pack_conv_weights_sw image of the 1x1 layer)
   const float* tail_bias;           // [32]
   // Chain kernel (conv_chain.cuh), flat mode: rows of ONE frame (H * W); a work item is `slots` rows of one frame and

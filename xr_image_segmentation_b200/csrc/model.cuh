@@ -250,21 +250,33 @@ class Net {
     }
   }
 
-  // Proto: cv2 (3x3, 64 -> 64, SiLU) -> cv3 (1x1, 64 -> 32, SiLU).  cv3 is the only consumer of cv2's output and rows are
-  // independent for a 1x1, so cv3 runs inside cv2's launch as a second set of MMAs on the epilogue's fp16 tile kept in tensor
-  // memory (ConvParams::tail_n): the 64-channel 160x160 tensor (3.3 MB per frame, written and read back) never exists in HBM.
-  // The kernel side is built for exactly this shape (Ntile 64 -> 32); anything else keeps its two launches.
+  // A 3x3 convolution whose ONLY consumer is a 1x1 convolution (rows are independent for a 1x1) runs that 1x1 inside its own
+  // launch as a second set of MMAs on the epilogue's fp16 tile kept in tensor memory (ConvParams::tail_n, conv_tma.cuh): the
+  // intermediate tensor is never written to HBM or read back.  The kernel side handles 32 / 64 channels on either side; the
+  // pairs below are the ones whose TMEM budget works out on the n scale:
+  //   proto.cv2 (64) -> proto.cv3 (32)   in place (512 accumulator columns are all in use)
+  //   b1 (32) -> b2.cv1 (32),  b3 (64) -> b4.cv1 (64)   the stride-2 stage convs feed only the next C3k2 block's cv1;
+  //                                                      256 + 256 columns
+  // Anything else keeps its two launches.
   void fuse_tail_1x1() {
     static const bool env_on = [] { const char* e = getenv("XRSEG_FUSE_TAIL"); return !(e && e[0] == '0'); }();
+    // the stage pairs are opt-in: measured b1 + b2.cv1 76 + 43 -> 113 us, b3 + b4.cv1 66 + 27 -> 88 us, frames/s unchanged -- these
+    // layers are bound by their epilogue, and two epilogue passes in one launch cost what the second launch did
+    static const bool env_stage = [] { const char* e = getenv("XRSEG_FUSE_TAIL_STAGE"); return e && e[0] == '1'; }();
     if (!fuse_tail || !env_on) return;
     for (size_t i = 0; i + 1 < ops.size(); ++i) {
       Op& a = ops[i];
       const Op b = ops[i + 1];
       if (a.kind != OP_CONV || b.kind != OP_CONV || a.layer2 >= 0 || b.layer2 >= 0 || a.tail_layer >= 0) continue;
-      if (layers[a.layer].name != "proto.cv2" || layers[b.layer].name != "proto.cv3") continue;
-      const bool ok = a.k == 3 && a.stride == 1 && !a.transposed && a.act && !a.has_res && b.k == 1 && b.stride == 1 && !b.transposed &&
-                      !b.has_res && b.x.off == a.y.off && b.x.pitch == a.y.pitch && a.y.Cp == 64 && b.x.Cp == 64 && b.y.Cp == 32 &&
-                      a.branch == b.branch && b.wait_tag == 0 && a.signal_tag == 0 && a.x.W + 2 <= 256;
+      const std::string &na = layers[a.layer].name, &nb = layers[b.layer].name;
+      const bool proto = na == "proto.cv2" && nb == "proto.cv3" && a.stride == 1 && a.y.Cp == 64 && b.y.Cp == 32;
+      const bool stage = env_stage && a.stride == 2 &&
+                         ((na == "b1" && nb == "b2.cv1" && a.y.Cp == 32 && b.y.Cp == 32 && a.y.W == 160) ||
+                          (na == "b3" && nb == "b4.cv1" && a.y.Cp == 64 && b.y.Cp == 64 && a.y.W == 80));
+      if (!proto && !stage) continue;
+      const bool ok = a.k == 3 && !a.transposed && a.act && !a.has_res && b.k == 1 && b.stride == 1 && !b.transposed && !b.has_res &&
+                      b.x.off == a.y.off && b.x.pitch == a.y.pitch && b.x.Cp == a.y.Cp && a.branch == b.branch && b.wait_tag == 0 &&
+                      a.signal_tag == 0;
       if (!ok) continue;
       a.tail_layer = b.layer;
       a.tail_act = b.act;

@@ -387,20 +387,31 @@ void upload_layers(xrseg_runner* r, const std::vector<HostLayerWeights>& hw) {
         // fused trailing 1x1 (model.cuh: fuse_tail_1x1): W2 as the 128-byte-swizzled image of a 1x1 layer with Ntile = 32, cb = 64
         const LayerRec& lt = net.layers[o.tail_layer];
         const HostLayerWeights& wt = hw[o.tail_layer];
-        XR_CHECK(d.use_tma && d.cp.mode == MODE_HALO_TMA && d.cp.sw && d.cp.Ntile == 64 && d.cp.n_tiles == 1 && d.cp.b_resident &&
-                     (d.cp.nbuf == 0 || d.cp.nbuf == 2) && !d.cp.st_tma && o.ytail.Cp == 32 && lt.cin <= 64,
-                 "fused trailing 1x1 needs the halo plan with Ntile 64, resident weights and two accumulator sets (%s)", l.name.c_str());
+        const int N1 = d.cp.Ntile, N2 = o.ytail.Cp;
+        XR_CHECK(d.use_tma && (d.cp.mode == MODE_HALO_TMA || d.cp.mode == MODE_S2_TMA) && d.cp.sw && (N1 == 32 || N1 == 64) &&
+                     (N2 == 32 || N2 == 64) && d.cp.n_tiles == 1 && d.cp.b_resident && (d.cp.nbuf == 0 || d.cp.nbuf == 2) &&
+                     !d.cp.st_tma && lt.cin <= N1,
+                 "fused trailing 1x1 needs a halo / stride-2 TMA plan with Ntile 32 / 64, resident weights and two accumulator sets (%s)",
+                 l.name.c_str());
+        // TMEM: in place when the main accumulators fill all 512 columns (64 -> 32 only), else a region of its own behind them
+        const int main_cols = 2 * d.cp.nsub * N1, tail_cols = 2 * d.cp.nsub * N2;
+        const bool inplace = main_cols + tail_cols > 512;
+        XR_CHECK(!inplace || (N1 == 64 && N2 == 32), "no tensor-memory room for the fused 1x1 (%s: %d + %d columns)", l.name.c_str(),
+                 main_cols, tail_cols);
         ConvParams t{};
-        t.Ntile = 32; t.n_tiles = 1; t.cb = 64; t.sw = 3; t.taps = 1; t.nks = 1; t.kps = 1; t.b_stage_bytes = 32 * 128; t.Cout = 32;
+        t.Ntile = N2; t.n_tiles = 1; t.cb = N1; t.sw = N1 == 64 ? 3 : 2; t.taps = 1; t.nks = 1; t.kps = 1; t.b_stage_bytes = N2 * N1 * 2;
+        t.Cout = N2;
         std::vector<__half> wp2;
         std::vector<float> bp2;
         pack_conv_weights_sw<__half>(t, wt.w.data(), wt.b.data(), lt.cin, lt.cout, wp2, bp2);
         r->dl[o.tail_layer].tail_w = dev_upload(wp2);
         r->dl[o.tail_layer].tail_bias = dev_upload(bp2);
-        d.cp.tail_n = 32;
+        d.cp.tail_n = N2;
         d.cp.tail_act = o.tail_act;
+        d.cp.tail_inplace = inplace ? 1 : 0;
+        if (!inplace) d.cp.tmem_cols = pow2_ceil(main_cols + tail_cols);
         d.cp.smem_off_w2 = round_up(d.cp.smem_bytes, 1024);
-        d.cp.smem_bytes = d.cp.smem_off_w2 + 32 * 128;
+        d.cp.smem_bytes = d.cp.smem_off_w2 + N2 * N1 * 2;
         XR_CHECK(d.cp.smem_bytes <= CONV_SMEM_MAX, "no room for the tail's weights (%s)", l.name.c_str());
       }
 #ifdef XRSEG_DEBUG_API

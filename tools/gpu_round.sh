@@ -23,7 +23,7 @@ echo "conv_halo_tma launches per pass: $NC"
 full stem stem_ 1 1                             # stem_rows_kernel (packed RGB) or stem_mma_kernel
 full s2_b1 conv_halo_tma $((NC + 0)) 1         # b1 (3x3 stride 2, parity-plane TMA) of pass 2
 full flat_b2cv1 conv_halo_tma $((NC + 1)) 1    # b2.cv1 (1x1, flat TMA) of pass 2
-full halo_protocv2 conv_halo_tma $((NC + NC - 2)) 1  # proto.cv2 (3x3 stride 1, halo TMA) of pass 2
+full halo_protocv2 conv_halo_tma $((NC + NC - 1)) 1  # proto.cv2+cv3 (3x3 stride 1, halo TMA, fused 1x1: the last conv) of pass 2
 full bneck_b2m0 bottleneck_mma 3 1             # b2.m0 (fused Bottleneck) of pass 2
 ND=$(grep -c dwconv3x3 gpurun_out/${T}_launches.csv)   # depthwise launches per pass (6 since the C2PSA pe rides in the attention kernel)
 full dw dwconv3x3 $((ND + 1)) 1                # h3.cls.1dw of pass 2

@@ -145,6 +145,12 @@ static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvP
   p.Hp1 = d.H + 1;
   int nsub_max = 256 / p.Ntile;
   if (nsub_max > 4) nsub_max = 4;
+  {
+    // experiment switch: smaller items (more items per CTA -> the fill / drain of the MMA <-> epilogue pipeline weighs less)
+    static const int cap = [] { const char* e = getenv("XRSEG_HALO_NSUB_MAX"); return e ? atoi(e) : 0; }();
+    static const int cap_w = [] { const char* e = getenv("XRSEG_HALO_NSUB_MAX_W"); return e ? atoi(e) : 100000; }();
+    if (cap > 0 && nsub_max > cap && d.W <= cap_w) nsub_max = cap;
+  }
   if (nsub_max < 1 || p.Wp > 256) return false;
   int R = (128 * nsub_max) / p.Wp;
   if (R > d.H) R = d.H;

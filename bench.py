@@ -423,10 +423,7 @@ def main():
         for i in range(args.latency_iters + LAT_WARM):
             t0 = time.perf_counter()
             r1.schedule_ptr(hf, 1, 960, 1280, 3)
-            r1.wait()
-            r1.readback(0)
-            r1.readback(1)
-            r1.masks(_lib.MASK_BITS_160)
+            r1.collect(_lib.MASK_BITS_160)                   # waits, then boxes + labels + bit masks in one call / one sync
             ts.append(time.perf_counter() - t0)
         ts = np.array(ts[LAT_WARM:]) * 1e3
         lat = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99)), "iters": int(len(ts)),

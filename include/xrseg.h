@@ -169,6 +169,13 @@ int xrseg_decode(xrseg_runner* r, float screen_w, float screen_h, int convention
 /* ↔ IEMasker.DrawMask / DrawSingleMask + PixelInBoundingBox (IEM:82-119,124-196,232-247).  Returns the number of masks
  * written.  out == NULL: the masks are computed into the runner's device scratch only (no device->host copy). */
 int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* p, uint8_t* out, size_t cap_bytes);
+/* Extension: what a frame loop reads back, in ONE call and ONE synchronisation -- waits for the run like xrseg_wait, then
+ * output_0 (boxes f32 [N,4]) -> boxes, output_1 (labels i32 [N]) -> labels and, when p and masks are given, the masks of
+ * xrseg_masks(p) -> masks.  Replaces ReadbackRequest x N + the IsReadbackRequestDone polling loop of IEE:419-456 for callers that
+ * do not need the four raw tensors.  Any of boxes / labels / masks may be NULL.  Returns N (the number of detections over the
+ * batch; counts per frame: xrseg_counts) or a negative error (XRSEG_ERR_CAPACITY: cap_dets < N or masks_cap too small). */
+int xrseg_collect(xrseg_runner* r, float* boxes, int32_t* labels, int cap_dets, const xrseg_mask_params* p, uint8_t* masks,
+                  size_t masks_cap);
 /* Kept anchor indices (0..8399) and scores of the finished run, compacted like output_0. */
 int xrseg_keep_indices(xrseg_runner* r, int32_t* idx, float* scores, int cap);
 

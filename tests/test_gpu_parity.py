@@ -892,6 +892,26 @@ def test_config1_post_kernels_exact_on_own_logits(lib):
     r.close()
 
 
+def test_collect_is_the_three_readbacks_in_one_call(golden, product_runner):
+    """xrseg_collect (one call, one synchronisation) returns exactly what xrseg_wait + xrseg_readback(0) + xrseg_readback(1) +
+    xrseg_masks return, for every mask mode it supports; an empty frame gives N = 0."""
+    r = product_runner
+    r.schedule(golden["inputs"]["bus"][None])
+    counts, boxes, labels, bits = r.collect(_lib.MASK_BITS_160)
+    assert counts.tolist() == r.counts().tolist() and len(boxes) == int(counts.sum()) > 0
+    assert np.array_equal(boxes, r.readback(0)) and np.array_equal(labels, r.readback(1))
+    assert np.array_equal(bits, r.masks(_lib.MASK_BITS_160))
+    for mode in (_lib.MASK_REFERENCE_160, _lib.MASK_CROP_160):
+        _, b2, l2, m = r.collect(mode, screen_w=1920.0, screen_h=1080.0, image_w=1920, image_h=1080)
+        assert np.array_equal(b2, boxes) and np.array_equal(l2, labels)
+        assert np.array_equal(m, r.masks(mode, screen_w=1920.0, screen_h=1080.0, image_w=1920, image_h=1080))
+    _, b3, l3, m3 = r.collect(None)
+    assert np.array_equal(b3, boxes) and m3 is None
+    r.schedule(np.zeros((1, 640, 640, 3), np.uint8))
+    counts, boxes, labels, bits = r.collect()
+    assert int(counts.sum()) == 0 and len(boxes) == 0 and len(labels) == 0 and bits.shape == (0, 160, 5)
+
+
 def test_mask_threshold_parameter_reaches_the_kernels(golden):
     """IEMasker._confidenceThreshold (IEM:104,176; IEE:32) other than 0.5: DrawMask / bit masks use the caller's value."""
     ex = E.IEExecutor(golden["model"].pack, golden["labels"], screen=(1920.0, 1080.0), confidenceThreshold=0.3)

@@ -82,6 +82,7 @@ PRODUCT_SIGNATURES = {
     "xrseg_readback": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, _P(C.c_int64), _P(C.c_int)]),
     "xrseg_decode": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_int, _P(Box), C.c_int, _P(C.c_int)]),
     "xrseg_masks": (C.c_int, [C.c_void_p, _P(MaskParams), C.c_void_p, C.c_size_t]),
+    "xrseg_collect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, _P(MaskParams), C.c_void_p, C.c_size_t]),
     "xrseg_keep_indices": (C.c_int, [C.c_void_p, _P(C.c_int32), _P(C.c_float), C.c_int]),
     "xrseg_layer_count": (C.c_int, [C.c_int]),
     "xrseg_layer_info_get": (C.c_int, [C.c_int, C.c_int, _P(LayerInfo)]),

@@ -1351,9 +1351,17 @@ int xrseg_create(const xrseg_config* cfg_in, xrseg_runner** out) {
     r->device = c.device;
     r->num_sms = prop.multiProcessorCount;
     XR_CUDA(cudaSetDevice(c.device));
-    XR_CUDA(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
-    XR_CUDA(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
-    for (auto& s : r->side) XR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    {
+      // XRSEG_PRIO=1: the main stream (the dependent chain backbone -> neck -> P5 head) above the side branches (head / prototype
+      // chains), so that its small launches are not queued behind the branches' big ones; captured kernel nodes inherit the
+      // priority of the stream they were captured on
+      static const bool prio = [] { const char* e = getenv("XRSEG_PRIO"); return e && e[0] == '1'; }();
+      int lo = 0, hi = 0;
+      XR_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));        // lo = lowest priority (largest number)
+      XR_CUDA(cudaStreamCreateWithPriority(&r->stream, cudaStreamNonBlocking, prio ? hi : 0));
+      XR_CUDA(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+      for (auto& s : r->side) XR_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio ? lo : 0));
+    }
     for (auto& e : r->ev_tag) XR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : r->ev_join) XR_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     XR_CUDA(cudaEventCreateWithFlags(&r->ev_done, cudaEventDisableTiming));
@@ -1612,7 +1620,9 @@ int xrseg_decode(xrseg_runner* r, float screen_w, float screen_h, int convention
   return XRSEG_OK;
 }
 
-int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size_t cap_bytes) {
+// Enqueues the mask kernels (and the device->host copy when out != NULL) on the runner's stream; sync = false leaves the
+// synchronisation to the caller (xrseg_collect puts boxes, labels and masks behind ONE).
+static int masks_enqueue(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size_t cap_bytes, bool sync) {
   if (!r || !mp || mp->struct_size != sizeof(xrseg_mask_params)) return XRSEG_ERR_INVALID;
   int rc = finish(r);
   if (rc < 0) return rc;
@@ -1671,7 +1681,7 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
     XR_CUDA(cudaGetLastError());
     if (out) {   // out == NULL: the masks stay in the runner's device scratch (kernel timing, device-side consumers)
       XR_CUDA(cudaMemcpyAsync(out, d_out, per * count, cudaMemcpyDeviceToHost, r->stream));
-      XR_CUDA(cudaStreamSynchronize(r->stream));
+      if (sync) XR_CUDA(cudaStreamSynchronize(r->stream));
     }
   } catch (const CudaError& e) {
     r->err = e.msg;
@@ -1684,6 +1694,37 @@ int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size
     return XRSEG_ERR_CUDA;
   }
   return count;
+}
+
+int xrseg_masks(xrseg_runner* r, const xrseg_mask_params* mp, uint8_t* out, size_t cap_bytes) {
+  return masks_enqueue(r, mp, out, cap_bytes, true);
+}
+
+int xrseg_collect(xrseg_runner* r, float* boxes, int32_t* labels, int cap_dets, const xrseg_mask_params* mp, uint8_t* masks,
+                  size_t masks_cap) {
+  if (!r) return XRSEG_ERR_INVALID;
+  int rc = finish(r);
+  if (rc < 0) return rc;
+  const int total = r->h_offsets[r->batch];
+  if (total == 0) return 0;
+  if ((boxes || labels) && cap_dets < total) { r->err = "xrseg_collect: detection buffers too small"; return XRSEG_ERR_CAPACITY; }
+  try {
+    XR_CUDA(cudaSetDevice(r->device));
+    if (boxes) XR_CUDA(cudaMemcpyAsync(boxes, r->o_boxes, sizeof(float) * 4 * total, cudaMemcpyDeviceToHost, r->stream));
+    if (labels) XR_CUDA(cudaMemcpyAsync(labels, r->o_labels, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, r->stream));
+  } catch (const CudaError& e) {
+    r->err = e.msg;
+    return XRSEG_ERR_CUDA;
+  } catch (...) {
+    r->err = "unknown exception";
+    return XRSEG_ERR_CUDA;
+  }
+  if (mp && masks) {
+    rc = masks_enqueue(r, mp, masks, masks_cap, false);
+    if (rc < 0) return rc;
+  }
+  if (cudaStreamSynchronize(r->stream) != cudaSuccess) { r->err = "xrseg_collect: synchronisation failed"; return XRSEG_ERR_CUDA; }
+  return total;
 }
 
 int xrseg_extract_points(xrseg_runner* r, const xrseg_depth_params* dp, const uint16_t* depth_host, float* out_xyzd, int cap,

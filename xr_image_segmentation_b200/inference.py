@@ -81,6 +81,8 @@ class Runner:
         _lib.check(self.lib.xrseg_create(C.byref(cfg), C.byref(self.h)), None, self.lib)
         self.max_batch = max_batch
         self.batch = 0
+        self._max_det = max_det if max_det > 0 else 300          # the library's default cap per frame (xrseg_config.max_det)
+        self._collect_buf = None
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
@@ -203,6 +205,37 @@ class Runner:
             return None
         self._ck(self.lib.xrseg_masks(self.h, C.byref(p), out.ctypes.data, out.nbytes))
         return out.view(np.uint32).reshape(n, 160, 5) if mode == _lib.MASK_BITS_160 else out
+
+    def collect(self, mask_mode: int = _lib.MASK_BITS_160, box_convention=_lib.BOX_DRAWBOXES, screen_w=640.0, screen_h=640.0,
+                image_w=640, image_h=640, threshold=0.0):
+        """xrseg_collect: waits for the run and returns (counts, boxes f32 [N,4], labels i32 [N], masks) with ONE call and ONE
+        synchronisation (what a frame loop reads back; the four raw tensors stay available through readback()).  mask_mode None:
+        no masks.  max_det bounds the buffers, so nothing is peeked first."""
+        cap = self.max_batch * self._max_det
+        if self._collect_buf is None or self._collect_buf[0].shape[0] < cap:
+            per = {_lib.MASK_BITS_160: 160 * 20, _lib.MASK_REFERENCE_160: 160 * 160, _lib.MASK_CROP_160: 160 * 160}
+            self._collect_buf = (np.empty((cap, 4), np.float32), np.empty(cap, np.int32), {m: None for m in per}, per)
+        boxes, labels, mbufs, per = self._collect_buf
+        mp = None
+        masks = None
+        if mask_mode is not None:
+            if mask_mode not in per:
+                raise XrsegError(_lib.ERR_INVALID, "collect(): mask mode not supported here (use masks())")
+            if mbufs[mask_mode] is None:
+                mbufs[mask_mode] = np.empty(cap * per[mask_mode], np.uint8)
+            masks = mbufs[mask_mode]
+            mp = _lib.MaskParams(C.sizeof(_lib.MaskParams), mask_mode, box_convention, screen_w, screen_h, image_w, image_h, 0, 0,
+                                 threshold)
+        n = self.lib.xrseg_collect(self.h, boxes.ctypes.data, labels.ctypes.data, cap, C.byref(mp) if mp is not None else None,
+                                   masks.ctypes.data if masks is not None else None, masks.nbytes if masks is not None else 0)
+        if n == _lib.ERR_CAPACITY and self.overflow():          # a truncated run: same contract as wait()
+            self._ck(n)
+        n = self._ck(n)
+        m = None
+        if masks is not None:
+            m = masks[:n * per[mask_mode]]
+            m = m.view(np.uint32).reshape(n, 160, 5) if mask_mode == _lib.MASK_BITS_160 else m.reshape(n, 160, 160)
+        return self.counts(), boxes[:n], labels[:n], m
 
     def extract_points(self, detection: int, depth_half: np.ndarray, screen_w: float, screen_h: float, camera_position,
                        camera_rotation, focal_length, principal_point, sensor_resolution, sampling_step=5, max_points=8000,
@@ -341,6 +374,9 @@ class PipelinedRunner:
             return (r.counts(),) + tuple(r.readback_into(i, *pinned[i]) for i in range(4))
         if contract:
             return (r.counts(),) + tuple(r.readback(i) for i in range(4))
+        if mask_mode in (_lib.MASK_BITS_160, _lib.MASK_REFERENCE_160, _lib.MASK_CROP_160):
+            c, b, l, m = r.collect(mask_mode)                 # one call, one synchronisation
+            return c, b.copy(), l.copy(), m.copy()
         return r.counts(), r.readback(0), r.readback(1), r.masks(mask_mode)
 
     def close(self):

@@ -35,3 +35,21 @@ print(f"schedule + collect() {np.median(np.array(T2[100:])) * 1e6:7.1f} us (one 
 assert np.array_equal(b, r1.readback(0)) and np.array_equal(l, r1.readback(1)) and np.array_equal(m, r1.masks(_lib.MASK_BITS_160))
 tm = r1.timings() if hasattr(r1, "timings") else None
 print("device timings", tm)
+# per-launch device time of the batch-1 pass (launches timed alone: an upper bound of what the graph + PDL overlap)
+ops = r1.profile_ops(20)
+tot = sum(o[1] for o in ops)
+print(f"batch-1 launches {len(ops)}, sum of isolated launch times {tot * 1e3:.0f} us")
+grp = {}
+for name, ms, fl, by in ops:
+    k = name.split(".")[0] if not name.startswith("post") else "post"
+    grp[k] = grp.get(k, 0) + ms * 1e3
+print({k: round(v, 1) for k, v in grp.items()})
+print(sorted(((round(ms * 1e3, 1), n) for n, ms, _, _ in ops), reverse=True)[:12])
+# device time of the whole batch-1 run (events around schedule .. done)
+import torch
+r1.event_record(0)
+for _ in range(50):
+    r1.schedule_ptr(hf, 1, 960, 1280, 3)
+    r1.wait()
+r1.event_record(1); r1.sync()
+print(f"50 frames back to back: {r1.event_elapsed_ms(0, 1) / 50 * 1e3:.1f} us per frame on the stream (H2D + network + post)")

@@ -1160,21 +1160,22 @@ __device__ __forceinline__ void tma_epilogue_loop_tail(const ConvParams& p, uint
     if (PROBE) { e_wait += clock64() - t0; t0 = clock64(); }
     tc_fence_after();
     const uint32_t acc = lane_taddr + static_cast<uint32_t>(buf * nsub * N1);
-    // ---- pass 1: accumulators -> packed fp16 in tensor memory
+    // ---- pass 1: accumulators -> packed fp16 in tensor memory.  One 16-register buffer: the next unit's TMEM load is issued as
+    // soon as the current values are packed (the double-buffered form spilled at the 80-register cap and the spill reloads
+    // -- local memory behind an L1 the TMA traffic keeps busy -- were the longest stalls of this loop).
     {
-      uint32_t va[16], vb[16];
-      if (u1 < nsub) tmem_ld16(acc + static_cast<uint32_t>(u1 * N1 + 16 * c1), va);
+      uint32_t v[16];
+      if (u1 < nsub) tmem_ld16(acc + static_cast<uint32_t>(u1 * N1 + 16 * c1), v);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int u = u1 + k * step1;
         if (u >= nsub) break;
         tmem_ld_wait();
-        if (u + step1 < nsub) tmem_ld16(acc + static_cast<uint32_t>((u + step1) * N1 + 16 * c1), (k & 1) ? va : vb);
-        const uint32_t (&v)[16] = (k & 1) ? vb : va;
         uint32_t o[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           o[i] = silu_pack_from_half_arg(fmaf(__uint_as_float(v[2 * i]), 0.5f, hbr[2 * i]), fmaf(__uint_as_float(v[2 * i + 1]), 0.5f, hbr[2 * i + 1]));
+        if (u + step1 < nsub) tmem_ld16(acc + static_cast<uint32_t>((u + step1) * N1 + 16 * c1), v);
         tmem_st8(acc + static_cast<uint32_t>(u * N1) + pk_col, o);
       }
       tmem_st_wait();

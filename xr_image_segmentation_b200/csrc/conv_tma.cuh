@@ -574,8 +574,14 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
 // this form -- b2.cv1 42 -> 60 us, b4.cv1 26 -> 35 us, 35.6k -> 34.1k frames/s: one tile per CTA means the epilogue of item
 // i + 1 waits for the TMA unit to have read item i, plus two 512-thread barriers per item, which costs more than the L1 tag
 // cycles it saves.  Opt-in (XRSEG_ST_TMA=1) until the tile is double-buffered.
+// The store path is compiled into the kernel only with -DXRSEG_ST_TMA_BUILD=1 (make variant NAME=sttma FLAGS=-DXRSEG_ST_TMA_BUILD=1):
+// in the product build its address arithmetic and the two extra live registers per unit cost the direct-store epilogue spills
+// and instruction-cache misses in its hot loop (ncu: "no instruction" was the second largest stall of the thin layers).
+#ifndef XRSEG_ST_TMA_BUILD
+#define XRSEG_ST_TMA_BUILD 0
+#endif
 static inline bool tma_store_enabled() {
-  static const bool on = [] { const char* e = getenv("XRSEG_ST_TMA"); return e && e[0] == '1'; }();
+  static const bool on = [] { const char* e = getenv("XRSEG_ST_TMA"); return XRSEG_ST_TMA_BUILD && e && e[0] == '1'; }();
   return on;
 }
 static inline int tma_store_tile_bytes(const ConvParams& p) { return 128 * p.nsub * p.Ntile * 2 + 1024; }
@@ -882,16 +888,34 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
   float hbr[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) hbr[i] = BREG ? bias_s[gc0 * 16 + i] : 0.f;
-  int tcount = 0;
+  // Accumulator set / use count of the current item, kept incrementally: `tcount % nbuf` and `tcount / nbuf` are integer
+  // divisions by a kernel parameter (I2F + MUFU.RCP + fix-up, ~30 dependent instructions each) and were, together with the
+  // per-item `G / nch`, a fifth of the stall samples of the thin layers' epilogue (ncu source page of b2.cv1).
+  int buf_c = 0, use_c = 0;
+  // BREG invariants (fixed chunk per group: nch divides G, n_tiles == 1): destination base, pitch, accumulator column
+  const int breg_ustep = BREG ? (nch == 1 ? G : (nch == 2 ? G / 2 : (nch == 4 ? G / 4 : 1))) : 1;
+  const int breg_n = gc0 * 16;
+  __half* breg_gbase = outp + breg_n;
+  int breg_gpitch = out_pitch;
+  if (BREG) {
+    if (KIND == 2) {
+      const int pos = fd_div(fd_cout, breg_n);
+      breg_gbase = outp + static_cast<size_t>((pos >> 1) * Wo + (pos & 1)) * out_pitch + (breg_n - pos * Cout);
+    } else if (KIND == 1 && breg_n >= split_n) {
+      breg_gbase = out2p + (breg_n - split_n);
+      breg_gpitch = out2_pitch;
+    }
+  }
   long long e_wait = 0, e_work = 0, t0 = 0;
   pdl_wait();   // before the first residual read / output store
-  for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
+  for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
     const int tile = n_tiles == 1 ? w : (w >> 1);
     const int n_tile = n_tiles == 1 ? 0 : (w & 1);
     const int b = fd_div(fd_tpi, tile);
     const int y0 = (tile - b * tpi) * Rr;
-    const int buf = tcount % nbuf;
-    const int use = tcount / nbuf;
+    const int buf = buf_c;
+    const int use = use_c;
+    if (++buf_c == nbuf) { buf_c = 0; ++use_c; }
     // this lane's output pixel in each sub-tile (-1: padding column / row past the image / row past the matrix);
     // ConvTranspose: the top-left pixel of the 2x2 output block of input pixel (image, h, w)
     int pix[4];
@@ -930,23 +954,12 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
       // Fixed chunk per group (nch divides G): this group's units are chunk gc0 of sub-tiles gu0, gu0 + G / nch, ...  The
       // destination (tensor, channel offset, ConvTranspose position) is the same for all of them: one base pointer per
       // launch, one pixel offset per sub-tile, no per-unit control flow; lanes without a pixel run the math and skip the store.
-      const int ustep = G / nch;
-      const int n = gc0 * 16;                                            // n_tiles == 1
-      __half* gbase;
-      int gpitch;
-      if (KIND == 2) {
-        const int pos = fd_div(fd_cout, n);
-        gbase = outp + static_cast<size_t>((pos >> 1) * Wo + (pos & 1)) * out_pitch + (n - pos * Cout);
-        gpitch = out_pitch;
-      } else if (KIND == 1 && n >= split_n) {
-        gbase = out2p + (n - split_n);
-        gpitch = out2_pitch;
-      } else {
-        gbase = outp + n;
-        gpitch = out_pitch;
-      }
+      const int ustep = breg_ustep;
+      const int n = breg_n;                                              // n_tiles == 1
+      __half* const gbase = breg_gbase;
+      const int gpitch = breg_gpitch;
       const uint32_t acc_g = acc + static_cast<uint32_t>(gc0 * 16);
-      const bool st_tma = KIND != 2 && p.st_tma != 0;
+      const bool st_tma = XRSEG_ST_TMA_BUILD && KIND != 2 && p.st_tma != 0;
       if (st_tma) {
         // the previous item's tile must have left shared memory before anyone overwrites it
         if (ew == 0 && lane == 0) bulk_wait_group_read0();
@@ -1093,7 +1106,7 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
     if (lane == 0) mbar_arrive(&tempty[buf]);
     if (PROBE) e_work += clock64() - t0;
   }
-  if (BREG && KIND != 2 && p.st_tma && ew == 0 && lane == 0) bulk_wait_group0();   // the last tile is in global memory before the CTA exits
+  if (XRSEG_ST_TMA_BUILD && BREG && KIND != 2 && p.st_tma && ew == 0 && lane == 0) bulk_wait_group0();   // the last tile is in global memory before the CTA exits
   if (PROBE && p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {
     p.dbg_clk[blockIdx.x * 12 + 6] = e_wait;
     p.dbg_clk[blockIdx.x * 12 + 7] = e_work;
@@ -1266,7 +1279,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     prefetch_tensormap(&tmap);
     if (p.mode == MODE_S2_TMA)
       for (int i = 1; i < 4; ++i) prefetch_tensormap(&tmaps.m[i]);
-    if (p.st_tma) {
+    if (XRSEG_ST_TMA_BUILD && p.st_tma) {
       prefetch_tensormap(&tmaps.m[4]);
       if (p.split_n) prefetch_tensormap(&tmaps.m[5]);
     }
@@ -1308,18 +1321,24 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
                             (p.mode == MODE_S2_TMA ? 4u : 1u);                                           // (* parity planes)
       const uint32_t b_stride = p.sw ? static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023) : static_cast<uint32_t>(p.b_stage_bytes);
       pdl_wait();   // the weights above are constants; the activations below are the previous kernels' output
-      int it = 0;
+      // ring position kept incrementally (slot = it % S, round = it / S): the divisions by the kernel parameter S cost the
+      // single producer / issuer thread ~60 dependent instructions per stage hand-over
+      int slot_c = 0;
+      uint32_t round_c = 0;
       long long t_wait = 0, t0 = 0;
       const bool flat = p.mode == MODE_FLAT_TMA;
+      const int S = p.S;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int tile = p.n_tiles == 1 ? w : (w >> 1);
         const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
         const int b = fd_div(p.fd_hp1, tile);
         const int y0 = (tile - b * p.tpi) * p.R;
-        for (int ks = 0; ks < p.nks; ++ks, ++it) {
-          const int slot = it % p.S;
+        for (int ks = 0; ks < p.nks; ++ks) {
+          const int slot = slot_c;
+          const uint32_t round = round_c;
+          if (++slot_c == S) { slot_c = 0; ++round_c; }
           if (PROBE) t0 = clock64();
-          if (it >= p.S) mbar_wait(&empty[slot], static_cast<uint32_t>((it / p.S) - 1) & 1u);
+          if (round > 0) mbar_wait(&empty[slot], (round - 1u) & 1u);
           if (PROBE) {
             t_wait += clock64() - t0;
             if (p.dbg_skip & 4) { mbar_arrive(&full[slot]); continue; }
@@ -1430,19 +1449,25 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         return true;
       };
       int tail_pending = -1;                      // item whose 1x1 has not been issued yet
-      int it = 0, tcount = 0;
+      int tcount = 0;
+      int slot_c = 0, buf_c = 0, use_c = 0;       // ring slot / accumulator set, kept incrementally (no divisions by S / nbuf)
+      uint32_t round_c = 0;
+      const int S = p.S;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tcount) {
-        const int buf = tcount % nbuf;
-        const int use = tcount / nbuf;
+        const int buf = buf_c;
+        const int use = use_c;
+        if (++buf_c == nbuf) { buf_c = 0; ++use_c; }
         if (PROBE) t0 = clock64();
         if (use >= 1) mbar_wait(&tempty[buf], static_cast<uint32_t>(use - 1) & 1u);
         if (PROBE) t_tempty += clock64() - t0;
         tc_fence_after();
         const uint32_t d_base = tmem_base + static_cast<uint32_t>(buf * p.nsub * p.Ntile);
-        for (int ks = 0; ks < p.nks; ++ks, ++it) {
-          const int slot = it % p.S;
+        for (int ks = 0; ks < p.nks; ++ks) {
+          const int slot = slot_c;
+          const uint32_t round = round_c;
+          if (++slot_c == S) { slot_c = 0; ++round_c; }
           if (PROBE) t0 = clock64();
-          mbar_wait(&full[slot], static_cast<uint32_t>(it / p.S) & 1u);
+          mbar_wait(&full[slot], round & 1u);
           if (PROBE) { t_full += clock64() - t0; t0 = clock64(); }
           tc_fence_after();
           if (PROBE) { t_fence += clock64() - t0; t0 = clock64(); }

@@ -262,15 +262,15 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, int n_layers, int n_fra
                 const uint32_t d_tmem = d_base + static_cast<uint32_t>(my_u) * ntile_u;
                 const uint32_t acc0 = ks > 0 ? 1u : 0u;
                 switch ((p.mode == MODE_HALO_TMA ? 0 : p.mode == MODE_S2_TMA ? 4 : 8) + (kj == 4 ? 2 : kj == 2 ? 1 : 0)) {
-                  case 0: issue_taps<0, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 1: issue_taps<0, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 2: issue_taps<0, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 4: issue_taps<1, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 5: issue_taps<1, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 6: issue_taps<1, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 8: issue_taps<2, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 9: issue_taps<2, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  default: issue_taps<2, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                  case 0: issue_taps<0, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 1: issue_taps<0, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 2: issue_taps<0, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 4: issue_taps<1, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 5: issue_taps<1, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 6: issue_taps<1, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 8: issue_taps<2, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 9: issue_taps<2, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  default: issue_taps<2, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
                 }
                 umma_commit(&empty[slot]);
               }

@@ -740,12 +740,11 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 // (3x3 s2), 2 flat (1x1 / ConvT, kps K-blocks of one tap).  KJ = k16 steps per K-block.  a_sub / b_lo: low descriptor
 // words (start address >> 4 | LBO field) of the sub-tile's first row and of the stage's first weight tile.
 template <int MODE, int KJ>
-__device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem, uint32_t a_sub, uint32_t b_lo, uint64_t hi_sw,
-                                           uint32_t idesc, uint32_t acc0, uint32_t row16, uint32_t tap16) {
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_sub, uint32_t b_lo, uint64_t hi_sw,
+                                           uint32_t idesc, uint32_t acc0, uint32_t row16, uint32_t tap16, uint32_t wp16,
+                                           uint32_t plane16, uint32_t blk16, int kps) {
   uint32_t acc = acc0;
   if (MODE == 2) {
-    const uint32_t blk16 = static_cast<uint32_t>(p.slots) * row16;
-    const int kps = p.kps > 1 ? p.kps : 1;
     for (int kb = 0; kb < kps; ++kb) {
 #pragma unroll
       for (int j = 0; j < KJ; ++j) {
@@ -754,11 +753,10 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
       }
       a_sub += blk16;
       b_lo += tap16;
+      asm volatile("" : "+r"(a_sub), "+r"(b_lo));   // the next K-block's descriptors are computed after these MMAs were issued
     }
     return;
   }
-  const uint32_t wp16 = static_cast<uint32_t>(p.Wp) * row16;
-  const uint32_t plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -773,6 +771,7 @@ __device__ __forceinline__ void issue_taps(const ConvParams& p, uint32_t d_tmem,
         acc = 1;
       }
       b_lo += tap16;
+      asm volatile("" : "+r"(a_sub), "+r"(b_lo));     // the next tap's descriptors are computed after this tap's MMAs were issued
     }
   }
 }
@@ -1417,7 +1416,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         const int jb = j & 1;
         const uint32_t ph = static_cast<uint32_t>(j >> 1) & 1u;
         if (blocking) mbar_wait(&tready[jb], ph);
-        else if (!__any_sync(0xffffffffu, mbar_try_wait(&tready[jb], ph))) return false;
+        else if (!__any_sync(0xffffffffu, mbar_test_wait(&tready[jb], ph))) return false;
         tc_fence_after();
         if (elect_one()) {
           const int N1 = p.Ntile, N2 = p.tail_n, nch1 = N1 >> 4;
@@ -1448,6 +1447,21 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
         __syncwarp();
         return true;
       };
+      // Per-launch constants of the swizzled issue loop.  The issuing warps all wait for the same operand barrier, so whatever
+      // they execute between that barrier and their first tcgen05.mma is time the tensor pipe may run dry: the per-stage
+      // arithmetic is reduced to two multiply-adds here, and issue_taps keeps the descriptor arithmetic of tap t + 1 BEHIND the
+      // MMAs of tap t (the compiler used to hoist all 18..72 descriptor words of a stage above its first MMA: ~280 instructions
+      // in lockstep on all four issuers per 1152 cycles of tensor work in proto.cv2 -- ncu source page, gpurun_out s11).
+      uint32_t c_a_stage16 = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+      uint32_t c_b_step16 = (p.b_resident ? static_cast<uint32_t>(p.b_stage_bytes) : b_stride_sw) >> 4;
+      uint32_t c_a_lo = (((a_u32 >> 4) & 0x3FFFu) | (1u << 16)) + static_cast<uint32_t>(my_u) * sub16;
+      uint32_t c_b_lo = ((b_u32 >> 4) & 0x3FFFu) | (1u << 16);
+      uint32_t c_d_off = static_cast<uint32_t>(my_u) * ntile_u;
+      uint32_t c_sel = static_cast<uint32_t>((p.mode == MODE_HALO_TMA ? 0 : p.mode == MODE_S2_TMA ? 4 : 8) + (kj == 4 ? 2 : kj == 2 ? 1 : 0));
+      uint32_t c_bres = p.b_resident ? 1u : 0u;
+      const uint32_t c_wp16 = static_cast<uint32_t>(p.Wp) * row16, c_plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;   // (not pinned: one LDC inside the mode's case)
+      const uint32_t c_blk16 = static_cast<uint32_t>(p.slots) * row16;
+      const int c_kps = p.kps > 1 ? p.kps : 1;
       int tail_pending = -1;                      // item whose 1x1 has not been issued yet
       int tcount = 0;
       int slot_c = 0, buf_c = 0, use_c = 0;       // ring slot / accumulator set, kept incrementally (no divisions by S / nbuf)
@@ -1477,29 +1491,28 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
             // Measured on B200: the UMMA swizzle is a function of the ABSOLUTE shared-memory address bits (like the
             // TMA write side), so a descriptor may start at any row with the base-offset field left 0; filling that
             // field with (addr >> 7) & 7 for unaligned starts produces wrong results.
-            const uint32_t b_base = b_u32 + (p.b_resident ? ks * p.b_stage_bytes : slot * b_stride_sw);
-            // descriptor low words: start address >> 4 plus offsets in 16-byte units (never carries out of bits 0-13)
-            const uint32_t a_lo_stage = ((a_base >> 4) & 0x3FFFu) | (1u << 16);
-            uint32_t b_lo = ((b_base >> 4) & 0x3FFFu) | (1u << 16);
+            // descriptor low words: start address >> 4 plus offsets in 16-byte units (never carries out of bits 0-13; the
+            // stage buffers are 1024-byte aligned and a weight stage is a multiple of 16 bytes, so the shifts distribute)
+            uint32_t b_lo = c_b_lo + static_cast<uint32_t>(c_bres ? ks : slot) * c_b_step16;
             // Loop order: sub-tile innermost, so that consecutive MMAs target different accumulators.  Everything is
             // unrolled with guards folded into the issue predicate: a handful of uniform adds per MMA, no branches.
             if (elect_one()) {   // one branch per stage; inside, a single lane issues the whole MMA batch
               if (mma_on) {
-                const uint32_t a_sub = a_lo_stage + static_cast<uint32_t>(my_u) * sub16;
-                const uint32_t d_tmem = d_base + static_cast<uint32_t>(my_u) * ntile_u;
+                const uint32_t a_sub = c_a_lo + static_cast<uint32_t>(slot) * c_a_stage16;
+                const uint32_t d_tmem = d_base + c_d_off;
                 const uint32_t acc0 = ks > 0 ? 1u : 0u;
                 // straight-line issue code per (mode, k16 steps): the issuing thread is the bottleneck of thin layers, so
                 // everything but the two descriptor adds per MMA is resolved at compile time
-                switch ((p.mode == MODE_HALO_TMA ? 0 : p.mode == MODE_S2_TMA ? 4 : 8) + (kj == 4 ? 2 : kj == 2 ? 1 : 0)) {
-                  case 0: issue_taps<0, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 1: issue_taps<0, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 2: issue_taps<0, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 4: issue_taps<1, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 5: issue_taps<1, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 6: issue_taps<1, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 8: issue_taps<2, 1>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  case 9: issue_taps<2, 2>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
-                  default: issue_taps<2, 4>(p, d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16); break;
+                switch (c_sel) {
+                  case 0: issue_taps<0, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 1: issue_taps<0, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 2: issue_taps<0, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 4: issue_taps<1, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 5: issue_taps<1, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 6: issue_taps<1, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 8: issue_taps<2, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 9: issue_taps<2, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  default: issue_taps<2, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
                 }
               }
               umma_commit(&empty[slot]);

@@ -995,7 +995,7 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (elect_one()) mbar_arrive(&tempty[buf]);
       if (st_tma) {
         fence_proxy_async_smem();                      // generic-proxy writes of the tile -> visible to the TMA unit
         epi_bar_sync();
@@ -1102,7 +1102,7 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty[buf]);
+    if (elect_one()) mbar_arrive(&tempty[buf]);
     if (PROBE) e_work += clock64() - t0;
   }
   if (XRSEG_ST_TMA_BUILD && BREG && KIND != 2 && p.st_tma && ew == 0 && lane == 0) bulk_wait_group0();   // the last tile is in global memory before the CTA exits
@@ -1194,7 +1194,7 @@ __device__ __forceinline__ void tma_epilogue_loop_tail(const ConvParams& p, uint
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tready[buf]);
+    if (elect_one()) mbar_arrive(&tready[buf]);
     // ---- pass 2: the 1x1's channels
     float hb2[16];
 #pragma unroll
@@ -1221,7 +1221,7 @@ __device__ __forceinline__ void tma_epilogue_loop_tail(const ConvParams& p, uint
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty[buf]);
+    if (elect_one()) mbar_arrive(&tempty[buf]);
     if (PROBE) e_work += clock64() - t0;
   }
   if (PROBE && p.dbg_clk && warp == TMA_FIRST_EPI_WARP && lane == 0) {

@@ -309,8 +309,8 @@ __global__ void __launch_bounds__(128, NV == 2 ? 8 : 4) dwconv3x3_kernel(const D
   sums_of(rl, rc, rr, s_up0, dummy, dummy);
   load_raw(y0, rl, rc, rr);
   sums_of(rl, rc, rr, s_mid0, s_mid1, dummy);
-  load_raw(y0 + 1, rl, rc, rr);                  // the loop always has the NEXT input row's loads in flight
-  size_t opix = (static_cast<size_t>(b) * p.H + y0) * p.W + x;
+  load_raw(y0 + 1, rl, rc, rr);                  // the loop always has the NEXT input row's loads in flight (two rows ahead:
+  size_t opix = (static_cast<size_t>(b) * p.H + y0) * p.W + x;   // 107 registers, h3.cls.0dw 47.7 -> 45.5 us, 1dw 51.5 -> 53.2 us: no gain)
   for (int y = y0; y < y1; ++y, opix += p.W) {
     Vec nl, nc, nr;
     load_raw(y + 2, nl, nc, nr);                 // prefetch for the next iteration (zero rows past the image)
@@ -947,7 +947,7 @@ constexpr int STEM2_CHUNKS = 26;                        // 16-byte chunks per pa
 constexpr int STEM2_PITCH = STEM2_CHUNKS * 16;          // shared bytes per patch row
 
 template <int NT>
-__global__ void __launch_bounds__(256, NT == 2 ? 5 : 3) stem_rows_kernel(const StemMmaParams p) {
+__global__ void __launch_bounds__(256, NT == 2 ? 4 : 3) stem_rows_kernel(const StemMmaParams p) {
   XR_PDL_ENTRY();
   __shared__ __align__(16) uint8_t patch[STEM2_PR * STEM2_PITCH];
   const int Ho = p.H >> 1, Wo = p.W >> 1;
@@ -970,24 +970,39 @@ __global__ void __launch_bounds__(256, NT == 2 ? 5 : 3) stem_rows_kernel(const S
     bs[nt][0] = p.bias[nt * 8 + 2 * t];
     bs[nt][1] = p.bias[nt * 8 + 2 * t + 1];
   }
-  // stage the raw patch: shared byte s of row r = image byte a0 + s - 1 of row 2 oy0 - 1 + r (zero outside the image)
-  for (int u = tid; u < STEM2_PR * STEM2_CHUNKS; u += 256) {
-    const int r = u / STEM2_CHUNKS, j = u - r * STEM2_CHUNKS;
-    const int iy = 2 * oy0 - 1 + r;
-    const int off = a0 + 16 * j;                        // first image byte of the 16-byte load
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    uint32_t prev = 0u;
-    if (iy >= 0 && iy < p.H) {
-      const uint8_t* rowp = img + static_cast<size_t>(p.flip ? p.H - 1 - iy : iy) * p.stride_bytes;
-      if (off >= 0 && off < row_bytes) v = __ldg(reinterpret_cast<const uint4*>(rowp + off));
-      if (off >= 4 && off - 4 < row_bytes) prev = __ldg(reinterpret_cast<const uint32_t*>(rowp + off - 4));
+  // stage the raw patch: shared byte s of row r = image byte a0 + s - 1 of row 2 oy0 - 1 + r (zero outside the image).
+  // ALL of a thread's loads are issued before the first one is used: as a rolled loop (load, wait, shift, store, next) every
+  // thread had one 16-byte load in flight and a quarter of the kernel's stall samples sat on the funnel shift behind it
+  // (ncu source page, profiles/r2final_full_stem); four CTAs per SM instead of five pay for the registers.
+  {
+    constexpr int TOTAL = STEM2_PR * STEM2_CHUNKS, ITERS = (TOTAL + 255) / 256;
+    uint4 v[ITERS];
+    uint32_t prev[ITERS];
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int u = tid + 256 * k;
+      const int r = u / STEM2_CHUNKS, j = u - r * STEM2_CHUNKS;
+      const int iy = 2 * oy0 - 1 + r;
+      const int off = a0 + 16 * j;                      // first image byte of the 16-byte load
+      v[k] = make_uint4(0u, 0u, 0u, 0u);
+      prev[k] = 0u;
+      if (u < TOTAL && iy >= 0 && iy < p.H) {
+        const uint8_t* rowp = img + static_cast<size_t>(p.flip ? p.H - 1 - iy : iy) * p.stride_bytes;
+        if (off >= 0 && off < row_bytes) v[k] = __ldg(reinterpret_cast<const uint4*>(rowp + off));
+        if (off >= 4 && off - 4 < row_bytes) prev[k] = __ldg(reinterpret_cast<const uint32_t*>(rowp + off - 4));
+      }
     }
-    uint4 o;
-    o.x = __funnelshift_l(prev, v.x, 8);                // shift the byte stream up by one byte
-    o.y = __funnelshift_l(v.x, v.y, 8);
-    o.z = __funnelshift_l(v.y, v.z, 8);
-    o.w = __funnelshift_l(v.z, v.w, 8);
-    *reinterpret_cast<uint4*>(patch + r * STEM2_PITCH + 16 * j) = o;
+#pragma unroll
+    for (int k = 0; k < ITERS; ++k) {
+      const int u = tid + 256 * k;
+      const int r = u / STEM2_CHUNKS, j = u - r * STEM2_CHUNKS;
+      uint4 o;
+      o.x = __funnelshift_l(prev[k], v[k].x, 8);        // shift the byte stream up by one byte
+      o.y = __funnelshift_l(v[k].x, v[k].y, 8);
+      o.z = __funnelshift_l(v[k].y, v[k].z, 8);
+      o.w = __funnelshift_l(v[k].z, v[k].w, 8);
+      if (u < TOTAL) *reinterpret_cast<uint4*>(patch + r * STEM2_PITCH + 16 * j) = o;
+    }
   }
   __syncthreads();
   auto cvt = [](uint32_t pair) {                        // two bytes -> two fp16 values

@@ -352,8 +352,12 @@ static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvPar
       const int nks = d.Cin / cb, nsub = ceil_div(R * p.Wp, 128);
       // operand fetch.  XRSEG_S2_ROWCOST=1 models it as ~1.5 cycles per TMA box row whatever its width
       // (tools/probe_tma_rate.cu), four plane boxes per K-block, and the MMA issue as parallel over the sub-tile warps;
-      // measured on the network: n17 33 -> 28 us but b3 65 -> 70 us, so the old bytes / 40 B/clk estimate stays the default
-      static const bool rowcost = [] { const char* e = getenv("XRSEG_S2_ROWCOST"); return e && e[0] == '1'; }();
+      // measured on the network (gpurun_out s17, s19): n17 (80 -> 40) alone 40.7 -> 27.4 us, b5 51 -> 50 us, b3 (160 -> 80) 64 -> 69 us;
+      // restricted to output maps up to 40 x 40 (XRSEG_S2_ROWCOST=2) one runner alone gains 1 %, but four runners LOSE 2 % (38.1k ->
+      // 37.3k frames/s, three A/B pairs): n17's new plan has 512 items and leaves the half-width rule of the small launches
+      // (xrseg_api.cu), and side by side beats faster.  The bytes / 40 B/clk estimate stays the default.
+      static const int rowcost_env = [] { const char* e = getenv("XRSEG_S2_ROWCOST"); return e ? atoi(e) : 0; }();
+      const bool rowcost = rowcost_env == 1 || (rowcost_env == 2 && Ho <= 40);
       // one issuing warp per sub-tile: the issue cost (~50 cycles per MMA, ~600 per stage hand-over) is paid in parallel,
       // the tensor pipe (128 x N x 16 MACs per MMA at 4096 MACs / cycle) is shared
       const double t_issue = nks * 600.0 + 9.0 * (d.Cin / 16) * 50.0;

@@ -541,9 +541,20 @@ void add_network_launches(xrseg_runner* r, int nb, std::vector<Launch>& out) {
             static const int tiny_grid = [] { const char* e = getenv("XRSEG_TINY_GRID"); return e ? atoi(e) : -1; }();
             static const int tiny_work = [] { const char* e = getenv("XRSEG_TINY_WORK"); return e ? atoi(e) : 296; }();
             static const int tiny_flat = [] { const char* e = getenv("XRSEG_TINY_FLAT_WORK"); return e ? atoi(e) : 800; }();
+            // XRSEG_TINY_MMA_CYC (experiment switch, default off): keep tensor-heavy layers at full width -- few items say nothing
+            // about their size (b7: 256 items of 72 N = 256 MMAs each, 21 us of tensor time on half the SMs against 10.5 us on all
+            // of them; h5.box.0, n20, h4.box.1, n13.cv1, b9.cv2 likewise).  Value = largest tensor time (cycles) of the busiest CTA
+            // of a half-width launch.  Measured with 9000 (gpurun_out s18): those launches alone 43 -> 28, 30 -> 21, 27 -> 21,
+            // 27 -> 19, 37 -> 28, 24 -> 21 us and one runner alone 32.0k -> 32.5k frames/s, but four runners 39.1k -> 38.2k and
+            // e2e 35.9k -> 35.6k: side by side on disjoint SMs beats taking turns even for these.
+            static const long tiny_mma = [] { const char* e = getenv("XRSEG_TINY_MMA_CYC"); return e ? atol(e) : (1L << 60); }();
             const int cap = tiny_grid < 0 ? r->num_sms / 2 : tiny_grid;
             const int work = p.m_tiles * p.n_tiles;
-            if (cap > 0 && d.use_tma && p.grid > cap && work <= (p.mode == MODE_FLAT_TMA ? tiny_flat : tiny_work)) p.grid = cap;
+            if (cap > 0 && d.use_tma && p.grid > cap && work <= (p.mode == MODE_FLAT_TMA ? tiny_flat : tiny_work)) {
+              const long mma_item = static_cast<long>(p.nks) * (p.kps > 1 ? p.kps : 1) * (p.taps > 0 ? p.taps : 1) * (p.cb / 16) * p.nsub *
+                                    (p.Ntile / 2 > 16 ? p.Ntile / 2 : 16);
+              if (ceil_div(work, cap) * mma_item <= tiny_mma) p.grid = cap;
+            }
           }
           p.in = ptr_of(r, o.x); p.out = ptr_of(r, o.y);
           if (o.layer2 >= 0) { p.out2 = ptr_of(r, o.y2); p.split_n = o.y.Cp; p.out2_pitch = o.y2.pitch; }

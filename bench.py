@@ -510,7 +510,14 @@ def main():
                                "frac_of_sustained_tensor_peak": conv_fl / (conv_ms * 1e-3) / 1e12 / tf_sust,
                                "gbs": sum(o[3] for o in conv) / (conv_ms * 1e-3) / 1e9,
                                "frac_of_hbm_peak": sum(o[3] for o in conv) / (conv_ms * 1e-3) / 1e9 / hbm, "ms": conv_ms},
-                "post": {o[0]: {"ms": o[1], "gbs": o[3] / (o[1] * 1e-3) / 1e9, "frac_of_hbm_peak": o[3] / (o[1] * 1e-3) / 1e9 / hbm} for o in post},
+                # per launch: timed here with CUDA events around the single launch (a ~20 us kernel carries the ~4 us of an isolated
+                # launch in that figure) and, beside it, the duration of the same launch in the committed ncu capture
+                # (profiles/traffic.json: gpu__time_duration of tools/gpu_round.sh, cold caches, the kernel alone)
+                "post": {o[0]: dict({"ms": o[1], "gbs": o[3] / (o[1] * 1e-3) / 1e9, "frac_of_hbm_peak": o[3] / (o[1] * 1e-3) / 1e9 / hbm},
+                                    **({"ncu_us": traffic_tab[o[0]]["us_under_ncu"],
+                                        "ncu_gbs": o[3] / (traffic_tab[o[0]]["us_under_ncu"] * 1e-6) / 1e9,
+                                        "ncu_frac_of_hbm_peak": o[3] / (traffic_tab[o[0]]["us_under_ncu"] * 1e-6) / 1e9 / hbm}
+                                       if traffic_tab.get(o[0], {}).get("us_under_ncu") else {})) for o in post},
                 "sum_launch_ms": tot,
                 # the whole step against the same peaks: all algorithmic FLOPs / bytes of one pass over the TIMED step (`value`:
                 # four runners overlapped, sustained clocks) -- the per-launch figures above time every launch ALONE with its

@@ -9,6 +9,8 @@ rng = np.random.default_rng(0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 #        name        cin cout  h    w   k  s
 cases = [("b2.cv2", 48, 64, 160, 160, 1, 1), ("proto.cv2", 64, 64, 160, 160, 3, 1), ("b3", 64, 64, 160, 160, 3, 2)]
+if os.environ.get("CASES") == "small":   # the latency-bound launches of the 20x20 / 40x40 stages
+    cases = [("b8.m0.m0.cv2", 64, 64, 20, 20, 3, 1), ("b8.cv2", 384, 256, 20, 20, 1, 1), ("n13.m0.cv2", 32, 64, 40, 40, 3, 1), ("b10.ffn.1", 256, 128, 20, 20, 1, 1)]
 os.environ["XRSEG_DBG_TIME"] = "1"
 for name, cin, cout, h, w, k, s in cases:
     x = rng.standard_normal((B, cin, h, w), dtype=np.float32)

@@ -62,12 +62,12 @@ int main(int argc, char** argv) {
       // tensor = 128 x N x 16 MACs per MMA at 4096 MACs / cycle, HBM = algorithmic bytes at 6.5 TB/s over the whole chip
       const int kps = p.kps > 1 ? p.kps : 1;
       const double rows_item = p.mode == MODE_FLAT_TMA ? static_cast<double>(p.slots) * kps * p.nks
-                               : p.mode == MODE_S2_TMA ? 4.0 * p.slots * p.nks : static_cast<double>(p.slots) * p.nks;
+                               : p.mode == MODE_S2_TMA ? (p.pair ? 2.0 : 4.0) * p.slots * p.nks : static_cast<double>(p.slots) * p.nks;
       const double per_cta = ceil(static_cast<double>(work) / p.grid);
       const double tma_us = rows_item * 1.5 * per_cta / 1900.0;
       const double mma_item = static_cast<double>(p.nsub) * p.taps * (p.mode == MODE_FLAT_TMA ? kps * p.nks : p.nks) * (p.cb / 16) * (p.Ntile / 2.0 > 16 ? p.Ntile / 2.0 : 16);
       const double mma_us = mma_item * per_cta / 1900.0;
-      printf("  est_us tma %.1f mma %.1f\n", tma_us, mma_us);
+      printf("  est_us tma %.1f mma %.1f%s\n", tma_us, mma_us, p.pair ? "  pixel-pair rows" : "");
     }
     if (p.smem_bytes <= 113 * 1024) ++total_smem_small;
   }

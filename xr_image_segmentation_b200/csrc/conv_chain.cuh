@@ -33,7 +33,7 @@ static inline bool plan_chain_layer(const ConvDesc& d, ConvParams& p) {
   tma_budget_ref() = CONV_SMEM_MAX - 12288;       // room for the kernel's tail region (plans of all layers, second bias buffer)
   if (d.k == 3 && d.stride == 1 && !d.transposed) ok = plan_conv_halo_tma_impl(one, 1, p);
   else if (d.k == 1 && d.stride == 1 && !d.transposed) ok = plan_conv_flat_tma_impl(one, 1, p, /*chain=*/true);
-  else if (d.k == 3 && d.stride == 2 && !d.transposed) ok = plan_conv_s2_tma_impl(one, 1, p);
+  else if (d.k == 3 && d.stride == 2 && !d.transposed) ok = plan_conv_s2_tma_impl(one, 1, p, false);
   tma_budget_ref() = CONV_SMEM_MAX;
   if (!ok || !p.sw || p.n_tiles > 2 || 2 * p.nsub * p.Ntile > 512) return false;
   p.B = d.B;
@@ -262,15 +262,15 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, int n_layers, int n_fra
                 const uint32_t d_tmem = d_base + static_cast<uint32_t>(my_u) * ntile_u;
                 const uint32_t acc0 = ks > 0 ? 1u : 0u;
                 switch ((p.mode == MODE_HALO_TMA ? 0 : p.mode == MODE_S2_TMA ? 4 : 8) + (kj == 4 ? 2 : kj == 2 ? 1 : 0)) {
-                  case 0: issue_taps<0, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  case 1: issue_taps<0, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  case 2: issue_taps<0, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  case 4: issue_taps<1, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  case 5: issue_taps<1, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  case 6: issue_taps<1, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  case 8: issue_taps<2, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  case 9: issue_taps<2, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
-                  default: issue_taps<2, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, static_cast<uint32_t>(p.lbo_a) >> 4, static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1); break;
+                  case 0: issue_taps<0, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  case 1: issue_taps<0, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  case 2: issue_taps<0, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  case 4: issue_taps<1, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  case 5: issue_taps<1, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  case 6: issue_taps<1, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  case 8: issue_taps<2, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  case 9: issue_taps<2, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
+                  default: issue_taps<2, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, static_cast<uint32_t>(p.Wp) * row16, 2u * (static_cast<uint32_t>(p.lbo_a) >> 4), static_cast<uint32_t>(p.slots) * row16, p.kps > 1 ? p.kps : 1, hi_sw, static_cast<uint32_t>(p.lbo_a) >> 4); break;
                 }
                 umma_commit(&empty[slot]);
               }

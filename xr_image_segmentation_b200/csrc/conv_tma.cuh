@@ -309,7 +309,7 @@ static inline CUtensorMap make_tensor_map_4d(const __half* base, const cuuint64_
 // out-of-bounds coordinates are the convolution's zero padding.  The input is read ~(R+1)/R times instead of 2.25x by
 // the im2col gather, and nothing but one thread touches addresses.
 // NOTE: p.H / p.W / p.Wp hold the OUTPUT geometry (Ho, Wo, Wo+1) in this mode -- that is what the epilogue indexes.
-static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvParams& p) {
+static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvParams& p, bool allow_pair = true) {
   if (!(d.k == 3 && d.stride == 2 && !d.transposed) || (d.H & 1) || (d.W & 1)) return false;
   p = ConvParams{};
   const int Ho = d.H / 2, Wo = d.W / 2;
@@ -396,6 +396,24 @@ static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvPar
   p.smem_off_a = p.smem_off_b + round_up(b_region, 1024) + 1024;        // one pad row block before the stages (offset -1)
   p.smem_bytes = p.smem_off_a + p.S * p.a_stage_bytes + 128 * rb + p.Wp * rb + 1024;   // tail: rows read past the last plane
   if (p.smem_bytes > XR_TMA_BUDGET) return false;
+  // PIXEL-PAIR rows: when a K-block is the whole pixel (cb == Cin == pixel pitch, <= 32 channels) the even and the odd pixel of
+  // a column pair are 2 * rb contiguous bytes in global memory, so the two x-parity planes of a row parity become ONE plane whose
+  // rows are [even pixel | odd pixel]: two TMA boxes per K-block with rows twice as wide instead of four -- the TMA unit
+  // delivers ~1.5 cycles per box row whatever its width (tools/probe_tma_rate.cu), and b1 (16 channels = 32-byte rows) was bound
+  // by exactly that.  The x parity of a tap becomes a +rb offset inside the row (like a k16 step), the operand swizzle is the
+  // one of the 2 * rb row; weights are unchanged.  XRSEG_S2_PAIR=0 turns it off.
+  static const bool pair_on = [] { const char* e = getenv("XRSEG_S2_PAIR"); return !(e && e[0] == '0'); }();
+  if (allow_pair && pair_on && p.nks == 1 && cb == d.Cin && d.in_pitch == d.Cin && cb <= 32) {
+    const int rba = 2 * rb;
+    const int lbo = round_up(p.slots * rba, 1024);
+    const int bytes = p.smem_off_a + p.S * 2 * lbo + 128 * rba + p.Wp * rba + 1024;
+    if (bytes <= XR_TMA_BUDGET) {
+      p.pair = 1;
+      p.lbo_a = lbo;
+      p.a_stage_bytes = 2 * lbo;
+      p.smem_bytes = bytes;
+    }
+  }
   const int work = p.m_tiles * p.n_tiles;
   p.grid = work < num_sms ? work : num_sms;
   p.fd_wp = make_fastdiv(p.Wp);
@@ -410,6 +428,16 @@ static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvPar
 // The four parity-plane maps of an NHWC input [B,H,W,C] (pixel pitch `pitch`): index py*2 + px.
 static inline TmapSet make_s2_tensor_maps(const __half* base, int B, int H, int W, int C, int pitch, const ConvParams& p) {
   TmapSet t{};
+  if (p.pair) {   // index py: rows of 2 C channels = the pixel pair (2 xs, 2 xs + 1) of row 2 ys + py
+    const cuuint64_t pdims[4] = {static_cast<cuuint64_t>(2 * C), static_cast<cuuint64_t>(W / 2), static_cast<cuuint64_t>(H / 2),
+                                 static_cast<cuuint64_t>(B)};
+    const cuuint64_t pstrides[3] = {static_cast<cuuint64_t>(pitch) * 4, static_cast<cuuint64_t>(W) * pitch * 4,
+                                    static_cast<cuuint64_t>(H) * W * pitch * 2};
+    const cuuint32_t pbox[4] = {static_cast<cuuint32_t>(2 * p.cb), static_cast<cuuint32_t>(p.Wp), static_cast<cuuint32_t>(p.hbox), 1};
+    for (int py = 0; py < 2; ++py)
+      t.m[py] = make_tensor_map_4d(base + static_cast<size_t>(py) * W * pitch, pdims, pstrides, pbox, p.sw + 1);
+    return t;
+  }
   const cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W / 2), static_cast<cuuint64_t>(H / 2),
                               static_cast<cuuint64_t>(B)};
   const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch) * 4, static_cast<cuuint64_t>(W) * pitch * 4,
@@ -746,13 +774,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 template <int MODE, int KJ>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_sub, uint32_t b_lo, uint64_t hi_sw,
                                            uint32_t idesc, uint32_t acc0, uint32_t row16, uint32_t tap16, uint32_t wp16,
-                                           uint32_t plane16, uint32_t blk16, int kps) {
+                                           uint32_t plane16, uint32_t blk16, int kps, uint64_t hi_a, uint32_t planex16) {
   uint32_t acc = acc0;
   if (MODE == 2) {
     for (int kb = 0; kb < kps; ++kb) {
 #pragma unroll
       for (int j = 0; j < KJ; ++j) {
-        umma_f16(d_tmem, hi_sw | (a_sub + 2u * j), hi_sw | (b_lo + 2u * j), idesc, acc);
+        umma_f16(d_tmem, hi_a | (a_sub + 2u * j), hi_sw | (b_lo + 2u * j), idesc, acc);
         acc = 1;
       }
       a_sub += blk16;
@@ -767,11 +795,13 @@ __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t a_sub, uint
     for (int kw = 0; kw < 3; ++kw) {
       uint32_t a_tap;
       if (MODE == 0) a_tap = a_sub + kh * wp16 + (kw - 1) * row16;                       // row shift kh*Wp + kw - 1
-      else a_tap = a_sub + (kh != 1 ? 2u : 0u) * plane16 + (kw != 1 ? plane16 : 0u) +    // plane (kh != 1, kw != 1)
-                   (kh == 2 ? wp16 : 0u) - (kw == 0 ? row16 : 0u);                        // row shift (kh == 2) Wp - (kw == 0)
+      else a_tap = a_sub + (kh != 1 ? plane16 : 0u) + (kw != 1 ? planex16 : 0u) +        // plane (kh != 1, kw != 1): plane16 = two plane
+                   (kh == 2 ? wp16 : 0u) - (kw == 0 ? row16 : 0u);                        // buffers, planex16 = one (pixel-pair rows: one
+                                                                                          // buffer / the odd pixel's offset in the row);
+                                                                                          // row shift (kh == 2) Wp - (kw == 0)
 #pragma unroll
       for (int j = 0; j < KJ; ++j) {
-        umma_f16(d_tmem, hi_sw | (a_tap + 2u * j), hi_sw | (b_lo + 2u * j), idesc, acc);
+        umma_f16(d_tmem, hi_a | (a_tap + 2u * j), hi_sw | (b_lo + 2u * j), idesc, acc);
         acc = 1;
       }
       b_lo += tap16;
@@ -1281,7 +1311,7 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
     mbar_fence_init();
     prefetch_tensormap(&tmap);
     if (p.mode == MODE_S2_TMA)
-      for (int i = 1; i < 4; ++i) prefetch_tensormap(&tmaps.m[i]);
+      for (int i = 1; i < (p.pair ? 2 : 4); ++i) prefetch_tensormap(&tmaps.m[i]);
     if (XRSEG_ST_TMA_BUILD && p.st_tma) {
       prefetch_tensormap(&tmaps.m[4]);
       if (p.split_n) prefetch_tensormap(&tmaps.m[5]);
@@ -1350,8 +1380,12 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
           const uint32_t a_dst = a_u32 + slot * p.a_stage_bytes;
           if (p.mode == MODE_S2_TMA) {
             // four parity planes: columns xs = -1 .. Wo-1, rows ys = y0 - py .. y0 - py + R  (y0 = first OUTPUT row)
-            for (int pl = 0; pl < 4; ++pl)
-              tma_load_4d(a_dst + pl * p.lbo_a, &tmaps.m[pl], &full[slot], ks * p.cb, -1, y0 - (pl >> 1), b);
+            if (p.pair) {   // two row-parity planes of pixel-pair rows (nks == 1)
+              for (int pl = 0; pl < 2; ++pl) tma_load_4d(a_dst + pl * p.lbo_a, &tmaps.m[pl], &full[slot], 0, -1, y0 - pl, b);
+            } else {
+              for (int pl = 0; pl < 4; ++pl)
+                tma_load_4d(a_dst + pl * p.lbo_a, &tmaps.m[pl], &full[slot], ks * p.cb, -1, y0 - (pl >> 1), b);
+            }
           } else if (flat) {
             // rows [tile*slots, +slots) of the activation matrix, hbox rows per box, kps K-blocks per stage; rows past
             // the end and channels past Cin arrive as zeros
@@ -1394,13 +1428,16 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const int kj = p.cb >> 4;
       const uint32_t idesc = p.idesc;
       const uint32_t ntile_u = static_cast<uint32_t>(p.Ntile);
-      const uint32_t rb = static_cast<uint32_t>(p.cb) * 2u;                 // swizzled row bytes
-      const uint32_t row16 = rb >> 4;                                        // one row in 16-byte units
+      const uint32_t rb = static_cast<uint32_t>(p.cb) * 2u;                 // swizzled row bytes of a K-block (weights; operand rows unless paired)
+      const uint32_t rba = p.pair ? 2u * rb : rb;                            // operand row bytes (pixel-pair rows: two K-blocks wide)
+      const uint32_t row16 = rba >> 4;                                       // one operand row in 16-byte units
       const uint32_t sub16 = 128u * row16;                                   // one 128-row sub-tile
       const uint32_t tap16 = (ntile_u * rb) >> 4;                            // one tap's weight tile
       const uint32_t b_stride_sw = static_cast<uint32_t>((p.b_stage_bytes + 1023) & ~1023);
       const uint32_t layout = p.sw == 3 ? 2u : (p.sw == 2 ? 4u : 6u);
       const uint64_t hi_sw = static_cast<uint64_t>(((8u * rb) >> 4) | (1u << 14) | (layout << 29)) << 32;
+      const uint32_t layout_a = p.pair ? (p.sw == 2 ? 2u : 4u) : layout;   // pair: the swizzle one step wider than the weights'
+      const uint64_t hi_a = static_cast<uint64_t>(((8u * rba) >> 4) | (1u << 14) | (layout_a << 29)) << 32;
       const bool mma_on = !PROBE || !(p.dbg_skip & 1);
       long long t_start = 0, t_bres = 0, t_tempty = 0, t_full = 0, t_issue = 0, t_fence = 0, t_commit = 0, t0 = 0;
       long long g_start = 0;
@@ -1463,7 +1500,9 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       uint32_t c_d_off = static_cast<uint32_t>(my_u) * ntile_u;
       uint32_t c_sel = static_cast<uint32_t>((p.mode == MODE_HALO_TMA ? 0 : p.mode == MODE_S2_TMA ? 4 : 8) + (kj == 4 ? 2 : kj == 2 ? 1 : 0));
       uint32_t c_bres = p.b_resident ? 1u : 0u;
-      const uint32_t c_wp16 = static_cast<uint32_t>(p.Wp) * row16, c_plane16 = static_cast<uint32_t>(p.lbo_a) >> 4;   // (not pinned: one LDC inside the mode's case)
+      const uint32_t c_wp16 = static_cast<uint32_t>(p.Wp) * row16;
+      const uint32_t c_planex16 = p.pair ? (rb >> 4) : static_cast<uint32_t>(p.lbo_a) >> 4;      // x parity: odd pixel inside the row / one plane buffer
+      const uint32_t c_plane16 = p.pair ? static_cast<uint32_t>(p.lbo_a) >> 4 : 2u * (static_cast<uint32_t>(p.lbo_a) >> 4);   // y parity
       const uint32_t c_blk16 = static_cast<uint32_t>(p.slots) * row16;
       const int c_kps = p.kps > 1 ? p.kps : 1;
       int tail_pending = -1;                      // item whose 1x1 has not been issued yet
@@ -1508,15 +1547,15 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
                 // straight-line issue code per (mode, k16 steps): the issuing thread is the bottleneck of thin layers, so
                 // everything but the two descriptor adds per MMA is resolved at compile time
                 switch (c_sel) {
-                  case 0: issue_taps<0, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  case 1: issue_taps<0, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  case 2: issue_taps<0, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  case 4: issue_taps<1, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  case 5: issue_taps<1, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  case 6: issue_taps<1, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  case 8: issue_taps<2, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  case 9: issue_taps<2, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
-                  default: issue_taps<2, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps); break;
+                  case 0: issue_taps<0, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  case 1: issue_taps<0, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  case 2: issue_taps<0, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  case 4: issue_taps<1, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  case 5: issue_taps<1, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  case 6: issue_taps<1, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  case 8: issue_taps<2, 1>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  case 9: issue_taps<2, 2>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
+                  default: issue_taps<2, 4>(d_tmem, a_sub, b_lo, hi_sw, idesc, acc0, row16, tap16, c_wp16, c_plane16, c_blk16, c_kps, hi_a, c_planex16); break;
                 }
               }
               umma_commit(&empty[slot]);

@@ -231,6 +231,9 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
             assert int(f["R"]) >= 1, l
         else:
             assert int(f["nsub"]) in (1, 2, 4), l   # an item is whole TMA boxes of <= 256 rows (batch > 64 once picked 3)
+    # pixel-pair operand rows (conv_tma.cuh plan_conv_s2_tma_impl): only where a K-block is the whole pixel -- the n scale's b1
+    paired = [l.split()[0] for l in rows if "pixel-pair rows" in l]
+    assert paired == (["b1"] if scale == "n" else []), paired
 
 
 @pytest.mark.parametrize("scale,whole_block,expect", [

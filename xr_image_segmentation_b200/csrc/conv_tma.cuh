@@ -1288,10 +1288,10 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role code uses the uniform datapath
   const int lane = tid & 31;
-  const int total_work = p.m_tiles * p.n_tiles;
+  const int total_work = p.total_work;        // = m_tiles * n_tiles (launch_conv_halo_tma)
 
   const int n_issuers = p.sw ? p.nsub : 1;    // MMA-issuing warps (swizzled path: one per sub-tile)
-  const int nbuf = p.nbuf > 2 ? p.nbuf : 2;   // TMEM accumulator sets in flight
+  const int nbuf = p.nbuf;                    // TMEM accumulator sets in flight (>= 2: launch_conv_halo_tma)
   if (tid == 0) {
     for (int i = 0; i < CONV_MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
@@ -1649,7 +1649,10 @@ static inline void conv_tma_prepare_device() {
 #endif
 }
 
-static inline void launch_conv_halo_tma(const ConvParams& p, const TmapSet& maps, cudaStream_t stream) {
+static inline void launch_conv_halo_tma(const ConvParams& p_in, const TmapSet& maps, cudaStream_t stream) {
+  ConvParams p = p_in;                        // values the kernel would otherwise compute and keep (or spill) per thread
+  p.total_work = p.m_tiles * p.n_tiles;
+  if (p.nbuf < 2) p.nbuf = 2;
 #ifdef XRSEG_DEBUG_API
   if (p.dbg_skip || p.dbg_clk) {   // probe instantiation: only reachable through xrseg_debug_conv
     launch_k(conv_halo_tma_kernel<true>, p.grid, TMA_THREADS, p.smem_bytes, stream, p, maps);

@@ -93,6 +93,8 @@ struct ConvParams {
   int flat_rows;                    // MODE_FLAT_TMA: B*H*W rows of the activation matrix
   int kps;                          // MODE_FLAT_TMA: K-blocks (of cb channels) per pipeline stage; 0 / 1 elsewhere
   int nbuf;                         // TMA kernel: TMEM accumulator sets in flight (0 = 2)
+  int total_work;                   // TMA kernel: m_tiles * n_tiles, filled in by launch_conv_halo_tma (a kernel-parameter read instead of a
+                                    // computed value the register allocator spills: the reload sat on the item loop's back edge)
   int pair;                         // s2 TMA mode: operand rows hold a PIXEL PAIR (2 cb channels, conv_tma.cuh plan_conv_s2_tma_impl)
   // Sibling fusion (TMA kernel): two convolutions that read the same input run as ONE GEMM with N = Cout_a + Cout_b;
   // output columns >= split_n go to out2 (pixel pitch out2_pitch), relative to split_n.  split_n == 0: single output.

@@ -139,6 +139,15 @@ static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvP
   p.Ntile = d.Cout <= 256 ? d.Cout : 256;
   if (d.Cout % p.Ntile) return false;
   p.n_tiles = d.Cout / p.Ntile;
+  // Wide maps with 128 output channels (the s scale's proto.cv2, 160 x 160): two sub-tiles of 128 columns fill the accumulator set,
+  // and 256 positions hold ONE 162-position row -- 63 % of every MMA's rows valid, the halo read three times.  Two N tiles of 64
+  // channels give four sub-tiles = three rows per item (95 % valid) for the same TMEM columns; the input is read once per N tile.
+  // XRSEG_HALO_SPLIT_N=0 turns it off.
+  static const bool split_n_on = [] { const char* e = getenv("XRSEG_HALO_SPLIT_N"); return !(e && e[0] == '0'); }();
+  if (split_n_on && p.n_tiles == 1 && p.Ntile == 128 && 256 / (d.W + 2) < 2 && 512 / (d.W + 2) >= 2) {
+    p.Ntile = 64;
+    p.n_tiles = 2;
+  }
   p.idesc = umma_idesc_f16(p.Ntile, 0);
   p.mode = MODE_HALO_TMA;
   p.Wp = d.W + 2;

@@ -243,8 +243,9 @@ def main():
     if args.config == 2:
         args.scale = "s"
         args.batch = 512 // world_env if world_env in (2, 4, 8) else 64
-        args.value_streams = min(args.value_streams, 2)       # 256-frame YOLO11s arenas: keep the runner count down
-        args.e2e_depth = min(args.e2e_depth, 2)
+        if args.batch > 64:                                   # 128 / 256-frame YOLO11s arenas: keep the runner count down
+            args.value_streams = min(args.value_streams, 2)
+            args.e2e_depth = min(args.e2e_depth, 2)
     if args.scale == "s":
         SCALE, SEED_WEIGHTS = "s", 3
         WORKLOAD = (f"YOLO11s-seg 640x640, batch {args.batch} synthetic uint8 frames per GPU, random-init weights (seed 3); "

@@ -103,6 +103,23 @@ static inline int tma_preferred_budget() {
   return kb > 0 && kb * 1024 < CONV_SMEM_MAX ? kb * 1024 : CONV_SMEM_MAX;
 }
 #define XR_TMA_BUDGET (tma_budget_ref())
+// Few work items (batch-1 streaming: a 20x20 layer is one or two items): a layer with >= 128 output channels whose items would
+// keep at most half the SMs busy is planned as TWO N tiles -- twice the CTAs, half the MMAs (and half the streamed weights) on
+// each one's critical path.  Set by the plan_conv_*_tma wrappers for a second planning pass; XRSEG_SPLIT_SMALL=0 turns it off.
+static inline int& tma_force_split_ref() {
+  static thread_local int f = 0;
+  return f;
+}
+static inline void tma_apply_split(ConvParams& p, int ncols) {
+  if (tma_force_split_ref() && p.n_tiles == 1 && p.Ntile >= 128 && (p.Ntile / 2) % 16 == 0 && ncols == p.Ntile) {
+    p.Ntile /= 2;
+    p.n_tiles = 2;
+  }
+}
+static inline bool tma_wants_split(const ConvParams& p, int num_sms) {
+  static const bool on = [] { const char* e = getenv("XRSEG_SPLIT_SMALL"); return !(e && e[0] == '0'); }();
+  return on && p.n_tiles == 1 && p.Ntile >= 128 && (p.Ntile / 2) % 16 == 0 && !p.transposed && 2 * p.m_tiles <= num_sms;
+}
 
 // A CTA never has more than ceil(work / grid) * nks stages to fetch: a deeper ring only costs shared memory, and a small
 // footprint is what lets the next kernel's CTAs become co-resident early (programmatic dependent launch) so that their
@@ -148,6 +165,7 @@ static inline bool plan_conv_halo_tma_impl(const ConvDesc& d, int num_sms, ConvP
     p.Ntile = 64;
     p.n_tiles = 2;
   }
+  tma_apply_split(p, d.Cout);
   p.idesc = umma_idesc_f16(p.Ntile, 0);
   p.mode = MODE_HALO_TMA;
   p.Wp = d.W + 2;
@@ -329,6 +347,7 @@ static inline bool plan_conv_s2_tma_impl(const ConvDesc& d, int num_sms, ConvPar
   p.Ntile = d.Cout <= 256 ? d.Cout : 256;
   if (d.Cout % p.Ntile) return false;
   p.n_tiles = d.Cout / p.Ntile;
+  tma_apply_split(p, d.Cout);
   p.idesc = umma_idesc_f16(p.Ntile, 0);
   p.mode = MODE_S2_TMA;
   p.taps = 9;
@@ -478,6 +497,7 @@ static inline bool plan_conv_flat_tma_impl(const ConvDesc& d, int num_sms, ConvP
   p.Ntile = ncols <= 256 ? ncols : 256;
   if (ncols % p.Ntile) return false;
   p.n_tiles = ncols / p.Ntile;
+  if (!convt) tma_apply_split(p, ncols);
   p.idesc = umma_idesc_f16(p.Ntile, 0);
   p.mode = MODE_FLAT_TMA;
   p.taps = 1;
@@ -557,7 +577,13 @@ static inline bool same_tiling(const ConvParams& a, const ConvParams& b) {
 }
 static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams& p, bool swizzled = true, int max_budget = CONV_SMEM_MAX) {
   tma_budget_ref() = max_budget;
-  const bool ok = plan_conv_halo_tma_impl(d, num_sms, p, swizzled);
+  bool ok = plan_conv_halo_tma_impl(d, num_sms, p, swizzled);
+  if (ok && swizzled && tma_wants_split(p, num_sms)) {
+    ConvParams q;
+    tma_force_split_ref() = 1;
+    if (plan_conv_halo_tma_impl(d, num_sms, q, swizzled)) p = q;
+    tma_force_split_ref() = 0;
+  }
   tma_budget_ref() = CONV_SMEM_MAX;
   if (!ok) return false;
   if (max_budget != CONV_SMEM_MAX) return true;
@@ -571,7 +597,13 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
 }
 static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& p, int max_budget = CONV_SMEM_MAX) {
   tma_budget_ref() = max_budget;
-  const bool ok = plan_conv_s2_tma_impl(d, num_sms, p);
+  bool ok = plan_conv_s2_tma_impl(d, num_sms, p);
+  if (ok && tma_wants_split(p, num_sms)) {
+    ConvParams q;
+    tma_force_split_ref() = 1;
+    if (plan_conv_s2_tma_impl(d, num_sms, q)) p = q;
+    tma_force_split_ref() = 0;
+  }
   tma_budget_ref() = CONV_SMEM_MAX;
   if (!ok) return false;
   if (max_budget != CONV_SMEM_MAX) return true;
@@ -585,7 +617,13 @@ static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& 
 }
 static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams& p, int max_budget = CONV_SMEM_MAX) {
   tma_budget_ref() = max_budget;
-  const bool ok = plan_conv_flat_tma_impl(d, num_sms, p);
+  bool ok = plan_conv_flat_tma_impl(d, num_sms, p);
+  if (ok && tma_wants_split(p, num_sms)) {
+    ConvParams q;
+    tma_force_split_ref() = 1;
+    if (plan_conv_flat_tma_impl(d, num_sms, q)) p = q;
+    tma_force_split_ref() = 0;
+  }
   tma_budget_ref() = CONV_SMEM_MAX;
   if (!ok) return false;
   if (max_budget != CONV_SMEM_MAX) return true;

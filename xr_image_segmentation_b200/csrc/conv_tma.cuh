@@ -111,14 +111,18 @@ static inline int& tma_force_split_ref() {
   return f;
 }
 static inline void tma_apply_split(ConvParams& p, int ncols) {
-  if (tma_force_split_ref() && p.n_tiles == 1 && p.Ntile >= 128 && (p.Ntile / 2) % 16 == 0 && ncols == p.Ntile) {
-    p.Ntile /= 2;
-    p.n_tiles = 2;
+  const int f = tma_force_split_ref();          // 0, 2 or 4 N tiles
+  if (f && p.n_tiles == 1 && p.Ntile >= 64 * f && (p.Ntile / f) % 16 == 0 && ncols == p.Ntile) {
+    p.Ntile /= f;
+    p.n_tiles = f;
   }
 }
-static inline bool tma_wants_split(const ConvParams& p, int num_sms) {
-  static const bool on = [] { const char* e = getenv("XRSEG_SPLIT_SMALL"); return !(e && e[0] == '0'); }();
-  return on && p.n_tiles == 1 && p.Ntile >= 128 && (p.Ntile / 2) % 16 == 0 && !p.transposed && 2 * p.m_tiles <= num_sms;
+// 0: no split; 2 / 4: N tiles for the second planning pass (four only for 256 output channels on at most a quarter of the SMs)
+static inline int tma_wants_split(const ConvParams& p, int num_sms) {
+  static const int mode = [] { const char* e = getenv("XRSEG_SPLIT_SMALL"); return e ? atoi(e) : 4; }();   // 0 off, 2: halves only
+  if (!mode || p.n_tiles != 1 || p.Ntile < 128 || p.transposed || 2 * p.m_tiles > num_sms) return 0;
+  if (mode >= 4 && p.Ntile == 256 && 4 * p.m_tiles <= num_sms) return 4;
+  return (p.Ntile / 2) % 16 == 0 ? 2 : 0;
 }
 
 // A CTA never has more than ceil(work / grid) * nks stages to fetch: a deeper ring only costs shared memory, and a small
@@ -580,7 +584,7 @@ static inline bool plan_conv_halo_tma(const ConvDesc& d, int num_sms, ConvParams
   bool ok = plan_conv_halo_tma_impl(d, num_sms, p, swizzled);
   if (ok && swizzled && tma_wants_split(p, num_sms)) {
     ConvParams q;
-    tma_force_split_ref() = 1;
+    tma_force_split_ref() = tma_wants_split(p, num_sms);
     if (plan_conv_halo_tma_impl(d, num_sms, q, swizzled)) p = q;
     tma_force_split_ref() = 0;
   }
@@ -600,7 +604,7 @@ static inline bool plan_conv_s2_tma(const ConvDesc& d, int num_sms, ConvParams& 
   bool ok = plan_conv_s2_tma_impl(d, num_sms, p);
   if (ok && tma_wants_split(p, num_sms)) {
     ConvParams q;
-    tma_force_split_ref() = 1;
+    tma_force_split_ref() = tma_wants_split(p, num_sms);
     if (plan_conv_s2_tma_impl(d, num_sms, q)) p = q;
     tma_force_split_ref() = 0;
   }
@@ -620,7 +624,7 @@ static inline bool plan_conv_flat_tma(const ConvDesc& d, int num_sms, ConvParams
   bool ok = plan_conv_flat_tma_impl(d, num_sms, p);
   if (ok && tma_wants_split(p, num_sms)) {
     ConvParams q;
-    tma_force_split_ref() = 1;
+    tma_force_split_ref() = tma_wants_split(p, num_sms);
     if (plan_conv_flat_tma_impl(d, num_sms, q)) p = q;
     tma_force_split_ref() = 0;
   }
@@ -989,8 +993,8 @@ __device__ __forceinline__ void tma_epilogue_loop(const ConvParams& p, uint32_t 
   long long e_wait = 0, e_work = 0, t0 = 0;
   pdl_wait();   // before the first residual read / output store
   for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-    const int tile = n_tiles == 1 ? w : (w >> 1);
-    const int n_tile = n_tiles == 1 ? 0 : (w & 1);
+    const int tile = w >> (n_tiles == 4 ? 2 : (n_tiles == 2 ? 1 : 0));   // n_tiles is 1, 2 or 4: work item = (row tile, N tile), N tile fastest
+    const int n_tile = w & (n_tiles - 1);
     const int b = fd_div(fd_tpi, tile);
     const int y0 = (tile - b * tpi) * Rr;
     const int buf = buf_c;
@@ -1409,8 +1413,8 @@ conv_halo_tma_kernel(const __grid_constant__ ConvParams p, const __grid_constant
       const bool flat = p.mode == MODE_FLAT_TMA;
       const int S = p.S;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int tile = p.n_tiles == 1 ? w : (w >> 1);
-        const int n_tile = p.n_tiles == 1 ? 0 : (w & 1);
+        const int tile = w >> (p.n_tiles == 4 ? 2 : (p.n_tiles == 2 ? 1 : 0));
+        const int n_tile = w & (p.n_tiles - 1);
         const int b = fd_div(p.fd_hp1, tile);
         const int y0 = (tile - b * p.tpi) * p.R;
         for (int ks = 0; ks < p.nks; ++ks) {

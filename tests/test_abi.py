@@ -231,6 +231,15 @@ def test_every_conv_plan_respects_the_hardware_limits(plan_dump, batch, scale):
             assert int(f["R"]) >= 1, l
         else:
             assert int(f["nsub"]) in (1, 2, 4), l   # an item is whole TMA boxes of <= 256 rows (batch > 64 once picked 3)
+    # N tiles: two for the s scale's wide 128-channel proto.cv2 at every batch; two / four for >= 128 / 256-channel layers whose
+    # work items keep at most half / a quarter of the SMs busy (batch-1 streaming); one everywhere else at the bench batch
+    nt = {l.split()[0]: int(l.split()[l.split().index("ntiles") + 1]) for l in rows}
+    if batch == 64 and scale == "n":
+        assert all(v == 1 for v in nt.values()), nt
+    if batch == 64 and scale == "s":
+        assert nt["proto.cv2"] == 2 and nt["proto.cv1"] == 1 and nt["b7"] == 2, nt      # (512-channel layers are two tiles of 256 anyway)
+    if batch == 1 and scale == "n":
+        assert nt["b8.cv2"] == 4 and nt["b9.cv2"] == 4 and nt["b6.cv1"] == 2 and nt["b2.cv2"] == 1 and nt["proto.cv2"] == 1, nt
     # pixel-pair operand rows (conv_tma.cuh plan_conv_s2_tma_impl): only where a K-block is the whole pixel -- the n scale's b1
     paired = [l.split()[0] for l in rows if "pixel-pair rows" in l]
     assert paired == (["b1"] if scale == "n" else []), paired

@@ -67,7 +67,7 @@ int main(int argc, char** argv) {
       const double tma_us = rows_item * 1.5 * per_cta / 1900.0;
       const double mma_item = static_cast<double>(p.nsub) * p.taps * (p.mode == MODE_FLAT_TMA ? kps * p.nks : p.nks) * (p.cb / 16) * (p.Ntile / 2.0 > 16 ? p.Ntile / 2.0 : 16);
       const double mma_us = mma_item * per_cta / 1900.0;
-      printf("  est_us tma %.1f mma %.1f%s\n", tma_us, mma_us, p.pair ? "  pixel-pair rows" : "");
+      printf("  est_us tma %.1f mma %.1f  ntiles %d%s\n", tma_us, mma_us, p.n_tiles, p.pair ? "  pixel-pair rows" : "");
     }
     if (p.smem_bytes <= 113 * 1024) ++total_smem_small;
   }
